@@ -1,0 +1,298 @@
+/* meep_b200.h — C ABI of the B200 (sm_100a) FDTD time-stepping engine.
+ *
+ * This is the drop-in boundary for ONE path of NanoComp/meep: meep::fields::step() and the
+ * inner loops it drives.  Every entry point takes plain pointers and sizes only (no C++ types,
+ * no torch types).  Each "job" struct is the argument list of one reference inner-loop function
+ * with the grid_volume / ivec arguments already reduced to the integers the reference's loop
+ * macros derive from them; the citation next to each struct names the reference interface it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - All array pointers inside jobs are DEVICE pointers obtained from mb200_malloc().
+ *  - Arrays use the reference's own per-chunk layout (src/vec.cpp:482-494: (nx+1)(ny+1)(nz+1),
+ *    last direction fastest); index arithmetic is therefore identical on host and device.
+ *  - dtype selects realnum: MB200_F64 (reference default) or MB200_F32 (--enable-single,
+ *    src/meep.hpp:42-46).  Scalars travel as double and are narrowed to realnum in the kernel,
+ *    exactly where the reference narrows them (a realnum function parameter).
+ *  - A "plan" is a batch of jobs of one kind uploaded once (descriptor table + tile map in HBM)
+ *    and launched as ONE grid per run; plans are rebuilt only when the chunk layout changes.
+ *  - Everything is asynchronous on the context's stream; mb200_sync()/mb200_d2h() synchronise.
+ *  - Return value 0 = success; otherwise nonzero and mb200_last_error() describes the failure.
+ *    There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef MEEP_B200_H
+#define MEEP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB200_ABI_VERSION 1
+
+enum { MB200_F64 = 0, MB200_F32 = 1 };
+
+typedef struct mb200_ctx mb200_ctx;
+typedef struct mb200_plan mb200_plan;
+
+/* ---- loop box: what LOOP_OVER_IVECS(gv, is, ie, idx) expands to (src/meep/vec.hpp:151-169):
+ *      idx = idx0 + i1*s[0] + i2*s[1] + i3*s[2],  0 <= ik < n[k].  Unused loops have n = 1. */
+typedef struct {
+  int64_t idx0;
+  int64_t s[3];
+  int32_t n[3];
+  int32_t reserved;
+} mb200_box_t;
+
+/* ---- PML coefficient lookup: KSTRIDE_DEF / KDEF (src/meep_internals.hpp:217-226):
+ *      k = k0 + ks[0]*i1 + ks[1]*i2 + ks[2]*i3 indexes the 1-D arrays sig/kap/siginv
+ *      (src/structure.cpp:665-688).  sig == NULL means "NO_DIRECTION" (term absent). */
+typedef struct {
+  const void *sig, *kap, *siginv;
+  int32_t k0;
+  int32_t ks[3];
+} mb200_pml_t;
+
+/* ---- step_curl (src/meep_internals.hpp:90-95, src/step_generic.cpp:65-249), called from
+ *      fields_chunk::step_db (src/step_db.cpp:124-127).  Same semantics incl. the g1==NULL swap. */
+typedef struct {
+  mb200_box_t box;
+  void *f;
+  const void *g1, *g2;
+  int64_t s1, s2;
+  double dtdx, dt;
+  mb200_pml_t pml;  /* dsig : sig, kap, siginv */
+  mb200_pml_t pmlu; /* dsigu: sigu, kapu, siginvu */
+  void *fu;
+  const void *cnd, *cndinv;
+  void *fcnd;
+} mb200_curl_job_t;
+
+/* ---- step_update_EDHB (src/meep_internals.hpp:97-101, src/step_generic.cpp:566-785), called
+ *      from fields_chunk::update_eh (src/update_eh.cpp:190-195).  pmlw.sig/kap = sigw/kapw
+ *      (pmlw.siginv is unused).  Same semantics incl. the g1/g2 swap rule (line 573). */
+typedef struct {
+  mb200_box_t box;
+  void *f;
+  const void *g, *g1, *g2;
+  const void *u, *u1, *u2;
+  int64_t s, s1, s2;
+  const void *chi2, *chi3;
+  void *fw;
+  mb200_pml_t pmlw;
+} mb200_edhb_job_t;
+
+/* ---- lorentzian_susceptibility::update_P (src/susceptibility.cpp:188-262), one job per
+ *      (component, cmp).  Constants are computed by the caller in realnum arithmetic exactly as
+ *      lines 192-195 do.  s1/w1 (and s2/w2) NULL => isotropic / 2x2 cases. */
+typedef struct {
+  mb200_box_t box;
+  void *p, *pp;
+  const void *w, *s;
+  const void *w1, *s1, *w2, *s2;
+  int64_t is, is1, is2;
+  double gamma1inv, gamma1, omega0dtsqr, omega0dtsqr_denom;
+} mb200_lorentz_job_t;
+
+/* ---- f_minus_p initialisation: memcpy D -> f_minus_p (src/update_eh.cpp:114-120) followed by
+ *      lorentzian_susceptibility::subtract_P for each polarisation (src/susceptibility.cpp:264-281):
+ *      fmp[i] = (d ? d[i] : fmp[i]) - sum_k p[k][i],  0 <= i < ntot. */
+#define MB200_MAX_P 8
+typedef struct {
+  void *fmp;
+  const void *d;
+  const void *p[MB200_MAX_P];
+  int32_t np;
+  int32_t reserved;
+  int64_t ntot;
+} mb200_fmp_job_t;
+
+/* ---- fields_chunk::step_source (src/step.cpp:295-318) [mode 0] and the integrated-source dipole
+ *      subtraction in fields_chunk::update_eh (src/update_eh.cpp:128-138) [mode 1].
+ *      amp = src_vol::amp (complex<double>, interleaved), index = src_vol::index.
+ *      Per run the caller supplies scalars[scalar_slot] = src_time::current() (mode 0) or
+ *      src_time::dipole() (mode 1) as interleaved complex<double>.
+ *      mode 0: A = amp[j]*scalar*dt*(cndinv ? cndinv[i] : 1);  mode 1: A = amp[j]*scalar;
+ *      f_re[i] -= Re A;  if (f_im) f_im[i] -= Im A.   (computed in double, narrowed at the store) */
+typedef struct {
+  void *f_re, *f_im;
+  const void *cndinv;
+  const int64_t *index;
+  const double *amp;
+  int64_t npts;
+  double dt;
+  int32_t scalar_slot;
+  int32_t mode;
+} mb200_src_job_t;
+
+/* ---- chunk-boundary exchange: fields::step_boundaries gather + process_incoming_chunk_data
+ *      scatter (src/step.cpp:172-223, 251-278) for chunk pairs resident on the same device.
+ *      src/dst are device arrays of device ADDRESSES (the translated connections_out /
+ *      connections_in vectors, src/meep.hpp:1476-1479), ordered PHASE || NEGATE || COPY:
+ *      first 2*n_phase entries are (re,im) pairs multiplied by phase[k] (complex<realnum>),
+ *      next n_negate entries are negated, the last n_copy are copied. */
+typedef struct {
+  const uint64_t *src;
+  const uint64_t *dst;
+  const void *phase;
+  int64_t n_phase, n_negate, n_copy;
+} mb200_halo_job_t;
+
+/* ---- fields_chunk::zero_metal (src/boundaries.cpp:310-313): *ptrs[k] = 0. */
+typedef struct {
+  const uint64_t *ptrs;
+  int64_t n;
+} mb200_zero_job_t;
+
+/* ---- dft_chunk::update_dft (src/dft.cpp:266-308).  wgt_* are the per-loop-direction edge
+ *      weights of IVEC_LOOP_WEIGHT (src/meep/vec.hpp:372-383): s0,s1,e0,e1 .in_direction(loop_dk).
+ *      Per run the caller supplies the phase table dft_phase[] (complex<realnum>, computed in
+ *      double on the host as polar(1, omega*t)*scale then narrowed: src/dft.cpp:270-271);
+ *      this job reads phases[phase_slot .. phase_slot+nomega).
+ *      dft[nomega*p + i] += phase[i] * f,  p = (i1*n2 + i2)*n3 + i3. */
+typedef struct {
+  mb200_box_t box;
+  const void *f_re, *f_im;
+  int64_t avg1, avg2;
+  double wgt_s0[3], wgt_s1[3], wgt_e0[3], wgt_e1[3];
+  double dV0, dV1;
+  int32_t use_weights, sqrt_weights;
+  void *dft;
+  int32_t nomega;
+  int32_t phase_slot;
+} mb200_dft_job_t;
+
+/* ---- dft_flux::flux inner sum (src/dft.cpp:542-556): out[i] += sum_k Re(E[k*nomega+i] *
+ *      conj(H[k*nomega+i])), accumulated in double on the device (out: double[nomega]). */
+typedef struct {
+  const void *e, *h;
+  int64_t npts;
+  int32_t nomega;
+  int32_t reserved;
+  double *out;
+} mb200_flux_job_t;
+
+/* ---- fused half-step over one 3-D chunk: the three step_curl calls that fields_chunk::step_db
+ *      makes for one field type and cmp (src/step_db.cpp:47-127), and — where it is legal
+ *      (diagonal chi1inv, no chi2/chi3, no f_minus_p) — the step_update_EDHB call that
+ *      fields_chunk::update_eh makes for the same component (src/update_eh.cpp:190-195), in ONE
+ *      pass over the chunk, so every array is read once and written once per half-step
+ *      (9R + 15R = 24R bytes per cell-step).  Each component keeps exactly the
+ *      step_curl / step_update_EDHB argument meaning; lo/hi are the inclusive array-index
+ *      ranges of little_owned_corner0(c)..big_corner (src/meep/vec.hpp:1102-1104) and the pml
+ *      lookups are re-based to array index (0,0,0): k = k0 + ks[0]*ix + ks[1]*iy + ks[2]*iz.
+ *      A component with f == NULL is skipped; e == NULL means "no fused E/H update". */
+typedef struct {
+  int32_t lo[3], hi[3];
+  void *f;
+  const void *g1, *g2;
+  int64_t s1, s2;
+  double dtdx;
+  mb200_pml_t pml, pmlu;
+  void *fu;
+  const void *cnd, *cndinv;
+  void *fcnd;
+  void *e;
+  const void *u;
+  void *fw;
+  mb200_pml_t pmlw;
+} mb200_step3_comp_t;
+
+typedef struct {
+  int32_t n[3]; /* chunk size in cells; the index box is [0..n[d]] per direction */
+  int32_t reserved;
+  int64_t stride[3];
+  double dt;
+  mb200_step3_comp_t c[3];
+} mb200_step3_job_t;
+
+enum {
+  MB200_K_CURL = 0,
+  MB200_K_EDHB = 1,
+  MB200_K_LORENTZ = 2,
+  MB200_K_FMP = 3,
+  MB200_K_SOURCE = 4,
+  MB200_K_HALO = 5,
+  MB200_K_ZERO = 6,
+  MB200_K_DFT = 7,
+  MB200_K_FLUX = 8,
+  MB200_K_STEP3 = 9,
+  MB200_NUM_KINDS = 10
+};
+
+/* ---- context ------------------------------------------------------------------------------- */
+int mb200_abi_version(void);
+const char *mb200_last_error(void);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int mb200_device_count(void);
+/* create a context on CUDA device `device` (own non-blocking stream). */
+int mb200_init(int device, mb200_ctx **out);
+void mb200_destroy(mb200_ctx *ctx);
+int mb200_sync(mb200_ctx *ctx);
+
+/* ---- device memory ------------------------------------------------------------------------- */
+int mb200_malloc(mb200_ctx *ctx, size_t bytes, void **out);
+int mb200_free(mb200_ctx *ctx, void *p);
+int mb200_memset(mb200_ctx *ctx, void *p, int value, size_t bytes);
+int mb200_h2d(mb200_ctx *ctx, void *dst, const void *src, size_t bytes); /* async if src pinned */
+int mb200_d2h(mb200_ctx *ctx, void *dst, const void *src, size_t bytes); /* synchronises */
+int mb200_d2d(mb200_ctx *ctx, void *dst, const void *src, size_t bytes);
+int mb200_host_alloc(size_t bytes, void **out); /* pinned host memory */
+int mb200_host_free(void *p);
+/* bytes currently allocated through mb200_malloc on this context */
+size_t mb200_bytes_allocated(mb200_ctx *ctx);
+
+/* ---- plans --------------------------------------------------------------------------------- */
+/* jobs: host array of njobs structs of the kind's job type.  The table is copied; the caller
+ * may free it.  Device pointers inside must stay valid for the life of the plan. */
+int mb200_plan_create(mb200_ctx *ctx, int kind, int dtype, const void *jobs, int njobs,
+                      mb200_plan **out);
+/* run_data: per-run side input, copied to the device before launch:
+ *   MB200_K_SOURCE: interleaved complex<double> scalars[], run_bytes = 16*nslots
+ *   MB200_K_DFT   : complex<realnum> phase table, run_bytes = 2*sizeof(realnum)*nphases
+ *   others        : NULL / 0 */
+int mb200_plan_run(mb200_ctx *ctx, mb200_plan *plan, const void *run_data, size_t run_bytes);
+void mb200_plan_destroy(mb200_ctx *ctx, mb200_plan *plan);
+/* algorithmic HBM bytes one run of this plan must move (each distinct array element read once
+ * and written once; neighbour re-reads served on chip) — used for roofline accounting. */
+double mb200_plan_bytes(const mb200_plan *plan);
+/* number of loop points (cells) one run updates */
+double mb200_plan_points(const mb200_plan *plan);
+
+/* ---- one-shot, reference-shaped calls (plan_create + plan_run + plan_destroy) --------------- */
+int mb200_step_curl(mb200_ctx *ctx, int dtype, const mb200_curl_job_t *jobs, int njobs);
+int mb200_step_update_EDHB(mb200_ctx *ctx, int dtype, const mb200_edhb_job_t *jobs, int njobs);
+int mb200_lorentzian_update_P(mb200_ctx *ctx, int dtype, const mb200_lorentz_job_t *jobs,
+                              int njobs);
+int mb200_subtract_P(mb200_ctx *ctx, int dtype, const mb200_fmp_job_t *jobs, int njobs);
+int mb200_step_source(mb200_ctx *ctx, int dtype, const mb200_src_job_t *jobs, int njobs,
+                      const double *scalars, int nslots);
+int mb200_step_boundaries(mb200_ctx *ctx, int dtype, const mb200_halo_job_t *jobs, int njobs);
+int mb200_zero_metal(mb200_ctx *ctx, int dtype, const mb200_zero_job_t *jobs, int njobs);
+int mb200_update_dft(mb200_ctx *ctx, int dtype, const mb200_dft_job_t *jobs, int njobs,
+                     const void *phases, int nphases);
+int mb200_dft_flux(mb200_ctx *ctx, int dtype, const mb200_flux_job_t *jobs, int njobs);
+int mb200_step3(mb200_ctx *ctx, int dtype, const mb200_step3_job_t *jobs, int njobs);
+
+/* ---- finiteness probe (replaces the per-step host read in fields::step, src/step.cpp:137-138):
+ *      sets *flag (device int32) to 1 if any of the n listed array elements is NaN/Inf. */
+int mb200_check_finite(mb200_ctx *ctx, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+/* CUDA-event stopwatch on the context's stream. */
+int mb200_timer_start(mb200_ctx *ctx);
+int mb200_timer_stop(mb200_ctx *ctx, double *ms); /* synchronises */
+/* per-kind profiling: when on, every plan_run is bracketed by CUDA events. */
+int mb200_profile_enable(mb200_ctx *ctx, int on);
+int mb200_profile_reset(mb200_ctx *ctx);
+/* sums since the last reset (synchronises): launches, device ms, algorithmic bytes */
+int mb200_profile_get(mb200_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes);
+/* total kernels launched by this context since creation */
+int64_t mb200_launch_count(mb200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEEP_B200_H */

@@ -1,0 +1,430 @@
+// capi.cu — the C ABI of include/meep_b200.h on CUDA (sm_100a).
+// Thin by design: context + device memory + "plans" (job table + tile prefix in HBM, one grid
+// per run).  All numerical work is in kernels.cuh / point_ops.h.  No host execution path.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "kernels.cuh"
+#include "fused.cuh"
+#include "plan_metrics.h"
+
+using namespace mb200;
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+  } while (0)
+
+struct ProfRec {
+  int kind;
+  cudaEvent_t a, b;
+  double bytes;
+};
+
+struct mb200_ctx {
+  int device;
+  cudaStream_t stream;
+  size_t bytes_allocated;
+  int64_t launches;
+  cudaEvent_t t0, t1;
+  bool profiling;
+  std::vector<ProfRec> recs;
+  int64_t prof_launches[MB200_NUM_KINDS];
+  double prof_ms[MB200_NUM_KINDS], prof_bytes[MB200_NUM_KINDS];
+  void *run_buf;
+  size_t run_cap;
+};
+
+struct mb200_plan {
+  int kind, dtype, njobs;
+  void *d_jobs;
+  int64_t *d_prefix;
+  int64_t tiles;
+  double bytes, points;
+  size_t job_size;
+};
+
+template <typename T>
+static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
+  const dim3 grid((unsigned)p->tiles), block(kThreads);
+  cudaStream_t s = c->stream;
+  switch (p->kind) {
+    case MB200_K_CURL:
+      curl_kernel<T><<<grid, block, 0, s>>>((const mb200_curl_job_t *)p->d_jobs, p->d_prefix,
+                                            p->njobs);
+      break;
+    case MB200_K_EDHB:
+      edhb_kernel<T><<<grid, block, 0, s>>>((const mb200_edhb_job_t *)p->d_jobs, p->d_prefix,
+                                            p->njobs);
+      break;
+    case MB200_K_LORENTZ:
+      lorentz_kernel<T><<<grid, block, 0, s>>>((const mb200_lorentz_job_t *)p->d_jobs, p->d_prefix,
+                                               p->njobs);
+      break;
+    case MB200_K_FMP:
+      fmp_kernel<T><<<grid, block, 0, s>>>((const mb200_fmp_job_t *)p->d_jobs, p->d_prefix,
+                                           p->njobs);
+      break;
+    case MB200_K_SOURCE:
+      source_kernel<T><<<grid, block, 0, s>>>((const mb200_src_job_t *)p->d_jobs, p->d_prefix,
+                                              p->njobs, (const double *)d_run);
+      break;
+    case MB200_K_HALO:
+      halo_kernel<T><<<grid, block, 0, s>>>((const mb200_halo_job_t *)p->d_jobs, p->d_prefix,
+                                            p->njobs);
+      break;
+    case MB200_K_ZERO:
+      zero_kernel<T><<<grid, block, 0, s>>>((const mb200_zero_job_t *)p->d_jobs, p->d_prefix,
+                                            p->njobs);
+      break;
+    case MB200_K_DFT:
+      dft_kernel<T><<<grid, block, 0, s>>>((const mb200_dft_job_t *)p->d_jobs, p->d_prefix,
+                                           p->njobs, (const T *)d_run);
+      break;
+    case MB200_K_FLUX:
+      flux_kernel<T><<<grid, block, 0, s>>>((const mb200_flux_job_t *)p->d_jobs, p->d_prefix,
+                                            p->njobs);
+      break;
+    case MB200_K_STEP3:
+      launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles, s);
+      break;
+  }
+  return cudaGetLastError();
+}
+
+extern "C" {
+
+int mb200_abi_version(void) { return MB200_ABI_VERSION; }
+const char *mb200_last_error(void) { return g_err; }
+
+int mb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int mb200_init(int device, mb200_ctx **out) {
+  if (!out) return fail("mb200_init: out == NULL");
+  *out = nullptr;
+  int n = 0;
+  CUDA_TRY(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n)
+    return fail("mb200_init: device %d not available (%d CUDA devices visible)", device, n);
+  CUDA_TRY(cudaSetDevice(device));
+  mb200_ctx *c = new mb200_ctx();
+  c->device = device;
+  c->bytes_allocated = 0;
+  c->launches = 0;
+  c->profiling = false;
+  c->run_buf = nullptr;
+  c->run_cap = 0;
+  memset(c->prof_launches, 0, sizeof(c->prof_launches));
+  memset(c->prof_ms, 0, sizeof(c->prof_ms));
+  memset(c->prof_bytes, 0, sizeof(c->prof_bytes));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&c->t0));
+  CUDA_TRY(cudaEventCreate(&c->t1));
+  *out = c;
+  return 0;
+}
+
+void mb200_destroy(mb200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto &r : c->recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (c->run_buf) cudaFree(c->run_buf);
+  cudaEventDestroy(c->t0);
+  cudaEventDestroy(c->t1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int mb200_sync(mb200_ctx *c) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int mb200_malloc(mb200_ctx *c, size_t bytes, void **out) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  *out = nullptr;
+  if (bytes == 0) bytes = 8;
+  CUDA_TRY(cudaMalloc(out, bytes));
+  c->bytes_allocated += bytes;
+  return 0;
+}
+
+int mb200_free(mb200_ctx *c, void *p) {
+  if (!p) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFree(p));
+  return 0;
+}
+
+int mb200_memset(mb200_ctx *c, void *p, int value, size_t bytes) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemsetAsync(p, value, bytes, c->stream));
+  return 0;
+}
+
+int mb200_h2d(mb200_ctx *c, void *dst, const void *src, size_t bytes) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+int mb200_d2h(mb200_ctx *c, void *dst, const void *src, size_t bytes) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int mb200_d2d(mb200_ctx *c, void *dst, const void *src, size_t bytes) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+int mb200_host_alloc(size_t bytes, void **out) {
+  CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 8));
+  return 0;
+}
+
+int mb200_host_free(void *p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return 0;
+}
+
+size_t mb200_bytes_allocated(mb200_ctx *c) { return c->bytes_allocated; }
+
+// ---- plans -------------------------------------------------------------------------------------
+
+int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int njobs,
+                      mb200_plan **out) {
+  if (!out) return fail("mb200_plan_create: out == NULL");
+  *out = nullptr;
+  const size_t js = job_size_of(kind);
+  if (!js) return fail("mb200_plan_create: unknown kind %d", kind);
+  if (dtype != MB200_F64 && dtype != MB200_F32)
+    return fail("mb200_plan_create: unknown dtype %d", dtype);
+  if (njobs < 0 || (njobs > 0 && !jobs)) return fail("mb200_plan_create: bad job table");
+  CUDA_TRY(cudaSetDevice(c->device));
+  mb200_plan *p = new mb200_plan();
+  p->kind = kind;
+  p->dtype = dtype;
+  p->njobs = njobs;
+  p->job_size = js;
+  p->d_jobs = nullptr;
+  p->d_prefix = nullptr;
+  p->bytes = p->points = 0;
+  std::vector<int64_t> prefix(njobs + 1, 0);
+  for (int j = 0; j < njobs; ++j) {
+    int64_t t;
+    double b, pts;
+    job_metrics(kind, dtype, jobs, j, &t, &b, &pts);
+    prefix[j + 1] = prefix[j] + t;
+    p->bytes += b;
+    p->points += pts;
+  }
+  p->tiles = prefix[njobs];
+  if (p->tiles > 0x7fffffffLL) {
+    delete p;
+    return fail("mb200_plan_create: too many tiles (%lld)", (long long)p->tiles);
+  }
+  if (njobs > 0) {
+    CUDA_TRY(cudaMalloc(&p->d_jobs, js * njobs));
+    CUDA_TRY(cudaMalloc((void **)&p->d_prefix, sizeof(int64_t) * (njobs + 1)));
+    CUDA_TRY(cudaMemcpyAsync(p->d_jobs, jobs, js * njobs, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_prefix, prefix.data(), sizeof(int64_t) * (njobs + 1),
+                             cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream)); // prefix is a stack-owned vector
+  }
+  *out = p;
+  return 0;
+}
+
+void mb200_plan_destroy(mb200_ctx *c, mb200_plan *p) {
+  if (!p) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (p->d_jobs) cudaFree(p->d_jobs);
+  if (p->d_prefix) cudaFree(p->d_prefix);
+  delete p;
+}
+
+double mb200_plan_bytes(const mb200_plan *p) { return p ? p->bytes : 0; }
+double mb200_plan_points(const mb200_plan *p) { return p ? p->points : 0; }
+
+int mb200_plan_run(mb200_ctx *c, mb200_plan *p, const void *run_data, size_t run_bytes) {
+  if (!p) return fail("mb200_plan_run: plan == NULL");
+  if (p->tiles == 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const bool needs_run = p->kind == MB200_K_SOURCE || p->kind == MB200_K_DFT;
+  if (needs_run) {
+    if (!run_data || !run_bytes) return fail("mb200_plan_run: kind %d needs run_data", p->kind);
+    if (run_bytes > c->run_cap) {
+      // NB: previous launches may still be reading the old buffer
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (c->run_buf) CUDA_TRY(cudaFree(c->run_buf));
+      c->run_cap = run_bytes * 2 + 4096;
+      CUDA_TRY(cudaMalloc(&c->run_buf, c->run_cap));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->run_buf, run_data, run_bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  ProfRec rec;
+  if (c->profiling) {
+    rec.kind = p->kind;
+    rec.bytes = p->bytes;
+    CUDA_TRY(cudaEventCreate(&rec.a));
+    CUDA_TRY(cudaEventCreate(&rec.b));
+    CUDA_TRY(cudaEventRecord(rec.a, c->stream));
+  }
+  cudaError_t e = p->dtype == MB200_F64 ? launch_plan<double>(c, p, c->run_buf)
+                                        : launch_plan<float>(c, p, c->run_buf);
+  if (e != cudaSuccess)
+    return fail("kernel launch (kind %d, %lld tiles) failed: %s", p->kind, (long long)p->tiles,
+                cudaGetErrorString(e));
+  c->launches += 1;
+  if (c->profiling) {
+    CUDA_TRY(cudaEventRecord(rec.b, c->stream));
+    c->recs.push_back(rec);
+  }
+  return 0;
+}
+
+static int one_shot(mb200_ctx *c, int kind, int dtype, const void *jobs, int njobs,
+                    const void *run, size_t run_bytes) {
+  mb200_plan *p = nullptr;
+  if (mb200_plan_create(c, kind, dtype, jobs, njobs, &p)) return 1;
+  int rc = mb200_plan_run(c, p, run, run_bytes);
+  mb200_plan_destroy(c, p);
+  return rc;
+}
+
+int mb200_step_curl(mb200_ctx *c, int dtype, const mb200_curl_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_CURL, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_step_update_EDHB(mb200_ctx *c, int dtype, const mb200_edhb_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_EDHB, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_lorentzian_update_P(mb200_ctx *c, int dtype, const mb200_lorentz_job_t *jobs,
+                              int njobs) {
+  return one_shot(c, MB200_K_LORENTZ, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_subtract_P(mb200_ctx *c, int dtype, const mb200_fmp_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_FMP, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_step_source(mb200_ctx *c, int dtype, const mb200_src_job_t *jobs, int njobs,
+                      const double *scalars, int nslots) {
+  return one_shot(c, MB200_K_SOURCE, dtype, jobs, njobs, scalars, 16 * (size_t)nslots);
+}
+int mb200_step_boundaries(mb200_ctx *c, int dtype, const mb200_halo_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_HALO, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_zero_metal(mb200_ctx *c, int dtype, const mb200_zero_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_ZERO, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_update_dft(mb200_ctx *c, int dtype, const mb200_dft_job_t *jobs, int njobs,
+                     const void *phases, int nphases) {
+  const size_t R = dtype == MB200_F64 ? 8 : 4;
+  return one_shot(c, MB200_K_DFT, dtype, jobs, njobs, phases, 2 * R * (size_t)nphases);
+}
+int mb200_dft_flux(mb200_ctx *c, int dtype, const mb200_flux_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_FLUX, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_STEP3, dtype, jobs, njobs, nullptr, 0);
+}
+
+int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag) {
+  if (n <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const unsigned grid = (unsigned)ceil_div(n, 256);
+  if (dtype == MB200_F64) check_finite_kernel<double><<<grid, 256, 0, c->stream>>>(ptrs, n, flag);
+  else check_finite_kernel<float><<<grid, 256, 0, c->stream>>>(ptrs, n, flag);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
+// ---- measurement -------------------------------------------------------------------------------
+int mb200_timer_start(mb200_ctx *c) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventRecord(c->t0, c->stream));
+  return 0;
+}
+int mb200_timer_stop(mb200_ctx *c, double *ms) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaEventRecord(c->t1, c->stream));
+  CUDA_TRY(cudaEventSynchronize(c->t1));
+  float f = 0;
+  CUDA_TRY(cudaEventElapsedTime(&f, c->t0, c->t1));
+  *ms = f;
+  return 0;
+}
+
+static int prof_collect(mb200_ctx *c) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (auto &r : c->recs) {
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, r.a, r.b));
+    c->prof_launches[r.kind] += 1;
+    c->prof_ms[r.kind] += f;
+    c->prof_bytes[r.kind] += r.bytes;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  c->recs.clear();
+  return 0;
+}
+
+int mb200_profile_enable(mb200_ctx *c, int on) {
+  if (!on && c->profiling) {
+    if (prof_collect(c)) return 1;
+  }
+  c->profiling = on != 0;
+  return 0;
+}
+int mb200_profile_reset(mb200_ctx *c) {
+  if (prof_collect(c)) return 1;
+  memset(c->prof_launches, 0, sizeof(c->prof_launches));
+  memset(c->prof_ms, 0, sizeof(c->prof_ms));
+  memset(c->prof_bytes, 0, sizeof(c->prof_bytes));
+  return 0;
+}
+int mb200_profile_get(mb200_ctx *c, int kind, int64_t *launches, double *ms, double *bytes) {
+  if (kind < 0 || kind >= MB200_NUM_KINDS) return fail("mb200_profile_get: bad kind");
+  if (prof_collect(c)) return 1;
+  if (launches) *launches = c->prof_launches[kind];
+  if (ms) *ms = c->prof_ms[kind];
+  if (bytes) *bytes = c->prof_bytes[kind];
+  return 0;
+}
+int64_t mb200_launch_count(mb200_ctx *c) { return c->launches; }
+
+} // extern "C"

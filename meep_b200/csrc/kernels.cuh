@@ -1,0 +1,324 @@
+// kernels.cuh — sm_100a kernels of the FDTD hot path (generic, table-driven versions).
+//
+// Launch model: one grid per plan run.  A plan holds a device table of jobs (each job = the
+// argument list of one reference inner-loop call, see include/meep_b200.h) and a prefix sum of
+// per-job tile counts; every CTA binary-searches its job, stages the descriptor in shared
+// memory and processes one tile.  So a whole phase of fields::step over all 27+ chunks of a
+// GPU is ONE launch instead of (chunks x components x cmp) launches.
+//
+// Tile shapes for 3-loop ("box") jobs.  The arrays keep the reference layout (last loop
+// stride 1).  A CTA of 256 threads covers a (t2 x t3) patch of loops 2,3 and marches over up
+// to MB200_T1 planes of loop 1, so the +/-s2 neighbour rows of a stencil hit L1 and the
+// per-thread index/PML setup is amortised.  For thin boxes (n3 < 24, e.g. z-PML slabs with
+// n3 = 10) loops 2,3 are flattened instead so that lanes stay dense.
+#ifndef MEEP_B200_KERNELS_CUH
+#define MEEP_B200_KERNELS_CUH
+
+#include "point_ops.h"
+
+namespace mb200 {
+
+constexpr int kThreads = 256;
+constexpr int kT1 = 8; // loop-1 planes marched per CTA
+constexpr int kItems1D = 4;  // elements per thread for streaming 1-D jobs
+constexpr int kDftPts = 64;  // monitor points per CTA in dft_kernel
+constexpr int kFluxPts = 256; // points per CTA in flux_kernel
+
+// host+device: tile decomposition of a box
+struct BoxTiling {
+  int t3;      // threads along loop 3 (0 => flattened mode)
+  int nb23;    // tiles over loops (2,3)
+  int nb3;     // tiles along loop 3 (patch mode)
+  int nb1;     // tiles along loop 1
+};
+
+MB200_HD BoxTiling box_tiling(const mb200_box_t &b) {
+  BoxTiling t;
+  if (b.n[2] >= 48) t.t3 = 64;
+  else if (b.n[2] >= 24) t.t3 = 32;
+  else t.t3 = 0;
+  if (t.t3) {
+    const int t2 = kThreads / t.t3;
+    t.nb3 = (b.n[2] + t.t3 - 1) / t.t3;
+    t.nb23 = t.nb3 * ((b.n[1] + t2 - 1) / t2);
+  }
+  else {
+    const int64_t nq = (int64_t)b.n[1] * b.n[2];
+    t.nb3 = 1;
+    t.nb23 = (int)((nq + kThreads - 1) / kThreads);
+  }
+  t.nb1 = (b.n[0] + kT1 - 1) / kT1;
+  return t;
+}
+MB200_HD int64_t box_tiles(const mb200_box_t &b) {
+  if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return 0;
+  BoxTiling t = box_tiling(b);
+  return (int64_t)t.nb1 * t.nb23;
+}
+
+// map (tile, thread) -> loop indices; returns false if this thread has no (i2,i3)
+MB200_HD bool box_thread_point(const mb200_box_t &b, int64_t tile, int tid, int &i1_0, int &i1_end,
+                               int &i2, int &i3) {
+  const BoxTiling t = box_tiling(b);
+  const int b1 = (int)(tile / t.nb23);
+  const int b23 = (int)(tile - (int64_t)b1 * t.nb23);
+  i1_0 = b1 * kT1;
+  i1_end = i1_0 + kT1 < b.n[0] ? i1_0 + kT1 : b.n[0];
+  if (t.t3) {
+    const int b2 = b23 / t.nb3, b3 = b23 - b2 * t.nb3;
+    const int l3 = tid & (t.t3 - 1), l2 = tid / t.t3;
+    i3 = b3 * t.t3 + l3;
+    i2 = b2 * (kThreads / t.t3) + l2;
+    return i3 < b.n[2] && i2 < b.n[1];
+  }
+  else {
+    const int64_t q = (int64_t)b23 * kThreads + tid;
+    if (q >= (int64_t)b.n[1] * b.n[2]) return false;
+    i2 = (int)(q / b.n[2]);
+    i3 = (int)(q - (int64_t)i2 * b.n[2]);
+    return true;
+  }
+}
+
+
+// ---- per-thread bodies of the box kernels (shared with the test-only emulator) ------------------
+template <typename T> MB200_HD void curl_thread(const mb200_curl_job_t &J, int64_t tile, int tid) {
+  int i1_0, i1_end, i2, i3;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  const int variant = curl_variant(J);
+  const T dtdx = (T)J.dtdx, dt2 = (T)J.dt * T(0.5);
+  int64_t i = box_index(J.box, i1_0, i2, i3);
+  int k = pml_k(J.pml, i1_0, i2, i3), ku = pml_k(J.pmlu, i1_0, i2, i3);
+  const int64_t s1 = J.box.s[0];
+  const int dk = J.pml.ks[0], dku = J.pmlu.ks[0];
+  switch (variant) {
+#define MB200_CASE(v)                                                                              \
+  case v:                                                                                          \
+    for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1, k += dk, ku += dku)                            \
+      curl_point<T, ((v)&8) != 0, ((v)&4) != 0, ((v)&2) != 0, ((v)&1) != 0>(J, i, k, ku, dtdx,     \
+                                                                             dt2);                 \
+    break;
+    MB200_CASE(0) MB200_CASE(1) MB200_CASE(2) MB200_CASE(3) MB200_CASE(4) MB200_CASE(5)
+    MB200_CASE(6) MB200_CASE(7) MB200_CASE(8) MB200_CASE(9) MB200_CASE(10) MB200_CASE(11)
+    MB200_CASE(12) MB200_CASE(13) MB200_CASE(14) MB200_CASE(15)
+#undef MB200_CASE
+  }
+}
+
+template <typename T> MB200_HD void edhb_thread(const mb200_edhb_job_t &J, int64_t tile, int tid) {
+  int i1_0, i1_end, i2, i3;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  int64_t i = box_index(J.box, i1_0, i2, i3);
+  int kw = pml_k(J.pmlw, i1_0, i2, i3);
+  const int64_t s1 = J.box.s[0];
+  const int dk = J.pmlw.ks[0];
+  for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1, kw += dk)
+    edhb_point<T>(J, i, kw);
+}
+
+template <typename T>
+MB200_HD void lorentz_thread(const mb200_lorentz_job_t &J, int64_t tile, int tid) {
+  int i1_0, i1_end, i2, i3;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  int64_t i = box_index(J.box, i1_0, i2, i3);
+  const int64_t s1 = J.box.s[0];
+  for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1)
+    lorentz_point<T>(J, i);
+}
+
+#ifdef __CUDACC__
+
+// ---- job lookup: tile_prefix[j] <= tile < tile_prefix[j+1] -------------------------------------
+__device__ __forceinline__ int find_job(const int64_t *__restrict__ tile_prefix, int njobs,
+                                        int64_t tile) {
+  int lo = 0, hi = njobs; // invariant: prefix[lo] <= tile < prefix[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(tile_prefix + mid) <= tile) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <typename JOB>
+__device__ __forceinline__ void stage_job(JOB *sm, const JOB *__restrict__ jobs,
+                                          const int64_t *__restrict__ tile_prefix, int njobs,
+                                          int64_t *tile_in_job) {
+  __shared__ int s_job;
+  __shared__ int64_t s_tile;
+  if (threadIdx.x == 0) {
+    const int64_t tile = blockIdx.x;
+    const int j = find_job(tile_prefix, njobs, tile);
+    s_job = j;
+    s_tile = tile - __ldg(tile_prefix + j);
+  }
+  __syncthreads();
+  const int *src = reinterpret_cast<const int *>(jobs + s_job);
+  int *dst = reinterpret_cast<int *>(sm);
+  for (int k = threadIdx.x; k < (int)(sizeof(JOB) / sizeof(int)); k += blockDim.x)
+    dst[k] = __ldg(src + k);
+  __syncthreads();
+  *tile_in_job = s_tile;
+}
+
+// ---- step_curl ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    curl_kernel(const mb200_curl_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                int njobs) {
+  __shared__ mb200_curl_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  curl_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- step_update_EDHB --------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    edhb_kernel(const mb200_edhb_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                int njobs) {
+  __shared__ mb200_edhb_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  edhb_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- lorentzian update_P -----------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    lorentz_kernel(const mb200_lorentz_job_t *__restrict__ jobs,
+                   const int64_t *__restrict__ tile_prefix, int njobs) {
+  __shared__ mb200_lorentz_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  lorentz_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- 1-D jobs ----------------------------------------------------------------------------------
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    fmp_kernel(const mb200_fmp_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+               int njobs) {
+  __shared__ mb200_fmp_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  const int64_t base = tile * (kThreads * kItems1D) + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < kItems1D; ++r) {
+    const int64_t i = base + (int64_t)r * kThreads;
+    if (i < J.ntot) fmp_point<T>(J, i);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    source_kernel(const mb200_src_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                  int njobs, const double *__restrict__ scalars) {
+  __shared__ mb200_src_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  const int64_t j = tile * kThreads + threadIdx.x;
+  if (j < J.npts) source_point<T>(J, j, scalars);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    halo_kernel(const mb200_halo_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                int njobs) {
+  __shared__ mb200_halo_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  const int64_t n = tile * kThreads + threadIdx.x;
+  if (n < halo_count(J)) halo_transfer<T>(J, n);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    zero_kernel(const mb200_zero_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                int njobs) {
+  __shared__ mb200_zero_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  const int64_t n = tile * kThreads + threadIdx.x;
+  if (n < J.n) *(T *)(uintptr_t)J.ptrs[n] = T(0);
+}
+
+// ---- dft_chunk::update_dft ---------------------------------------------------------------------
+// A CTA takes kDftPts consecutive monitor points (in IVEC_LOOP_COUNTER order): the first
+// kDftPts threads form the weighted/averaged field values into shared memory, then all threads
+// sweep the (point, frequency) plane in dft-array order, so the read-modify-write of the
+// point-major/frequency-minor dft array is fully coalesced.
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    dft_kernel(const mb200_dft_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+               int njobs, const T *__restrict__ phases) {
+  __shared__ mb200_dft_job_t J;
+  __shared__ T s_fr[kDftPts], s_fi[kDftPts];
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  const int64_t npts = (int64_t)J.box.n[0] * J.box.n[1] * J.box.n[2];
+  const int64_t p0 = tile * kDftPts;
+  const int np = (int)min((int64_t)kDftPts, npts - p0);
+  if ((int)threadIdx.x < np) {
+    const int64_t p = p0 + threadIdx.x;
+    const int n23 = J.box.n[1] * J.box.n[2];
+    const int i1 = (int)(p / n23);
+    const int r = (int)(p - (int64_t)i1 * n23);
+    const int i2 = r / J.box.n[2], i3 = r - i2 * J.box.n[2];
+    T fr, fi;
+    dft_field_value<T>(J, i1, i2, i3, fr, fi);
+    s_fr[threadIdx.x] = fr;
+    s_fi[threadIdx.x] = fi;
+  }
+  __syncthreads();
+  const int nomega = J.nomega;
+  const bool is_complex = J.f_im != nullptr;
+  const T *ph = phases + 2 * (int64_t)J.phase_slot;
+  T *dft = (T *)J.dft + 2 * p0 * nomega;
+  const int total = np * nomega;
+  for (int e = threadIdx.x; e < total; e += kThreads) {
+    const int lp = e / nomega, w = e - lp * nomega;
+    dft_accumulate<T>(dft + 2 * (int64_t)e, is_complex, __ldg(ph + 2 * w), __ldg(ph + 2 * w + 1),
+                      s_fr[lp], s_fi[lp]);
+  }
+}
+
+// ---- dft_flux::flux inner sum ------------------------------------------------------------------
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    flux_kernel(const mb200_flux_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                int njobs) {
+  __shared__ mb200_flux_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  const int64_t p0 = tile * kFluxPts;
+  const int np = (int)min((int64_t)kFluxPts, J.npts - p0);
+  const T *e = (const T *)J.e + 2 * p0 * J.nomega, *h = (const T *)J.h + 2 * p0 * J.nomega;
+  for (int w = threadIdx.x; w < J.nomega; w += kThreads) {
+    double acc = 0;
+    for (int p = 0; p < np; ++p) {
+      const int64_t o = 2 * ((int64_t)p * J.nomega + w);
+      // Re(E conj(H)) = Er*Hr + Ei*Hi, formed in realnum then widened (src/dft.cpp:547-550)
+      acc += (double)(e[o] * h[o] + e[o + 1] * h[o + 1]);
+    }
+    atomicAdd(J.out + w, acc);
+  }
+}
+
+// ---- finiteness probe --------------------------------------------------------------------------
+template <typename T>
+__global__ void check_finite_kernel(const uint64_t *__restrict__ ptrs, int64_t n, int32_t *flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const T v = *(const T *)(uintptr_t)ptrs[i];
+    if (!isfinite(v)) *flag = 1;
+  }
+}
+
+#endif // __CUDACC__
+
+} // namespace mb200
+#endif

@@ -1,0 +1,119 @@
+// plan_metrics.h — per-job tile counts and algorithmic-byte accounting shared by the CUDA
+// implementation of the C ABI (capi.cu) and the test-only emulator (tests/emu).
+#ifndef MEEP_B200_PLAN_METRICS_H
+#define MEEP_B200_PLAN_METRICS_H
+#include "kernels.cuh"
+#include "fused.cuh"
+
+namespace mb200 {
+
+inline size_t job_size_of(int kind) {
+  switch (kind) {
+    case MB200_K_CURL: return sizeof(mb200_curl_job_t);
+    case MB200_K_EDHB: return sizeof(mb200_edhb_job_t);
+    case MB200_K_LORENTZ: return sizeof(mb200_lorentz_job_t);
+    case MB200_K_FMP: return sizeof(mb200_fmp_job_t);
+    case MB200_K_SOURCE: return sizeof(mb200_src_job_t);
+    case MB200_K_HALO: return sizeof(mb200_halo_job_t);
+    case MB200_K_ZERO: return sizeof(mb200_zero_job_t);
+    case MB200_K_DFT: return sizeof(mb200_dft_job_t);
+    case MB200_K_FLUX: return sizeof(mb200_flux_job_t);
+    case MB200_K_STEP3: return sizeof(mb200_step3_job_t);
+    default: return 0;
+  }
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline double box_points(const mb200_box_t &b) {
+  return (double)b.n[0] * (double)b.n[1] * (double)b.n[2];
+}
+
+// tiles, algorithmic bytes and points of job j
+inline void job_metrics(int kind, int dtype, const void *jobs, int j, int64_t *tiles, double *bytes,
+                        double *points) {
+  const double R = dtype == MB200_F64 ? 8.0 : 4.0;
+  switch (kind) {
+    case MB200_K_CURL: {
+      const mb200_curl_job_t &J = ((const mb200_curl_job_t *)jobs)[j];
+      *tiles = box_tiles(J.box);
+      *points = box_points(J.box);
+      int arrays = 2 + 1 + (J.g1 && J.g2 ? 1 : 0) + (J.pmlu.sig ? 2 : 0) +
+                   (J.cnd ? 2 + (J.pml.sig ? 2 : 0) : 0);
+      *bytes = R * arrays * *points;
+      break;
+    }
+    case MB200_K_EDHB: {
+      const mb200_edhb_job_t &J = ((const mb200_edhb_job_t *)jobs)[j];
+      *tiles = box_tiles(J.box);
+      *points = box_points(J.box);
+      int arrays = 1 + 1 + (J.u ? 1 : 0) + (J.u1 ? 2 : 0) + (J.u2 ? 2 : 0) + (J.chi3 ? 2 : 0) +
+                   (J.pmlw.sig ? 3 : 0);
+      *bytes = R * arrays * *points;
+      break;
+    }
+    case MB200_K_LORENTZ: {
+      const mb200_lorentz_job_t &J = ((const mb200_lorentz_job_t *)jobs)[j];
+      *tiles = box_tiles(J.box);
+      *points = box_points(J.box);
+      int arrays = 4 + 2 + (J.s1 ? 2 : 0) + (J.s2 ? 2 : 0);
+      *bytes = R * arrays * *points;
+      break;
+    }
+    case MB200_K_FMP: {
+      const mb200_fmp_job_t &J = ((const mb200_fmp_job_t *)jobs)[j];
+      *tiles = ceil_div(J.ntot, kThreads * kItems1D);
+      *points = (double)J.ntot;
+      *bytes = R * (2 + J.np) * *points;
+      break;
+    }
+    case MB200_K_SOURCE: {
+      const mb200_src_job_t &J = ((const mb200_src_job_t *)jobs)[j];
+      *tiles = ceil_div(J.npts, kThreads);
+      *points = (double)J.npts;
+      *bytes = (24 + 2 * R * (J.f_im ? 2 : 1)) * *points;
+      break;
+    }
+    case MB200_K_HALO: {
+      const mb200_halo_job_t &J = ((const mb200_halo_job_t *)jobs)[j];
+      const int64_t n = J.n_phase + J.n_negate + J.n_copy;
+      *tiles = ceil_div(n, kThreads);
+      *points = (double)(2 * J.n_phase + J.n_negate + J.n_copy);
+      *bytes = (16 + 2 * R) * *points;
+      break;
+    }
+    case MB200_K_ZERO: {
+      const mb200_zero_job_t &J = ((const mb200_zero_job_t *)jobs)[j];
+      *tiles = ceil_div(J.n, kThreads);
+      *points = (double)J.n;
+      *bytes = (8 + R) * *points;
+      break;
+    }
+    case MB200_K_DFT: {
+      const mb200_dft_job_t &J = ((const mb200_dft_job_t *)jobs)[j];
+      const int64_t npts = (int64_t)J.box.n[0] * J.box.n[1] * J.box.n[2];
+      *tiles = ceil_div(npts, kDftPts);
+      *points = (double)npts;
+      *bytes = (4 * R * J.nomega + R * (J.f_im ? 2 : 1)) * *points;
+      break;
+    }
+    case MB200_K_FLUX: {
+      const mb200_flux_job_t &J = ((const mb200_flux_job_t *)jobs)[j];
+      *tiles = ceil_div(J.npts, kFluxPts);
+      *points = (double)J.npts;
+      *bytes = 4 * R * J.nomega * *points;
+      break;
+    }
+    case MB200_K_STEP3: {
+      const mb200_step3_job_t &J = ((const mb200_step3_job_t *)jobs)[j];
+      *tiles = step3_tiles(J);
+      *points = step3_points(J);
+      *bytes = step3_bytes(J, R);
+      break;
+    }
+    default: *tiles = 0; *bytes = 0; *points = 0;
+  }
+}
+
+
+} // namespace mb200
+#endif

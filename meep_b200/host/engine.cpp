@@ -1,0 +1,624 @@
+// engine.cpp — see engine.hpp.
+#include "engine.hpp"
+#include "meep_internals.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <typeinfo>
+#include <unordered_map>
+
+using namespace meep;
+
+namespace meep_b200 {
+
+Engine *Engine::current_ = nullptr;
+
+static std::unordered_map<const fields *, Engine *> &table() {
+  static std::unordered_map<const fields *, Engine *> t;
+  return t;
+}
+
+void check(int rc, const char *what) {
+  if (rc) meep::abort("meep_b200: %s failed: %s", what, mb200_last_error());
+}
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+Engine &Engine::get(fields *f) {
+  auto &t = table();
+  auto it = t.find(f);
+  if (it != t.end()) return *it->second;
+  Engine *e = new Engine(f);
+  t[f] = e;
+  return *e;
+}
+
+Engine *Engine::find(const fields *f) {
+  auto &t = table();
+  auto it = t.find(f);
+  return it == t.end() ? nullptr : it->second;
+}
+
+void Engine::drop(const fields *f) {
+  auto &t = table();
+  auto it = t.find(f);
+  if (it == t.end()) return;
+  delete it->second;
+  t.erase(it);
+}
+
+bool Engine::mirrors(const void *host) const {
+  const uintptr_t a = (uintptr_t)host;
+  auto it = arrs_.upper_bound(a);
+  if (it == arrs_.begin()) return false;
+  --it;
+  return a >= it->first && a < it->first + it->second.bytes;
+}
+
+Engine *Engine::owner_of(const void *p) {
+  if (!p) return nullptr;
+  for (auto &kv : table())
+    if (kv.second->mirrors(p)) return kv.second;
+  return nullptr;
+}
+
+void Engine::for_each(const std::function<void(Engine &)> &fn) {
+  for (auto &kv : table())
+    fn(*kv.second);
+}
+
+Engine::Engine(fields *) {
+  if (mb200_abi_version() != MB200_ABI_VERSION)
+    meep::abort("meep_b200: libmeepb200 ABI version mismatch");
+  if (mb200_device_count() < 1)
+    meep::abort("meep_b200: no CUDA device visible — this build of libmeep has no CPU "
+                "time-stepping path (fields::step requires a B200)");
+  int device = env_int("MEEP_B200_DEVICE", env_int("LOCAL_RANK", 0));
+  if (device >= mb200_device_count()) device = device % mb200_device_count();
+  check(mb200_init(device, &ctx), "mb200_init");
+  fuse = env_int("MEEP_B200_FUSE", 1) != 0;
+  eager = env_int("MEEP_B200_EAGER", 0) != 0;
+  nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
+  if (nan_check_every < 1) nan_check_every = 1;
+}
+
+Engine::~Engine() {
+  if (current_ == this) current_ = nullptr;
+  recording_ = false;
+  invalidate_plans();
+  for (auto &kv : arrs_)
+    mb200_free(ctx, kv.second.dev);
+  arrs_.clear();
+  if (probe_flag_) mb200_free(ctx, probe_flag_);
+  mb200_destroy(ctx);
+}
+
+// ---- mirror --------------------------------------------------------------------------------------
+
+void *Engine::dev(const void *host) const {
+  if (!host) return nullptr;
+  const uintptr_t a = (uintptr_t)host;
+  auto it = arrs_.upper_bound(a);
+  if (it != arrs_.begin()) {
+    --it;
+    if (a >= it->first && a < it->first + it->second.bytes)
+      return (char *)it->second.dev + (a - it->first);
+  }
+  meep::abort("meep_b200: host pointer %p is not part of any mirrored array", host);
+  return nullptr;
+}
+
+void *Engine::ensure(const void *host, size_t bytes, bool is_field, int init) {
+  if (!host || bytes == 0) return nullptr;
+  const uintptr_t a = (uintptr_t)host;
+  auto it = arrs_.find(a);
+  if (it != arrs_.end()) {
+    if (it->second.bytes == bytes) {
+      it->second.seen = true;
+      return it->second.dev;
+    }
+    mb200_free(ctx, it->second.dev); // same address, different size: the host re-allocated
+    arrs_.erase(it);
+    invalidate_plans();
+  }
+  Arr arr;
+  arr.bytes = bytes;
+  arr.is_field = is_field;
+  arr.seen = true;
+  check(mb200_malloc(ctx, bytes, &arr.dev), "mb200_malloc");
+  if (init == 0) {
+    check(mb200_h2d(ctx, arr.dev, host, bytes), "mb200_h2d");
+    stats.h2d_bytes += bytes;
+  }
+  arrs_[a] = arr;
+  invalidate_plans();
+  return arr.dev;
+}
+
+void Engine::ensure_from(const void *host, size_t bytes, const void *src_host) {
+  void *d = ensure(host, bytes, true, 1);
+  if (src_host) check(mb200_d2d(ctx, d, dev(src_host), bytes), "mb200_d2d");
+  else check(mb200_memset(ctx, d, 0, bytes), "mb200_memset");
+}
+
+void Engine::forget(const void *host) {
+  auto it = arrs_.find((uintptr_t)host);
+  if (it == arrs_.end()) return;
+  invalidate_plans();
+  mb200_free(ctx, it->second.dev);
+  arrs_.erase(it);
+}
+
+void *Engine::aux_upload(const void *host, size_t bytes) {
+  void *d = nullptr;
+  if (!recording_) meep::abort("meep_b200: aux_upload outside a phase recording");
+  check(mb200_malloc(ctx, bytes ? bytes : 8, &d), "mb200_malloc(aux)");
+  if (bytes) check(mb200_h2d(ctx, d, host, bytes), "mb200_h2d(aux)");
+  rec_aux_.push_back(d);
+  return d;
+}
+
+void Engine::free_phase(Phase &ph) {
+  for (Launch &l : ph.launches)
+    if (l.plan) mb200_plan_destroy(ctx, l.plan);
+  ph.launches.clear();
+  for (void *p : ph.aux)
+    mb200_free(ctx, p);
+  ph.aux.clear();
+  ph.valid = false;
+}
+
+void Engine::invalidate_plans() {
+  if (recording_) {
+    pending_invalidate_ = true;
+    return;
+  }
+  for (int id = 0; id < PH_COUNT; ++id)
+    for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
+      free_phase(phases_[id][ft]);
+  if (probe_ptrs_) {
+    mb200_free(ctx, probe_ptrs_);
+    probe_ptrs_ = nullptr;
+    probe_n_ = 0;
+  }
+}
+
+static inline void hash_mix(uint64_t &h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+}
+
+// Everything that determines the job tables: which arrays exist (by address), chunk shapes,
+// sources and DFT monitors.
+uint64_t Engine::fingerprint(fields *f) const {
+  uint64_t h = 1469598103934665603ULL;
+  hash_mix(h, (uint64_t)f->num_chunks);
+  hash_mix(h, (uint64_t)f->is_real);
+  for (int i = 0; i < f->num_chunks; ++i) {
+    fields_chunk *fc = f->chunks[i];
+    if (!fc->is_mine()) continue;
+    hash_mix(h, (uint64_t)fc->gv.ntot());
+    hash_mix(h, (uint64_t)(uintptr_t)fc->s);
+    FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
+      hash_mix(h, (uint64_t)(uintptr_t)fc->f[c][cmp]);
+      hash_mix(h, (uint64_t)(uintptr_t)fc->f_u[c][cmp]);
+      hash_mix(h, (uint64_t)(uintptr_t)fc->f_w[c][cmp]);
+      hash_mix(h, (uint64_t)(uintptr_t)fc->f_cond[c][cmp]);
+      hash_mix(h, (uint64_t)(uintptr_t)fc->f_minus_p[c][cmp]);
+      hash_mix(h, (uint64_t)(uintptr_t)fc->f_w_prev[c][cmp]);
+    }
+    const structure_chunk *s = fc->s;
+    FOR_COMPONENTS(c) {
+      hash_mix(h, (uint64_t)(uintptr_t)s->chi2[c]);
+      hash_mix(h, (uint64_t)(uintptr_t)s->chi3[c]);
+      FOR_DIRECTIONS(d) {
+        hash_mix(h, (uint64_t)(uintptr_t)s->chi1inv[c][d]);
+        hash_mix(h, (uint64_t)(uintptr_t)s->conductivity[c][d]);
+        hash_mix(h, (uint64_t)(uintptr_t)s->condinv[c][d]);
+      }
+    }
+    for (int d = 0; d < 6; ++d) {
+      hash_mix(h, (uint64_t)(uintptr_t)s->sig[d]);
+      hash_mix(h, (uint64_t)s->sigsize[d]);
+    }
+    FOR_FIELD_TYPES(ft) {
+      for (polarization_state *p = fc->pol[ft]; p; p = p->next) {
+        hash_mix(h, (uint64_t)(uintptr_t)p->data);
+        hash_mix(h, (uint64_t)(uintptr_t)p->s);
+      }
+      for (const src_vol &sv : fc->get_sources(ft)) {
+        hash_mix(h, (uint64_t)sv.num_points());
+        hash_mix(h, (uint64_t)(uintptr_t)sv.t());
+        hash_mix(h, (uint64_t)sv.c);
+        if (sv.num_points()) hash_mix(h, (uint64_t)(uintptr_t)&sv.amplitude_at(0));
+      }
+    }
+    for (dft_chunk *d = fc->dft_chunks; d; d = d->next_in_chunk) {
+      hash_mix(h, (uint64_t)(uintptr_t)d);
+      hash_mix(h, (uint64_t)(uintptr_t)d->dft);
+      hash_mix(h, (uint64_t)d->get_decimation_factor());
+    }
+  }
+  return h;
+}
+
+void Engine::scan(fields *f) {
+  for (auto &kv : arrs_)
+    kv.second.seen = false;
+  const size_t R = sizeof(realnum);
+  for (int i = 0; i < f->num_chunks; ++i) {
+    fields_chunk *fc = f->chunks[i];
+    if (!fc->is_mine()) continue;
+    const size_t nb = fc->gv.ntot() * R;
+    FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
+      ensure(fc->f[c][cmp], nb, true);
+      ensure(fc->f_u[c][cmp], nb, true);
+      ensure(fc->f_w[c][cmp], nb, true);
+      ensure(fc->f_cond[c][cmp], nb, true);
+      // f_minus_p is scratch that is fully rewritten before every use: no upload needed
+      ensure(fc->f_minus_p[c][cmp], nb, true, 1);
+      if (fc->f_w_prev[c][cmp])
+        meep::abort("meep_b200: susceptibilities that need W_prev (multilevel atoms) are not "
+                    "supported on the device path");
+      if (fc->f_bfast[c][cmp])
+        meep::abort("meep_b200: BFAST fields are not supported on the device path");
+    }
+    const structure_chunk *s = fc->s;
+    FOR_COMPONENTS(c) {
+      ensure(s->chi2[c], nb, false);
+      ensure(s->chi3[c], nb, false);
+      FOR_DIRECTIONS(d) {
+        ensure(s->chi1inv[c][d], nb, false);
+        ensure(s->conductivity[c][d], nb, false);
+        ensure(s->condinv[c][d], nb, false);
+      }
+    }
+    for (int d = 0; d < 5; ++d)
+      if (s->sigsize[d] > 1) {
+        ensure(s->sig[d], s->sigsize[d] * R, false);
+        ensure(s->kap[d], s->sigsize[d] * R, false);
+        ensure(s->siginv[d], s->sigsize[d] * R, false);
+      }
+    FOR_FIELD_TYPES(ft) {
+      if (ft != E_stuff && ft != H_stuff) continue;
+      for (susceptibility *sus = s->chiP[ft]; sus; sus = sus->next)
+        FOR_COMPONENTS(c) FOR_DIRECTIONS(d) ensure(sus->sigma[c][d], nb, false);
+      for (polarization_state *p = fc->pol[ft]; p; p = p->next)
+        if (p->data) {
+          if (typeid(*p->s) != typeid(lorentzian_susceptibility))
+            meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) polarisations "
+                        "are supported on the device path");
+          lorentzian_data_layout *d = (lorentzian_data_layout *)p->data;
+          const size_t hdr = offsetof(lorentzian_data_layout, data);
+          if (d->sz_data > hdr) ensure(d->data, d->sz_data - hdr, true);
+        }
+    }
+    for (dft_chunk *d = fc->dft_chunks; d; d = d->next_in_chunk)
+      ensure(d->dft, d->N * d->omega.size() * 2 * R, true);
+  }
+  // drop mirrors of arrays the host no longer has
+  for (auto it = arrs_.begin(); it != arrs_.end();) {
+    if (!it->second.seen) {
+      mb200_free(ctx, it->second.dev);
+      it = arrs_.erase(it);
+      invalidate_plans();
+    }
+    else
+      ++it;
+  }
+}
+
+void Engine::upload_fields() {
+  for (auto &kv : arrs_)
+    if (kv.second.is_field) {
+      check(mb200_h2d(ctx, kv.second.dev, (const void *)kv.first, kv.second.bytes), "h2d");
+      stats.h2d_bytes += kv.second.bytes;
+    }
+  stats.uploads++;
+}
+
+void Engine::download_fields() {
+  for (auto &kv : arrs_)
+    if (kv.second.is_field) {
+      check(mb200_d2h(ctx, (void *)kv.first, kv.second.dev, kv.second.bytes), "d2h");
+      stats.d2h_bytes += kv.second.bytes;
+    }
+  stats.downloads++;
+}
+
+void Engine::upload_materials() {
+  for (auto &kv : arrs_)
+    if (!kv.second.is_field) {
+      check(mb200_h2d(ctx, kv.second.dev, (const void *)kv.first, kv.second.bytes), "h2d");
+      stats.h2d_bytes += kv.second.bytes;
+    }
+  materials_dirty = false;
+}
+
+void Engine::sync_host() {
+  if (state == DEVICE_NEWER) {
+    download_fields();
+    state = COHERENT;
+  }
+}
+
+void Engine::enter(fields *f) {
+  if (depth++ > 0) return;
+  current_ = this;
+  const uint64_t fp = fingerprint(f);
+  if (fp != last_fingerprint || arrs_.empty()) {
+    const size_t before = arrs_.size();
+    // arrays that are new to us are uploaded from the host by ensure(); existing mirrors keep
+    // their (possibly newer) device contents
+    scan(f);
+    (void)before;
+    last_fingerprint = fp;
+    invalidate_plans();
+    materials_dirty = true;
+  }
+  if (materials_dirty) upload_materials();
+  if (state == HOST_NEWER) {
+    upload_fields();
+    state = COHERENT;
+  }
+}
+
+void Engine::leave(fields *f, bool modified) {
+  if (--depth > 0) return;
+  if (modified) state = DEVICE_NEWER;
+  // lazily allocated arrays changed the pointer set: remember the new fingerprint so the next
+  // step does not rescan
+  last_fingerprint = fingerprint(f);
+  current_ = nullptr;
+  if (!in_step) {
+    // The caller is reference/user code running a piece of the schedule by itself (e.g.
+    // synchronize_magnetic_fields, initialize_field): it works on the host arrays right
+    // before and after this call, so hand them back and assume it will modify them.
+    sync_host();
+    state = HOST_NEWER;
+  }
+}
+
+// ---- finiteness probe (stands in for the host read of src/step.cpp:137-138) ----------------------
+
+void Engine::setup_probe(fields *f) {
+  if (probe_ptrs_) return;
+  std::vector<uint64_t> ptrs;
+  const ivec centre = f->gv.round_vec(f->gv.center());
+  for (int i = 0; i < f->num_chunks; ++i) {
+    fields_chunk *fc = f->chunks[i];
+    if (!fc->is_mine()) continue;
+    FOR_COMPONENTS(c) {
+      if (!fc->f[c][0] || !(is_D(c) || is_B(c) || is_electric(c) || is_magnetic(c))) continue;
+      // nearest Yee point of component c at or above the cell centre, if this chunk holds it
+      ivec p = centre;
+      LOOP_OVER_DIRECTIONS(f->gv.dim, d) {
+        int v = p.in_direction(d), par = fc->gv.iyee_shift(c).in_direction(d) & 1;
+        if ((v & 1) != par) v += 1;
+        p.set_direction(d, v);
+      }
+      if (!fc->gv.owns(p)) continue;
+      const ptrdiff_t idx = fc->gv.index(c, p);
+      for (int cmp = 0; cmp < 2; ++cmp)
+        if (fc->f[c][cmp]) ptrs.push_back(dev_addr(fc->f[c][cmp] + idx));
+    }
+  }
+  probe_n_ = (int64_t)ptrs.size();
+  if (!probe_n_) return;
+  check(mb200_malloc(ctx, ptrs.size() * 8, &probe_ptrs_), "malloc(probe)");
+  check(mb200_h2d(ctx, probe_ptrs_, ptrs.data(), ptrs.size() * 8), "h2d(probe)");
+  if (!probe_flag_) {
+    void *p = nullptr;
+    check(mb200_malloc(ctx, 8, &p), "malloc(flag)");
+    probe_flag_ = (int32_t *)p;
+    check(mb200_memset(ctx, probe_flag_, 0, 8), "memset(flag)");
+  }
+}
+
+void Engine::check_probe(fields *f, bool force) {
+  setup_probe(f);
+  if (!probe_n_) return;
+  check(mb200_check_finite(ctx, dtype, (const uint64_t *)probe_ptrs_, probe_n_, probe_flag_),
+        "check_finite");
+  if (force || (stats.steps % nan_check_every) == 0) {
+    int32_t flag = 0;
+    check(mb200_d2h(ctx, &flag, probe_flag_, 4), "d2h(flag)");
+    stats.d2h_bytes += 4;
+    if (flag) meep::abort("simulation fields are NaN or Inf");
+  }
+}
+
+// ---- phases --------------------------------------------------------------------------------------
+
+static mb200_plan *make_plan(Engine &E, int kind, const void *jobs, size_t n) {
+  if (!n) return nullptr;
+  mb200_plan *p = nullptr;
+  check(mb200_plan_create(E.ctx, kind, E.dtype, jobs, (int)n, &p), "mb200_plan_create");
+  E.stats.plan_builds++;
+  return p;
+}
+
+static void push(Phase &ph, int kind, mb200_plan *p) {
+  if (!p) return;
+  Launch l;
+  l.kind = kind;
+  l.plan = p;
+  ph.launches.push_back(l);
+}
+
+// try to turn the three step_curl jobs of one chunk/cmp into one fused job
+static bool fuse_group(const Recorder &R, const Recorder::Group &g, mb200_step3_job_t &out) {
+  const fields_chunk *fc = g.fc;
+  if (fc->gv.dim != D3 || g.count != 3) return false;
+  memset(&out, 0, sizeof(out));
+  const direction dirs[3] = {X, Y, Z};
+  for (int d = 0; d < 3; ++d) {
+    out.n[d] = fc->gv.num_direction(dirs[d]);
+    out.stride[d] = fc->gv.stride(dirs[d]);
+  }
+  out.dt = R.curl[g.first].dt;
+  for (int c = 0; c < 3; ++c) {
+    const mb200_curl_job_t &J = R.curl[g.first + c];
+    if (!J.g1 || !J.g2) return false;
+    mb200_step3_comp_t &C = out.c[c];
+    // box -> inclusive index ranges (3-D: loops 1,2,3 are X,Y,Z)
+    int64_t rem = J.box.idx0;
+    for (int d = 0; d < 3; ++d) {
+      if (J.box.s[d] != out.stride[d]) return false;
+      C.lo[d] = (int)(rem / out.stride[d]);
+      rem -= (int64_t)C.lo[d] * out.stride[d];
+      C.hi[d] = C.lo[d] + J.box.n[d] - 1;
+    }
+    C.f = J.f;
+    C.g1 = J.g1;
+    C.g2 = J.g2;
+    C.s1 = J.s1;
+    C.s2 = J.s2;
+    C.dtdx = J.dtdx;
+    C.pml = J.pml;
+    C.pmlu = J.pmlu;
+    // re-base PML lookups from loop indices to array indices
+    for (int d = 0; d < 3; ++d) {
+      C.pml.k0 -= C.pml.ks[d] * C.lo[d];
+      C.pmlu.k0 -= C.pmlu.ks[d] * C.lo[d];
+    }
+    C.fu = J.fu;
+    C.cnd = J.cnd;
+    C.cndinv = J.cndinv;
+    C.fcnd = J.fcnd;
+    C.e = nullptr;
+  }
+  return true;
+}
+
+void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
+  (void)f;
+  Recorder &R = rec_;
+  free_phase(ph);
+  switch (id) {
+    case PH_DB: {
+      std::vector<mb200_step3_job_t> s3;
+      std::vector<mb200_curl_job_t> rest;
+      std::vector<char> used(R.curl.size(), 0);
+      if (fuse)
+        for (const Recorder::Group &g : R.curl_groups) {
+          mb200_step3_job_t j;
+          if (fuse_group(R, g, j)) {
+            s3.push_back(j);
+            for (int k = 0; k < g.count; ++k)
+              used[g.first + k] = 1;
+          }
+        }
+      for (size_t k = 0; k < R.curl.size(); ++k)
+        if (!used[k]) rest.push_back(R.curl[k]);
+      push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3.data(), s3.size()));
+      push(ph, MB200_K_CURL, make_plan(*this, MB200_K_CURL, rest.data(), rest.size()));
+      break;
+    }
+    case PH_SRC: {
+      mb200_plan *p = make_plan(*this, MB200_K_SOURCE, R.src.data(), R.src.size());
+      if (p) {
+        Launch l;
+        l.kind = MB200_K_SOURCE;
+        l.plan = p;
+        l.src_times = R.src_times;
+        l.src_dipole = false;
+        ph.launches.push_back(l);
+      }
+      break;
+    }
+    case PH_BND:
+      push(ph, MB200_K_ZERO, make_plan(*this, MB200_K_ZERO, R.zero.data(), R.zero.size()));
+      push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.halo.data(), R.halo.size()));
+      break;
+    case PH_EH: {
+      push(ph, MB200_K_FMP, make_plan(*this, MB200_K_FMP, R.fmp.data(), R.fmp.size()));
+      mb200_plan *p = make_plan(*this, MB200_K_SOURCE, R.dip.data(), R.dip.size());
+      if (p) {
+        Launch l;
+        l.kind = MB200_K_SOURCE;
+        l.plan = p;
+        l.src_times = R.dip_times;
+        l.src_dipole = true;
+        ph.launches.push_back(l);
+      }
+      push(ph, MB200_K_EDHB, make_plan(*this, MB200_K_EDHB, R.edhb.data(), R.edhb.size()));
+      break;
+    }
+    case PH_POLS:
+      push(ph, MB200_K_LORENTZ,
+           make_plan(*this, MB200_K_LORENTZ, R.lorentz.data(), R.lorentz.size()));
+      break;
+    case PH_DFT:
+      for (auto &kv : R.dft) {
+        mb200_plan *p = make_plan(*this, MB200_K_DFT, kv.second.data(), kv.second.size());
+        if (!p) continue;
+        Launch l;
+        l.kind = MB200_K_DFT;
+        l.plan = p;
+        l.dft_chunks = R.dft_chunks[kv.first];
+        l.decimation = kv.first;
+        ph.launches.push_back(l);
+      }
+      break;
+    default: break;
+  }
+  ph.aux.swap(rec_aux_);
+  rec_aux_.clear();
+  ph.valid = true;
+  rec_ = Recorder();
+  recording_ = false;
+  if (pending_invalidate_) { // arrays appeared while recording: every OTHER phase is stale
+    pending_invalidate_ = false;
+    for (int i = 0; i < PH_COUNT; ++i)
+      for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
+        if (&phases_[i][ft] != &ph) free_phase(phases_[i][ft]);
+    if (probe_ptrs_) {
+      mb200_free(ctx, probe_ptrs_);
+      probe_ptrs_ = nullptr;
+      probe_n_ = 0;
+    }
+  }
+}
+
+void Engine::run(Phase &ph, fields *f) {
+  for (Launch &l : ph.launches) {
+    if (l.kind == MB200_K_SOURCE) {
+      std::vector<double> scal(2 * l.src_times.size());
+      for (size_t k = 0; k < l.src_times.size(); ++k) {
+        const std::complex<double> v =
+            l.src_dipole ? l.src_times[k]->dipole() : l.src_times[k]->current();
+        scal[2 * k] = v.real();
+        scal[2 * k + 1] = v.imag();
+      }
+      check(mb200_plan_run(ctx, l.plan, scal.data(), scal.size() * sizeof(double)), "run(source)");
+      stats.h2d_bytes += scal.size() * sizeof(double);
+    }
+    else if (l.kind == MB200_K_DFT) {
+      if (f->t % l.decimation != 0) continue;
+      // phase tables: dft_phase[i] = polar(1, omega_i * t) * scale, computed in double on the
+      // host and narrowed to complex<realnum> (reference src/dft.cpp:270-271)
+      std::vector<std::complex<realnum> > ph_tab;
+      const double timeE = f->time(), timeH = f->time() - 0.5 * f->dt;
+      for (dft_chunk *d : l.dft_chunks) {
+        const double tm = is_H_or_B(d->c) ? timeH : timeE;
+        for (size_t i = 0; i < d->omega.size(); ++i) {
+          d->dft_phase[i] = std::polar(1.0, d->omega[i] * tm) * d->scale;
+          ph_tab.push_back(d->dft_phase[i]);
+        }
+      }
+      check(mb200_plan_run(ctx, l.plan, ph_tab.data(),
+                           ph_tab.size() * sizeof(std::complex<realnum>)),
+            "run(dft)");
+      stats.h2d_bytes += ph_tab.size() * sizeof(std::complex<realnum>);
+    }
+    else
+      check(mb200_plan_run(ctx, l.plan, nullptr, 0), "mb200_plan_run");
+  }
+}
+
+} // namespace meep_b200

@@ -1,0 +1,228 @@
+// engine.hpp — device mirror + plan cache behind the unchanged meep::fields API.
+//
+// One Engine per meep::fields object (side table keyed by the fields pointer; the reference's
+// meep.hpp is compiled unmodified, so no member can be added).  The Engine
+//   * mirrors every per-chunk array the hot path touches (fields_chunk::f, f_u, f_w, f_cond,
+//     f_minus_p, polarisation P/P_prev, dft_chunk::dft; structure_chunk::chi1inv, conductivity,
+//     condinv, chi2, chi3, sig/kap/siginv, susceptibility sigma) in HBM, in the reference's own
+//     array layout, so every index/stride/pointer offset the host code computes is valid on
+//     the device as is;
+//   * records, per phase of fields::step(), the jobs our replacement member functions emit,
+//     turns them into plans (include/meep_b200.h) and replays the plans every step until the
+//     chunk layout changes;
+//   * tracks which side (host/device) holds the current field values.
+#ifndef MEEP_B200_ENGINE_HPP
+#define MEEP_B200_ENGINE_HPP
+
+#include <complex>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "meep.hpp"
+#include "../../include/meep_b200.h"
+
+namespace meep_b200 {
+
+using meep::realnum;
+
+enum PhaseId {
+  PH_DB = 0,     // step_db(ft)
+  PH_SRC,        // step_source(ft)
+  PH_BND,        // step_boundaries(ft)
+  PH_EH,         // update_eh(ft)
+  PH_POLS,       // update_pols(ft)
+  PH_DFT,        // update_dfts
+  PH_COUNT
+};
+
+// a recorded launch: plan + how to build its per-run side data
+struct Launch {
+  int kind = -1;
+  mb200_plan *plan = nullptr;
+  // SOURCE: src_time objects whose current()/dipole() fill the scalar slots at run time
+  std::vector<const meep::src_time *> src_times;
+  bool src_dipole = false;
+  // DFT: the dft_chunks whose phase tables are concatenated at run time
+  std::vector<meep::dft_chunk *> dft_chunks;
+  int decimation = 1;
+};
+
+struct Phase {
+  bool valid = false;
+  std::vector<Launch> launches;
+  std::vector<void *> aux; // device side tables (index lists, ...) owned by this phase
+};
+
+// job recorder used while a phase is being (re)built
+struct Recorder {
+  std::vector<mb200_curl_job_t> curl;
+  std::vector<mb200_edhb_job_t> edhb;
+  std::vector<mb200_lorentz_job_t> lorentz;
+  std::vector<mb200_fmp_job_t> fmp;
+  std::vector<mb200_src_job_t> src;       // mode 0 (currents)
+  std::vector<const meep::src_time *> src_times;
+  std::vector<mb200_src_job_t> dip;       // mode 1 (integrated dipoles)
+  std::vector<const meep::src_time *> dip_times;
+  std::vector<mb200_halo_job_t> halo;
+  std::vector<mb200_zero_job_t> zero;
+  std::map<int, std::vector<mb200_dft_job_t> > dft; // by decimation factor
+  std::map<int, std::vector<meep::dft_chunk *> > dft_chunks;
+  // grouping info for the fused kernel: curl jobs [first, first+count) belong to one chunk/cmp
+  struct Group {
+    int first, count;
+    const meep::fields_chunk *fc;
+    int cmp;
+  };
+  std::vector<Group> curl_groups;
+};
+
+struct Stats {
+  int64_t steps = 0;
+  int64_t uploads = 0, downloads = 0;
+  double h2d_bytes = 0, d2h_bytes = 0;
+  int64_t plan_builds = 0;
+};
+
+class Engine {
+public:
+  static Engine &get(meep::fields *f);          // create on first use
+  static Engine *find(const meep::fields *f);   // NULL if none
+  static void drop(const meep::fields *f);      // fields destroyed
+  static Engine *current() { return current_; }
+  // the Engine whose mirror table contains host address p (NULL if none)
+  static Engine *owner_of(const void *p);
+  bool mirrors(const void *p) const;
+  static void for_each(const std::function<void(Engine &)> &fn);
+
+  explicit Engine(meep::fields *f);
+  ~Engine();
+
+  // ---- coherence ------------------------------------------------------------------------------
+  enum State { HOST_NEWER, COHERENT, DEVICE_NEWER };
+  State state = HOST_NEWER;
+  int depth = 0; // nesting of our own entry points (0 => called from reference/user code)
+  bool in_step = false; // the outermost entry point is fields::step()
+
+  // Brackets every interposed entry point.  On the outermost entry it validates the mirror
+  // (array set, materials) and uploads field arrays if the host copy is (or may be) newer.
+  void enter(meep::fields *f);
+  void leave(meep::fields *f, bool modified_fields);
+  // make the host arrays current (called by the interposed readers in hooks.cpp)
+  void sync_host();
+  void mark_host_dirty() { if (state != DEVICE_NEWER) state = HOST_NEWER; }
+
+  // ---- mirror ---------------------------------------------------------------------------------
+  struct Arr {
+    void *dev = nullptr;
+    size_t bytes = 0;
+    bool is_field = false; // true: device-authoritative between steps; false: material (host)
+    bool seen = false;
+  };
+  // device address of a host element pointer (NULL -> NULL); aborts if the array is unknown
+  void *dev(const void *host) const;
+  uint64_t dev_addr(const void *host) const { return (uint64_t)(uintptr_t)dev(host); }
+  // register (or find) a mirror; init: 0 = upload host contents, 1 = leave uninitialised
+  void *ensure(const void *host, size_t bytes, bool is_field, int init = 0);
+  // lazily allocated array created inside a step: host array `host` was just new[]'d;
+  // its device twin is initialised from device array `src_host` (or zeros if NULL).
+  void ensure_from(const void *host, size_t bytes, const void *src_host);
+  void forget(const void *host);
+  void scan(meep::fields *f);          // (re)register everything reachable from f
+  void upload_fields();
+  void download_fields();
+  void upload_materials();
+
+  // ---- phases ---------------------------------------------------------------------------------
+  Phase &phase(PhaseId id, int ft) { return phases_[id][ft]; }
+  // drop every cached plan.  While a phase is being recorded (a lazily allocated array just
+  // appeared) the drop is deferred to end_record and spares the phase being recorded.
+  void invalidate_plans();
+  void free_phase(Phase &ph);
+  void begin_record() { rec_ = Recorder(); recording_ = true; }
+  Recorder &rec() { return rec_; }
+  bool recording() const { return recording_; }
+  void end_record(Phase &ph, PhaseId id, meep::fields *f);
+  void run(Phase &ph, meep::fields *f);
+
+  // ---- misc -----------------------------------------------------------------------------------
+  mb200_ctx *ctx = nullptr;
+  int dtype = sizeof(realnum) == 8 ? MB200_F64 : MB200_F32;
+  Stats stats;
+  bool fuse = true;        // MEEP_B200_FUSE=0 disables the fused step3 path
+  bool eager = false;      // MEEP_B200_EAGER=1: download after every step (debug/safety)
+  int nan_check_every = 16;
+  // finiteness probe
+  void setup_probe(meep::fields *f);
+  void check_probe(meep::fields *f, bool force);
+
+  uint64_t fingerprint(meep::fields *f) const;
+  uint64_t last_fingerprint = 0;
+  bool materials_dirty = true;
+
+private:
+  std::map<uintptr_t, Arr> arrs_; // keyed by host base address
+  std::vector<void *> rec_aux_; // side tables uploaded while recording the current phase
+  bool pending_invalidate_ = false;
+  Phase phases_[PH_COUNT][meep::NUM_FIELD_TYPES];
+  Recorder rec_;
+  bool recording_ = false;
+  void *probe_ptrs_ = nullptr;
+  int64_t probe_n_ = 0;
+  int32_t *probe_flag_ = nullptr;
+  static Engine *current_;
+  friend struct Scope;
+
+public:
+  // device side table owned by the phase being recorded
+  void *aux_upload(const void *host, size_t bytes);
+};
+
+// RAII bracket for interposed entry points
+struct Scope {
+  Engine &E;
+  meep::fields *f;
+  bool modified;
+  Scope(Engine &e, meep::fields *ff, bool mod = true) : E(e), f(ff), modified(mod) { E.enter(f); }
+  ~Scope() { E.leave(f, modified); }
+};
+
+void check(int rc, const char *what);
+
+// run one phase: replay the cached plans, or (re)record them by calling `record`
+template <typename F>
+inline void run_phase(Engine &E, meep::fields *f, PhaseId id, int ft, bool cacheable, F record) {
+  if (cacheable) {
+    Phase &ph = E.phase(id, ft);
+    if (!ph.valid) {
+      E.begin_record();
+      record();
+      E.end_record(ph, id, f);
+    }
+    E.run(ph, f);
+  }
+  else { // one-off (solve_cw variants etc.): record, run, discard
+    Phase tmp;
+    E.begin_record();
+    record();
+    E.end_record(tmp, id, f);
+    E.run(tmp, f);
+    E.free_phase(tmp);
+  }
+}
+
+
+// restated layout of the file-local struct in the reference's src/susceptibility.cpp:98-104
+// (the block new_internal_data/init_internal_data allocate; ABI between reference and us)
+struct lorentzian_data_layout {
+  size_t sz_data;
+  size_t ntot;
+  realnum *P[meep::NUM_FIELD_COMPONENTS][2];
+  realnum *P_prev[meep::NUM_FIELD_COMPONENTS][2];
+  realnum data[1];
+};
+
+} // namespace meep_b200
+#endif

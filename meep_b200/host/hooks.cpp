@@ -1,0 +1,253 @@
+// hooks.cpp — keeps the reference's HOST-side readers and writers of field / DFT arrays correct
+// while the arrays live in HBM.
+//
+// libmeep_b200 is linked in front of (or LD_PRELOADed over) the installed libmeep.  The
+// definitions below interpose a handful of reference entry points: each one first makes the
+// host arrays current (or reads the few values it needs straight from the device), then
+// forwards to the reference's own definition found with dlsym(RTLD_NEXT, <its own symbol>).
+// Nothing here computes fields.
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "engine.hpp"
+#include "meep_internals.hpp"
+
+using namespace std;
+using namespace meep_b200;
+
+namespace {
+
+// The reference's definition of the function we were called from: look up the caller's own
+// (mangled) symbol name with dladdr and ask the dynamic linker for the next definition.
+__attribute__((noinline)) void *next_definition_of_caller() {
+  Dl_info info;
+  void *ra = __builtin_extract_return_addr(__builtin_return_address(0));
+  if (!dladdr(ra, &info) || !info.dli_sname) {
+    fprintf(stderr, "meep_b200: cannot resolve the interposed symbol of a hook\n");
+    abort();
+  }
+  void *p = dlsym(RTLD_NEXT, info.dli_sname);
+  if (!p) {
+    fprintf(stderr,
+            "meep_b200: %s is not defined by any library loaded after libmeep_b200 — "
+            "libmeep_b200 must be linked/preloaded in FRONT of the reference libmeep\n",
+            info.dli_sname);
+    abort();
+  }
+  return p;
+}
+
+// every Engine whose fields may be read by the caller
+void sync_all_hosts() {
+  Engine::for_each([](Engine &E) { E.sync_host(); });
+}
+
+} // namespace
+
+namespace meep {
+
+// ---- lifetime -------------------------------------------------------------------------------------
+extern "C" {
+void mb200_hook_fields_D1(fields *self) __asm__("_ZN4meep6fieldsD1Ev");
+void mb200_hook_fields_D2(fields *self) __asm__("_ZN4meep6fieldsD2Ev");
+}
+void mb200_hook_fields_D1(fields *self) {
+  static void (*next)(fields *) = (void (*)(fields *))next_definition_of_caller();
+  Engine::drop(self);
+  next(self);
+}
+void mb200_hook_fields_D2(fields *self) {
+  static void (*next)(fields *) = (void (*)(fields *))next_definition_of_caller();
+  Engine::drop(self);
+  next(self);
+}
+
+// ---- point probes: every fields::get_field variant funnels into this one (reference
+//      src/monitor.cpp:128-133).  Reads the one or two values from HBM when the device copy is
+//      the current one, so monitoring a point every step does not download whole arrays.
+complex<double> fields_chunk::get_field(component c, const ivec &iloc) const {
+  if (!is_mine() || !f[c][0]) return 0.0;
+  const ptrdiff_t idx = gv.index(c, iloc);
+  Engine *E = Engine::owner_of(f[c][0]);
+  if (E && E->state == Engine::DEVICE_NEWER) {
+    realnum re = 0, im = 0;
+    check(mb200_d2h(E->ctx, &re, E->dev(f[c][0] + idx), sizeof(realnum)), "d2h(get_field)");
+    if (f[c][1])
+      check(mb200_d2h(E->ctx, &im, E->dev(f[c][1] + idx), sizeof(realnum)), "d2h(get_field)");
+    E->stats.d2h_bytes += (f[c][1] ? 2 : 1) * sizeof(realnum);
+    return complex<double>(re, im);
+  }
+  return f[c][1] ? complex<double>(f[c][0][idx], f[c][1][idx]) : complex<double>(f[c][0][idx]);
+}
+
+// ---- bulk readers: integrate, get_array_slice, output_hdf5, max_abs, energy/flux in box,
+//      add_dft / add_source set-up all go through loop_in_chunks (src/loop_in_chunks.cpp:339).
+void fields::loop_in_chunks(field_chunkloop chunkloop, void *chunkloop_data, const volume &where,
+                            component cgrid, bool use_symmetry, bool snap_unit_dims) {
+  typedef void (*fn)(fields *, field_chunkloop, void *, const volume &, component, bool, bool);
+  static fn next = (fn)next_definition_of_caller();
+  if (Engine *E = Engine::find(this)) E->sync_host();
+  next(this, chunkloop, chunkloop_data, where, cgrid, use_symmetry, snap_unit_dims);
+}
+
+// ---- host-side writers of field arrays -----------------------------------------------------------
+#define MB200_WRITER_HOOK(NAME)                                                                    \
+  void fields::NAME() {                                                                            \
+    typedef void (*fn)(fields *);                                                                  \
+    static fn next = (fn)next_definition_of_caller();                                              \
+    Engine *E = Engine::find(this);                                                                \
+    if (E) E->sync_host();                                                                         \
+    next(this);                                                                                    \
+    if (E) E->state = Engine::HOST_NEWER;                                                          \
+  }
+MB200_WRITER_HOOK(zero_fields)
+MB200_WRITER_HOOK(use_real_fields)
+MB200_WRITER_HOOK(synchronize_magnetic_fields)
+MB200_WRITER_HOOK(restore_magnetic_fields)
+MB200_WRITER_HOOK(remove_susceptibilities)
+#undef MB200_WRITER_HOOK
+
+void fields::initialize_field(component c, complex<double> func(const vec &)) {
+  typedef void (*fn)(fields *, component, complex<double> (*)(const vec &));
+  static fn next = (fn)next_definition_of_caller();
+  Engine *E = Engine::find(this);
+  if (E) E->sync_host();
+  if (E) E->state = Engine::HOST_NEWER;
+  next(this, c, func);
+  if (E) E->state = Engine::HOST_NEWER;
+}
+
+void fields::load(const char *filename, bool single_parallel_file) {
+  typedef void (*fn)(fields *, const char *, bool);
+  static fn next = (fn)next_definition_of_caller();
+  Engine *E = Engine::find(this);
+  if (E) E->sync_host();
+  next(this, filename, single_parallel_file);
+  if (E) E->state = Engine::HOST_NEWER;
+}
+
+void fields::dump(const char *filename, bool single_parallel_file) {
+  typedef void (*fn)(fields *, const char *, bool);
+  static fn next = (fn)next_definition_of_caller();
+  if (Engine *E = Engine::find(this)) E->sync_host();
+  next(this, filename, single_parallel_file);
+}
+
+// ---- host-side readers / writers of DFT arrays ---------------------------------------------------
+void dft_chunk::scale_dft(complex<double> scale_) {
+  typedef void (*fn)(dft_chunk *, complex<double>);
+  static fn next = (fn)next_definition_of_caller();
+  Engine *E = Engine::owner_of(dft);
+  if (E) E->sync_host();
+  next(this, scale_);
+  if (E) E->state = Engine::HOST_NEWER;
+}
+
+void dft_chunk::operator-=(const dft_chunk &chunk) {
+  typedef void (*fn)(dft_chunk *, const dft_chunk &);
+  static fn next = (fn)next_definition_of_caller();
+  Engine *E = Engine::owner_of(dft), *E2 = Engine::owner_of(chunk.dft);
+  if (E) E->sync_host();
+  if (E2) E2->sync_host();
+  next(this, chunk);
+  if (E) E->state = Engine::HOST_NEWER;
+}
+
+double dft_chunk::norm2(grid_volume fgv) const {
+  typedef double (*fn)(const dft_chunk *, grid_volume);
+  static fn next = (fn)next_definition_of_caller();
+  if (Engine *E = Engine::owner_of(dft)) E->sync_host();
+  return next(this, fgv);
+}
+
+std::vector<complex<double> > dft_flux::complexflux() {
+  typedef std::vector<complex<double> > (*fn)(dft_flux *);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  return next(this);
+}
+
+complex<double> dft_chunk::process_dft_component(int rank, direction *ds, ivec min_corner,
+                                                 ivec max_corner, int num_freq, h5file *file,
+                                                 realnum *buffer, int reim,
+                                                 complex<realnum> *field_array, void *mode1_data,
+                                                 void *mode2_data, int ic_conjugate,
+                                                 bool retain_interp_weights, fields *parent) {
+  typedef complex<double> (*fn)(dft_chunk *, int, direction *, ivec, ivec, int, h5file *,
+                                realnum *, int, complex<realnum> *, void *, void *, int, bool,
+                                fields *);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  return next(this, rank, ds, min_corner, max_corner, num_freq, file, buffer, reim, field_array,
+              mode1_data, mode2_data, ic_conjugate, retain_interp_weights, parent);
+}
+
+void save_dft_hdf5(dft_chunk *dft_chunks, const char *name, h5file *file, const char *dprefix,
+                   bool single_parallel_file) {
+  typedef void (*fn)(dft_chunk *, const char *, h5file *, const char *, bool);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  next(dft_chunks, name, file, dprefix, single_parallel_file);
+}
+
+void load_dft_hdf5(dft_chunk *dft_chunks, const char *name, h5file *file, const char *dprefix,
+                   bool single_parallel_file) {
+  typedef void (*fn)(dft_chunk *, const char *, h5file *, const char *, bool);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  next(dft_chunks, name, file, dprefix, single_parallel_file);
+  Engine::for_each([](Engine &E) { E.state = Engine::HOST_NEWER; });
+}
+
+void dft_near2far::farfield_lowlevel(complex<double> *EH, const vec &x, double freq_) {
+  typedef void (*fn)(dft_near2far *, complex<double> *, const vec &, double);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  next(this, EH, x, freq_);
+}
+
+void dft_ldos::update(fields &f) {
+  typedef void (*fn)(dft_ldos *, fields &);
+  static fn next = (fn)next_definition_of_caller();
+  if (Engine *E = Engine::find(&f)) E->sync_host();
+  next(this, f);
+}
+
+} // namespace meep
+
+// ---- explicit controls for code that touches fields_chunk arrays directly -------------------------
+extern "C" {
+// make the host arrays of `f` current (e.g. before reading fields_chunk::f yourself)
+void meep_b200_sync_host(meep::fields *f) {
+  if (Engine *E = Engine::find(f)) E->sync_host();
+}
+// tell the engine that host code modified the arrays of `f` (re-uploaded before the next step)
+void meep_b200_mark_host_dirty(meep::fields *f) {
+  if (Engine *E = Engine::find(f)) {
+    E->sync_host();
+    E->state = Engine::HOST_NEWER;
+  }
+}
+// counters: [0] steps, [1] H2D bytes, [2] D2H bytes, [3] kernel launches, [4] plan builds,
+// [5] full uploads, [6] full downloads, [7] device bytes allocated
+void meep_b200_get_stats(meep::fields *f, double out[8]) {
+  for (int i = 0; i < 8; ++i)
+    out[i] = 0;
+  if (Engine *E = Engine::find(f)) {
+    out[0] = (double)E->stats.steps;
+    out[1] = E->stats.h2d_bytes;
+    out[2] = E->stats.d2h_bytes;
+    out[3] = (double)mb200_launch_count(E->ctx);
+    out[4] = (double)E->stats.plan_builds;
+    out[5] = (double)E->stats.uploads;
+    out[6] = (double)E->stats.downloads;
+    out[7] = (double)mb200_bytes_allocated(E->ctx);
+  }
+}
+// the C-ABI context driving `f` (for CUDA-event timing / profiling from a bench driver)
+mb200_ctx *meep_b200_ctx(meep::fields *f) {
+  Engine *E = Engine::find(f);
+  return E ? E->ctx : nullptr;
+}
+}

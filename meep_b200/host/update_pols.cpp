@@ -1,0 +1,152 @@
+// update_pols.cpp — B200 replacement for the reference translation unit src/update_pols.cpp,
+// plus the two hot member functions of src/susceptibility.cpp
+// (lorentzian_susceptibility::update_P / subtract_P).
+//
+// fields_chunk::update_pols keeps the reference's lazy allocation of the polarisation state
+// (new_internal_data / init_internal_data run on the host, reference code) and then calls
+// lorentzian_susceptibility::update_P — OUR definition, which emits one mb200_lorentz_job_t
+// per (component, cmp) instead of looping (reference src/susceptibility.cpp:188-262).
+#include <assert.h>
+#include <string.h>
+#include <typeinfo>
+
+#include "engine.hpp"
+#include "loop_desc.hpp"
+#include "meep_internals.hpp"
+
+using namespace std;
+using namespace meep_b200;
+
+namespace meep {
+
+void fields::update_pols(field_type ft) {
+  Engine &E = Engine::get(this);
+  Scope scope(E, this);
+  run_phase(E, this, PH_POLS, ft, true, [&]() {
+    for (int i = 0; i < num_chunks; i++)
+      if (chunks[i]->is_mine())
+        if (chunks[i]->update_pols(ft)) {
+          chunk_connections_valid = false;
+          assert(changed_materials);
+        }
+  });
+}
+
+bool fields_chunk::update_pols(field_type ft) {
+  Engine *E = Engine::current();
+  if (!E || !E->recording()) meep::abort("meep_b200: fields_chunk::update_pols outside a phase");
+  bool allocated_fields = false;
+
+  realnum *w[NUM_FIELD_COMPONENTS][2];
+  FOR_COMPONENTS(c) DOCMP2 { w[c][cmp] = f_w[c][cmp] ? f_w[c][cmp] : f[c][cmp]; }
+
+  for (polarization_state *p = pol[ft]; p; p = p->next) {
+    if (typeid(*p->s) != typeid(lorentzian_susceptibility))
+      meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) polarisations are "
+                  "supported on the device path");
+
+    // Lazily allocate internal polarization data (host block laid out by the reference;
+    // the device twin starts at zero exactly like init_internal_data's memset):
+    if (!p->data) {
+      p->data = p->s->new_internal_data(f, gv);
+      if (p->data) {
+        p->s->init_internal_data(f, dt, gv, p->data);
+        lorentzian_data_layout *d = (lorentzian_data_layout *)p->data;
+        const size_t hdr = offsetof(lorentzian_data_layout, data);
+        if (d->sz_data > hdr) E->ensure_from(d->data, d->sz_data - hdr, NULL);
+        allocated_fields = true;
+      }
+    }
+
+    // Finally, timestep the polarizations (emits jobs):
+    static_cast<const lorentzian_susceptibility *>(p->s)->lorentzian_susceptibility::update_P(
+        w, f_w_prev, dt, gv, p->data);
+  }
+
+  return allocated_fields;
+}
+
+// Job emission for one susceptibility on one chunk.  W holds HOST pointers (as in the
+// reference); they are translated to device addresses through the Engine's mirror table.
+void lorentzian_susceptibility::update_P(realnum *W[NUM_FIELD_COMPONENTS][2],
+                                         realnum *W_prev[NUM_FIELD_COMPONENTS][2], realnum dt,
+                                         const grid_volume &gv, void *P_internal_data) const {
+  Engine *E = Engine::current();
+  if (!E || !E->recording())
+    meep::abort("meep_b200: lorentzian_susceptibility::update_P called outside a device phase "
+                "(this build has no CPU time-stepping path)");
+  if (!P_internal_data) return;
+  Recorder &R = E->rec();
+  lorentzian_data_layout *d = (lorentzian_data_layout *)P_internal_data;
+  // constants in realnum arithmetic, exactly as src/susceptibility.cpp:192-195
+  const realnum omega2pi = 2 * pi * omega_0, g2pi = gamma * 2 * pi;
+  const realnum omega0dtsqr = omega2pi * omega2pi * dt * dt;
+  const realnum gamma1inv = 1 / (1 + g2pi * dt / 2), gamma1 = (1 - g2pi * dt / 2);
+  const realnum omega0dtsqr_denom = no_omega_0_denominator ? 0 : omega0dtsqr;
+  (void)W_prev; // unused;
+
+  FOR_COMPONENTS(c) DOCMP2 {
+    if (d->P[c][cmp]) {
+      const realnum *w = W[c][cmp], *s = sigma[c][component_direction(c)];
+      if (w && s) {
+        realnum *p = d->P[c][cmp], *pp = d->P_prev[c][cmp];
+
+        // directions/strides for offdiagonal terms, similar to update_eh
+        const direction dd = component_direction(c);
+        const ptrdiff_t is = gv.stride(dd) * (is_magnetic(c) ? -1 : +1);
+        direction d1 = cycle_direction(gv.dim, dd, 1);
+        component c1 = direction_component(c, d1);
+        ptrdiff_t is1 = gv.stride(d1) * (is_magnetic(c) ? -1 : +1);
+        const realnum *w1 = W[c1][cmp];
+        const realnum *s1 = w1 ? sigma[c][d1] : NULL;
+        direction d2 = cycle_direction(gv.dim, dd, 2);
+        component c2 = direction_component(c, d2);
+        ptrdiff_t is2 = gv.stride(d2) * (is_magnetic(c) ? -1 : +1);
+        const realnum *w2 = W[c2][cmp];
+        const realnum *s2 = w2 ? sigma[c][d2] : NULL;
+
+        if (s2 && !s1) { // make s1 the non-NULL one if possible
+          std::swap(d1, d2);
+          std::swap(c1, c2);
+          std::swap(is1, is2);
+          std::swap(w1, w2);
+          std::swap(s1, s2);
+        }
+        mb200_lorentz_job_t J;
+        memset(&J, 0, sizeof(J));
+        J.box = make_box(gv, gv.little_owned_corner(c), gv.big_corner()); // PLOOP_OVER_VOL_OWNED
+        J.p = E->dev(p);
+        J.pp = E->dev(pp);
+        J.w = E->dev(w);
+        J.s = E->dev(s);
+        if (s1) {
+          J.w1 = E->dev(w1);
+          J.s1 = E->dev(s1);
+        }
+        if (s1 && s2) {
+          J.w2 = E->dev(w2);
+          J.s2 = E->dev(s2);
+        }
+        J.is = is;
+        J.is1 = is1;
+        J.is2 = is2;
+        J.gamma1inv = gamma1inv;
+        J.gamma1 = gamma1;
+        J.omega0dtsqr = omega0dtsqr;
+        J.omega0dtsqr_denom = omega0dtsqr_denom;
+        if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.lorentz.push_back(J);
+      }
+    }
+  }
+}
+
+// The reference calls this from fields_chunk::update_eh; our update_eh folds the subtraction
+// into its f_minus_p job (update_eh.cpp), so reaching this function means some CPU code path
+// is trying to time-step on stale host arrays.
+void lorentzian_susceptibility::subtract_P(field_type, realnum *[NUM_FIELD_COMPONENTS][2],
+                                           void *) const {
+  meep::abort("meep_b200: lorentzian_susceptibility::subtract_P: this build has no CPU "
+              "time-stepping path");
+}
+
+} // namespace meep
