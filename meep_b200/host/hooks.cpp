@@ -207,6 +207,27 @@ void dft_near2far::farfield_lowlevel(complex<double> *EH, const vec &x, double f
   next(this, EH, x, freq_);
 }
 
+double *dft_force::force() {
+  typedef double *(*fn)(dft_force *);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  return next(this);
+}
+
+double *dft_energy::electric() {
+  typedef double *(*fn)(dft_energy *);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  return next(this);
+}
+
+double *dft_energy::magnetic() {
+  typedef double *(*fn)(dft_energy *);
+  static fn next = (fn)next_definition_of_caller();
+  sync_all_hosts();
+  return next(this);
+}
+
 void dft_ldos::update(fields &f) {
   typedef void (*fn)(dft_ldos *, fields &);
   static fn next = (fn)next_definition_of_caller();

@@ -1,0 +1,285 @@
+// gen_golden.cpp — produces the golden vectors under tests/golden/ by calling the REFERENCE's own
+// inner-loop functions (meep::step_curl, meep::step_update_EDHB,
+// meep::lorentzian_susceptibility::update_P, meep::dft_chunk::update_dft) from the unmodified
+// reference build in oracle/_ref on small seeded inputs.  Linked against the reference ONLY.
+//
+// Each case file holds: the initial arrays, the loop descriptors as derived by
+// meep_b200/host/loop_desc.hpp (stored as float64 vectors), scalars, and the arrays after the call.
+// tests/test_oracle.py replays the case through oracle/fdtd_oracle.c, tests/test_kernels_gpu.py
+// through the CUDA C ABI.
+//
+// usage: gen_golden_ref_<prec> <outdir>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <complex>
+#include <string>
+#include <vector>
+
+#include "meep.hpp"
+#include "meep_internals.hpp"
+#include "loop_desc.hpp"
+
+using namespace meep;
+using namespace meep_b200;
+using std::complex;
+
+static FILE *g_out = NULL;
+static void dump(const std::string &name, const void *data, unsigned elem_size, size_t count) {
+  unsigned nl = (unsigned)name.size();
+  unsigned long long c = count;
+  fwrite(&nl, 4, 1, g_out);
+  fwrite(name.data(), 1, nl, g_out);
+  fwrite(&elem_size, 4, 1, g_out);
+  fwrite(&c, 8, 1, g_out);
+  fwrite(data, elem_size, count, g_out);
+}
+static void dump_d(const std::string &name, const std::vector<double> &v) {
+  dump(name, v.data(), 8, v.size());
+}
+static void dump_r(const std::string &name, const realnum *p, size_t n) {
+  if (p) dump(name, p, sizeof(realnum), n);
+}
+static void dump_box(const std::string &name, const mb200_box_t &b) {
+  dump_d(name, {(double)b.idx0, (double)b.s[0], (double)b.s[1], (double)b.s[2], (double)b.n[0],
+                (double)b.n[1], (double)b.n[2]});
+}
+static void dump_pml(const std::string &name, const mb200_pml_t &p, bool present) {
+  dump_d(name, {present ? 1.0 : 0.0, (double)p.k0, (double)p.ks[0], (double)p.ks[1],
+                (double)p.ks[2]});
+}
+
+// deterministic pseudo-random numbers (LCG), independent of libc
+static unsigned long long g_seed = 12345;
+static double urand() {
+  g_seed = g_seed * 6364136223846793005ULL + 1442695040888963407ULL;
+  return (double)((g_seed >> 11) & ((1ULL << 53) - 1)) / (double)(1ULL << 53);
+}
+static realnum *rand_array(size_t n, double lo = -1, double hi = 1) {
+  realnum *a = new realnum[n];
+  for (size_t i = 0; i < n; ++i)
+    a[i] = (realnum)(lo + (hi - lo) * urand());
+  return a;
+}
+
+static void open_case(const std::string &dir, const std::string &name) {
+  std::string path = dir + "/" + name + (sizeof(realnum) == 8 ? "_f64.bin" : "_f32.bin");
+  g_out = fopen(path.c_str(), "wb");
+  if (!g_out) { perror(path.c_str()); exit(2); }
+}
+
+// ---- step_curl ---------------------------------------------------------------------------------
+static void gen_curl(const std::string &dir, const grid_volume &gv, const char *tag) {
+  const size_t n = gv.ntot();
+  // D-type update of the component along the first field direction: reads the low neighbours
+  const component cc = gv.dim == D3 ? Dx : Dz; // 2D: TM (Dz from Hx,Hy)
+  direction d1, d2;
+  if (gv.dim == D3) { d1 = Y; d2 = Z; } else { d1 = X; d2 = Y; }
+  const ivec is = gv.little_owned_corner0(cc), ie = gv.big_corner();
+  const direction dsig0 = gv.dim == D3 ? Y : X, dsigu0 = gv.dim == D3 ? Z : Y;
+  for (int variant = 0; variant < 16; ++variant) {
+    const bool PML = variant & 8, FU = variant & 4, CND = variant & 2, G2 = variant & 1;
+    char nm[64];
+    snprintf(nm, sizeof nm, "curl_%s_v%02d", tag, variant);
+    open_case(dir, nm);
+    realnum *f = rand_array(n), *g1 = rand_array(n), *g2 = G2 ? rand_array(n) : NULL;
+    realnum *fu = FU ? rand_array(n) : NULL, *fcnd = (CND && PML) ? rand_array(n) : NULL;
+    realnum *cnd = CND ? rand_array(n, 0, 2) : NULL, *cndinv = CND ? rand_array(n, 0.5, 1) : NULL;
+    const int ns = 2 * gv.num_direction(dsig0) + 2, nsu = 2 * gv.num_direction(dsigu0) + 2;
+    realnum *sig = rand_array(ns, 0, 0.5), *kap = rand_array(ns, 1, 2), *siginv = rand_array(ns, 0.3, 1);
+    realnum *sigu = rand_array(nsu, 0, 0.5), *kapu = rand_array(nsu, 1, 2), *siginvu = rand_array(nsu, 0.3, 1);
+    const ptrdiff_t s1 = -gv.stride(d1), s2 = -gv.stride(d2);
+    const realnum dtdx = 0.5, dt = 0.05;
+    const direction dsig = PML ? dsig0 : NO_DIRECTION, dsigu = FU ? dsigu0 : NO_DIRECTION;
+    dump_r("in.f", f, n); dump_r("in.g1", g1, n); dump_r("in.g2", g2, n);
+    dump_r("in.fu", fu, n); dump_r("in.fcnd", fcnd, n); dump_r("in.cnd", cnd, n);
+    dump_r("in.cndinv", cndinv, n);
+    dump_r("in.sig", sig, ns); dump_r("in.kap", kap, ns); dump_r("in.siginv", siginv, ns);
+    dump_r("in.sigu", sigu, nsu); dump_r("in.kapu", kapu, nsu); dump_r("in.siginvu", siginvu, nsu);
+    dump_box("box", make_box(gv, is, ie));
+    dump_pml("pml", make_pml(gv, is, dsig, sig, kap, siginv), PML);
+    dump_pml("pmlu", make_pml(gv, is, dsigu, sigu, kapu, siginvu), FU);
+    dump_d("scalars", {(double)s1, (double)s2, (double)dtdx, (double)dt});
+    // THE REFERENCE CALL (dispatch macro picks the stride-1 build exactly as step_db does)
+    STEP_CURL(f, cc, g1, g2, s1, s2, gv, is, ie, dtdx, dsig, sig, kap, siginv, fu, dsigu, sigu, kapu,
+              siginvu, dt, cnd, cndinv, fcnd);
+    dump_r("out.f", f, n); dump_r("out.fu", fu, n); dump_r("out.fcnd", fcnd, n);
+    fclose(g_out);
+  }
+}
+
+// ---- step_update_EDHB --------------------------------------------------------------------------
+static void gen_edhb(const std::string &dir, const grid_volume &gv, const char *tag) {
+  const size_t n = gv.ntot();
+  const component ec = gv.dim == D3 ? Ey : Ex;
+  const direction d_ec = component_direction(ec);
+  const direction d_1 = cycle_direction(gv.dim, d_ec, 1), d_2 = cycle_direction(gv.dim, d_ec, 2);
+  const ivec is = gv.little_owned_corner0(ec), ie = gv.big_corner();
+  // (has_u, noff, chi3, pml)
+  const int cfgs[][4] = {{1, 0, 0, 0}, {0, 0, 0, 0}, {1, 1, 0, 0}, {1, 2, 0, 0}, {1, 0, 1, 0}, {1, 1, 1, 0},
+                         {1, 2, 1, 0}, {1, 0, 0, 1}, {0, 0, 0, 1}, {1, 1, 0, 1}, {1, 2, 0, 1}, {1, 2, 1, 1},
+                         {1, 0, 1, 1}};
+  for (size_t k = 0; k < sizeof(cfgs) / sizeof(cfgs[0]); ++k) {
+    int has_u = cfgs[k][0], noff = cfgs[k][1], nl = cfgs[k][2], pmlw = cfgs[k][3];
+    if (gv.dim == D2 && noff == 2) noff = 1; // only one in-plane partner in 2-D
+    char nm[64];
+    snprintf(nm, sizeof nm, "edhb_%s_c%02d", tag, (int)k);
+    open_case(dir, nm);
+    realnum *f = rand_array(n), *g = rand_array(n);
+    // when chi3 is present the reference also reads g1/g2 neighbours if they exist
+    realnum *g1 = (noff >= 1 || nl) ? rand_array(n) : NULL;
+    realnum *g2 = (noff >= 2 || (nl && gv.dim == D3)) ? rand_array(n) : NULL;
+    realnum *u = has_u ? rand_array(n, 0.1, 1) : NULL;
+    realnum *u1 = noff >= 1 ? rand_array(n, -0.1, 0.1) : NULL, *u2 = noff >= 2 ? rand_array(n, -0.1, 0.1) : NULL;
+    realnum *chi2 = nl ? rand_array(n, 0, 0.1) : NULL, *chi3 = nl ? rand_array(n, 0, 0.1) : NULL;
+    realnum *fw = pmlw ? rand_array(n) : NULL;
+    const int ns = 2 * gv.num_direction(d_ec) + 2;
+    realnum *sigw = rand_array(ns, 0, 0.5), *kapw = rand_array(ns, 1, 2);
+    const ptrdiff_t s = gv.stride(d_ec), s1 = gv.stride(d_1), s2 = gv.stride(d_2);
+    const direction dsigw = pmlw ? d_ec : NO_DIRECTION;
+    dump_r("in.f", f, n); dump_r("in.g", g, n); dump_r("in.g1", g1, n); dump_r("in.g2", g2, n);
+    dump_r("in.u", u, n); dump_r("in.u1", u1, n); dump_r("in.u2", u2, n);
+    dump_r("in.chi2", chi2, n); dump_r("in.chi3", chi3, n); dump_r("in.fw", fw, n);
+    dump_r("in.sigw", sigw, ns); dump_r("in.kapw", kapw, ns);
+    dump_box("box", make_box(gv, is, ie));
+    dump_pml("pmlw", make_pml(gv, is, dsigw, sigw, kapw, NULL), pmlw);
+    dump_d("scalars", {(double)s, (double)s1, (double)s2});
+    STEP_UPDATE_EDHB(f, ec, gv, is, ie, g, g1, g2, u, u1, u2, s, s1, s2, chi2, chi3, fw, dsigw, sigw, kapw);
+    dump_r("out.f", f, n); dump_r("out.fw", fw, n);
+    fclose(g_out);
+  }
+}
+
+// ---- lorentzian_susceptibility::update_P ---------------------------------------------------------
+struct lorentzian_data_layout {
+  size_t sz_data;
+  size_t ntot;
+  realnum *P[NUM_FIELD_COMPONENTS][2];
+  realnum *P_prev[NUM_FIELD_COMPONENTS][2];
+  realnum data[1];
+};
+
+static void gen_lorentz(const std::string &dir, const grid_volume &gv, const char *tag) {
+  const size_t n = gv.ntot();
+  for (int noff = 0; noff <= 2; ++noff)
+    for (int drude = 0; drude <= 1; ++drude) {
+      char nm[64];
+      snprintf(nm, sizeof nm, "lorentz_%s_o%d_d%d", tag, noff, drude);
+      open_case(dir, nm);
+      lorentzian_susceptibility sus(0.7, 0.13, drude != 0);
+      const component c = Ey;
+      const direction d = component_direction(c);
+      const direction d1 = cycle_direction(gv.dim, d, 1), d2 = cycle_direction(gv.dim, d, 2);
+      realnum *W[NUM_FIELD_COMPONENTS][2];
+      FOR_COMPONENTS(cc) { W[cc][0] = W[cc][1] = NULL; }
+      FOR_ELECTRIC_COMPONENTS(cc) { W[cc][0] = rand_array(n); }
+      sus.ntot = n;
+      sus.sigma[c][d] = rand_array(n, 0, 1);
+      for (size_t i = 0; i < n; i += 7) sus.sigma[c][d][i] = 0; // exercise the s[i] != 0 guard
+      sus.trivial_sigma[c][d] = false;
+      if (noff >= 1) { sus.sigma[c][d1] = rand_array(n, -0.2, 0.2); sus.trivial_sigma[c][d1] = false; }
+      if (noff >= 2) { sus.sigma[c][d2] = rand_array(n, -0.2, 0.2); sus.trivial_sigma[c][d2] = false; }
+      lorentzian_data_layout *data = (lorentzian_data_layout *)sus.new_internal_data(W, gv);
+      sus.init_internal_data(W, 0.05, gv, data);
+      if (!data->P[c][0]) { fprintf(stderr, "gen_lorentz: no P allocated\n"); exit(3); }
+      for (size_t i = 0; i < n; ++i) {
+        data->P[c][0][i] = (realnum)(2 * urand() - 1);
+        data->P_prev[c][0][i] = (realnum)(2 * urand() - 1);
+      }
+      const realnum dt = 0.05;
+      // constants exactly as src/susceptibility.cpp:192-195, in realnum arithmetic
+      const realnum omega_0 = 0.7, gamma = 0.13;
+      const realnum omega2pi = 2 * pi * omega_0, g2pi = gamma * 2 * pi;
+      const realnum omega0dtsqr = omega2pi * omega2pi * dt * dt;
+      const realnum gamma1inv = 1 / (1 + g2pi * dt / 2), gamma1 = (1 - g2pi * dt / 2);
+      const realnum omega0dtsqr_denom = drude ? 0 : omega0dtsqr;
+      dump_r("in.p", data->P[c][0], n); dump_r("in.pp", data->P_prev[c][0], n);
+      dump_r("in.w", W[c][0], n); dump_r("in.s", sus.sigma[c][d], n);
+      dump_r("in.w1", noff >= 1 ? W[direction_component(c, d1)][0] : NULL, n);
+      dump_r("in.s1", sus.sigma[c][d1], n);
+      dump_r("in.w2", noff >= 2 ? W[direction_component(c, d2)][0] : NULL, n);
+      dump_r("in.s2", sus.sigma[c][d2], n);
+      dump_box("box", make_box(gv, gv.little_owned_corner(c), gv.big_corner()));
+      dump_d("scalars", {(double)gv.stride(d), (double)gv.stride(d1), (double)gv.stride(d2),
+                         (double)gamma1inv, (double)gamma1, (double)omega0dtsqr, (double)omega0dtsqr_denom});
+      sus.update_P(W, NULL, dt, gv, data);
+      dump_r("out.p", data->P[c][0], n); dump_r("out.pp", data->P_prev[c][0], n);
+      fclose(g_out);
+      sus.delete_internal_data(data);
+    }
+}
+
+// ---- dft_chunk::update_dft -----------------------------------------------------------------------
+static double one(const vec &) { return 1.0; }
+
+static void gen_dft(const std::string &dir, bool three_d, bool complex_fields, const char *tag) {
+  char nm[64];
+  snprintf(nm, sizeof nm, "dft_%s", tag);
+  open_case(dir, nm);
+  grid_volume gv = three_d ? vol3d(0.9, 0.8, 0.7, 10) : voltwo(1.2, 0.9, 10);
+  structure s(gv, one);
+  fields f(&s);
+  if (!complex_fields) f.use_real_fields();
+  f.add_point_source(three_d ? Ex : Ez, 0.3, 1.0, 0.0, 2.0, gv.center());
+  f.add_point_source(three_d ? Hy : Hx, 0.3, 1.0, 0.0, 2.0, gv.center());
+  volume where = three_d ? volume(vec(0.2, 0.15, 0.35), vec(0.7, 0.65, 0.35))
+                         : volume(vec(0.25, 0.45), vec(0.95, 0.45));
+  dft_flux fl = f.add_dft_flux_plane(where, 0.2, 0.4, 5);
+  // fill every allocated field array of every chunk with seeded random numbers
+  for (int i = 0; i < f.num_chunks; ++i)
+    FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) if (f.chunks[i]->f[c][cmp])
+      for (size_t k = 0; k < f.chunks[i]->gv.ntot(); ++k)
+        f.chunks[i]->f[c][cmp][k] = (realnum)(2 * urand() - 1);
+  int nchunks = 0;
+  const double time = 1.234;
+  for (int i = 0; i < f.num_chunks; ++i) {
+    fields_chunk *fc = f.chunks[i];
+    for (dft_chunk *d = fc->dft_chunks; d; d = d->next_in_chunk, ++nchunks) {
+      char p[64];
+      snprintf(p, sizeof p, "k%d.", nchunks);
+      const std::string P = p;
+      const size_t nd = 2 * d->N * d->omega.size();
+      for (size_t k = 0; k < nd / 2; ++k)
+        d->dft[k] = complex<realnum>((realnum)(urand() - 0.5), (realnum)(urand() - 0.5));
+      dump_r(P + "in.f_re", fc->f[d->c][0], fc->gv.ntot());
+      dump_r(P + "in.f_im", fc->f[d->c][1], fc->gv.ntot());
+      dump_r(P + "in.dft", (realnum *)d->dft, nd);
+      dump_box(P + "box", make_box(fc->gv, d->is, d->ie));
+      std::vector<double> w;
+      for (int k = 0; k < 3; ++k) {
+        const direction dk = fc->gv.yucky_direction(k);
+        w.push_back(d->s0.in_direction(dk)); w.push_back(d->s1.in_direction(dk));
+        w.push_back(d->e0.in_direction(dk)); w.push_back(d->e1.in_direction(dk));
+      }
+      dump_d(P + "weights", w);
+      dump_d(P + "scalars", {(double)d->avg1, (double)d->avg2, d->dV0, d->dV1,
+                             d->include_dV_and_interp_weights ? 1.0 : 0.0,
+                             d->sqrt_dV_and_interp_weights ? 1.0 : 0.0, (double)d->omega.size()});
+      d->update_dft(time); // THE REFERENCE CALL (fills dft_phase and accumulates)
+      dump_r(P + "phase", (realnum *)d->dft_phase, 2 * d->omega.size());
+      dump_r(P + "out.dft", (realnum *)d->dft, nd);
+    }
+  }
+  dump_d("nchunks", {(double)nchunks});
+  double *F = fl.flux();
+  dump_d("flux", std::vector<double>(F, F + fl.freq.size()));
+  delete[] F;
+  fclose(g_out);
+}
+
+int main(int argc, char **argv) {
+  initialize mpi(argc, argv);
+  verbosity = 0;
+  if (argc < 2) { fprintf(stderr, "usage: %s <outdir>\n", argv[0]); return 2; }
+  const std::string dir = argv[1];
+  grid_volume g3 = vol3d(0.5, 0.4, 0.6, 10); // 5 x 4 x 6 cells
+  grid_volume g2 = voltwo(0.7, 0.5, 10);     // 7 x 5 cells
+  gen_curl(dir, g3, "3d");
+  gen_curl(dir, g2, "2d");
+  gen_edhb(dir, g3, "3d");
+  gen_edhb(dir, g2, "2d");
+  gen_lorentz(dir, g3, "3d");
+  gen_dft(dir, true, false, "3d_real");
+  gen_dft(dir, false, true, "2d_complex");
+  return 0;
+}

@@ -1,0 +1,125 @@
+"""Helpers shared by the parity tests: run a parity driver arm, parse its dump, compare arrays."""
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TBUILD = os.path.join(ROOT, "tests", "_build")
+
+# parity gates stated by BASELINE.json's north_star: relative L2 over whole arrays
+TOL = {"f64": 1e-12, "f32": 1e-5}
+
+
+def read_dump(path):
+    """-> dict name -> np.ndarray (records: u32 name_len, name, u32 elem_size, u64 count, data)."""
+    out = {}
+    with open(path, "rb") as fh:
+        data = fh.read()
+    off = 0
+    while off < len(data):
+        (nl,) = struct.unpack_from("<I", data, off)
+        off += 4
+        name = data[off:off + nl].decode()
+        off += nl
+        es, cnt = struct.unpack_from("<IQ", data, off)
+        off += 12
+        dt = {8: np.float64, 4: np.float32}[es]
+        out[name] = np.frombuffer(data, dtype=dt, count=cnt, offset=off).copy()
+        off += es * cnt
+    return out
+
+
+def driver(name, arm, prec):
+    return os.path.join(TBUILD, "%s_%s_%s" % (name, arm, prec))
+
+
+def run_case(arm, prec, case, nsteps, num_chunks=0, env=None, name="sim_driver", timeout=900):
+    exe = driver(name, arm, prec)
+    if not os.path.exists(exe):
+        raise FileNotFoundError(exe)
+    fd, path = tempfile.mkstemp(suffix=".bin", prefix="mb200_%s_%s_" % (case, arm))
+    os.close(fd)
+    e = dict(os.environ)
+    e.setdefault("OMP_NUM_THREADS", "4")
+    if env:
+        e.update(env)
+    try:
+        r = subprocess.run([exe, case, str(nsteps), path, str(num_chunks)], env=e, timeout=timeout,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("%s %s failed (rc=%d):\n%s" % (exe, case, r.returncode, r.stdout[-4000:]))
+        return read_dump(path)
+    finally:
+        if os.path.exists(path):
+            os.unlink(path)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    nb = np.linalg.norm(b)
+    d = np.linalg.norm(a - b)
+    if nb == 0:
+        return 0.0 if d == 0 else float("inf")
+    return d / nb
+
+
+def _group(name):
+    """chunk3.f_u.bz.1 -> 'f_u.b' : one group per (array kind, field type), all chunks, all
+    components, both cmp.  The north_star gate is a relative L2 over whole fields; a component
+    that is zero by symmetry (e.g. Bz of an Ez dipole) only holds rounding noise of its
+    siblings and is judged together with them, as SURVEY §7 / BASELINE.md prescribe."""
+    parts = name.split(".")
+    if not parts[0].startswith("chunk"):
+        return name
+    kind = parts[1]
+    if kind.startswith("dft"):
+        return "dft." + parts[2][0]
+    if kind.startswith("P"):
+        return kind.rstrip("0123456789") + "." + parts[2][0]
+    return kind + "." + parts[2][0]
+
+
+def _ftype(group):
+    """field-type pool of a group: 'f_u.b' -> 'b' (f, f_u, f_cond of B share units and scale)."""
+    return group.split(".")[-1] if "." in group else group
+
+
+def compare(got, ref, tol, skip_prefix=()):
+    """Gate: for every group g (see _group), with T its field-type pool over all array kinds,
+
+        ||got_g - ref_g||_2  <=  tol * ||ref_g||_2  +  64 * eps * ||ref_T||_2
+
+    i.e. the north_star relative-L2 tolerance on each group, plus the unavoidable rounding floor
+    of the field type it belongs to (a group that is zero by symmetry still receives noise of
+    size eps * |fields| from its siblings in the reference itself).  Returns {group: rel err}."""
+    assert set(got) == set(ref), "array sets differ: only-got=%s only-ref=%s" % (
+        sorted(set(got) - set(ref))[:8], sorted(set(ref) - set(got))[:8])
+    num, den, pool = {}, {}, {}
+    eps = None
+    for k in sorted(ref):
+        if any(k.startswith(p) for p in skip_prefix):
+            continue
+        if eps is None or ref[k].dtype == np.float32:
+            eps = float(np.finfo(ref[k].dtype).eps) if k.startswith("chunk") else eps
+        a, b = got[k].astype(np.float64), ref[k].astype(np.float64)
+        assert a.shape == b.shape, k
+        assert np.all(np.isfinite(a)), "non-finite values in %s" % k
+        g = _group(k)
+        d = a - b
+        num[g] = num.get(g, 0.0) + float(np.dot(d, d))
+        den[g] = den.get(g, 0.0) + float(np.dot(b, b))
+        pool[_ftype(g)] = pool.get(_ftype(g), 0.0) + float(np.dot(b, b))
+    eps = eps or float(np.finfo(np.float64).eps)
+    report, bad = {}, []
+    for g in num:
+        dn, rn, pn = np.sqrt(num[g]), np.sqrt(den[g]), np.sqrt(pool[_ftype(g)])
+        allowed = tol * rn + 64 * eps * pn
+        report[g] = 0.0 if dn == 0 else (dn / rn if rn > 0 else float("inf"))
+        if dn > allowed:
+            bad.append((g, dn, rn, pn))
+    assert not bad, "parity gate failed (group, ||diff||, ||ref||, ||pool||): %s" % bad[:6]
+    return report

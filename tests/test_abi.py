@@ -1,0 +1,98 @@
+"""The C-ABI library loads, exports every symbol include/meep_b200.h declares, its structs have
+the layout the Python binding assumes, and it FAILS LOUDLY without a CUDA device (no fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import have_gpu
+from meep_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "meep_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb200_[a-zA-Z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = capi.load()
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), "libmeepb200.so does not export %s" % n
+    # and the Python binding declares every one of them
+    assert set(capi.declare(lib)) == set(names)
+
+
+def test_struct_layouts_match_the_header():
+    """compile a tiny C program that prints sizeof() of every job struct and compare with ctypes"""
+    names = ["mb200_box_t", "mb200_pml_t", "mb200_curl_job_t", "mb200_edhb_job_t", "mb200_lorentz_job_t",
+             "mb200_fmp_job_t", "mb200_src_job_t", "mb200_halo_job_t", "mb200_zero_job_t", "mb200_dft_job_t",
+             "mb200_flux_job_t", "mb200_step3_comp_t", "mb200_step3_job_t"]
+    types = [capi.Box, capi.Pml, capi.CurlJob, capi.EdhbJob, capi.LorentzJob, capi.FmpJob, capi.SrcJob,
+             capi.HaloJob, capi.ZeroJob, capi.DftJob, capi.FluxJob, capi.Step3Comp, capi.Step3Job]
+    prog = '#include <stdio.h>\n#include "meep_b200.h"\nint main(void){%s return 0;}\n' % "".join(
+        'printf("%%zu\\n", sizeof(%s));' % n for n in names)
+    d = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(d, exist_ok=True)
+    src, exe = os.path.join(d, "sizes.c"), os.path.join(d, "sizes")
+    open(src, "w").write(prog)
+    subprocess.check_call(["/usr/bin/gcc", "-I" + os.path.join(ROOT, "include"), src, "-o", exe])
+    sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(t) for t in types]
+
+
+def test_abi_version():
+    assert capi.load().mb200_abi_version() == 1
+
+
+@pytest.mark.skipif(have_gpu(), reason="this check is for machines without a GPU")
+def test_fails_loudly_without_a_device():
+    lib = capi.load()
+    assert lib.mb200_device_count() == 0
+    ctx = C.c_void_p()
+    assert lib.mb200_init(0, C.byref(ctx)) != 0
+    assert b"cuda" in lib.mb200_last_error().lower() or b"device" in lib.mb200_last_error().lower()
+    with pytest.raises(capi.Error):
+        capi.Context(0)
+
+
+@pytest.mark.skipif(have_gpu(), reason="this check is for machines without a GPU")
+def test_dropin_has_no_cpu_time_stepping_path():
+    """fields::step() through the real drop-in aborts with a clear message when no GPU exists"""
+    exe = os.path.join(ROOT, "tests", "_build", "sim_driver_b200_f64")
+    r = subprocess.run([exe, "3d_metal", "2", "/tmp/mb200_nogpu.bin"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert r.returncode != 0
+    assert "no CUDA device" in r.stdout
+
+
+def test_product_libraries_do_not_link_the_oracle_or_the_emulator():
+    for name in ["libmeepb200.so", "libmeep_b200_f64.so", "libmeep_b200_f32.so"]:
+        out = subprocess.check_output(["readelf", "-d", os.path.join(capi.LIBDIR, name)], text=True)
+        assert "liboracle" not in out and "emu" not in out, name
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(capi.LIBDIR, "libmeepb200.so")],
+                                   text=True)
+    assert "mb200_is_emulator" not in syms
+
+
+def test_dropin_interposes_the_hot_path_symbols():
+    """the replacement library defines exactly the hot-path symbols SURVEY §8b lists"""
+    syms = subprocess.check_output(
+        ["nm", "-D", "--defined-only", "-C", os.path.join(capi.LIBDIR, "libmeep_b200_f64.so")], text=True)
+    for want in ["meep::fields::step()", "meep::fields::step_db(", "meep::fields_chunk::step_db(",
+                 "meep::fields::update_eh(", "meep::fields_chunk::update_eh(", "meep::fields::update_pols(",
+                 "meep::fields_chunk::update_pols(", "meep::fields::step_boundaries(",
+                 "meep::fields::step_source(", "meep::fields::calc_sources(", "meep::fields::phase_material()",
+                 "meep::fields::process_incoming_chunk_data(", "meep::fields::update_dfts()",
+                 "meep::dft_chunk::update_dft(", "meep::dft_flux::flux()",
+                 "meep::lorentzian_susceptibility::update_P(", "meep::lorentzian_susceptibility::subtract_P(",
+                 "meep::step_curl(", "meep::step_update_EDHB(", "meep::step_curl_stride1(",
+                 "meep::fields_chunk::needs_W_prev("]:
+        assert want in syms, want

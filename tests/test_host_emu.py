@@ -1,0 +1,73 @@
+"""Host-side engine logic (job construction from meep::fields_chunk, connection-table
+translation, lazy allocation, mirror protocol, plan caching) exercised WITHOUT a GPU: the
+drop-in library is linked against the test-only emulator of the C ABI (tests/emu), and the full
+simulations are compared array by array with the unmodified reference build (oracle/_ref)."""
+import os
+import subprocess
+
+import pytest
+
+from parity_util import TBUILD, TOL, compare, run_case
+
+CASES = [  # (case, steps, num_chunks)
+    ("c2_3d_pml", 30, 0),
+    ("c2_3d_pml", 20, 3),
+    ("c2_3d_pml_integrated", 20, 0),
+    ("c2_3d_pml_complex", 12, 0),
+    ("3d_metal", 30, 2),
+    ("3d_bloch", 30, 0),
+    ("3d_xperiodic_ypml", 30, 0),
+    ("2d_bend_flux", 150, 0),
+    ("2d_te_pml", 60, 2),
+    ("1d_polariton", 100, 3),
+    ("c3_au_sphere", 20, 0),
+    ("lorentz_3d", 30, 2),
+    ("c4_aniso_ring", 15, 0),
+    ("offdiag_2d", 60, 0),
+    ("cond_chi3_3d", 30, 0),
+    ("dft_fields_3d", 30, 0),
+]
+
+
+@pytest.mark.parametrize("case,steps,chunks", CASES)
+def test_emulated_dropin_matches_reference_f64(case, steps, chunks):
+    ref = run_case("ref", "f64", case, steps, chunks)
+    got = run_case("emu", "f64", case, steps, chunks)
+    assert any((v != 0).any() for v in ref.values())
+    compare(got, ref, TOL["f64"])
+
+
+@pytest.mark.parametrize("case,steps,chunks", [("c2_3d_pml", 20, 0), ("lorentz_3d", 20, 0),
+                                               ("2d_bend_flux", 100, 0), ("3d_bloch", 20, 0)])
+def test_emulated_dropin_matches_reference_f32(case, steps, chunks):
+    ref = run_case("ref", "f32", case, steps, chunks)
+    got = run_case("emu", "f32", case, steps, chunks)
+    compare(got, ref, TOL["f32"])
+
+
+@pytest.mark.parametrize("case,steps", [("c2_3d_pml", 20), ("lorentz_3d", 15)])
+def test_fused_and_unfused_paths_agree(case, steps):
+    ref = run_case("ref", "f64", case, steps)
+    a = run_case("emu", "f64", case, steps, env={"MEEP_B200_FUSE": "0"})
+    b = run_case("emu", "f64", case, steps, env={"MEEP_B200_FUSE": "1"})
+    compare(a, ref, TOL["f64"])
+    compare(b, ref, TOL["f64"])
+
+
+def test_eager_mirror_mode():
+    ref = run_case("ref", "f64", "3d_metal", 10)
+    got = run_case("emu", "f64", "3d_metal", 10, env={"MEEP_B200_EAGER": "1"})
+    compare(got, ref, TOL["f64"])
+
+
+@pytest.mark.parametrize("name", ["known_results", "three_d", "one_dimensional", "physical", "integrate",
+                                  "stress_tensor"])
+def test_reference_test_program_passes_through_the_dropin(name):
+    """the reference's own C++ test programs, compiled from /root/reference/tests unmodified and
+    linked with the (emulated) drop-in in front of libmeep"""
+    exe = os.path.join(TBUILD, "reftest_%s_emu_f64" % name)
+    if not os.path.exists(exe):
+        pytest.skip("not built")
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    r = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
