@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py — Yee cell-updates/s of meep::fields::step() on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # device arm (one process per GPU)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path, host cores
+
+Workload (N=1): BASELINE.json configs[1] — 3-D dielectric box 512^3, PML on all faces,
+non-dispersive, Gaussian dipole source, double precision, built through the reference's public
+C++ API (meep::structure / meep::fields) by bench/bench_driver.cpp and stepped with
+fields::step().  A "step" is one FDTD time step (one pass of the hot path over the grid).
+
+  value   : cells * K / device time (CUDA events on the engine's stream), fields resident in HBM
+  e2e     : the same K steps through the public API as a user's monitoring loop runs them:
+            every step uploads that step's source amplitudes (H2D) and reads one field probe back
+            (D2H, fields::get_field), timed on the host around the API calls
+  roofline: dominant kernel (fused D/B update) algorithmic bytes / CUDA-event time / measured HBM peak
+  cpu_baseline: the unmodified reference (oracle/_ref) on this box's host cores, bounded sample
+
+N>1: this round the path does not shard across processes (no inter-process halo transport yet):
+"replicas only" — every rank steps its own 512^3 problem, value is the aggregate (weak scaling).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+LIB = os.path.join(ROOT, "meep_b200", "lib")
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 3 + i and s[3 + i].lower().startswith("active")
+                                                         for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """the reference's own CPU implementation (oracle/_ref) on the host cores, bounded sample"""
+    exe = os.path.join(LIB, "bench_ref_%s" % args.prec)
+    if not os.path.exists(exe):
+        raise RuntimeError("%s missing: run __graft_entry__.build() where the reference sources exist" % exe)
+    cores = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    out = subprocess.run([exe, "c2", str(args.cpu_n), str(args.warmup), str(args.steps)], env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=3000)
+    if out.returncode != 0:
+        raise RuntimeError("reference arm failed: " + out.stderr[-2000:])
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    r["cores"] = cores
+    return r
+
+
+def cpu_baseline_obj(r):
+    return {"value": r["cells_per_s"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference",
+            "sample": "same workload at %d^3 (%d chunks), %d timed steps after %d warm-up, OpenMP on all host "
+                      "cores (MPI is not installed: the reference's OpenMP path stands in for its MPI path)"
+                      % (r["n"], r["num_chunks"], r["steps"], r["warmup"])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="cells per edge of the c2 workload")
+    ap.add_argument("--cpu-n", type=int, default=192, help="edge of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = run_reference(args)
+        line = {"impl": "reference", "metric": "Yee cell-updates/s", "value": r["cells_per_s"],
+                "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"],
+                "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
+                "config": {"workload": "c2: 3D dielectric box + PML, Gaussian dipole (bounded sample %d^3 of "
+                                       "the 512^3 config)" % r["n"], "n": r["n"], "num_chunks": r["num_chunks"]},
+                "cpu_baseline": cpu_baseline_obj(r),
+                "e2e": {"value": r["cells_per_s"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---- device arm ----------------------------------------------------------------------------
+    import torch  # plumbing only: process group for the barrier / max-over-ranks
+    import torch.distributed as dist
+    from meep_b200 import capi
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    os.environ["MEEP_B200_DEVICE"] = str(local_rank)
+
+    lib = capi.load()  # libmeepb200.so (CUDA kernels + C ABI); raises if missing
+    if lib.mb200_device_count() < 1:
+        raise RuntimeError("bench.py: no CUDA device visible; the device arm has no CPU fallback")
+    C.CDLL(os.path.join(LIB, "libmeep_b200_%s.so" % args.prec), mode=C.RTLD_GLOBAL)
+    drv = C.CDLL(os.path.join(LIB, "libmeep_b200_bench_%s.so" % args.prec), mode=C.RTLD_GLOBAL)
+    drv.mb200_bench_create.restype = C.c_void_p
+    drv.mb200_bench_create.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    for fn in ("mb200_bench_cells", "mb200_bench_probe", "mb200_bench_field_bytes",
+               "mb200_bench_algorithmic_bytes_per_step"):
+        getattr(drv, fn).restype = C.c_double
+        getattr(drv, fn).argtypes = [C.c_void_p]
+    drv.mb200_bench_step.argtypes = [C.c_void_p, C.c_int]
+    drv.mb200_bench_fields.restype = C.c_void_p
+    drv.mb200_bench_fields.argtypes = [C.c_void_p]
+    drv.mb200_bench_num_chunks.argtypes = [C.c_void_p]
+    drv.mb200_bench_destroy.argtypes = [C.c_void_p]
+    host = C.CDLL(os.path.join(LIB, "libmeep_b200_%s.so" % args.prec), mode=C.RTLD_GLOBAL)
+    host.meep_b200_ctx.restype = C.c_void_p
+    host.meep_b200_ctx.argtypes = [C.c_void_p]
+    host.meep_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    host.meep_b200_sync_host.argtypes = [C.c_void_p]
+
+    t0 = time.time()
+    h = drv.mb200_bench_create(b"c2", args.n, 0)
+    if not h:
+        raise RuntimeError("bench driver failed to build the workload")
+    t_setup = time.time() - t0
+    cells = drv.mb200_bench_cells(h)
+    fptr = drv.mb200_bench_fields(h)
+
+    def stats():
+        a = (C.c_double * 8)()
+        host.meep_b200_get_stats(fptr, a)
+        return list(a)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    # warm-up: first step uploads all arrays, allocates PML aux fields, builds connection
+    # tables (reference host code) and all launch plans
+    t0 = time.time()
+    if drv.mb200_bench_step(h, args.warmup):
+        raise RuntimeError("warm-up failed")
+    ctx = host.meep_b200_ctx(fptr)
+    lib.mb200_sync(ctx)
+    t_warm = time.time() - t0
+
+    # ---- timed region 1: device-resident throughput (CUDA events on the engine's stream) --------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    s0 = stats()
+    barrier()
+    lib.mb200_sync(ctx)
+    lib.mb200_timer_start(ctx)
+    if drv.mb200_bench_step(h, args.steps):
+        raise RuntimeError("timed steps failed")
+    ms = C.c_double()
+    lib.mb200_timer_stop(ctx, C.byref(ms))  # synchronises
+    barrier()
+    s1 = stats()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    dev_ms = max_over_ranks(ms.value)
+    launches = int(s1[3] - s0[3])
+
+    # ---- timed region 2: end to end through the public API, host-visible result every step -------
+    barrier()
+    lib.mb200_sync(ctx)
+    e0 = stats()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for _ in range(args.steps):
+        drv.mb200_bench_step(h, 1)
+        acc += drv.mb200_bench_probe(h)  # fields::get_field -> D2H of the probed values
+    lib.mb200_sync(ctx)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e1 = stats()
+    e2e_s = max_over_ranks(e2e_s)
+    if acc != acc:
+        raise RuntimeError("NaN in the probed field")
+
+    # ---- profiling pass (separate, not part of any reported throughput): per-kind CUDA events ---
+    lib.mb200_profile_reset(ctx)
+    lib.mb200_profile_enable(ctx, 1)
+    nprof = min(args.steps, 10)
+    drv.mb200_bench_step(h, nprof)
+    lib.mb200_profile_enable(ctx, 0)
+    prof = {}
+    kinds = ["curl", "edhb", "lorentz", "fmp", "source", "halo", "zero", "dft", "flux", "step3"]
+    for k, name in enumerate(kinds):
+        n_, ms_, by_ = C.c_int64(), C.c_double(), C.c_double()
+        lib.mb200_profile_get(ctx, k, C.byref(n_), C.byref(ms_), C.byref(by_))
+        if n_.value:
+            prof[name] = {"launches_per_step": n_.value / nprof, "ms_per_step": ms_.value / nprof,
+                          "alg_bytes_per_step": by_.value / nprof}
+
+    peaks, peak_src = measured_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_step = drv.mb200_bench_algorithmic_bytes_per_step(h)
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms_per_step"]) if prof else (None, None)
+    roofline = None
+    if dom[0]:
+        d = dom[1]
+        per_launch_bytes = d["alg_bytes_per_step"] / d["launches_per_step"]
+        per_launch_ms = d["ms_per_step"] / d["launches_per_step"]
+        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                    "share_of_step": d["ms_per_step"] / sum(v["ms_per_step"] for v in prof.values()),
+                    "whole_step": {"alg_bytes_per_step": alg_step,
+                                   "achieved": alg_step / (dev_ms / args.steps * 1e-3) / 1e9,
+                                   "frac": alg_step / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
+                                   "bytes_per_cell": alg_step / cells},
+                    "kernels": prof}
+
+    value = cells * args.steps * world / (dev_ms * 1e-3)
+    line = {"metric": "Yee cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.prec,
+            "data": "synthetic",
+            "config": {"workload": "c2: 3D dielectric box %d^3, PML(1.0) on all faces, non-dispersive, Gaussian "
+                                   "Ez dipole, res 10, Courant 0.5, real fields (BASELINE.json configs[1])" % args.n,
+                       "n": args.n, "num_chunks": drv.mb200_bench_num_chunks(h),
+                       "parallelism": "replicas only" if world > 1 else "single GPU",
+                       "l2_policy": "inputs larger than L2: %.1f GB of field arrays streamed per step vs 126 MB L2"
+                                    % (drv.mb200_bench_field_bytes(h) / 1e9),
+                       "setup_s": t_setup, "warmup_s": t_warm},
+            "e2e": {"value": cells * args.steps * world / e2e_s, "unit": "cell-updates/s",
+                    "h2d_bytes_per_step": (e1[1] - e0[1]) / args.steps,
+                    "d2h_bytes_per_step": (e1[2] - e0[2]) / args.steps,
+                    "what": "K x (fields::step() + fields::get_field probe) through the meep C++ API; field "
+                            "arrays stay resident in HBM between steps (state, like model weights)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        a2 = argparse.Namespace(**vars(args))
+        a2.steps, a2.warmup = args.cpu_steps, 3
+        try:
+            line["cpu_baseline"] = cpu_baseline_obj(run_reference(a2))
+        except Exception as e:  # the baseline is reported, never required for the device number
+            line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": os.cpu_count(),
+                                    "kind": "reference", "sample": "failed: %s" % e}
+    drv.mb200_bench_destroy(h)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

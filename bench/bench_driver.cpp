@@ -1,0 +1,209 @@
+// bench_driver.cpp — builds BASELINE.json's benchmark workloads with the reference's public C++
+// API (meep::structure / meep::fields, exactly as a user program would) and times
+// fields::step().  The same source is built three ways (meep_b200/build.py):
+//
+//   meep_b200/lib/libmeep_b200_bench_<p>.so  linked with libmeep_b200 in FRONT of the reference
+//                                            libmeep: fields::step() runs on the B200.  Loaded
+//                                            in-process by bench.py / __graft_entry__.py (ctypes).
+//   meep_b200/lib/bench_ref_<p>              executable linked against the unmodified reference
+//                                            ONLY: the CPU baseline / `--impl reference` arm.
+//
+// Workloads (SURVEY §8d "synthetic inputs"; resolution 10, Courant 0.5, real fields):
+//   c2 : n^3 cells, eps = 12 cube of half the cell size, pml(1.0) on all faces, Gaussian Ez
+//        point dipole (BASELINE config 2 at n = 512; config 5 at n = 1024)
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <complex>
+#include <string>
+
+#include "meep.hpp"
+using namespace meep;
+
+namespace {
+
+double g_L = 1;
+
+// thread-safe (so set_chi1inv runs under OpenMP: anisotropic_averaging.cpp:252) eps = 12 cube
+class cube_material : public material_function {
+public:
+  virtual double chi1p1(field_type ft, const vec &r) {
+    if (ft != E_stuff) return 1.0;
+    double m = 0;
+    LOOP_OVER_DIRECTIONS(r.dim, d) {
+      double x = fabs(r.in_direction(d) - 0.5 * g_L);
+      if (x > m) m = x;
+    }
+    return m < 0.25 * g_L ? 12.0 : 1.0;
+  }
+  virtual double eps(const vec &r) { return chi1p1(E_stuff, r); }
+  virtual bool is_thread_safe() const { return true; }
+};
+
+struct Bench {
+  structure *s = nullptr;
+  fields *f = nullptr;
+  grid_volume gv;
+  double cells = 0;
+  vec probe_pt;
+};
+
+} // namespace
+
+extern "C" {
+
+// returns NULL on failure (message on stderr)
+void *mb200_bench_create(const char *workload, int n, int num_chunks) {
+  static initialize *mpi = nullptr;
+  if (!mpi) {
+    static int argc = 1;
+    static char arg0[] = "bench";
+    static char *argvv[] = {arg0, nullptr};
+    static char **argv = argvv;
+    mpi = new initialize(argc, argv);
+  }
+  verbosity = 0;
+  try {
+    Bench *b = new Bench();
+    const double a = 10.0;
+    if (std::string(workload) == "c2") {
+      g_L = n / a;
+      b->gv = vol3d(g_L, g_L, g_L, a);
+      cube_material mat;
+      b->s = new structure(b->gv, mat, pml(1.0), identity(), num_chunks, 0.5, false);
+      b->f = new fields(b->s);
+      b->f->use_real_fields();
+      gaussian_src_time src(0.15, 0.1);
+      src.is_integrated = false; // a current source, the Python front end's default
+      b->f->add_point_source(Ez, src, b->gv.center() + vec(0.05, 0.05, 0.05));
+      b->probe_pt = b->gv.center() + vec(0.35, 0.25, 0.15);
+      b->cells = (double)n * n * n;
+    }
+    else {
+      fprintf(stderr, "mb200_bench_create: unknown workload %s\n", workload);
+      delete b;
+      return nullptr;
+    }
+    return b;
+  } catch (std::exception &e) {
+    fprintf(stderr, "mb200_bench_create: %s\n", e.what());
+    return nullptr;
+  }
+}
+
+int mb200_bench_step(void *h, int nsteps) {
+  Bench *b = (Bench *)h;
+  try {
+    for (int i = 0; i < nsteps; ++i)
+      b->f->step();
+    return 0;
+  } catch (std::exception &e) {
+    fprintf(stderr, "mb200_bench_step: %s\n", e.what());
+    return 1;
+  }
+}
+
+// what a user's monitoring loop does after each step: read one field value on the host
+double mb200_bench_probe(void *h) {
+  Bench *b = (Bench *)h;
+  return real(b->f->get_field(Ez, b->probe_pt));
+}
+
+double mb200_bench_cells(void *h) { return ((Bench *)h)->cells; }
+int mb200_bench_num_chunks(void *h) { return ((Bench *)h)->f->num_chunks; }
+int mb200_bench_time_step(void *h) { return ((Bench *)h)->f->t; }
+void *mb200_bench_fields(void *h) { return ((Bench *)h)->f; }
+
+// total bytes of field-like host arrays (what a cold start uploads / a final sync downloads)
+double mb200_bench_field_bytes(void *h) {
+  Bench *b = (Bench *)h;
+  double bytes = 0;
+  for (int i = 0; i < b->f->num_chunks; ++i) {
+    fields_chunk *fc = b->f->chunks[i];
+    FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
+      if (fc->f[c][cmp] && !(is_magnetic(c) &&
+                             fc->f[c][cmp] == fc->f[direction_component(Bx, component_direction(c))][cmp]))
+        bytes += fc->gv.ntot() * sizeof(realnum);
+      if (fc->f_u[c][cmp]) bytes += fc->gv.ntot() * sizeof(realnum);
+      if (fc->f_w[c][cmp]) bytes += fc->gv.ntot() * sizeof(realnum);
+      if (fc->f_cond[c][cmp]) bytes += fc->gv.ntot() * sizeof(realnum);
+    }
+  }
+  return bytes;
+}
+
+// algorithmic HBM bytes per time step (SURVEY §8d accounting, evaluated on the actual chunk
+// layout): every array element that a half-step must read is counted once, every element it
+// must write once; neighbour re-reads are free (on chip); D->E fused.
+double mb200_bench_algorithmic_bytes_per_step(void *h) {
+  Bench *b = (Bench *)h;
+  const double R = sizeof(realnum);
+  double bytes = 0;
+  for (int i = 0; i < b->f->num_chunks; ++i) {
+    fields_chunk *fc = b->f->chunks[i];
+    const double owned = (double)fc->gv.nx() * fc->gv.ny() * fc->gv.nz();
+    int arrays = 0;
+    FOR_COMPONENTS(c) {
+      if (!fc->f[c][0]) continue;
+      const component bc = direction_component(Bx, component_direction(c));
+      if (is_B(c)) arrays += 2;                                   // B r/w
+      if (is_D(c)) arrays += 2;                                   // D r/w
+      if (is_electric(c)) arrays += 1 /* read by the B curl */ + 1 /* written by update_eh */;
+      if (is_magnetic(c)) {
+        arrays += 1;                                              // read by the D curl
+        if (fc->f[c][0] != fc->f[bc][0]) arrays += 1;             // separate H: written
+      }
+      if (fc->f_u[c][0]) arrays += 2;
+      if (fc->f_cond[c][0]) arrays += 2;
+      if (fc->f_w[c][0]) arrays += 2 + 1;                         // fw r/w + E/H read (+=)
+      if (is_electric(c) || is_magnetic(c)) {
+        const direction d = component_direction(c);
+        if (fc->s->chi1inv[c][d]) arrays += 1;
+      }
+    }
+    bytes += R * arrays * owned;
+  }
+  return bytes;
+}
+
+void mb200_bench_destroy(void *h) {
+  Bench *b = (Bench *)h;
+  if (!b) return;
+  delete b->f;
+  delete b->s;
+  delete b;
+}
+
+} // extern "C"
+
+#ifdef MB200_BENCH_MAIN
+// CPU arm: time fields::step() of the unmodified reference on the host cores.
+// usage: bench_ref_<p> <workload> <n> <warmup> <steps> [num_chunks]
+int main(int argc, char **argv) {
+  if (argc < 5) {
+    fprintf(stderr, "usage: %s <workload> <n> <warmup> <steps> [num_chunks]\n", argv[0]);
+    return 2;
+  }
+  const int n = atoi(argv[2]), warm = atoi(argv[3]), steps = atoi(argv[4]);
+  const int nchunks = argc > 5 ? atoi(argv[5]) : 0;
+  double t0 = wall_time();
+  void *h = mb200_bench_create(argv[1], n, nchunks);
+  if (!h) return 1;
+  double t_setup = wall_time() - t0;
+  t0 = wall_time();
+  if (mb200_bench_step(h, warm)) return 1; // includes the one-time connect_the_chunks
+  double t_warm = wall_time() - t0;
+  t0 = wall_time();
+  if (mb200_bench_step(h, steps)) return 1;
+  double t = wall_time() - t0;
+  printf("{\"workload\": \"%s\", \"n\": %d, \"cells\": %.0f, \"steps\": %d, \"warmup\": %d, "
+         "\"seconds\": %.6f, \"cells_per_s\": %.6e, \"setup_s\": %.3f, \"warmup_s\": %.3f, "
+         "\"probe\": %.17g, \"num_chunks\": %d, \"realnum_bytes\": %d}\n",
+         argv[1], n, mb200_bench_cells(h), steps, warm, t, mb200_bench_cells(h) * steps / t, t_setup,
+         t_warm, mb200_bench_probe(h), mb200_bench_num_chunks(h), (int)sizeof(realnum));
+  mb200_bench_destroy(h);
+  return 0;
+}
+#endif

@@ -210,6 +210,27 @@ def build_reference_tests(prec, arms=("ref", "b200", "emu"), names=None):
     return outs
 
 
+def build_bench(prec):
+    """bench/bench_driver.cpp -> in-process GPU arm (.so) and the CPU reference arm (executable)."""
+    src = os.path.join(ROOT, "bench", "bench_driver.cpp")
+    so = os.path.join(LIB, "libmeep_b200_bench_%s.so" % prec)
+    exe = os.path.join(LIB, "bench_ref_%s" % prec)
+    if not have_reference():
+        for o in (so, exe):
+            if not os.path.exists(o):
+                raise RuntimeError("%s missing and the reference headers are not available" % o)
+        return so, exe
+    common = [GXX, "-std=c++14", "-O2", "-w", "-fopenmp"] + _ref_includes(prec)
+    if _stale(so, [src, os.path.join(LIB, "libmeep_b200_%s.so" % prec)]):
+        _run(common + ["-fPIC", "-shared", src, "-o", so, "-Wl,--no-as-needed", "-L" + LIB,
+                       "-lmeep_b200_" + prec, "-lmeepb200", "-L" + OREF, "-lmeep_ref_" + prec,
+                       "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-ldl"])
+    if _stale(exe, [src, os.path.join(OREF, "libmeep_ref_%s.so" % prec)]):
+        _run(common + ["-DMB200_BENCH_MAIN", src, "-o", exe, "-L" + OREF, "-lmeep_ref_" + prec,
+                       "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-ldl"])
+    return so, exe
+
+
 def build_all(precs=PRECS, verbose=False):
     build_cuda()
     build_reference(precs)
@@ -220,6 +241,7 @@ def build_all(precs=PRECS, verbose=False):
         build_host(p, "emu")
         build_drivers(p)
         build_reference_tests(p)
+        build_bench(p)
 
 
 if __name__ == "__main__":

@@ -60,7 +60,9 @@ class DevMem:
 
     def __init__(self, prec):
         self.prec = prec
-        self.ctx = capi.Context(0)
+        # MEEP_B200_TEST_CAPI lets the test CODE be dry-run against the emulator on a GPU-less box
+        alt = os.environ.get("MEEP_B200_TEST_CAPI")
+        self.ctx = capi.Context(0, lib=capi.load(alt) if alt else None)
 
     def put(self, a):
         if a is None:

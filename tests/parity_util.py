@@ -37,6 +37,8 @@ def driver(name, arm, prec):
 
 
 def run_case(arm, prec, case, nsteps, num_chunks=0, env=None, name="sim_driver", timeout=900):
+    if arm == "b200":  # dry-run of the GPU test code against the emulator on a GPU-less box
+        arm = os.environ.get("MEEP_B200_TEST_ARM", arm)
     exe = driver(name, arm, prec)
     if not os.path.exists(exe):
         raise FileNotFoundError(exe)
