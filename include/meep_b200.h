@@ -183,7 +183,10 @@ typedef struct {
  *      step_curl / step_update_EDHB argument meaning; lo/hi are the inclusive array-index
  *      ranges of little_owned_corner0(c)..big_corner (src/meep/vec.hpp:1102-1104) and the pml
  *      lookups are re-based to array index (0,0,0): k = k0 + ks[0]*ix + ks[1]*iy + ks[2]*iz.
- *      A component with f == NULL is skipped; e == NULL means "no fused E/H update". */
+ *      A component with f == NULL is skipped; e == NULL means "no fused E/H update".
+ *      Only array indices ix_lo <= ix <= ix_hi along direction 0 are processed, so that a chunk
+ *      can be cut into slabs (e.g. the planes that hold source points, where step_source must
+ *      run between the D update and the E update, are launched without the fused E update). */
 typedef struct {
   int32_t lo[3], hi[3];
   void *f;
@@ -198,6 +201,10 @@ typedef struct {
   const void *u;
   void *fw;
   mb200_pml_t pmlw;
+  /* planes (array index along each direction, -1 = none) on which fields_chunk::zero_metal
+   * (src/boundaries.cpp:310-313) zeroes f right after this update: the fused E/H update uses
+   * f = 0 there, exactly what update_eh sees in the reference's order of operations */
+  int32_t metal_lo[3], metal_hi[3];
 } mb200_step3_comp_t;
 
 typedef struct {
@@ -205,6 +212,7 @@ typedef struct {
   int32_t reserved;
   int64_t stride[3];
   double dt;
+  int32_t ix_lo, ix_hi;
   mb200_step3_comp_t c[3];
 } mb200_step3_job_t;
 

@@ -87,12 +87,13 @@ class Step3Comp(C.Structure):
                 ("g1", C.c_void_p), ("g2", C.c_void_p), ("s1", C.c_int64), ("s2", C.c_int64),
                 ("dtdx", C.c_double), ("pml", Pml), ("pmlu", Pml), ("fu", C.c_void_p),
                 ("cnd", C.c_void_p), ("cndinv", C.c_void_p), ("fcnd", C.c_void_p),
-                ("e", C.c_void_p), ("u", C.c_void_p), ("fw", C.c_void_p), ("pmlw", Pml)]
+                ("e", C.c_void_p), ("u", C.c_void_p), ("fw", C.c_void_p), ("pmlw", Pml),
+                ("metal_lo", C.c_int32 * 3), ("metal_hi", C.c_int32 * 3)]
 
 
 class Step3Job(C.Structure):
     _fields_ = [("n", C.c_int32 * 3), ("reserved", C.c_int32), ("stride", C.c_int64 * 3),
-                ("dt", C.c_double), ("c", Step3Comp * 3)]
+                ("dt", C.c_double), ("ix_lo", C.c_int32), ("ix_hi", C.c_int32), ("c", Step3Comp * 3)]
 
 
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,

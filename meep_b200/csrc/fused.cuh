@@ -19,24 +19,36 @@ namespace mb200 {
 
 MB200_HD mb200_box_t step3_box(const mb200_step3_job_t &J) {
   mb200_box_t b;
-  b.idx0 = 0;
   for (int d = 0; d < 3; ++d) {
     b.s[d] = J.stride[d];
     b.n[d] = J.n[d] + 1;
   }
-  b.reserved = 0;
+  // restrict to the slab ix_lo..ix_hi along direction 0
+  const int lo = J.ix_lo > 0 ? J.ix_lo : 0;
+  const int hi = J.ix_hi < J.n[0] ? J.ix_hi : J.n[0];
+  b.idx0 = (int64_t)lo * J.stride[0];
+  b.n[0] = hi - lo + 1;
+  b.reserved = lo; // first ix of the box
   return b;
 }
 MB200_HD int64_t step3_tiles(const mb200_step3_job_t &J) { return box_tiles(step3_box(J)); }
+// owned points of component C inside the job's slab
+inline double step3_comp_points(const mb200_step3_job_t &J, const mb200_step3_comp_t &C) {
+  double q = 1;
+  for (int d = 0; d < 3; ++d) {
+    int lo = C.lo[d], hi = C.hi[d];
+    if (d == 0) {
+      if (J.ix_lo > lo) lo = J.ix_lo;
+      if (J.ix_hi < hi) hi = J.ix_hi;
+    }
+    q *= hi >= lo ? (double)(hi - lo + 1) : 0.0;
+  }
+  return q;
+}
 inline double step3_points(const mb200_step3_job_t &J) {
   double p = 0;
   for (int c = 0; c < 3; ++c)
-    if (J.c[c].f) {
-      double q = 1;
-      for (int d = 0; d < 3; ++d)
-        q *= (double)(J.c[c].hi[d] - J.c[c].lo[d] + 1);
-      p += q;
-    }
+    if (J.c[c].f) p += step3_comp_points(J, J.c[c]);
   return p / 3.0; // cells (each cell has three components)
 }
 inline double step3_bytes(const mb200_step3_job_t &J, double R) {
@@ -47,9 +59,7 @@ inline double step3_bytes(const mb200_step3_job_t &J, double R) {
   for (int c = 0; c < 3; ++c) {
     const mb200_step3_comp_t &C = J.c[c];
     if (!C.f) continue;
-    double q = 1;
-    for (int d = 0; d < 3; ++d)
-      q *= (double)(C.hi[d] - C.lo[d] + 1);
+    const double q = step3_comp_points(J, C);
     int arrays = 2 + (C.pmlu.sig ? 2 : 0) + (C.cnd ? 2 + (C.pml.sig ? 2 : 0) : 0);
     if (C.e) arrays += 1 + (C.u ? 1 : 0) + (C.pmlw.sig ? 3 : 0);
     const void *gs[2] = {C.g1, C.g2};
@@ -76,7 +86,11 @@ MB200_HD void step3_comp_point(const mb200_step3_comp_t &C, int variant, int64_t
     return;
   const int k = pml_k(C.pml, ix, iy, iz), ku = pml_k(C.pmlu, ix, iy, iz);
   const T d = curl_point_any<T>(C, variant, i, k, ku, (T)C.dtdx, dt2);
-  if (C.e) edhb_diag<T>(C, i, pml_k(C.pmlw, ix, iy, iz), d);
+  if (C.e) {
+    const bool metal = ix == C.metal_lo[0] || ix == C.metal_hi[0] || iy == C.metal_lo[1] ||
+                       iy == C.metal_hi[1] || iz == C.metal_lo[2] || iz == C.metal_hi[2];
+    edhb_diag<T>(C, i, pml_k(C.pmlw, ix, iy, iz), metal ? T(0) : d);
+  }
 }
 
 template <typename T>
@@ -90,6 +104,8 @@ MB200_HD void step3_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
   const int v2 = J.c[2].f ? curl_variant(J.c[2]) : -1;
   int64_t i = box_index(box, ix0, iy, iz);
   const int64_t sx = box.s[0];
+  ix0 += box.reserved; // loop index -> array index along direction 0
+  ix_end += box.reserved;
   for (int ix = ix0; ix < ix_end; ++ix, i += sx) {
     if (v0 >= 0) step3_comp_point<T>(J.c[0], v0, i, ix, iy, iz, dt2);
     if (v1 >= 0) step3_comp_point<T>(J.c[1], v1, i, ix, iy, iz, dt2);

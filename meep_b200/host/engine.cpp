@@ -83,6 +83,7 @@ Engine::Engine(fields *) {
   check(mb200_init(device, &ctx), "mb200_init");
   fuse = env_int("MEEP_B200_FUSE", 1) != 0;
   eager = env_int("MEEP_B200_EAGER", 0) != 0;
+  verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;
 }
@@ -171,6 +172,7 @@ void Engine::free_phase(Phase &ph) {
     mb200_free(ctx, p);
   ph.aux.clear();
   ph.valid = false;
+  ph.one_shot = false;
 }
 
 void Engine::invalidate_plans() {
@@ -181,6 +183,8 @@ void Engine::invalidate_plans() {
   for (int id = 0; id < PH_COUNT; ++id)
     for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
       free_phase(phases_[id][ft]);
+  for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
+    fused_eh[ft].clear();
   if (probe_ptrs_) {
     mb200_free(ctx, probe_ptrs_);
     probe_ptrs_ = nullptr;
@@ -450,10 +454,12 @@ static void push(Phase &ph, int kind, mb200_plan *p) {
   ph.launches.push_back(l);
 }
 
-// try to turn the three step_curl jobs of one chunk/cmp into one fused job
-static bool fuse_group(const Recorder &R, const Recorder::Group &g, mb200_step3_job_t &out) {
+// try to turn the three step_curl jobs of one chunk/cmp into fused jobs (one per x-slab)
+static bool fuse_group(const Recorder &R, const Recorder::Group &g,
+                       std::vector<mb200_step3_job_t> &out_jobs) {
   const fields_chunk *fc = g.fc;
   if (fc->gv.dim != D3 || g.count != 3) return false;
+  mb200_step3_job_t out;
   memset(&out, 0, sizeof(out));
   const direction dirs[3] = {X, Y, Z};
   for (int d = 0; d < 3; ++d) {
@@ -461,6 +467,8 @@ static bool fuse_group(const Recorder &R, const Recorder::Group &g, mb200_step3_
     out.stride[d] = fc->gv.stride(dirs[d]);
   }
   out.dt = R.curl[g.first].dt;
+  out.ix_lo = 0;
+  out.ix_hi = out.n[0];
   for (int c = 0; c < 3; ++c) {
     const mb200_curl_job_t &J = R.curl[g.first + c];
     if (!J.g1 || !J.g2) return false;
@@ -491,6 +499,43 @@ static bool fuse_group(const Recorder &R, const Recorder::Group &g, mb200_step3_
     C.cndinv = J.cndinv;
     C.fcnd = J.fcnd;
     C.e = nullptr;
+    for (int d = 0; d < 3; ++d)
+      C.metal_lo[d] = C.metal_hi[d] = -1;
+  }
+  if (!g.fuse_eh) {
+    out_jobs.push_back(out);
+    return true;
+  }
+  mb200_step3_job_t fused = out;
+  for (int c = 0; c < 3; ++c) {
+    fused.c[c].e = g.epi[c].e;
+    fused.c[c].u = g.epi[c].u;
+    fused.c[c].fw = g.epi[c].fw;
+    fused.c[c].pmlw = g.epi[c].pmlw;
+    for (int d = 0; d < 3; ++d) {
+      fused.c[c].metal_lo[d] = g.epi[c].metal_lo[d];
+      fused.c[c].metal_hi[d] = g.epi[c].metal_hi[d];
+    }
+  }
+  if (g.slab_lo > g.slab_hi) { // no source planes: the whole chunk is fused
+    out_jobs.push_back(fused);
+    return true;
+  }
+  if (g.slab_lo > 0) {
+    mb200_step3_job_t j = fused;
+    j.ix_hi = g.slab_lo - 1;
+    out_jobs.push_back(j);
+  }
+  {
+    mb200_step3_job_t j = out; // source planes: D only; E follows in update_eh after step_source
+    j.ix_lo = g.slab_lo;
+    j.ix_hi = g.slab_hi;
+    out_jobs.push_back(j);
+  }
+  if (g.slab_hi < out.n[0]) {
+    mb200_step3_job_t j = fused;
+    j.ix_lo = g.slab_hi + 1;
+    out_jobs.push_back(j);
   }
   return true;
 }
@@ -506,12 +551,13 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
       std::vector<char> used(R.curl.size(), 0);
       if (fuse)
         for (const Recorder::Group &g : R.curl_groups) {
-          mb200_step3_job_t j;
-          if (fuse_group(R, g, j)) {
-            s3.push_back(j);
+          if (fuse_group(R, g, s3)) {
             for (int k = 0; k < g.count; ++k)
               used[g.first + k] = 1;
           }
+          else if (g.fuse_eh)
+            meep::abort("meep_b200: internal error: E/H fusion promised for a chunk that cannot "
+                        "use the fused kernel");
         }
       for (size_t k = 0; k < R.curl.size(); ++k)
         if (!used[k]) rest.push_back(R.curl[k]);
@@ -567,13 +613,23 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
       break;
     default: break;
   }
+  if (verbose) {
+    static const char *names[] = {"step_db", "step_source", "step_boundaries", "update_eh",
+                                  "update_pols", "update_dfts"};
+    fprintf(stderr, "meep_b200: recorded %s:", names[id]);
+    for (const Launch &l : ph.launches)
+      fprintf(stderr, " [kind %d: %.0f points, %.3f MB]", l.kind, mb200_plan_points(l.plan),
+              mb200_plan_bytes(l.plan) / 1e6);
+    fprintf(stderr, "\n");
+  }
   ph.aux.swap(rec_aux_);
   rec_aux_.clear();
   ph.valid = true;
   rec_ = Recorder();
   recording_ = false;
-  if (pending_invalidate_) { // arrays appeared while recording: every OTHER phase is stale
-    pending_invalidate_ = false;
+  if (pending_invalidate_) { // arrays appeared while recording: every OTHER phase is stale,
+    pending_invalidate_ = false; // and this one must be re-recorded after it has run once
+    ph.one_shot = true;
     for (int i = 0; i < PH_COUNT; ++i)
       for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
         if (&phases_[i][ft] != &ph) free_phase(phases_[i][ft]);

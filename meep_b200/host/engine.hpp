@@ -52,6 +52,7 @@ struct Launch {
 
 struct Phase {
   bool valid = false;
+  bool one_shot = false; // recorded while the array set was changing: run once, then re-record
   std::vector<Launch> launches;
   std::vector<void *> aux; // device side tables (index lists, ...) owned by this phase
 };
@@ -71,10 +72,20 @@ struct Recorder {
   std::map<int, std::vector<mb200_dft_job_t> > dft; // by decimation factor
   std::map<int, std::vector<meep::dft_chunk *> > dft_chunks;
   // grouping info for the fused kernel: curl jobs [first, first+count) belong to one chunk/cmp
+  struct Epilogue { // fused update_eh of one component (valid when e != NULL)
+    void *e = nullptr;
+    const void *u = nullptr;
+    void *fw = nullptr;
+    mb200_pml_t pmlw; // re-based to array indices
+    int metal_lo[3] = {-1, -1, -1}, metal_hi[3] = {-1, -1, -1};
+  };
   struct Group {
     int first, count;
     const meep::fields_chunk *fc;
     int cmp;
+    bool fuse_eh = false;       // the E/H update of this chunk is folded into the D/B pass
+    int slab_lo = 1, slab_hi = 0; // planes (array index along direction 0) that hold source points
+    Epilogue epi[3];
   };
   std::vector<Group> curl_groups;
 };
@@ -105,6 +116,7 @@ public:
   State state = HOST_NEWER;
   int depth = 0; // nesting of our own entry points (0 => called from reference/user code)
   bool in_step = false; // the outermost entry point is fields::step()
+  bool connections_valid = false; // fields::chunk_connections_valid at the last step_db
 
   // Brackets every interposed entry point.  On the outermost entry it validates the mirror
   // (array set, materials) and uploads field arrays if the host copy is (or may be) newer.
@@ -152,11 +164,17 @@ public:
   int dtype = sizeof(realnum) == 8 ? MB200_F64 : MB200_F32;
   Stats stats;
   bool fuse = true;        // MEEP_B200_FUSE=0 disables the fused step3 path
+  bool verbose = false;    // MEEP_B200_VERBOSE=1: print the recorded plans
   bool eager = false;      // MEEP_B200_EAGER=1: download after every step (debug/safety)
   int nan_check_every = 16;
   // finiteness probe
   void setup_probe(meep::fields *f);
   void check_probe(meep::fields *f, bool force);
+
+  // chunks whose update_eh(ft) was folded into step_db of the matching D/B type in the current
+  // plan generation: value = [slab_lo, slab_hi] planes that were NOT fused (source planes;
+  // lo > hi: the whole chunk is fused).  Written by step_db, read by update_eh, in-step only.
+  std::map<const meep::fields_chunk *, std::pair<int, int> > fused_eh[meep::NUM_FIELD_TYPES];
 
   uint64_t fingerprint(meep::fields *f) const;
   uint64_t last_fingerprint = 0;
@@ -202,6 +220,7 @@ inline void run_phase(Engine &E, meep::fields *f, PhaseId id, int ft, bool cache
       E.end_record(ph, id, f);
     }
     E.run(ph, f);
+    if (ph.one_shot) E.free_phase(ph);
   }
   else { // one-off (solve_cw variants etc.): record, run, discard
     Phase tmp;

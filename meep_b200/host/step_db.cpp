@@ -10,6 +10,8 @@
 #include "engine.hpp"
 #include "loop_desc.hpp"
 #include "meep_internals.hpp"
+#include <stdio.h>
+#include <vector>
 
 using namespace std;
 using namespace meep_b200;
@@ -20,7 +22,18 @@ void fields::step_db(field_type ft) {
   if (ft != B_stuff && ft != D_stuff) meep::abort("step_db only works with B/D");
   Engine &E = Engine::get(this);
   Scope scope(E, this);
-  run_phase(E, this, PH_DB, ft, true, [&]() {
+  // (called by reference/user code outside fields::step(): never cached, never fused with E/H)
+  E.connections_valid = chunk_connections_valid;
+  run_phase(E, this, PH_DB, ft, E.in_step, [&]() {
+    // the E/H fusion decisions are remade with this recording: the matching update_eh phase
+    // must be re-recorded against them
+    // (only for the cached in-step plans; a stand-alone call from reference code is recorded
+    // unfused, run once and discarded, and must leave the in-step plans alone)
+    if (E.in_step) {
+      const field_type fte = ft == D_stuff ? E_stuff : H_stuff;
+      E.fused_eh[fte].clear();
+      E.free_phase(E.phase(PH_EH, fte));
+    }
     for (int i = 0; i < num_chunks; i++)
       if (chunks[i]->is_mine())
         if (chunks[i]->step_db(ft)) {
@@ -28,6 +41,138 @@ void fields::step_db(field_type ft) {
           assert(changed_materials);
         }
   });
+}
+
+// Decide whether fields_chunk::update_eh(E or H) of this chunk may be folded into the D (or B)
+// pass, i.e. whether E = chi1inv * D is a purely local, linear, diagonal operation here
+// (reference src/update_eh.cpp:66-195: no f_minus_p, no off-diagonal chi1inv, no chi2/chi3,
+// every array it needs already allocated), and describe the fused update per component.
+static void plan_eh_fusion_impl(fields_chunk *fc, field_type ft, int cmp, Recorder::Group &grp,
+                                Engine *E, bool doing_solve_cw) {
+  const field_type fte = ft == D_stuff ? E_stuff : H_stuff;
+  structure_chunk *s = fc->s;
+  const grid_volume &gv = fc->gv;
+#define WHY(msg) do { if (E->verbose) fprintf(stderr, "meep_b200: chunk %d ft %d: no E/H fusion: %s\n", fc->chunk_idx, (int)ft, msg); return; } while (0)
+  if (doing_solve_cw) return;
+  if (!E->connections_valid) WHY("chunk connections (and metal lists) not rebuilt yet");
+  if (cmp > 0 && !E->fused_eh[fte].count(fc)) return; // follow the decision made for cmp 0
+  if (fc->gvs_eh[fte].size() > 1) return; // tiled update_eh keeps its own loop order
+  for (const src_vol &sv : fc->get_sources(ft))
+    if (sv.t()->is_integrated) WHY("integrated source"); // needs f_minus_p
+  bool any = false;
+  Recorder::Epilogue epi[3];
+  int k = 0;
+  FOR_FT_COMPONENTS(ft, dc) {
+    if (!fc->f[dc][cmp]) continue; // (not a component of this grid, e.g. Dr/Dp in 3-D)
+    if (k >= 3) WHY("more than three components");
+    const component ec = field_type_component(fte, dc);
+    const direction d_ec = component_direction(ec);
+    const direction d_1 = cycle_direction(gv.dim, d_ec, 1), d_2 = cycle_direction(gv.dim, d_ec, 2);
+    if (!fc->f[ec][cmp]) WHY("missing E/H component");
+    for (polarization_state *p = fc->pol[fte]; p; p = p->next)
+      if (p->s->needs_P(ec, cmp, fc->f)) WHY("polarisation");
+    if (fc->f_minus_p[dc][cmp]) WHY("f_minus_p");
+    if (s->chi1inv[ec][d_1] || s->chi1inv[ec][d_2] || s->chi2[ec] || s->chi3[ec]) WHY("offdiag/chi3");
+    const direction dsigw = s->sigsize[d_ec] > 1 ? d_ec : NO_DIRECTION;
+    if (fc->f[ec][cmp] == fc->f[dc][cmp]) {
+      // H aliases B: update_eh is a no-op here, unless it is about to split them (first step)
+      if (s->chi1inv[ec][d_ec] || dsigw != NO_DIRECTION) WHY("H about to split from B");
+      ++k;
+      continue;
+    }
+    if (dsigw != NO_DIRECTION && !fc->f_w[ec][cmp]) WHY("f_w not allocated yet"); // lazily allocated by update_eh
+    Recorder::Epilogue &P = epi[k];
+    P.e = E->dev(fc->f[ec][cmp]);
+    P.u = E->dev(s->chi1inv[ec][d_ec]);
+    P.fw = E->dev(fc->f_w[ec][cmp]);
+    memset(&P.pmlw, 0, sizeof(P.pmlw));
+    if (dsigw != NO_DIRECTION) {
+      // array-index based lookup: k = 2*i_d + (yee offset of ec along d): evaluate at index 0
+      const ivec is0 = gv.little_corner() + gv.iyee_shift(ec);
+      P.pmlw = make_pml(gv, is0, dsigw, E->dev(s->sig[dsigw]), E->dev(s->kap[dsigw]), NULL);
+    }
+    // Points that zero_metal(ft) clears right after this update (src/step.cpp:243-245): they
+    // must form whole boundary planes of the owned box, which the kernel can mask.
+    {
+      const realnum *base = fc->f[dc][cmp];
+      const ivec is = gv.little_owned_corner0(dc), ie = gv.big_corner();
+      const mb200_box_t ob = make_box(gv, is, ie);
+      int lo[3], hi[3];
+      int64_t rem = ob.idx0;
+      const int64_t st[3] = {(int64_t)gv.stride(X), (int64_t)gv.stride(Y), (int64_t)gv.stride(Z)};
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = (int)(rem / st[d]);
+        rem -= (int64_t)lo[d] * st[d];
+        hi[d] = lo[d] + ob.n[d] - 1;
+      }
+      int64_t cnt_lo[3] = {0, 0, 0}, cnt_hi[3] = {0, 0, 0}, total = 0;
+      std::vector<int64_t> zidx;
+      for (size_t z = 0; z < fc->num_zeroes[ft]; ++z) {
+        const realnum *p = fc->zeroes[ft][z];
+        if (p < base || p >= base + gv.ntot()) continue;
+        zidx.push_back((int64_t)(p - base));
+      }
+      for (int64_t idx : zidx) {
+        int64_t r = idx;
+        int c3[3];
+        for (int d = 0; d < 3; ++d) {
+          c3[d] = (int)(r / st[d]);
+          r -= (int64_t)c3[d] * st[d];
+        }
+        ++total;
+        for (int d = 0; d < 3; ++d) {
+          if (c3[d] == lo[d]) ++cnt_lo[d];
+          if (c3[d] == hi[d]) ++cnt_hi[d];
+        }
+      }
+      if (total) {
+        int64_t plane[3];
+        for (int d = 0; d < 3; ++d)
+          plane[d] = (int64_t)ob.n[(d + 1) % 3] * ob.n[(d + 2) % 3];
+        for (int d = 0; d < 3; ++d) {
+          if (cnt_lo[d] == plane[d]) P.metal_lo[d] = lo[d];
+          if (cnt_hi[d] == plane[d] && hi[d] != lo[d]) P.metal_hi[d] = hi[d];
+        }
+        // every zeroed point must lie on one of the flagged planes
+        int64_t covered = 0;
+        for (int64_t idx : zidx) {
+          int64_t r = idx;
+          bool on = false;
+          for (int d = 0; d < 3; ++d) {
+            const int c = (int)(r / st[d]);
+            r -= (int64_t)c * st[d];
+            if (c == P.metal_lo[d] || c == P.metal_hi[d]) on = true;
+          }
+          if (on) ++covered;
+        }
+        if (covered != total) WHY("metal points do not form whole boundary planes");
+      }
+    }
+    any = true;
+    ++k;
+  }
+  if (k != 3) WHY("fewer than three components");
+  if (!any) WHY("nothing to fold"); // all aliased: plain fused curl
+  // planes that hold source points: step_source must run between the D and the E update there
+  int lo = 1, hi = 0;
+  const ptrdiff_t sx = gv.stride(X);
+  for (const src_vol &sv : fc->get_sources(ft))
+    for (size_t j = 0; j < sv.num_points(); ++j) {
+      const int ix = (int)(sv.index_at(j) / sx);
+      if (lo > hi) lo = hi = ix;
+      if (ix < lo) lo = ix;
+      if (ix > hi) hi = ix;
+    }
+  if (lo <= hi && (hi - lo + 1) * 2 > gv.nx() + 1) WHY("sources everywhere"); // not worth it
+  grp.fuse_eh = true;
+  grp.slab_lo = lo;
+  grp.slab_hi = hi;
+  for (int c = 0; c < 3; ++c)
+    grp.epi[c] = epi[c];
+  if (cmp == 0)
+    E->fused_eh[fte][fc] = std::make_pair(lo, hi);
+  else if (!E->fused_eh[fte].count(fc))
+    meep::abort("meep_b200: internal error: real and imaginary parts disagree on E/H fusion");
 }
 
 bool fields_chunk::step_db(field_type ft) {
@@ -119,7 +264,11 @@ bool fields_chunk::step_db(field_type ft) {
         }
       }
       grp.count = (int)R.curl.size() - grp.first;
-      if (gvs_tiled.size() == 1 && grp.count > 0) R.curl_groups.push_back(grp);
+      if (gvs_tiled.size() == 1 && grp.count > 0) {
+        if (grp.count == 3 && gv.dim == D3 && E->fuse && E->in_step)
+          plan_eh_fusion_impl(this, ft, cmp, grp, E, doing_solve_cw);
+        R.curl_groups.push_back(grp);
+      }
     }
   }
   return allocated_u;

@@ -7,6 +7,7 @@
 //   E = chi1inv * f_minus_p      (STEP_UPDATE_EDHB, lines 190-195)       -> mb200_edhb_job_t
 // are emitted as jobs and executed as at most three launches for all chunks together.
 #include <assert.h>
+#include <algorithm>
 #include <string.h>
 #include <typeinfo>
 
@@ -52,7 +53,7 @@ void fields::update_eh(field_type ft, bool skip_w_components) {
   for (int i = 0; i < num_chunks; i++)
     if (chunks[i]->is_mine() && chunks[i]->doing_solve_cw) cw = true;
 
-  run_phase(E, this, PH_EH, ft, !skip_w_components && !cw, [&]() {
+  run_phase(E, this, PH_EH, ft, E.in_step && !skip_w_components && !cw, [&]() {
     for (int i = 0; i < num_chunks; i++)
       if (chunks[i]->is_mine())
         if (chunks[i]->update_eh(ft, skip_w_components)) {
@@ -260,6 +261,22 @@ bool fields_chunk::update_eh(field_type ft, bool skip_w_components) {
             std::swap(J.s1, J.s2);
           }
           if (!J.u1 && J.u2) meep::abort("bug - didn't swap off-diagonal terms!?");
+          if (E->in_step) {
+            // this chunk's E/H update was folded into the D/B pass (step_db.cpp), except for
+            // the planes that hold source points
+            auto fz = E->fused_eh[ft].find(this);
+            if (fz != E->fused_eh[ft].end()) {
+              const int slab_lo = fz->second.first, slab_hi = fz->second.second;
+              if (slab_lo > slab_hi) continue;
+              // 3-D: loop 1 is X; first loop plane has array index idx0 / stride_x
+              const int ix0 = (int)(J.box.idx0 / J.box.s[0]);
+              const int lo = std::max(slab_lo, ix0), hi = std::min(slab_hi, ix0 + J.box.n[0] - 1);
+              if (lo > hi) continue;
+              J.box.idx0 += (int64_t)(lo - ix0) * J.box.s[0];
+              J.pmlw.k0 += J.pmlw.ks[0] * (lo - ix0);
+              J.box.n[0] = hi - lo + 1;
+            }
+          }
           if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.edhb.push_back(J);
         }
       }

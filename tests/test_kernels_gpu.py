@@ -124,10 +124,12 @@ def test_fused_step3_equals_separate_passes(prec):
                 J.n[k] = nn[k]
                 J.stride[k] = st[k]
             J.dt = 0.05
+            J.ix_lo, J.ix_hi = 0, nn[0]
             for d, c in enumerate(comps):
                 Cc = J.c[d]
                 for k in range(3):
                     Cc.lo[k], Cc.hi[k] = c["lo"][k], c["hi"][k]
+                    Cc.metal_lo[k] = Cc.metal_hi[k] = -1
                 Cc.f, Cc.g1, Cc.g2, Cc.s1, Cc.s2, Cc.dtdx = c["f"], c["g1"], c["g2"], c["s1"], c["s2"], 0.5
                 Cc.pml = pml_for(c["dsig"], c["lo"], True)
                 Cc.pmlu = pml_for(c["dsigu"], c["lo"], True)
