@@ -57,6 +57,7 @@ struct mb200_plan {
   int64_t tiles;
   double bytes, points;
   size_t job_size;
+  bool all_plain; // STEP3: every job qualifies for the fast-path kernel
 };
 
 template <typename T>
@@ -101,7 +102,8 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
                                             p->njobs);
       break;
     case MB200_K_STEP3:
-      launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles, s);
+      launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
+                      p->all_plain, s);
       break;
   }
   return cudaGetLastError();
@@ -241,6 +243,10 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
   p->d_jobs = nullptr;
   p->d_prefix = nullptr;
   p->bytes = p->points = 0;
+  p->all_plain = kind == MB200_K_STEP3 && njobs > 0;
+  if (kind == MB200_K_STEP3)
+    for (int j = 0; j < njobs; ++j)
+      if (!step3_is_plain(((const mb200_step3_job_t *)jobs)[j])) p->all_plain = false;
   std::vector<int64_t> prefix(njobs + 1, 0);
   for (int j = 0; j < njobs; ++j) {
     int64_t t;

@@ -22,6 +22,17 @@
 
 namespace mb200 {
 
+// load from an array that no kernel of the current launch writes (the "other" field type,
+// materials, PML tables): ld.global.nc lets the compiler hoist these loads above the stores of
+// the arrays being updated, which is what keeps enough bytes in flight per warp.
+template <typename T> MB200_HD T ldro(const T *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // index of loop point (i1,i2,i3) in a box
 MB200_HD int64_t box_index(const mb200_box_t &b, int i1, int i2, int i3) {
   return b.idx0 + (int64_t)i1 * b.s[0] + (int64_t)i2 * b.s[1] + (int64_t)i3 * b.s[2];
@@ -46,7 +57,7 @@ MB200_HD T curl_apply(const JOB &J, int64_t i, int k, int ku, T curl, T dt2) {
     if (!FU) {
       if (CND) { // lines 90-99
         const T *cnd = (const T *)J.cnd, *cndinv = (const T *)J.cndinv;
-        fnew = ((1 - dt2 * cnd[i]) * f[i] - curl) * cndinv[i];
+        fnew = ((1 - dt2 * ldro(cnd + i)) * f[i] - curl) * ldro(cndinv + i);
       }
       else // lines 102-109
         fnew = f[i] - curl;
@@ -59,12 +70,12 @@ MB200_HD T curl_apply(const JOB &J, int64_t i, int k, int ku, T curl, T dt2) {
       T fun;
       if (CND) {
         const T *cnd = (const T *)J.cnd, *cndinv = (const T *)J.cndinv;
-        fun = ((1 - dt2 * cnd[i]) * fprev - curl) * cndinv[i];
+        fun = ((1 - dt2 * ldro(cnd + i)) * fprev - curl) * ldro(cndinv + i);
       }
       else
         fun = fprev - curl;
       fu[i] = fun;
-      fnew = siginvu[ku] * ((kapu[ku] - sigu[ku]) * f[i] + fun - fprev);
+      fnew = ldro(siginvu + ku) * ((ldro(kapu + ku) - ldro(sigu + ku)) * f[i] + fun - fprev);
     }
   }
   else {
@@ -75,12 +86,12 @@ MB200_HD T curl_apply(const JOB &J, int64_t i, int k, int ku, T curl, T dt2) {
         const T *cnd = (const T *)J.cnd, *cndinv = (const T *)J.cndinv;
         T *fcnd = (T *)J.fcnd;
         const T fcnd_prev = fcnd[i];
-        const T fcn = ((1 - dt2 * cnd[i]) * fcnd_prev - curl) * cndinv[i];
+        const T fcn = ((1 - dt2 * ldro(cnd + i)) * fcnd_prev - curl) * ldro(cndinv + i);
         fcnd[i] = fcn;
-        fnew = ((kap[k] - sig[k]) * f[i] + (fcn - fcnd_prev)) * siginv[k];
+        fnew = ((ldro(kap + k) - ldro(sig + k)) * f[i] + (fcn - fcnd_prev)) * ldro(siginv + k);
       }
       else
-        fnew = ((kap[k] - sig[k]) * f[i] - curl) * siginv[k];
+        fnew = ((ldro(kap + k) - ldro(sig + k)) * f[i] - curl) * ldro(siginv + k);
     }
     else { // lines 195-247 (most general case 201-211)
       T *fu = (T *)J.fu;
@@ -92,14 +103,14 @@ MB200_HD T curl_apply(const JOB &J, int64_t i, int k, int ku, T curl, T dt2) {
         const T *cnd = (const T *)J.cnd, *cndinv = (const T *)J.cndinv;
         T *fcnd = (T *)J.fcnd;
         const T fcnd_prev = fcnd[i];
-        const T fcn = ((1 - dt2 * cnd[i]) * fcnd_prev - curl) * cndinv[i];
+        const T fcn = ((1 - dt2 * ldro(cnd + i)) * fcnd_prev - curl) * ldro(cndinv + i);
         fcnd[i] = fcn;
-        fun = ((kap[k] - sig[k]) * fprev + (fcn - fcnd_prev)) * siginv[k];
+        fun = ((ldro(kap + k) - ldro(sig + k)) * fprev + (fcn - fcnd_prev)) * ldro(siginv + k);
       }
       else
-        fun = ((kap[k] - sig[k]) * fprev - curl) * siginv[k];
+        fun = ((ldro(kap + k) - ldro(sig + k)) * fprev - curl) * ldro(siginv + k);
       fu[i] = fun;
-      fnew = siginvu[ku] * ((kapu[ku] - sigu[ku]) * f[i] + fun - fprev);
+      fnew = ldro(siginvu + ku) * ((ldro(kapu + ku) - ldro(sigu + ku)) * f[i] + fun - fprev);
     }
   }
   f[i] = fnew;
@@ -109,10 +120,10 @@ MB200_HD T curl_apply(const JOB &J, int64_t i, int k, int ku, T curl, T dt2) {
 // the g-difference of step_curl: g1[i+s1] - g1[i] + g2[i] - g2[i+s2]
 template <typename T, bool G2, typename JOB> MB200_HD T curl_dg(const JOB &J, int64_t i) {
   const T *g1 = (const T *)J.g1;
-  T dg = g1[i + J.s1] - g1[i];
+  T dg = ldro(g1 + i + J.s1) - ldro(g1 + i);
   if (G2) {
     const T *g2 = (const T *)J.g2;
-    dg = dg + g2[i] - g2[i + J.s2];
+    dg = dg + ldro(g2 + i) - ldro(g2 + i + J.s2);
   }
   return dg;
 }
@@ -154,7 +165,8 @@ template <typename T> MB200_HD T calc_nonlinear_u(T Dsqr, T Di, T chi1inv, T chi
 // OFFDIAG (lines 580-581)
 template <typename T>
 MB200_HD T offdiag(const T *u, const T *g, int64_t i, int64_t s, int64_t sx) {
-  return T(0.25) * ((g[i] + g[i - sx]) * u[i] + (g[i + s] + g[(i + s) - sx]) * u[i + s]);
+  return T(0.25) * ((ldro(g + i) + ldro(g + i - sx)) * ldro(u + i) +
+                    (ldro(g + i + s) + ldro(g + (i + s) - sx)) * ldro(u + i + s));
 }
 
 // store val = (u g) into f, through the fw ODE in PML (lines 596-602)
@@ -162,7 +174,7 @@ template <typename T>
 MB200_HD void edhb_store(T *f, T *fw, const mb200_pml_t &pmlw, int64_t i, int kw, T val) {
   if (pmlw.sig) {
     const T *sigw = (const T *)pmlw.sig, *kapw = (const T *)pmlw.kap;
-    const T fwprev = fw[i], kapwkw = kapw[kw], sigwkw = sigw[kw];
+    const T fwprev = fw[i], kapwkw = ldro(kapw + kw), sigwkw = ldro(sigw + kw);
     fw[i] = val;
     f[i] += (kapwkw + sigwkw) * val - (kapwkw - sigwkw) * fwprev;
   }
@@ -176,44 +188,44 @@ template <typename T> MB200_HD void edhb_point(const mb200_edhb_job_t &J, int64_
   const T *u = (const T *)J.u, *u1 = (const T *)J.u1, *u2 = (const T *)J.u2;
   const T *chi2 = (const T *)J.chi2, *chi3 = (const T *)J.chi3;
   const int64_t s = J.s, s1 = J.s1, s2 = J.s2;
-  const T gs = g[i];
+  const T gs = ldro(g + i);
   T val;
   if (u1 && u2) { // 3x3 (lines 588-615, 703-722)
-    const T us = u[i];
+    const T us = ldro(u + i);
     val = gs * us + offdiag(u1, g1, i, s, s1) + offdiag(u2, g2, i, s, s2);
     if (chi3) {
-      T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
-      T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
-      val = val * calc_nonlinear_u(gs * gs + T(0.0625) * (g1s * g1s + g2s * g2s), gs, us, chi2[i],
-                                   chi3[i]);
+      T g1s = ldro(g1 + i) + ldro(g1 + i + s) + ldro(g1 + i - s1) + ldro(g1 + i + (s - s1));
+      T g2s = ldro(g2 + i) + ldro(g2 + i + s) + ldro(g2 + i - s2) + ldro(g2 + i + (s - s2));
+      val = val * calc_nonlinear_u(gs * gs + T(0.0625) * (g1s * g1s + g2s * g2s), gs, us, ldro(chi2 + i),
+                                   ldro(chi3 + i));
     }
   }
   else if (u1) { // 2x2 (lines 616-639, 723-740)
-    const T us = u[i];
+    const T us = ldro(u + i);
     val = gs * us + offdiag(u1, g1, i, s, s1);
     if (chi3) {
-      T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
-      val = val * calc_nonlinear_u(gs * gs + T(0.0625) * (g1s * g1s), gs, us, chi2[i], chi3[i]);
+      T g1s = ldro(g1 + i) + ldro(g1 + i + s) + ldro(g1 + i - s1) + ldro(g1 + i + (s - s1));
+      val = val * calc_nonlinear_u(gs * gs + T(0.0625) * (g1s * g1s), gs, us, ldro(chi2 + i), ldro(chi3 + i));
     }
   }
   else if (chi3) { // diagonal, nonlinear (lines 644-681, 745-773)
-    const T us = u[i];
+    const T us = ldro(u + i);
     T dsqr;
     if (g1 && g2) {
-      T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
-      T g2s = g2[i] + g2[i + s] + g2[i - s2] + g2[i + (s - s2)];
+      T g1s = ldro(g1 + i) + ldro(g1 + i + s) + ldro(g1 + i - s1) + ldro(g1 + i + (s - s1));
+      T g2s = ldro(g2 + i) + ldro(g2 + i + s) + ldro(g2 + i - s2) + ldro(g2 + i + (s - s2));
       dsqr = gs * gs + T(0.0625) * (g1s * g1s + g2s * g2s);
     }
     else if (g1) {
-      T g1s = g1[i] + g1[i + s] + g1[i - s1] + g1[i + (s - s1)];
+      T g1s = ldro(g1 + i) + ldro(g1 + i + s) + ldro(g1 + i - s1) + ldro(g1 + i + (s - s1));
       dsqr = gs * gs + T(0.0625) * (g1s * g1s);
     }
     else
       dsqr = gs * gs;
-    val = (gs * us) * calc_nonlinear_u(dsqr, gs, us, chi2[i], chi3[i]);
+    val = (gs * us) * calc_nonlinear_u(dsqr, gs, us, ldro(chi2 + i), ldro(chi3 + i));
   }
   else if (u) // lines 682-691, 774-779
-    val = gs * u[i];
+    val = gs * ldro(u + i);
   else // lines 692-699, 781-782
     val = gs;
 
@@ -222,7 +234,7 @@ template <typename T> MB200_HD void edhb_point(const mb200_edhb_job_t &J, int64_
 
 // diagonal, linear update_eh fused behind a curl update (mb200_step3_comp_t): e = u * d
 template <typename T> MB200_HD void edhb_diag(const mb200_step3_comp_t &C, int64_t i, int kw, T d) {
-  const T val = C.u ? d * ((const T *)C.u)[i] : d;
+  const T val = C.u ? d * ldro((const T *)C.u + i) : d;
   edhb_store<T>((T *)C.e, (T *)C.fw, C.pmlw, i, kw, val);
 }
 
@@ -236,26 +248,26 @@ template <typename T> MB200_HD void lorentz_point(const mb200_lorentz_job_t &J, 
   const T gamma1inv = (T)J.gamma1inv, gamma1 = (T)J.gamma1, omega0dtsqr = (T)J.omega0dtsqr,
           omega0dtsqr_denom = (T)J.omega0dtsqr_denom;
   if (s1 && s2) { // 3x3 (lines 227-240)
-    if (s[i] != 0) {
+    if (ldro(s + i) != 0) {
       T pcur = p[i];
       p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] +
-                          omega0dtsqr * (s[i] * w[i] + offdiag(s1, w1, i, J.is, J.is1) +
+                          omega0dtsqr * (ldro(s + i) * ldro(w + i) + offdiag(s1, w1, i, J.is, J.is1) +
                                          offdiag(s2, w2, i, J.is, J.is2)));
       pp[i] = pcur;
     }
   }
   else if (s1) { // 2x2 (lines 241-250)
-    if (s[i] != 0) {
+    if (ldro(s + i) != 0) {
       T pcur = p[i];
       p[i] = gamma1inv * (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] +
-                          omega0dtsqr * (s[i] * w[i] + offdiag(s1, w1, i, J.is, J.is1)));
+                          omega0dtsqr * (ldro(s + i) * ldro(w + i) + offdiag(s1, w1, i, J.is, J.is1)));
       pp[i] = pcur;
     }
   }
   else { // isotropic (lines 251-257)
     T pcur = p[i];
     p[i] = gamma1inv *
-           (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] + omega0dtsqr * (s[i] * w[i]));
+           (pcur * (2 - omega0dtsqr_denom) - gamma1 * pp[i] + omega0dtsqr * (ldro(s + i) * ldro(w + i)));
     pp[i] = pcur;
   }
 }
@@ -264,9 +276,9 @@ template <typename T> MB200_HD void lorentz_point(const mb200_lorentz_job_t &J, 
 // f_minus_p = D - sum P (src/update_eh.cpp:114-123, src/susceptibility.cpp:264-281)
 template <typename T> MB200_HD void fmp_point(const mb200_fmp_job_t &J, int64_t i) {
   T *fmp = (T *)J.fmp;
-  T v = J.d ? ((const T *)J.d)[i] : fmp[i];
+  T v = J.d ? ldro((const T *)J.d + i) : fmp[i];
   for (int k = 0; k < J.np; ++k)
-    v -= ((const T *)J.p[k])[i];
+    v -= ldro((const T *)J.p[k] + i);
   fmp[i] = v;
 }
 

@@ -561,7 +561,18 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
         }
       for (size_t k = 0; k < R.curl.size(); ++k)
         if (!used[k]) rest.push_back(R.curl[k]);
-      push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3.data(), s3.size()));
+      // two launches: the fast-path kernel for plain (non-PML) chunks, the general one for the rest
+      std::vector<mb200_step3_job_t> s3_plain, s3_gen;
+      for (const mb200_step3_job_t &j : s3) {
+        bool plain = true;
+        for (int c = 0; c < 3; ++c) {
+          const mb200_step3_comp_t &C = j.c[c];
+          if (!C.f || C.pml.sig || C.pmlu.sig || C.cnd || !C.g2 || (C.e && C.pmlw.sig)) plain = false;
+        }
+        (plain ? s3_plain : s3_gen).push_back(j);
+      }
+      push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_plain.data(), s3_plain.size()));
+      push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_gen.data(), s3_gen.size()));
       push(ph, MB200_K_CURL, make_plan(*this, MB200_K_CURL, rest.data(), rest.size()));
       break;
     }

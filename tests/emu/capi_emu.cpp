@@ -70,9 +70,11 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
       }
       case MB200_K_STEP3: {
         const mb200_step3_job_t &J = ((const mb200_step3_job_t *)p->jobs.data())[j];
+        const bool plain = step3_is_plain(J);
         for (int64_t t = 0; t < ntiles; ++t)
           for (int tid = 0; tid < kThreads; ++tid)
-            step3_thread<T>(J, t, tid);
+            if (plain) step3_plain_thread<T>(J, t, tid);
+            else step3_thread<T>(J, t, tid);
         break;
       }
       case MB200_K_FMP: {
