@@ -209,7 +209,7 @@ typedef struct {
 
 typedef struct {
   int32_t n[3]; /* chunk size in cells; the index box is [0..n[d]] per direction */
-  int32_t reserved;
+  int32_t reserved; /* planes of direction 0 marched per CTA (0 = default 8) */
   int64_t stride[3];
   double dt;
   int32_t ix_lo, ix_hi;

@@ -31,7 +31,11 @@ MB200_HD mb200_box_t step3_box(const mb200_step3_job_t &J) {
   b.reserved = lo; // first ix of the box
   return b;
 }
-MB200_HD int64_t step3_tiles(const mb200_step3_job_t &J) { return box_tiles(step3_box(J)); }
+// planes of direction 0 marched per CTA: J.reserved (0 = default)
+MB200_HD int step3_t1(const mb200_step3_job_t &J) { return J.reserved > 0 ? J.reserved : kT1; }
+MB200_HD int64_t step3_tiles(const mb200_step3_job_t &J) {
+  return box_tiles(step3_box(J), step3_t1(J));
+}
 // owned points of component C inside the job's slab
 inline double step3_comp_points(const mb200_step3_job_t &J, const mb200_step3_comp_t &C) {
   double q = 1;
@@ -77,22 +81,6 @@ inline double step3_bytes(const mb200_step3_job_t &J, double R) {
   return bytes;
 }
 
-// one point, one component
-template <typename T>
-MB200_HD void step3_comp_point(const mb200_step3_comp_t &C, int variant, int64_t i, int ix, int iy,
-                               int iz, T dt2) {
-  if (ix < C.lo[0] || ix > C.hi[0] || iy < C.lo[1] || iy > C.hi[1] || iz < C.lo[2] ||
-      iz > C.hi[2])
-    return;
-  const int k = pml_k(C.pml, ix, iy, iz), ku = pml_k(C.pmlu, ix, iy, iz);
-  const T d = curl_point_any<T>(C, variant, i, k, ku, (T)C.dtdx, dt2);
-  if (C.e) {
-    const bool metal = ix == C.metal_lo[0] || ix == C.metal_hi[0] || iy == C.metal_lo[1] ||
-                       iy == C.metal_hi[1] || iz == C.metal_lo[2] || iz == C.metal_hi[2];
-    edhb_diag<T>(C, i, pml_k(C.pmlw, ix, iy, iz), metal ? T(0) : d);
-  }
-}
-
 // ---- fast path ---------------------------------------------------------------------------------
 // "plain" job: all three components present, none with PML / f_u / conductivity (the interior
 // chunk of a PML-padded cell: ~89 % of the cells of BASELINE config 2), fused E/H update
@@ -111,7 +99,7 @@ template <typename T>
 MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
   const mb200_box_t box = step3_box(J);
   int ix0, ix_end, iy, iz;
-  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz)) return;
+  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
   int64_t i = box_index(box, ix0, iy, iz);
   const int64_t sx = box.s[0];
   ix0 += box.reserved;
@@ -159,30 +147,143 @@ MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int t
   }
 }
 
+// ---- general path --------------------------------------------------------------------------------
+// Any mix of the 16 step_curl variants per component (PML in f, f_u level, conductivity with or
+// without f_cond) plus the diagonal update_eh with or without the f_w ODE.  The variants are
+// one formula with terms removed (reference src/step_generic.cpp:78-84); here the terms are
+// switched by per-component flags that are uniform over the CTA, and — as in the fast path —
+// every load of a grid point (all three components) is issued before its first store.
+//
+//   x      = fu if the f_u level exists, else f                       (the value the curl drives)
+//   no PML : x' = CND ? ((1 - dt/2 cnd) x - curl) cndinv : x - curl                (lines 85-153)
+//   PML    : x' = ((kap - sig) x - curl) siginv                                     (lines 179-193)
+//            with conductivity: fcnd' = ((1 - dt/2 cnd) fcnd - curl) cndinv,
+//                               x'    = ((kap - sig) x + (fcnd' - fcnd)) siginv     (lines 158-178)
+//   f_u    : fu = x',  f' = siginvu ((kapu - sigu) f + x' - fu_old)                 (lines 112-153)
+//   else   : f' = x'
+template <typename T> struct Step3Vals {
+  T f, a1, c1, c2, a2;       // field and the four curl operands
+  T fu, fcnd, cnd, cndinv;   // aux levels
+  T kms, sinv, kmsu, sinvu;  // (kap - sig), siginv for dsig and dsigu
+  T u, fw, e, kapw, sigw;    // fused update_eh operands
+};
+
+template <typename T>
+MB200_HD void step3_load(const mb200_step3_comp_t &C, int64_t i, int ix, int iy, int iz,
+                         Step3Vals<T> &v) {
+  const T *g1 = (const T *)C.g1, *g2 = (const T *)C.g2;
+  v.f = ((const T *)C.f)[i];
+  v.a1 = ldro(g1 + i + C.s1);
+  v.c1 = ldro(g1 + i);
+  v.c2 = ldro(g2 + i);
+  v.a2 = ldro(g2 + i + C.s2);
+  if (C.pmlu.sig) {
+    const int ku = pml_k(C.pmlu, ix, iy, iz);
+    v.fu = ((const T *)C.fu)[i];
+    v.kmsu = ldro((const T *)C.pmlu.kap + ku) - ldro((const T *)C.pmlu.sig + ku);
+    v.sinvu = ldro((const T *)C.pmlu.siginv + ku);
+  }
+  if (C.cnd) {
+    v.cnd = ldro((const T *)C.cnd + i);
+    v.cndinv = ldro((const T *)C.cndinv + i);
+    if (C.pml.sig) v.fcnd = ((const T *)C.fcnd)[i];
+  }
+  if (C.pml.sig) {
+    const int k = pml_k(C.pml, ix, iy, iz);
+    v.kms = ldro((const T *)C.pml.kap + k) - ldro((const T *)C.pml.sig + k);
+    v.sinv = ldro((const T *)C.pml.siginv + k);
+  }
+  if (C.e) {
+    v.u = C.u ? ldro((const T *)C.u + i) : T(1);
+    if (C.pmlw.sig) {
+      const int kw = pml_k(C.pmlw, ix, iy, iz);
+      v.fw = ((const T *)C.fw)[i];
+      v.e = ((const T *)C.e)[i];
+      v.kapw = ldro((const T *)C.pmlw.kap + kw);
+      v.sigw = ldro((const T *)C.pmlw.sig + kw);
+    }
+  }
+}
+
+template <typename T>
+MB200_HD void step3_compute_store(const mb200_step3_comp_t &C, int64_t i, bool metal, T dt2,
+                                  const Step3Vals<T> &v) {
+  T dg = v.a1 - v.c1;
+  dg = dg + v.c2 - v.a2;
+  const T curl = (T)C.dtdx * dg;
+  const bool FU = C.pmlu.sig != nullptr, PML = C.pml.sig != nullptr, CND = C.cnd != nullptr;
+  const T x = FU ? v.fu : v.f;
+  T xn;
+  if (!PML) {
+    if (CND) xn = ((1 - dt2 * v.cnd) * x - curl) * v.cndinv;
+    else xn = x - curl;
+  }
+  else if (CND) {
+    const T fcn = ((1 - dt2 * v.cnd) * v.fcnd - curl) * v.cndinv;
+    ((T *)C.fcnd)[i] = fcn;
+    xn = (v.kms * x + (fcn - v.fcnd)) * v.sinv;
+  }
+  else
+    xn = (v.kms * x - curl) * v.sinv;
+  T fn;
+  if (FU) {
+    ((T *)C.fu)[i] = xn;
+    fn = v.sinvu * (v.kmsu * v.f + xn - v.fu);
+  }
+  else
+    fn = xn;
+  ((T *)C.f)[i] = fn;
+  if (C.e) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
+    const T d = metal ? T(0) : fn;
+    const T val = C.u ? d * v.u : d;
+    if (C.pmlw.sig) {
+      ((T *)C.fw)[i] = val;
+      ((T *)C.e)[i] = v.e + ((v.kapw + v.sigw) * val - (v.kapw - v.sigw) * v.fw);
+    }
+    else
+      ((T *)C.e)[i] = val;
+  }
+}
+
 template <typename T>
 MB200_HD void step3_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
   const mb200_box_t box = step3_box(J);
   int ix0, ix_end, iy, iz;
-  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz)) return;
+  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
   const T dt2 = (T)J.dt * T(0.5);
-  const int v0 = J.c[0].f ? curl_variant(J.c[0]) : -1;
-  const int v1 = J.c[1].f ? curl_variant(J.c[1]) : -1;
-  const int v2 = J.c[2].f ? curl_variant(J.c[2]) : -1;
   int64_t i = box_index(box, ix0, iy, iz);
   const int64_t sx = box.s[0];
   ix0 += box.reserved; // loop index -> array index along direction 0
   ix_end += box.reserved;
+  bool myz[3], metal_yz[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const mb200_step3_comp_t &C = J.c[c];
+    myz[c] = C.f && iy >= C.lo[1] && iy <= C.hi[1] && iz >= C.lo[2] && iz <= C.hi[2];
+    metal_yz[c] = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
+                  iz == C.metal_hi[2];
+  }
   for (int ix = ix0; ix < ix_end; ++ix, i += sx) {
-    if (v0 >= 0) step3_comp_point<T>(J.c[0], v0, i, ix, iy, iz, dt2);
-    if (v1 >= 0) step3_comp_point<T>(J.c[1], v1, i, ix, iy, iz, dt2);
-    if (v2 >= 0) step3_comp_point<T>(J.c[2], v2, i, ix, iy, iz, dt2);
+    Step3Vals<T> v[3];
+    bool m[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      m[c] = myz[c] && ix >= J.c[c].lo[0] && ix <= J.c[c].hi[0];
+      if (m[c]) step3_load<T>(J.c[c], i, ix, iy, iz, v[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (m[c])
+        step3_compute_store<T>(J.c[c], i,
+                               metal_yz[c] || ix == J.c[c].metal_lo[0] || ix == J.c[c].metal_hi[0],
+                               dt2, v[c]);
   }
 }
 
 #ifdef __CUDACC__
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
     step3_kernel(const mb200_step3_job_t *__restrict__ jobs,
                  const int64_t *__restrict__ tile_prefix, int njobs) {
   __shared__ mb200_step3_job_t J;

@@ -32,7 +32,7 @@ struct BoxTiling {
   int nb1;     // tiles along loop 1
 };
 
-MB200_HD BoxTiling box_tiling(const mb200_box_t &b) {
+MB200_HD BoxTiling box_tiling(const mb200_box_t &b, int t1 = kT1) {
   BoxTiling t;
   if (b.n[2] >= 48) t.t3 = 64;
   else if (b.n[2] >= 24) t.t3 = 32;
@@ -47,23 +47,23 @@ MB200_HD BoxTiling box_tiling(const mb200_box_t &b) {
     t.nb3 = 1;
     t.nb23 = (int)((nq + kThreads - 1) / kThreads);
   }
-  t.nb1 = (b.n[0] + kT1 - 1) / kT1;
+  t.nb1 = (b.n[0] + t1 - 1) / t1;
   return t;
 }
-MB200_HD int64_t box_tiles(const mb200_box_t &b) {
+MB200_HD int64_t box_tiles(const mb200_box_t &b, int t1 = kT1) {
   if (b.n[0] <= 0 || b.n[1] <= 0 || b.n[2] <= 0) return 0;
-  BoxTiling t = box_tiling(b);
+  BoxTiling t = box_tiling(b, t1);
   return (int64_t)t.nb1 * t.nb23;
 }
 
 // map (tile, thread) -> loop indices; returns false if this thread has no (i2,i3)
 MB200_HD bool box_thread_point(const mb200_box_t &b, int64_t tile, int tid, int &i1_0, int &i1_end,
-                               int &i2, int &i3) {
-  const BoxTiling t = box_tiling(b);
+                               int &i2, int &i3, int t1 = kT1) {
+  const BoxTiling t = box_tiling(b, t1);
   const int b1 = (int)(tile / t.nb23);
   const int b23 = (int)(tile - (int64_t)b1 * t.nb23);
-  i1_0 = b1 * kT1;
-  i1_end = i1_0 + kT1 < b.n[0] ? i1_0 + kT1 : b.n[0];
+  i1_0 = b1 * t1;
+  i1_end = i1_0 + t1 < b.n[0] ? i1_0 + t1 : b.n[0];
   if (t.t3) {
     const int b2 = b23 / t.nb3, b3 = b23 - b2 * t.nb3;
     const int l3 = tid & (t.t3 - 1), l2 = tid / t.t3;

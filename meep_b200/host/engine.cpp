@@ -569,7 +569,13 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
           const mb200_step3_comp_t &C = j.c[c];
           if (!C.f || C.pml.sig || C.pmlu.sig || C.cnd || !C.g2 || (C.e && C.pmlw.sig)) plain = false;
         }
-        (plain ? s3_plain : s3_gen).push_back(j);
+        if (!plain) {
+          mb200_step3_job_t g = j;
+          g.reserved = 4; // thin PML slabs: shorter marches, more CTAs in flight
+          s3_gen.push_back(g);
+        }
+        else
+          s3_plain.push_back(j);
       }
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_plain.data(), s3_plain.size()));
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_gen.data(), s3_gen.size()));
