@@ -284,6 +284,26 @@ int mb200_update_dft(mb200_ctx *ctx, int dtype, const mb200_dft_job_t *jobs, int
 int mb200_dft_flux(mb200_ctx *ctx, int dtype, const mb200_flux_job_t *jobs, int njobs);
 int mb200_step3(mb200_ctx *ctx, int dtype, const mb200_step3_job_t *jobs, int njobs);
 
+/* ---- inter-process chunk exchange (one process per GPU).  Replaces the transport half of
+ *      fields::step_boundaries — comms_manager::send_real_async / receive_real_async over
+ *      MPI_Isend/MPI_Irecv (src/step.cpp:233-271, src/mympi.cpp:102-128) — with device-to-device
+ *      transfers over NVLink: the comm blocks (src/meep.hpp:2301-2315, one contiguous block of
+ *      comm_size_tot realnums per field type and chunk pair) are packed and unpacked on the device
+ *      by halo jobs and moved by one grouped ncclSend/ncclRecv per phase on the context's stream.
+ *      id: 128 opaque bytes made by mb200_comm_unique_id on one rank and given to all ranks. */
+typedef struct mb200_comm mb200_comm;
+typedef struct {
+  int32_t peer;   /* rank of the other process */
+  int32_t reserved;
+  void *buf;      /* contiguous device buffer */
+  int64_t count;  /* realnums */
+} mb200_xfer_t;
+int mb200_comm_unique_id(void *id128);
+int mb200_comm_create(mb200_ctx *ctx, int rank, int nranks, const void *id128, mb200_comm **out);
+void mb200_comm_destroy(mb200_comm *comm);
+int mb200_comm_exchange(mb200_ctx *ctx, mb200_comm *comm, int dtype, const mb200_xfer_t *sends,
+                        int nsend, const mb200_xfer_t *recvs, int nrecv);
+
 /* ---- finiteness probe (replaces the per-step host read in fields::step, src/step.cpp:137-138):
  *      sets *flag (device int32) to 1 if any of the n listed array elements is NaN/Inf. */
 int mb200_check_finite(mb200_ctx *ctx, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag);

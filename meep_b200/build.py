@@ -32,7 +32,8 @@ OREF = os.path.join(ROOT, "oracle", "_ref")
 OBUILD = os.path.join(ROOT, "oracle", "_build")
 TBUILD = os.path.join(ROOT, "tests", "_build")
 
-HOST_TUS = ["engine", "step", "step_db", "update_eh", "update_pols", "dft_hot", "hooks", "guards"]
+HOST_TUS = ["engine", "step", "step_db", "update_eh", "update_pols", "dft_hot", "hooks", "guards",
+            "mympi_b200"]
 
 
 def have_reference():

@@ -96,6 +96,10 @@ class Step3Job(C.Structure):
                 ("dt", C.c_double), ("ix_lo", C.c_int32), ("ix_hi", C.c_int32), ("c", Step3Comp * 3)]
 
 
+class Xfer(C.Structure):
+    _fields_ = [("peer", C.c_int32), ("reserved", C.c_int32), ("buf", C.c_void_p), ("count", C.c_int64)]
+
+
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,
              K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job}
 
@@ -135,6 +139,10 @@ def declare(lib):
         "mb200_update_dft": (i, [vp, i, vp, i, vp, i]),
         "mb200_dft_flux": (i, [vp, i, vp, i]),
         "mb200_step3": (i, [vp, i, vp, i]),
+        "mb200_comm_unique_id": (i, [vp]),
+        "mb200_comm_create": (i, [vp, i, i, vp, P(vp)]),
+        "mb200_comm_destroy": (None, [vp]),
+        "mb200_comm_exchange": (i, [vp, vp, i, vp, i, vp, i]),
         "mb200_check_finite": (i, [vp, i, vp, i64, vp]),
         "mb200_timer_start": (i, [vp]),
         "mb200_timer_stop": (i, [vp, P(d)]),

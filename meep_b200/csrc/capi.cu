@@ -2,6 +2,7 @@
 // Thin by design: context + device memory + "plans" (job table + tile prefix in HBM, one grid
 // per run).  All numerical work is in kernels.cuh / point_ops.h.  No host execution path.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -373,6 +374,103 @@ int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n,
   if (dtype == MB200_F64) check_finite_kernel<double><<<grid, 256, 0, c->stream>>>(ptrs, n, flag);
   else check_finite_kernel<float><<<grid, 256, 0, c->stream>>>(ptrs, n, flag);
   CUDA_TRY(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
+// ---- inter-process exchange (NCCL, resolved lazily so that single-GPU use needs no NCCL) -------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclFloat64 = 8 };
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.h) return 0;
+  // reuse an NCCL that the process already loaded (e.g. torch's), else the system one
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail("cannot load libnccl.so.2: %s", dlerror());
+#define MB200_SYM(field, name)                                                                     \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                                      \
+  if (!g_nccl.field) return fail("libnccl lacks %s", name)
+  MB200_SYM(GetUniqueId, "ncclGetUniqueId");
+  MB200_SYM(CommInitRank, "ncclCommInitRank");
+  MB200_SYM(CommDestroy, "ncclCommDestroy");
+  MB200_SYM(GroupStart, "ncclGroupStart");
+  MB200_SYM(GroupEnd, "ncclGroupEnd");
+  MB200_SYM(Send, "ncclSend");
+  MB200_SYM(Recv, "ncclRecv");
+  MB200_SYM(GetErrorString, "ncclGetErrorString");
+#undef MB200_SYM
+  g_nccl.h = h;
+  return 0;
+}
+} // namespace
+
+struct mb200_comm {
+  ncclComm_t comm;
+  int rank, nranks;
+};
+
+#define NCCL_TRY(expr)                                                                             \
+  do {                                                                                             \
+    ncclResult_t r_ = (expr);                                                                      \
+    if (r_ != 0) return fail("%s failed: %s", #expr, g_nccl.GetErrorString(r_));                   \
+  } while (0)
+
+int mb200_comm_unique_id(void *id128) {
+  if (load_nccl()) return 1;
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+int mb200_comm_create(mb200_ctx *c, int rank, int nranks, const void *id128, mb200_comm **out) {
+  *out = nullptr;
+  if (load_nccl()) return 1;
+  CUDA_TRY(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  mb200_comm *m = new mb200_comm();
+  m->rank = rank;
+  m->nranks = nranks;
+  NCCL_TRY(g_nccl.CommInitRank(&m->comm, nranks, id, rank));
+  *out = m;
+  return 0;
+}
+
+void mb200_comm_destroy(mb200_comm *m) {
+  if (!m) return;
+  if (g_nccl.h) g_nccl.CommDestroy(m->comm);
+  delete m;
+}
+
+int mb200_comm_exchange(mb200_ctx *c, mb200_comm *m, int dtype, const mb200_xfer_t *sends,
+                        int nsend, const mb200_xfer_t *recvs, int nrecv) {
+  if (!m) return fail("mb200_comm_exchange: no communicator");
+  if (nsend == 0 && nrecv == 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int dt = dtype == MB200_F64 ? ncclFloat64 : ncclFloat32;
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int k = 0; k < nrecv; ++k)
+    NCCL_TRY(g_nccl.Recv(recvs[k].buf, (size_t)recvs[k].count, dt, recvs[k].peer, m->comm, c->stream));
+  for (int k = 0; k < nsend; ++k)
+    NCCL_TRY(g_nccl.Send(sends[k].buf, (size_t)sends[k].count, dt, sends[k].peer, m->comm, c->stream));
+  NCCL_TRY(g_nccl.GroupEnd());
   c->launches += 1;
   return 0;
 }

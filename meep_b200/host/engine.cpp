@@ -1,6 +1,8 @@
 // engine.cpp — see engine.hpp.
 #include "engine.hpp"
 #include "meep_internals.hpp"
+#include "comm.hpp"
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -84,6 +86,7 @@ Engine::Engine(fields *) {
   fuse = env_int("MEEP_B200_FUSE", 1) != 0;
   eager = env_int("MEEP_B200_EAGER", 0) != 0;
   verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
+  emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;
 }
@@ -96,6 +99,7 @@ Engine::~Engine() {
     mb200_free(ctx, kv.second.dev);
   arrs_.clear();
   if (probe_flag_) mb200_free(ctx, probe_flag_);
+  if (comm) mb200_comm_destroy(comm);
   mb200_destroy(ctx);
 }
 
@@ -162,6 +166,25 @@ void *Engine::aux_upload(const void *host, size_t bytes) {
   if (bytes) check(mb200_h2d(ctx, d, host, bytes), "mb200_h2d(aux)");
   rec_aux_.push_back(d);
   return d;
+}
+
+void *Engine::aux_alloc(size_t bytes) {
+  void *d = nullptr;
+  if (!recording_) meep::abort("meep_b200: aux_alloc outside a phase recording");
+  check(mb200_malloc(ctx, bytes ? bytes : 8, &d), "mb200_malloc(aux)");
+  rec_aux_.push_back(d);
+  return d;
+}
+
+// One communicator per Engine; the 128-byte id is made on rank 0 and broadcast over the socket
+// runtime (comm.hpp).  Collective: every rank reaches this from its first step_boundaries.
+void Engine::ensure_comm() {
+  if (comm || comm_size() == 1) return;
+  char id[128];
+  memset(id, 0, sizeof(id));
+  if (comm_rank() == 0) check(mb200_comm_unique_id(id), "mb200_comm_unique_id");
+  comm_broadcast(0, id, sizeof(id));
+  check(mb200_comm_create(ctx, comm_rank(), comm_size(), id, &comm), "mb200_comm_create");
 }
 
 void Engine::free_phase(Phase &ph) {
@@ -597,6 +620,14 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
     case PH_BND:
       push(ph, MB200_K_ZERO, make_plan(*this, MB200_K_ZERO, R.zero.data(), R.zero.size()));
       push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.halo.data(), R.halo.size()));
+      if (!R.sends.empty() || !R.recvs.empty()) {
+        Launch l;
+        l.kind = KIND_EXCHANGE;
+        l.sends = R.sends;
+        l.recvs = R.recvs;
+        ph.launches.push_back(l);
+      }
+      push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.unpack.data(), R.unpack.size()));
       break;
     case PH_EH: {
       push(ph, MB200_K_FMP, make_plan(*this, MB200_K_FMP, R.fmp.data(), R.fmp.size()));
@@ -635,8 +666,11 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
                                   "update_pols", "update_dfts"};
     fprintf(stderr, "meep_b200: recorded %s:", names[id]);
     for (const Launch &l : ph.launches)
-      fprintf(stderr, " [kind %d: %.0f points, %.3f MB]", l.kind, mb200_plan_points(l.plan),
-              mb200_plan_bytes(l.plan) / 1e6);
+      if (l.kind == KIND_EXCHANGE)
+        fprintf(stderr, " [exchange: %zu sends, %zu recvs]", l.sends.size(), l.recvs.size());
+      else
+        fprintf(stderr, " [kind %d: %.0f points, %.3f MB]", l.kind, mb200_plan_points(l.plan),
+                mb200_plan_bytes(l.plan) / 1e6);
     fprintf(stderr, "\n");
   }
   ph.aux.swap(rec_aux_);
@@ -660,6 +694,25 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
 
 void Engine::run(Phase &ph, fields *f) {
   for (Launch &l : ph.launches) {
+    if (l.kind == KIND_EXCHANGE) {
+      if (emulated) {
+        // emulator: "device" buffers are host memory; move them through the socket runtime
+        const size_t R = sizeof(realnum);
+        std::vector<HostMsg> s, r;
+        for (const mb200_xfer_t &x : l.sends)
+          s.push_back(HostMsg{x.peer, x.buf, (size_t)x.count * R});
+        for (const mb200_xfer_t &x : l.recvs)
+          r.push_back(HostMsg{x.peer, x.buf, (size_t)x.count * R});
+        comm_sendrecv_all(s, r);
+      }
+      else {
+        ensure_comm();
+        check(mb200_comm_exchange(ctx, comm, dtype, l.sends.data(), (int)l.sends.size(),
+                                  l.recvs.data(), (int)l.recvs.size()),
+              "mb200_comm_exchange");
+      }
+      continue;
+    }
     if (l.kind == MB200_K_SOURCE) {
       std::vector<double> scal(2 * l.src_times.size());
       for (size_t k = 0; k < l.src_times.size(); ++k) {

@@ -48,7 +48,10 @@ struct Launch {
   // DFT: the dft_chunks whose phase tables are concatenated at run time
   std::vector<meep::dft_chunk *> dft_chunks;
   int decimation = 1;
+  // EXCHANGE (kind == KIND_EXCHANGE): comm blocks sent to / received from other processes
+  std::vector<mb200_xfer_t> sends, recvs;
 };
+enum { KIND_EXCHANGE = 100 };
 
 struct Phase {
   bool valid = false;
@@ -67,7 +70,9 @@ struct Recorder {
   std::vector<const meep::src_time *> src_times;
   std::vector<mb200_src_job_t> dip;       // mode 1 (integrated dipoles)
   std::vector<const meep::src_time *> dip_times;
-  std::vector<mb200_halo_job_t> halo;
+  std::vector<mb200_halo_job_t> halo;   // same-process pairs + packing of outgoing comm blocks
+  std::vector<mb200_halo_job_t> unpack; // scatter of received comm blocks
+  std::vector<mb200_xfer_t> sends, recvs;
   std::vector<mb200_zero_job_t> zero;
   std::map<int, std::vector<mb200_dft_job_t> > dft; // by decimation factor
   std::map<int, std::vector<meep::dft_chunk *> > dft_chunks;
@@ -161,6 +166,11 @@ public:
 
   // ---- misc -----------------------------------------------------------------------------------
   mb200_ctx *ctx = nullptr;
+  mb200_comm *comm = nullptr; // inter-process exchange (created on first use when WORLD_SIZE > 1)
+  bool emulated = false;      // the C ABI is served by the test-only emulator
+  void ensure_comm();
+  // plain device buffer owned by the phase being recorded
+  void *aux_alloc(size_t bytes);
   int dtype = sizeof(realnum) == 8 ? MB200_F64 : MB200_F32;
   Stats stats;
   bool fuse = true;        // MEEP_B200_FUSE=0 disables the fused step3 path

@@ -190,8 +190,8 @@ void fields_chunk::phase_material(int phasein_time) {
 // below) and never pass through comm_blocks, so this entry point only remains for API
 // compatibility; there is no multi-process transport in this build.
 void fields::process_incoming_chunk_data(field_type, const chunk_pair &) {
-  meep::abort("meep_b200: process_incoming_chunk_data: inter-process chunk exchange is not "
-              "available in this build (all chunks must be owned by this process)");
+  meep::abort("meep_b200: process_incoming_chunk_data: comm blocks are unpacked on the device by "
+              "fields::step_boundaries; there is no host-side scatter in this build");
 }
 
 void fields::step_boundaries(field_type ft) {
@@ -206,9 +206,7 @@ void fields::step_boundaries(field_type ft) {
   run_phase(E, this, PH_BND, ft, true, [&]() {
     Recorder &R = E.rec();
     for (int i = 0; i < num_chunks; i++) {
-      if (!chunks[i]->is_mine())
-        meep::abort("meep_b200: chunk %d is owned by another process; multi-process runs are not "
-                    "supported in this build", i);
+      if (!chunks[i]->is_mine()) continue;
       // Do the metals first!  (fields_chunk::zero_metal, src/boundaries.cpp:310-313)
       const size_t nz = chunks[i]->num_zeroes[ft];
       if (nz) {
@@ -221,41 +219,79 @@ void fields::step_boundaries(field_type ft) {
         R.zero.push_back(zj);
       }
     }
-    // gather + scatter of every chunk pair (j -> i), straight from connections_out[j] to
-    // connections_in[i] (positions match: both vectors are built by the same traversal,
-    // src/boundaries.cpp:476-594)
-    for (int i = 0; i < num_chunks; i++)
-      for (const auto &kv : chunks[i]->connections_in) {
-        const comms_key &key = kv.first;
-        if (key.ft != ft) continue;
-        const std::vector<realnum *> &in = kv.second;
-        if (in.empty()) continue;
-        const int j = key.pair.first;
-        auto it = chunks[j]->connections_out.find(key);
-        if (it == chunks[j]->connections_out.end() || it->second.size() != in.size())
-          meep::abort("meep_b200: inconsistent chunk connection tables");
-        const std::vector<realnum *> &out = it->second;
-        std::vector<uint64_t> src(in.size()), dst(in.size());
-        for (size_t k = 0; k < in.size(); ++k) {
-          src[k] = E.dev_addr(out[k]);
-          dst[k] = E.dev_addr(in[k]);
+    // Every chunk pair (j -> i) in a fixed global order (all processes enumerate the pairs
+    // identically, so the grouped sends and receives below match up).  Same-process pairs go
+    // straight from connections_out[j] to connections_in[i] (positions match: both vectors are
+    // built by the same traversal, src/boundaries.cpp:476-594).  For a pair that crosses
+    // processes the comm block of src/step.cpp:256-267 (PHASE || NEGATE || COPY) is packed into
+    // / unpacked from a contiguous device buffer and moved device-to-device.
+    const size_t Rsz = sizeof(realnum);
+    auto dev_list = [&](const std::vector<realnum *> &v, std::vector<uint64_t> &out) {
+      for (realnum *p : v)
+        out.push_back(E.dev_addr(p));
+    };
+    for (int j = 0; j < num_chunks; j++)
+      for (int i = 0; i < num_chunks; i++) {
+        const chunk_pair pair{j, i};
+        const size_t tot = comm_size_tot(ft, pair);
+        if (!tot) continue;
+        const bool j_mine = chunks[j]->is_mine(), i_mine = chunks[i]->is_mine();
+        if (!j_mine && !i_mine) continue;
+        uint64_t block = 0; // device comm block for a cross-process pair
+        if (j_mine != i_mine) {
+          block = (uint64_t)(uintptr_t)E.aux_alloc(tot * Rsz);
+          mb200_xfer_t x;
+          x.peer = j_mine ? chunks[i]->n_proc() : chunks[j]->n_proc();
+          x.reserved = 0;
+          x.buf = (void *)(uintptr_t)block;
+          x.count = (int64_t)tot;
+          (j_mine ? R.sends : R.recvs).push_back(x);
         }
-        mb200_halo_job_t hj;
-        memset(&hj, 0, sizeof(hj));
-        hj.src = (const uint64_t *)E.aux_upload(src.data(), src.size() * 8);
-        hj.dst = (const uint64_t *)E.aux_upload(dst.data(), dst.size() * 8);
-        if (key.phase == CONNECT_PHASE) {
-          const std::vector<std::complex<realnum> > &ph = chunks[i]->connection_phases.at(key);
-          if (ph.size() * 2 != in.size())
-            meep::abort("meep_b200: inconsistent connection phase table");
-          hj.phase = E.aux_upload(ph.data(), ph.size() * sizeof(std::complex<realnum>));
-          hj.n_phase = (int64_t)ph.size();
+        size_t off = 0; // position inside the comm block
+        for (connect_phase ip : all_connect_phases) {
+          const comms_key key = {ft, ip, pair};
+          const size_t n = get_comm_size(key);
+          if (!n) continue;
+          std::vector<uint64_t> src, dst;
+          if (j_mine) {
+            auto it = chunks[j]->connections_out.find(key);
+            if (it == chunks[j]->connections_out.end() || it->second.size() != n)
+              meep::abort("meep_b200: inconsistent outgoing chunk connection table");
+            dev_list(it->second, src);
+          }
+          if (i_mine) {
+            auto it = chunks[i]->connections_in.find(key);
+            if (it == chunks[i]->connections_in.end() || it->second.size() != n)
+              meep::abort("meep_b200: inconsistent incoming chunk connection table");
+            dev_list(it->second, dst);
+          }
+          mb200_halo_job_t hj;
+          memset(&hj, 0, sizeof(hj));
+          if (j_mine && !i_mine) { // pack: plain copy into the outgoing block
+            for (size_t k = 0; k < n; ++k)
+              dst.push_back(block + (off + k) * Rsz);
+            hj.n_copy = (int64_t)n;
+          }
+          else {
+            if (!j_mine) // unpack: the block is the source
+              for (size_t k = 0; k < n; ++k)
+                src.push_back(block + (off + k) * Rsz);
+            if (ip == CONNECT_PHASE) {
+              const std::vector<std::complex<realnum> > &ph = chunks[i]->connection_phases.at(key);
+              if (ph.size() * 2 != n) meep::abort("meep_b200: inconsistent connection phase table");
+              hj.phase = E.aux_upload(ph.data(), ph.size() * sizeof(std::complex<realnum>));
+              hj.n_phase = (int64_t)ph.size();
+            }
+            else if (ip == CONNECT_NEGATE)
+              hj.n_negate = (int64_t)n;
+            else
+              hj.n_copy = (int64_t)n;
+          }
+          hj.src = (const uint64_t *)E.aux_upload(src.data(), src.size() * 8);
+          hj.dst = (const uint64_t *)E.aux_upload(dst.data(), dst.size() * 8);
+          ((j_mine || i_mine) && j_mine == i_mine ? R.halo : (j_mine ? R.halo : R.unpack)).push_back(hj);
+          off += n;
         }
-        else if (key.phase == CONNECT_NEGATE)
-          hj.n_negate = (int64_t)in.size();
-        else
-          hj.n_copy = (int64_t)in.size();
-        R.halo.push_back(hj);
       }
   });
   finished_working();

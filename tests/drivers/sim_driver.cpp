@@ -177,7 +177,9 @@ int main(int argc, char **argv) {
   const std::string cs = argv[1];
   const int nsteps = atoi(argv[2]);
   const int num_chunks = argc > 4 ? atoi(argv[4]) : 0;
-  g_out = fopen(argv[3], "wb");
+  std::string outname = argv[3];
+  if (count_processors() > 1) outname += ".rank" + std::to_string(my_rank());
+  g_out = fopen(outname.c_str(), "wb");
   if (!g_out) { perror(argv[3]); return 2; }
   const double a = 10.0;
 

@@ -274,6 +274,25 @@ int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njob
   return one_shot(c, MB200_K_STEP3, dtype, jobs, njobs, nullptr, 0);
 }
 
+// the emulator has no device interconnect: the host engine moves "device" comm blocks (plain
+// host memory here) through its socket runtime instead (meep_b200/host/step.cpp)
+int mb200_comm_unique_id(void *id128) {
+  memset(id128, 0, 128);
+  return 0;
+}
+struct mb200_comm {
+  int rank, nranks;
+};
+int mb200_comm_create(mb200_ctx *, int rank, int nranks, const void *, mb200_comm **out) {
+  *out = new mb200_comm{rank, nranks};
+  return 0;
+}
+void mb200_comm_destroy(mb200_comm *m) { delete m; }
+int mb200_comm_exchange(mb200_ctx *, mb200_comm *, int, const mb200_xfer_t *, int, const mb200_xfer_t *,
+                        int) {
+  return fail("emu: mb200_comm_exchange is not available (the host engine uses its socket runtime)");
+}
+
 int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag) {
   for (int64_t i = 0; i < n; ++i) {
     const double v = dtype == MB200_F64 ? *(const double *)(uintptr_t)ptrs[i]

@@ -59,6 +59,54 @@ def run_case(arm, prec, case, nsteps, num_chunks=0, env=None, name="sim_driver",
             os.unlink(path)
 
 
+def run_case_mp(arm, prec, case, nsteps, num_chunks, world=2, env=None, name="sim_driver", timeout=900):
+    """the same driver as `world` cooperating processes (one per device), launched the way torchrun
+    launches ranks: RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT in the environment.
+    Returns the union of the per-rank dumps (each rank dumps the chunks it owns)."""
+    import socket
+    if arm == "b200":
+        arm = os.environ.get("MEEP_B200_TEST_ARM", arm)
+    exe = driver(name, arm, prec)
+    fd, path = tempfile.mkstemp(suffix=".bin", prefix="mb200_%s_%s_mp_" % (case, arm))
+    os.close(fd)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for r in range(world):
+        e = dict(os.environ)
+        e.setdefault("OMP_NUM_THREADS", "2")
+        e.update({"RANK": str(r), "WORLD_SIZE": str(world), "LOCAL_RANK": str(r),
+                  "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
+        if env:
+            e.update(env)
+        procs.append(subprocess.Popen([exe, case, str(nsteps), path, str(num_chunks)], env=e,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    out = {}
+    try:
+        for r, p in enumerate(procs):
+            so, _ = p.communicate(timeout=timeout)
+            if p.returncode != 0:
+                raise RuntimeError("rank %d of %s %s failed (rc=%d):\n%s" % (r, exe, case, p.returncode, so[-4000:]))
+        for r in range(world):
+            d = read_dump(path + ".rank%d" % r)
+            for k, v in d.items():
+                if k in out and k.startswith("chunk"):
+                    raise RuntimeError("array %s dumped by two ranks" % k)
+                out[k] = v
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for r in range(world):
+            if os.path.exists(path + ".rank%d" % r):
+                os.unlink(path + ".rank%d" % r)
+        if os.path.exists(path):
+            os.unlink(path)
+    return out
+
+
 def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
