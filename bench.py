@@ -16,8 +16,12 @@ fields::step().  A "step" is one FDTD time step (one pass of the hot path over t
   roofline: dominant kernel (fused D/B update) algorithmic bytes / CUDA-event time / measured HBM peak
   cpu_baseline: the unmodified reference (oracle/_ref) on this box's host cores, bounded sample
 
-N>1: this round the path does not shard across processes (no inter-process halo transport yet):
-"replicas only" — every rank steps its own 512^3 problem, value is the aggregate (weak scaling).
+N>1 (torchrun, one process per GPU): the cell is sharded with the reference's own split_by_cost —
+every rank owns one leaf of the binary partition (plus its PML sub-chunks) — and chunk boundaries
+that cross ranks are exchanged device-to-device (pack kernel -> grouped ncclSend/ncclRecv ->
+unpack kernel) once per sub-phase.  Weak scaling (default): n^3 cells per GPU, stacked along x
+(n*N x n x n); --scaling strong keeps n^3 in total.  rank/size and the few host-side reductions
+come from the MPI-free runtime in meep_b200/host/mympi_b200.cpp (MPI is not installed).
 """
 import argparse
 import ctypes as C
@@ -113,6 +117,9 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--replicas", action="store_true",
+                    help="N>1: independent replicas instead of one sharded problem")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -146,14 +153,18 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["MEEP_B200_DEVICE"] = str(local_rank)
+    if args.replicas:
+        os.environ["MEEP_B200_WORLD_SIZE"] = "1"  # the C++ runtime sees a single process
+        os.environ["MEEP_B200_RANK"] = "0"
+    sharded = world > 1 and not args.replicas
 
     lib = capi.load()  # libmeepb200.so (CUDA kernels + C ABI); raises if missing
     if lib.mb200_device_count() < 1:
         raise RuntimeError("bench.py: no CUDA device visible; the device arm has no CPU fallback")
     C.CDLL(os.path.join(LIB, "libmeep_b200_%s.so" % args.prec), mode=C.RTLD_GLOBAL)
     drv = C.CDLL(os.path.join(LIB, "libmeep_b200_bench_%s.so" % args.prec), mode=C.RTLD_GLOBAL)
-    drv.mb200_bench_create.restype = C.c_void_p
-    drv.mb200_bench_create.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    drv.mb200_bench_create3d.restype = C.c_void_p
+    drv.mb200_bench_create3d.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
     for fn in ("mb200_bench_cells", "mb200_bench_probe", "mb200_bench_field_bytes",
                "mb200_bench_algorithmic_bytes_per_step"):
         getattr(drv, fn).restype = C.c_double
@@ -170,12 +181,14 @@ def main():
     host.meep_b200_sync_host.argtypes = [C.c_void_p]
 
     t0 = time.time()
-    h = drv.mb200_bench_create(b"c2", args.n, 0)
+    nx = args.n * world if (sharded and args.scaling == "weak") else args.n
+    h = drv.mb200_bench_create3d(b"c2", nx, args.n, args.n, 0)
     if not h:
         raise RuntimeError("bench driver failed to build the workload")
     t_setup = time.time() - t0
-    cells = drv.mb200_bench_cells(h)
+    cells = drv.mb200_bench_cells(h)  # the whole (possibly sharded) cell
     fptr = drv.mb200_bench_fields(h)
+    ranks_per_problem = world if sharded else 1
 
     def stats():
         a = (C.c_double * 8)()
@@ -269,22 +282,27 @@ def main():
                     "whole_step": {"alg_bytes_per_step": alg_step,
                                    "achieved": alg_step / (dev_ms / args.steps * 1e-3) / 1e9,
                                    "frac": alg_step / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
-                                   "bytes_per_cell": alg_step / cells},
+                                   "bytes_per_cell": alg_step / (cells / ranks_per_problem)},
                     "kernels": prof}
 
-    value = cells * args.steps * world / (dev_ms * 1e-3)
+    nproblems = world // ranks_per_problem
+    if roofline and world > 1:
+        roofline["note"] = "rank 0's share of the cell; kernels are identical on every rank"
+    value = cells * args.steps * nproblems / (dev_ms * 1e-3)
     line = {"metric": "Yee cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.prec,
-            "data": "synthetic",
-            "config": {"workload": "c2: 3D dielectric box %d^3, PML(1.0) on all faces, non-dispersive, Gaussian "
-                                   "Ez dipole, res 10, Courant 0.5, real fields (BASELINE.json configs[1])" % args.n,
-                       "n": args.n, "num_chunks": drv.mb200_bench_num_chunks(h),
-                       "parallelism": "replicas only" if world > 1 else "single GPU",
+            "higher_is_better": True, "scaling": args.scaling if sharded else "weak", "vs_baseline": None,
+            "dtype": args.prec, "data": "synthetic",
+            "config": {"workload": "c2: 3D dielectric box %dx%dx%d, PML(1.0) on all faces, non-dispersive, Gaussian "
+                                   "Ez dipole, res 10, Courant 0.5, real fields (BASELINE.json configs[1]%s)"
+                                   % (nx, args.n, args.n, "" if world == 1 else "; configs[4] scaling form"),
+                       "n": args.n, "cell": [nx, args.n, args.n], "num_chunks": drv.mb200_bench_num_chunks(h),
+                       "parallelism": ("sharded: split_by_cost over %d ranks, device-to-device halo exchange" % world)
+                       if sharded else ("replicas only" if world > 1 else "single GPU"),
                        "l2_policy": "inputs larger than L2: %.1f GB of field arrays streamed per step vs 126 MB L2"
-                                    % (drv.mb200_bench_field_bytes(h) / 1e9),
+                                    % (drv.mb200_bench_field_bytes(h) / 1e9) + " (per rank)",
                        "setup_s": t_setup, "warmup_s": t_warm},
-            "e2e": {"value": cells * args.steps * world / e2e_s, "unit": "cell-updates/s",
+            "e2e": {"value": cells * args.steps * nproblems / e2e_s, "unit": "cell-updates/s",
                     "h2d_bytes_per_step": (e1[1] - e0[1]) / args.steps,
                     "d2h_bytes_per_step": (e1[2] - e0[2]) / args.steps,
                     "what": "K x (fields::step() + fields::get_field probe) through the meep C++ API; field "

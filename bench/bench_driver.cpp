@@ -17,25 +17,25 @@
 #include <stdlib.h>
 #include <string.h>
 #include <complex>
+#include <algorithm>
 #include <string>
+
+#include <omp.h>
 
 #include "meep.hpp"
 using namespace meep;
 
 namespace {
 
-double g_L = 1;
+double g_L = 1, g_cx = 0.5, g_cy = 0.5, g_cz = 0.5;
 
 // thread-safe (so set_chi1inv runs under OpenMP: anisotropic_averaging.cpp:252) eps = 12 cube
 class cube_material : public material_function {
 public:
   virtual double chi1p1(field_type ft, const vec &r) {
     if (ft != E_stuff) return 1.0;
-    double m = 0;
-    LOOP_OVER_DIRECTIONS(r.dim, d) {
-      double x = fabs(r.in_direction(d) - 0.5 * g_L);
-      if (x > m) m = x;
-    }
+    const double dx = fabs(r.x() - g_cx), dy = fabs(r.y() - g_cy), dz = fabs(r.z() - g_cz);
+    const double m = std::max(dx, std::max(dy, dz));
     return m < 0.25 * g_L ? 12.0 : 1.0;
   }
   virtual double eps(const vec &r) { return chi1p1(E_stuff, r); }
@@ -54,8 +54,17 @@ struct Bench {
 
 extern "C" {
 
+void *mb200_bench_create3d(const char *workload, int nx, int ny, int nz, int num_chunks);
+
 // returns NULL on failure (message on stderr)
 void *mb200_bench_create(const char *workload, int n, int num_chunks) {
+  return mb200_bench_create3d(workload, n, n, n, num_chunks);
+}
+
+// nx x ny x nz cells; the eps = 12 cube is centred and half as wide as the SHORTEST edge.  With
+// more than one process (torchrun: RANK / WORLD_SIZE) the reference's own split_by_cost cuts the
+// cell into count_processors() leaves (num_chunks = 0) and every process owns one of them.
+void *mb200_bench_create3d(const char *workload, int nx, int ny, int nz, int num_chunks) {
   static initialize *mpi = nullptr;
   if (!mpi) {
     static int argc = 1;
@@ -69,8 +78,12 @@ void *mb200_bench_create(const char *workload, int n, int num_chunks) {
     Bench *b = new Bench();
     const double a = 10.0;
     if (std::string(workload) == "c2") {
-      g_L = n / a;
-      b->gv = vol3d(g_L, g_L, g_L, a);
+      const int nmin = std::min(nx, std::min(ny, nz));
+      g_L = nmin / a;
+      g_cx = 0.5 * nx / a;
+      g_cy = 0.5 * ny / a;
+      g_cz = 0.5 * nz / a;
+      b->gv = vol3d(nx / a, ny / a, nz / a, a);
       cube_material mat;
       b->s = new structure(b->gv, mat, pml(1.0), identity(), num_chunks, 0.5, false);
       b->f = new fields(b->s);
@@ -79,7 +92,7 @@ void *mb200_bench_create(const char *workload, int n, int num_chunks) {
       src.is_integrated = false; // a current source, the Python front end's default
       b->f->add_point_source(Ez, src, b->gv.center() + vec(0.05, 0.05, 0.05));
       b->probe_pt = b->gv.center() + vec(0.35, 0.25, 0.15);
-      b->cells = (double)n * n * n;
+      b->cells = (double)nx * ny * nz;
     }
     else {
       fprintf(stderr, "mb200_bench_create: unknown workload %s\n", workload);
@@ -122,6 +135,7 @@ double mb200_bench_field_bytes(void *h) {
   double bytes = 0;
   for (int i = 0; i < b->f->num_chunks; ++i) {
     fields_chunk *fc = b->f->chunks[i];
+    if (!fc->is_mine()) continue;
     FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
       if (fc->f[c][cmp] && !(is_magnetic(c) &&
                              fc->f[c][cmp] == fc->f[direction_component(Bx, component_direction(c))][cmp]))
@@ -143,6 +157,7 @@ double mb200_bench_algorithmic_bytes_per_step(void *h) {
   double bytes = 0;
   for (int i = 0; i < b->f->num_chunks; ++i) {
     fields_chunk *fc = b->f->chunks[i];
+    if (!fc->is_mine()) continue;
     const double owned = (double)fc->gv.nx() * fc->gv.ny() * fc->gv.nz();
     int arrays = 0;
     FOR_COMPONENTS(c) {
@@ -187,6 +202,7 @@ int main(int argc, char **argv) {
     return 2;
   }
   const int n = atoi(argv[2]), warm = atoi(argv[3]), steps = atoi(argv[4]);
+  omp_set_num_threads(omp_get_max_threads());
   const int nchunks = argc > 5 ? atoi(argv[5]) : 0;
   double t0 = wall_time();
   void *h = mb200_bench_create(argv[1], n, nchunks);

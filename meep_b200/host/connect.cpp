@@ -1,0 +1,327 @@
+// connect.cpp — fast replacements for fields::connect_the_chunks and fields::find_metals
+// (reference src/boundaries.cpp:315-345 and 368-638).
+//
+// These build the tables that fields::step_boundaries consumes (connections_in/out,
+// connection_phases, comm_sizes, comms_sequence_for_field, zeroes).  The reference versions are
+// O(not-owned points x chunks) with several hash-map lookups per point and a full-volume scan for
+// metal points: 14 s at 256^3 / 27 chunks, ~1 min at 512^3, and they grow with the SQUARE of the
+// chunk count in a multi-GPU run.  Here the same tables (same contents, same order) are produced
+// with: the owner chunk of a point found by testing the previous owner first; table vectors
+// resolved once per (chunk pair, field type, phase class) instead of per point; a single pass
+// (sizes are read off the finished vectors); metal points found by walking only the boundary
+// planes of the owned volume.  Host code only — nothing here touches field values.
+#include <algorithm>
+#include <stdlib.h>
+#include <map>
+#include <vector>
+
+#include "engine.hpp"
+#include "meep_internals.hpp"
+
+using namespace std;
+
+namespace meep {
+
+namespace {
+
+// as optimize_comms_operations in the reference's anonymous namespace (src/boundaries.cpp:37-75)
+comms_sequence order_comms_operations(const std::vector<comms_operation> &operations) {
+  comms_sequence ret;
+  std::map<int, size_t> send_size_by_my_chunk_idx;
+  std::map<int, std::vector<comms_operation> > send_ops_by_my_chunk_idx;
+  for (const auto &op : operations) {
+    if (op.comm_direction == Incoming) {
+      ret.receive_ops.push_back(op);
+      continue;
+    }
+    if (op.other_proc_id != my_rank()) { send_size_by_my_chunk_idx[op.my_chunk_idx] += op.transfer_size; }
+    else { send_size_by_my_chunk_idx[op.my_chunk_idx] += 0; }
+    send_ops_by_my_chunk_idx[op.my_chunk_idx].push_back(op);
+  }
+  std::vector<std::pair<int, size_t> > send_op_sizes(send_size_by_my_chunk_idx.begin(),
+                                                     send_size_by_my_chunk_idx.end());
+  std::stable_sort(send_op_sizes.begin(), send_op_sizes.end(),
+                   [](const std::pair<int, size_t> &a, const std::pair<int, size_t> &b) -> bool {
+                     return a.second > b.second;
+                   });
+  for (const auto &size_pair : send_op_sizes) {
+    const auto &ops_vector = send_ops_by_my_chunk_idx[size_pair.first];
+    ret.send_ops.insert(std::end(ret.send_ops), std::begin(ops_vector), std::end(ops_vector));
+  }
+  return ret;
+}
+
+bool phase_isclose(std::complex<double> thephase, double realphase) {
+  return fabs(thephase.imag()) < 1e-13 && fabs(thephase.real() - realphase) < 1e-13;
+}
+connect_phase connect_phase_from_phase(std::complex<double> thephase) {
+  return phase_isclose(thephase, 1.0)    ? CONNECT_COPY
+         : phase_isclose(thephase, -1.0) ? CONNECT_NEGATE
+                                         : CONNECT_PHASE;
+}
+
+} // namespace
+
+// Walks LOOP_OVER_VOL_OWNED(vi, c, n) in the reference's order but visits only the points for
+// which IVEC_LOOP_AT_BOUNDARY (src/meep/vec.hpp:336-339) holds.
+template <typename F>
+static void for_each_owned_boundary_point(const grid_volume &vi, component c, F visit) {
+  const ivec is = vi.little_owned_corner(c), ie = vi.big_corner();
+  const ptrdiff_t is1 = is.yucky_val(0), is2 = is.yucky_val(1), is3 = is.yucky_val(2);
+  const ptrdiff_t n1 = (ie.yucky_val(0) - is1) / 2 + 1, n2 = (ie.yucky_val(1) - is2) / 2 + 1,
+                  n3 = (ie.yucky_val(2) - is3) / 2 + 1;
+  const direction d1 = vi.yucky_direction(0), d2 = vi.yucky_direction(1), d3 = vi.yucky_direction(2);
+  const ptrdiff_t s1 = vi.stride(d1), s2 = vi.stride(d2), s3 = vi.stride(d3);
+  const ivec rel = is - vi.little_corner();
+  const ptrdiff_t idx0 = rel.yucky_val(0) / 2 * s1 + rel.yucky_val(1) / 2 * s2 + rel.yucky_val(2) / 2 * s3;
+  if (n1 <= 0 || n2 <= 0 || n3 <= 0) return;
+  for (ptrdiff_t i1 = 0; i1 < n1; i1++) {
+    const bool b1 = s1 != 0 && (i1 == 0 || i1 == n1 - 1);
+    for (ptrdiff_t i2 = 0; i2 < n2; i2++) {
+      const bool b2 = s2 != 0 && (i2 == 0 || i2 == n2 - 1);
+      auto emit = [&](ptrdiff_t i3) {
+        ivec here(vi.dim);
+        here.set_direction(d1, is1 + 2 * i1);
+        here.set_direction(d2, is2 + 2 * i2);
+        here.set_direction(d3, is3 + 2 * i3);
+        visit(idx0 + i1 * s1 + i2 * s2 + i3 * s3, here);
+      };
+      if (b1 || b2) {
+        for (ptrdiff_t i3 = 0; i3 < n3; i3++)
+          emit(i3);
+      }
+      else if (s3 != 0) {
+        emit(0);
+        if (n3 > 1) emit(n3 - 1);
+      }
+    }
+  }
+}
+
+void fields::find_metals() {
+  for (int i = 0; i < num_chunks; i++)
+    if (chunks[i]->is_mine()) {
+      const grid_volume vi = chunks[i]->gv;
+      FOR_FIELD_TYPES(ft) {
+        delete[] chunks[i]->zeroes[ft];
+        std::vector<realnum *> found;
+        DOCMP FOR_COMPONENTS(c) {
+          if (type(c) == ft && chunks[i]->f[c][cmp])
+            for_each_owned_boundary_point(vi, c, [&](ptrdiff_t n, const ivec &here) {
+              if (on_metal_boundary(here)) found.push_back(chunks[i]->f[c][cmp] + n);
+            });
+        }
+        typedef realnum *realnum_ptr;
+        chunks[i]->num_zeroes[ft] = found.size();
+        chunks[i]->zeroes[ft] = new realnum_ptr[found.size()];
+        std::copy(found.begin(), found.end(), chunks[i]->zeroes[ft]);
+      }
+    }
+}
+
+void fields::connect_the_chunks() {
+  const double t_start = wall_time();
+  // (see the reference's comment at src/boundaries.cpp:369-377)
+  std::vector<int> B_redundant(num_chunks * 2 * 5);
+  for (int i = 0; i < num_chunks; ++i)
+    FOR_H_AND_B(hc, bc) {
+      B_redundant[5 * (num_chunks + i) + bc - Bx] = chunks[i]->f[hc][0] == chunks[i]->f[bc][0];
+    }
+  am_now_working_on(MpiAllTime);
+  and_to_all(B_redundant.data() + 5 * num_chunks, B_redundant.data(), 5 * num_chunks);
+  finished_working();
+
+  bool needs_W_notowned[NUM_FIELD_COMPONENTS];
+  FOR_COMPONENTS(c) { needs_W_notowned[c] = false; }
+  FOR_E_AND_H(c) {
+    for (int i = 0; i < num_chunks; i++)
+      needs_W_notowned[c] = needs_W_notowned[c] || chunks[i]->needs_W_notowned(c);
+  }
+  am_now_working_on(MpiAllTime);
+  FOR_E_AND_H(c) { needs_W_notowned[c] = or_to_all(needs_W_notowned[c]); }
+  finished_working();
+
+  comm_sizes.clear();
+
+  // per (field type, phase class, other chunk j) caches for the chunk i being processed
+  struct Slot {
+    std::vector<realnum *> *in = nullptr, *out = nullptr;
+    std::vector<std::complex<realnum> > *phases = nullptr;
+    size_t count = 0; // realnums of this key when neither vector is ours to fill (never both NULL)
+  };
+  std::vector<Slot> slots((size_t)NUM_FIELD_TYPES * NUM_CONNECT_PHASE_TYPES * num_chunks);
+
+  for (int i = 0; i < num_chunks; i++) {
+    const grid_volume &vi = chunks[i]->gv;
+    const bool i_is_mine = chunks[i]->is_mine();
+    std::fill(slots.begin(), slots.end(), Slot());
+    std::vector<char> touched(slots.size(), 0);
+    std::vector<size_t> touched_list;
+    auto slot = [&](field_type f, connect_phase ip, int j) -> Slot & {
+      const size_t k = ((size_t)f * NUM_CONNECT_PHASE_TYPES + (size_t)ip) * num_chunks + j;
+      if (!touched[k]) {
+        touched[k] = 1;
+        touched_list.push_back(k);
+        const comms_key key = {f, ip, {j, i}};
+        Slot &s = slots[k];
+        if (i_is_mine) {
+          s.in = &chunks[i]->connections_in[key];
+          if (ip == CONNECT_PHASE) s.phases = &chunks[i]->connection_phases[key];
+        }
+        if (chunks[j]->is_mine()) s.out = &chunks[j]->connections_out[key];
+      }
+      return slots[k];
+    };
+    int last_j = i;
+
+    FOR_COMPONENTS(corig) {
+      if (have_component(corig)) LOOP_OVER_VOL_NOTOWNED(vi, corig, n) {
+          IVEC_LOOP_ILOC(vi, here);
+          component c = corig;
+          // We're looking at a border element...
+          std::complex<double> thephase;
+          if (!locate_component_point(&c, &here, &thephase) || on_metal_boundary(here)) continue;
+          // the chunk that owns `here` (ownership is exclusive): try the previous owner first
+          int j = -1;
+          if (chunks[last_j]->gv.owns(here)) j = last_j;
+          else
+            for (int jj = 0; jj < num_chunks; jj++)
+              if (chunks[jj]->gv.owns(here)) {
+                j = jj;
+                break;
+              }
+          if (j < 0) continue;
+          last_j = j;
+          const bool j_is_mine = chunks[j]->is_mine();
+          if (!i_is_mine && !j_is_mine) continue;
+          if (is_B(corig) && is_B(c) && B_redundant[5 * i + corig - Bx] && B_redundant[5 * j + c - Bx])
+            continue;
+
+          const connect_phase ip = connect_phase_from_phase(thephase);
+          const ptrdiff_t m = chunks[j]->gv.index(c, here);
+          const std::complex<realnum> ph(thephase.real(), thephase.imag());
+          const int ncmp = 2 - is_real;
+
+          {
+            Slot &s = slot(type(c), ip, j);
+            if (i_is_mine) {
+              if (ip == CONNECT_PHASE) s.phases->push_back(ph);
+              for (int cmp = 0; cmp < ncmp; cmp++)
+                s.in->push_back(chunks[i]->f[corig][cmp] + n);
+            }
+            if (j_is_mine)
+              for (int cmp = 0; cmp < ncmp; cmp++)
+                s.out->push_back(chunks[j]->f[c][cmp] + m);
+          }
+
+          if (needs_W_notowned[corig]) {
+            Slot &s = slot(is_electric(corig) ? WE_stuff : WH_stuff, ip, j);
+            if (i_is_mine) {
+              if (ip == CONNECT_PHASE) s.phases->push_back(ph);
+              for (int cmp = 0; cmp < ncmp; cmp++)
+                s.in->push_back((chunks[i]->f_w[corig][cmp] ? chunks[i]->f_w[corig][cmp]
+                                                            : chunks[i]->f[corig][cmp]) +
+                                n);
+            }
+            if (j_is_mine)
+              for (int cmp = 0; cmp < ncmp; cmp++)
+                s.out->push_back(
+                    (chunks[j]->f_w[c][cmp] ? chunks[j]->f_w[c][cmp] : chunks[j]->f[c][cmp]) + m);
+          }
+
+          if (is_electric(corig) || is_magnetic(corig)) {
+            const field_type f = is_electric(corig) ? PE_stuff : PH_stuff;
+            for (polarization_state *pi = chunks[i]->pol[type(corig)]; pi; pi = pi->next)
+              for (polarization_state *pj = chunks[j]->pol[type(c)]; pj; pj = pj->next)
+                if (*pi->s == *pj->s) {
+                  polarization_state *po = NULL;
+                  if (pi->data && i_is_mine)
+                    po = pi;
+                  else if (pj->data && j_is_mine)
+                    po = pj;
+                  if (po) {
+                    const size_t ni = po->s->num_internal_notowned_needed(corig, po->data);
+                    if (ni) {
+                      Slot &s = slot(f, CONNECT_COPY, j);
+                      for (size_t k = 0; k < ni; ++k) {
+                        if (i_is_mine) s.in->push_back(po->s->internal_notowned_ptr(k, corig, n, pi->data));
+                        if (j_is_mine) s.out->push_back(po->s->internal_notowned_ptr(k, c, m, pj->data));
+                      }
+                    }
+                    const size_t cni = po->s->num_cinternal_notowned_needed(corig, po->data);
+                    if (cni) {
+                      Slot &s = slot(f, ip, j);
+                      for (size_t k = 0; k < cni; ++k) {
+                        if (i_is_mine) {
+                          if (ip == CONNECT_PHASE) s.phases->push_back(ph);
+                          for (int cmp = 0; cmp < ncmp; cmp++)
+                            s.in->push_back(po->s->cinternal_notowned_ptr(k, corig, cmp, n, pi->data));
+                        }
+                        if (j_is_mine)
+                          for (int cmp = 0; cmp < ncmp; cmp++)
+                            s.out->push_back(po->s->cinternal_notowned_ptr(k, c, cmp, m, pj->data));
+                      }
+                    }
+                  }
+                }
+          }
+        }
+    }
+
+    // sizes of the comm blocks of every pair (j -> i) that was touched (src/boundaries.cpp:406-451)
+    for (size_t k : touched_list) {
+      const Slot &s = slots[k];
+      const size_t sz = s.in ? s.in->size() : (s.out ? s.out->size() : 0);
+      const int j = (int)(k % num_chunks);
+      const size_t fi = k / num_chunks;
+      const comms_key key = {field_type(fi / NUM_CONNECT_PHASE_TYPES),
+                             connect_phase(fi % NUM_CONNECT_PHASE_TYPES), {j, i}};
+      if (sz) comm_sizes[key] = sz;
+      else { // nothing was connected under this key after all: leave no empty table behind
+        if (s.in) chunks[i]->connections_in.erase(key);
+        if (s.phases) chunks[i]->connection_phases.erase(key);
+        if (s.out) chunks[j]->connections_out.erase(key);
+      }
+    }
+  }
+
+  // (the host comm_blocks of the reference are not allocated: comm blocks live in HBM,
+  //  fields::step_boundaries in step.cpp)
+
+  FOR_FIELD_TYPES(f) {
+    std::vector<comms_operation> operations;
+    std::vector<int> tagto(count_processors());
+    for (int j = 0; j < num_chunks; j++) {
+      for (int i = 0; i < num_chunks; i++) {
+        const chunk_pair pair{j, i};
+        const size_t comm_size = comm_size_tot(f, pair);
+        if (!comm_size) continue;
+        const int pair_idx = j + i * num_chunks;
+        if (chunks[j]->is_mine()) {
+          operations.push_back(comms_operation{/*my_chunk_idx=*/j,
+                                               /*other_chunk_idx=*/i,
+                                               /*other_proc_id=*/chunks[i]->n_proc(),
+                                               /*pair_idx=*/pair_idx,
+                                               /*transfer_size=*/comm_size,
+                                               /*comm_direction=*/Outgoing,
+                                               /*tag=*/tagto[chunks[i]->n_proc()]++});
+        }
+        if (chunks[i]->is_mine()) {
+          operations.push_back(comms_operation{/*my_chunk_idx=*/i,
+                                               /*other_chunk_idx=*/j,
+                                               /*other_proc_id=*/chunks[j]->n_proc(),
+                                               /*pair_idx=*/pair_idx,
+                                               /*transfer_size=*/comm_size,
+                                               /*comm_direction=*/Incoming,
+                                               /*tag=*/tagto[chunks[j]->n_proc()]++});
+        }
+      }
+    }
+    comms_sequence_for_field[f] = order_comms_operations(operations);
+  }
+  if (getenv("MEEP_B200_VERBOSE") && atoi(getenv("MEEP_B200_VERBOSE")))
+    master_printf("meep_b200: connect_the_chunks: %d chunks, %.3f s\n", num_chunks,
+                  wall_time() - t_start);
+}
+
+} // namespace meep

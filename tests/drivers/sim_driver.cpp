@@ -185,7 +185,7 @@ int main(int argc, char **argv) {
 
   if (cs == "c2_3d_pml" || cs == "c2_3d_pml_integrated" || cs == "c2_3d_pml_complex") {
     // BASELINE config 2 (scaled twin): 3-D eps=12 cube + PML on all faces, Gaussian Ez dipole
-    g_L = 3.2;
+    g_L = getenv("MB200_TEST_L") ? atof(getenv("MB200_TEST_L")) : 3.2;
     grid_volume gv = vol3d(g_L, g_L, g_L, a);
     structure s(gv, eps_box, pml(1.0), identity(), num_chunks);
     fields f(&s);

@@ -71,3 +71,27 @@ def test_reference_test_program_passes_through_the_dropin(name):
     env = dict(os.environ, OMP_NUM_THREADS="2")
     r = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+# ---- N > 1: one process per (emulated) device, launched like torchrun launches ranks -------------
+from parity_util import run_case_mp  # noqa: E402
+
+MP_CASES = [  # (case, steps, num_chunks, world_size)
+    ("c2_3d_pml", 20, 2, 2),
+    ("3d_bloch", 20, 3, 2),
+    ("lorentz_3d", 15, 4, 2),
+    ("2d_bend_flux", 100, 4, 3),
+    ("c4_aniso_ring", 12, 2, 2),
+]
+
+
+@pytest.mark.parametrize("case,steps,chunks,world", MP_CASES)
+def test_sharded_multi_process_run_matches_single_process_reference(case, steps, chunks, world):
+    """chunks distributed over `world` processes by the reference's own split_by_cost /
+    is_mine() logic; rank, size and the small host reductions come from the MPI-free runtime
+    (meep_b200/host/mympi_b200.cpp, TCP on 127.0.0.1), comm blocks are packed/unpacked by halo
+    jobs and moved between the processes; every array of every rank must match the
+    single-process reference run."""
+    ref = run_case("ref", "f64", case, steps, chunks)
+    got = run_case_mp("emu", "f64", case, steps, chunks, world)
+    compare(got, ref, TOL["f64"])
