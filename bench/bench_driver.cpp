@@ -42,7 +42,45 @@ public:
   virtual bool is_thread_safe() const { return true; }
 };
 
+// C3: Drude + 5 Lorentz "Au" sphere of radius 0.2 L (constants: reference python/materials.py:340-364)
+class sphere_sigma : public material_function {
+public:
+  double scale;
+  explicit sphere_sigma(double s) : scale(s) {}
+  double inside(const vec &r) const {
+    const double dx = r.x() - g_cx, dy = r.y() - g_cy, dz = r.z() - g_cz;
+    return dx * dx + dy * dy + dz * dz < 0.04 * g_L * g_L ? 1.0 : 0.0;
+  }
+  virtual double chi1p1(field_type, const vec &r) { return scale * inside(r); }
+  virtual void sigma_row(component c, double sigrow[3], const vec &r) {
+    sigrow[0] = sigrow[1] = sigrow[2] = 0.0;
+    sigrow[component_index(c)] = scale * inside(r);
+  }
+  virtual bool is_thread_safe() const { return true; }
+};
+
+class vacuum_material : public material_function {
+public:
+  virtual double chi1p1(field_type, const vec &) { return 1.0; }
+  virtual double eps(const vec &) { return 1.0; }
+  virtual bool is_thread_safe() const { return true; }
+};
+
+// C4: Si ring in the xy-plane, subpixel smoothing -> off-diagonal chi1inv
+class ring_material : public material_function {
+public:
+  virtual double chi1p1(field_type ft, const vec &r) {
+    if (ft != E_stuff) return 1.0;
+    const double x = r.x() - g_cx, y = r.y() - g_cy, rr = sqrt(x * x + y * y);
+    const bool inz = fabs(r.z() - g_cz) < 0.11 * 2 * g_cz;
+    return (rr > 0.3 * 2 * g_cx && rr < 0.4 * 2 * g_cx && inz) ? 12.0 : 1.0;
+  }
+  virtual double eps(const vec &r) { return chi1p1(E_stuff, r); }
+  virtual bool is_thread_safe() const { return true; }
+};
+
 struct Bench {
+  dft_flux *flux = nullptr;
   structure *s = nullptr;
   fields *f = nullptr;
   grid_volume gv;
@@ -92,6 +130,54 @@ void *mb200_bench_create3d(const char *workload, int nx, int ny, int nz, int num
       src.is_integrated = false; // a current source, the Python front end's default
       b->f->add_point_source(Ez, src, b->gv.center() + vec(0.05, 0.05, 0.05));
       b->probe_pt = b->gv.center() + vec(0.35, 0.25, 0.15);
+      b->cells = (double)nx * ny * nz;
+    }
+    else if (std::string(workload) == "c3") {
+      // BASELINE config 3 (3D Drude-Lorentz Au nanoparticle + 100-frequency DFT flux box)
+      const int nmin = std::min(nx, std::min(ny, nz));
+      g_L = nmin / a;
+      g_cx = 0.5 * nx / a;
+      g_cy = 0.5 * ny / a;
+      g_cz = 0.5 * nz / a;
+      b->gv = vol3d(nx / a, ny / a, nz / a, a);
+      vacuum_material vac;
+      b->s = new structure(b->gv, vac, pml(1.0), identity(), num_chunks, 0.5, false);
+      const double eV = 1 / 1.23984193;
+      // (the 13.32 eV pole is moved to 4.5 eV: at resolution 10 it would have omega_0 dt > 2)
+      const double frq[6] = {1e-3, 0.415 * eV, 0.830 * eV, 2.969 * eV, 4.304 * eV, 4.5 * eV};
+      const double gam[6] = {0.053 * eV, 0.241 * eV, 0.345 * eV, 0.870 * eV, 2.494 * eV, 2.214 * eV};
+      const double wp = 9.03 * eV;
+      const double fstr[6] = {0.760, 0.024, 0.010, 0.071, 0.601, 4.384};
+      for (int k = 0; k < 6; ++k) {
+        sphere_sigma sg(fstr[k] * wp * wp / (frq[k] * frq[k]));
+        b->s->add_susceptibility(sg, E_stuff, lorentzian_susceptibility(frq[k], gam[k], k == 0));
+      }
+      b->f = new fields(b->s);
+      b->f->use_real_fields();
+      gaussian_src_time src(1.5, 1.0);
+      src.is_integrated = false;
+      b->f->add_point_source(Ez, src, vec(0.15 * nx / a, g_cy, g_cz));
+      volume box(vec(0.25 * nx / a, 0.25 * ny / a, 0.25 * nz / a),
+                 vec(0.75 * nx / a, 0.75 * ny / a, 0.75 * nz / a));
+      b->flux = new dft_flux(b->f->add_dft_flux_box(box, 1.0, 2.0, 100));
+      b->probe_pt = b->gv.center() + vec(0.35, 0.25, 0.15);
+      b->cells = (double)nx * ny * nz;
+    }
+    else if (std::string(workload) == "c4") {
+      // BASELINE config 4 (anisotropic subpixel-smoothed Si ring, off-diagonal chi1inv)
+      g_L = std::min(nx, ny) / a;
+      g_cx = 0.5 * nx / a;
+      g_cy = 0.5 * ny / a;
+      g_cz = 0.5 * nz / a;
+      b->gv = vol3d(nx / a, ny / a, nz / a, a);
+      ring_material mat;
+      b->s = new structure(b->gv, mat, pml(1.0), identity(), num_chunks, 0.5, true, 1e-2, 2000);
+      b->f = new fields(b->s);
+      b->f->use_real_fields();
+      gaussian_src_time src(0.3, 0.2);
+      src.is_integrated = false;
+      b->f->add_point_source(Hz, src, vec(g_cx + 0.35 * nx / a, g_cy, g_cz));
+      b->probe_pt = b->gv.center() + vec(0.35, 0.25, 0.05);
       b->cells = (double)nx * ny * nz;
     }
     else {
@@ -174,18 +260,47 @@ double mb200_bench_algorithmic_bytes_per_step(void *h) {
       if (fc->f_cond[c][0]) arrays += 2;
       if (fc->f_w[c][0]) arrays += 2 + 1;                         // fw r/w + E/H read (+=)
       if (is_electric(c) || is_magnetic(c)) {
-        const direction d = component_direction(c);
-        if (fc->s->chi1inv[c][d]) arrays += 1;
+        FOR_DIRECTIONS(d) if (fc->s->chi1inv[c][d]) arrays += 1;  // diagonal + off-diagonal chi1inv
+        // off-diagonal terms forbid the D->E fusion: D is re-read after its halo exchange
+        const direction dd = component_direction(c);
+        FOR_DIRECTIONS(d) if (d != dd && fc->s->chi1inv[c][d]) { arrays += 1; break; }
       }
+    }
+    // Lorentz/Drude polarisations: P, P_prev r/w + sigma r per polarised component (5R, fused
+    // with the E update: SURVEY 8d)
+    FOR_FIELD_TYPES(ft) for (polarization_state *p = fc->pol[ft]; p; p = p->next) FOR_COMPONENTS(c) {
+      if (p->s->sigma[c][component_direction(c)] && fc->f[c][0]) arrays += 5;
     }
     bytes += R * arrays * owned;
   }
   return bytes;
 }
 
+// sum of the flux spectrum (C3): forces the DFT arrays through dft_flux::flux()
+double mb200_bench_flux_sum(void *h) {
+  Bench *b = (Bench *)h;
+  if (!b->flux) return 0;
+  double *F = b->flux->flux(), s = 0;
+  for (size_t i = 0; i < b->flux->freq.size(); ++i)
+    s += F[i];
+  delete[] F;
+  return s;
+}
+
+// DFT state bytes (C3) and monitor points
+double mb200_bench_dft_bytes(void *h) {
+  Bench *b = (Bench *)h;
+  double bytes = 0;
+  for (int i = 0; i < b->f->num_chunks; ++i)
+    for (dft_chunk *d = b->f->chunks[i]->dft_chunks; d; d = d->next_in_chunk)
+      bytes += 2.0 * sizeof(realnum) * d->N * d->omega.size();
+  return bytes;
+}
+
 void mb200_bench_destroy(void *h) {
   Bench *b = (Bench *)h;
   if (!b) return;
+  delete b->flux;
   delete b->f;
   delete b->s;
   delete b;

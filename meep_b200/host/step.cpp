@@ -49,7 +49,7 @@ void fields::step() {
     if (changed_materials) E.materials_dirty = true;
     // update cached conductivity-inverse array, if needed (host; re-uploaded if it changed)
     for (int i = 0; i < num_chunks; i++) {
-      if (chunks[i]->s->condinv_stale) E.materials_dirty = true;
+      if (chunks[i]->is_mine() && chunks[i]->s->condinv_stale) E.materials_dirty = true;
       chunks[i]->s->update_condinv();
     }
     E.in_step = true;
