@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -59,7 +60,13 @@ struct mb200_plan {
   double bytes, points;
   size_t job_size;
   bool all_plain; // STEP3: every job qualifies for the fast-path kernel
+  std::vector<char> h_jobs;       // STEP3: host copy (jobs are passed by value in param space)
+  std::vector<int64_t> h_prefix;
 };
+
+// MEEP_B200_PARAMJOBS=1 passes fused-kernel job descriptors in kernel-parameter (constant) space
+// instead of staging them in shared memory (experiment; see profiles/ for the comparison)
+static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("MEEP_B200_PARAMJOBS")) != 0;
 
 template <typename T>
 static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
@@ -103,6 +110,11 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
                                             p->njobs);
       break;
     case MB200_K_STEP3:
+      if (g_param_jobs) {
+        launch_step3_params<T>((const mb200_step3_job_t *)p->h_jobs.data(), p->h_prefix.data(),
+                               p->njobs, p->all_plain, s);
+        break;
+      }
       launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
                       p->all_plain, s);
       break;
@@ -258,6 +270,10 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
     p->points += pts;
   }
   p->tiles = prefix[njobs];
+  if (kind == MB200_K_STEP3) {
+    p->h_jobs.assign((const char *)jobs, (const char *)jobs + js * njobs);
+    p->h_prefix = prefix;
+  }
   if (p->tiles > 0x7fffffffLL) {
     delete p;
     return fail("mb200_plan_create: too many tiles (%lld)", (long long)p->tiles);

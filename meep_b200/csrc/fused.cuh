@@ -302,6 +302,53 @@ __global__ void __launch_bounds__(kThreads)
   step3_plain_thread<T>(J, tile, threadIdx.x);
 }
 
+// ---- job table in kernel-parameter (constant) space ---------------------------------------------
+// The job descriptor is CTA-uniform.  Staging it in shared memory costs an LDS (and a short-
+// scoreboard stall) for every pointer/flag use inside the marching loop; passed by value as a
+// __grid_constant__ parameter it lives in the constant bank, where uniform operands are read by
+// the uniform datapath without occupying the LSU.  CUDA >= 12.1 allows 32764 bytes of
+// parameters, i.e. up to kParamJobs descriptors per launch (more jobs => more launches).
+constexpr int kParamJobs = (32764 - 16) / (int)(sizeof(mb200_step3_job_t) + sizeof(int64_t)) - 1;
+struct Step3Params {
+  int njobs;
+  int pad;
+  int64_t prefix[kParamJobs + 1];
+  mb200_step3_job_t jobs[kParamJobs];
+};
+static_assert(sizeof(Step3Params) <= 32764, "kernel parameter space exceeded");
+
+template <typename T, bool PLAIN>
+__global__ void __launch_bounds__(kThreads, PLAIN ? 1 : 2)
+    step3_param_kernel(const __grid_constant__ Step3Params P) {
+  int j = 0;
+  while (j + 1 < P.njobs && P.prefix[j + 1] <= (int64_t)blockIdx.x)
+    ++j;
+  const int64_t tile = (int64_t)blockIdx.x - P.prefix[j];
+  if (PLAIN) step3_plain_thread<T>(P.jobs[j], tile, threadIdx.x);
+  else step3_thread<T>(P.jobs[j], tile, threadIdx.x);
+}
+
+// host copies of the job table / prefix are needed to pass them by value
+template <typename T>
+static void launch_step3_params(const mb200_step3_job_t *h_jobs, const int64_t *h_prefix, int njobs,
+                                bool all_plain, cudaStream_t s) {
+  for (int j0 = 0; j0 < njobs; j0 += kParamJobs) {
+    Step3Params P;
+    P.njobs = njobs - j0 < kParamJobs ? njobs - j0 : kParamJobs;
+    P.pad = 0;
+    for (int k = 0; k <= P.njobs; ++k)
+      P.prefix[k] = h_prefix[j0 + k] - h_prefix[j0];
+    for (int k = 0; k < P.njobs; ++k)
+      P.jobs[k] = h_jobs[j0 + k];
+    const int64_t tiles = P.prefix[P.njobs];
+    if (tiles <= 0) continue;
+    if (all_plain)
+      step3_param_kernel<T, true><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(P);
+    else
+      step3_param_kernel<T, false><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(P);
+  }
+}
+
 template <typename T>
 static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
                          int64_t tiles, bool all_plain, cudaStream_t s) {
