@@ -105,6 +105,11 @@ template <typename T> MB200_HD void curl_thread(const mb200_curl_job_t &J, int64
   }
 }
 
+constexpr int kBatch = 4; // loop-1 planes whose loads are issued together
+
+// step_update_EDHB.  Diagonal, linear jobs (the common case when the update could not be fused
+// into the D/B pass: f_minus_p present, 1-D/2-D grids, tiled update_eh) take a batched path that
+// issues the loads of kBatch planes before the first store; everything else goes point by point.
 template <typename T> MB200_HD void edhb_thread(const mb200_edhb_job_t &J, int64_t tile, int tid) {
   int i1_0, i1_end, i2, i3;
   if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
@@ -112,16 +117,78 @@ template <typename T> MB200_HD void edhb_thread(const mb200_edhb_job_t &J, int64
   int kw = pml_k(J.pmlw, i1_0, i2, i3);
   const int64_t s1 = J.box.s[0];
   const int dk = J.pmlw.ks[0];
+  if (!J.u1 && !J.u2 && !J.chi3) {
+    T *f = (T *)J.f, *fw = (T *)J.fw;
+    const T *g = (const T *)J.g, *u = (const T *)J.u;
+    const T *sigw = (const T *)J.pmlw.sig, *kapw = (const T *)J.pmlw.kap;
+    for (int i1 = i1_0; i1 < i1_end; i1 += kBatch, i += kBatch * s1, kw += kBatch * dk) {
+      T gv[kBatch], uv[kBatch], fv[kBatch], fwv[kBatch], kv[kBatch], sv[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k)
+        if (i1 + k < i1_end) {
+          const int64_t idx = i + k * s1;
+          gv[k] = ldro(g + idx);
+          uv[k] = u ? ldro(u + idx) : T(1);
+          if (sigw) {
+            fv[k] = f[idx];
+            fwv[k] = fw[idx];
+            kv[k] = ldro(kapw + kw + k * dk);
+            sv[k] = ldro(sigw + kw + k * dk);
+          }
+        }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k)
+        if (i1 + k < i1_end) {
+          const int64_t idx = i + k * s1;
+          const T val = u ? gv[k] * uv[k] : gv[k];
+          if (sigw) { // src/step_generic.cpp:596-602
+            fw[idx] = val;
+            f[idx] = fv[k] + ((kv[k] + sv[k]) * val - (kv[k] - sv[k]) * fwv[k]);
+          }
+          else
+            f[idx] = val;
+        }
+    }
+    return;
+  }
   for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1, kw += dk)
     edhb_point<T>(J, i, kw);
 }
 
+// lorentzian update_P: the isotropic case (src/susceptibility.cpp:251-257) is batched the same way
 template <typename T>
 MB200_HD void lorentz_thread(const mb200_lorentz_job_t &J, int64_t tile, int tid) {
   int i1_0, i1_end, i2, i3;
   if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
   int64_t i = box_index(J.box, i1_0, i2, i3);
   const int64_t s1 = J.box.s[0];
+  if (!J.s1) {
+    T *p = (T *)J.p, *pp = (T *)J.pp;
+    const T *w = (const T *)J.w, *s = (const T *)J.s;
+    const T gamma1inv = (T)J.gamma1inv, gamma1 = (T)J.gamma1, omega0dtsqr = (T)J.omega0dtsqr,
+            omega0dtsqr_denom = (T)J.omega0dtsqr_denom;
+    for (int i1 = i1_0; i1 < i1_end; i1 += kBatch, i += kBatch * s1) {
+      T pv[kBatch], ppv[kBatch], sv[kBatch], wv[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k)
+        if (i1 + k < i1_end) {
+          const int64_t idx = i + k * s1;
+          pv[k] = p[idx];
+          ppv[k] = pp[idx];
+          sv[k] = ldro(s + idx);
+          wv[k] = ldro(w + idx);
+        }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k)
+        if (i1 + k < i1_end) {
+          const int64_t idx = i + k * s1;
+          p[idx] = gamma1inv * (pv[k] * (2 - omega0dtsqr_denom) - gamma1 * ppv[k] +
+                                omega0dtsqr * (sv[k] * wv[k]));
+          pp[idx] = pv[k];
+        }
+    }
+    return;
+  }
   for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1)
     lorentz_point<T>(J, i);
 }

@@ -277,8 +277,13 @@ template <typename T> MB200_HD void lorentz_point(const mb200_lorentz_job_t &J, 
 template <typename T> MB200_HD void fmp_point(const mb200_fmp_job_t &J, int64_t i) {
   T *fmp = (T *)J.fmp;
   T v = J.d ? ldro((const T *)J.d + i) : fmp[i];
-  for (int k = 0; k < J.np; ++k)
-    v -= ldro((const T *)J.p[k] + i);
+  T pv[MB200_MAX_P];
+#pragma unroll
+  for (int k = 0; k < MB200_MAX_P; ++k) // all loads first (they are independent)
+    pv[k] = k < J.np ? ldro((const T *)J.p[k] + i) : T(0);
+#pragma unroll
+  for (int k = 0; k < MB200_MAX_P; ++k)
+    if (k < J.np) v -= pv[k];
   fmp[i] = v;
 }
 
