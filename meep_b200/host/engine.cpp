@@ -86,6 +86,7 @@ Engine::Engine(fields *) {
   fuse = env_int("MEEP_B200_FUSE", 1) != 0;
   eager = env_int("MEEP_B200_EAGER", 0) != 0;
   verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
+  merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;
@@ -206,8 +207,10 @@ void Engine::invalidate_plans() {
   for (int id = 0; id < PH_COUNT; ++id)
     for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
       free_phase(phases_[id][ft]);
-  for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
+  for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft) {
     fused_eh[ft].clear();
+    deferred_exchange[ft] = false;
+  }
   if (probe_ptrs_) {
     mb200_free(ctx, probe_ptrs_);
     probe_ptrs_ = nullptr;

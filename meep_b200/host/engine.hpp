@@ -121,6 +121,10 @@ public:
   State state = HOST_NEWER;
   int depth = 0; // nesting of our own entry points (0 => called from reference/user code)
   bool in_step = false; // the outermost entry point is fields::step()
+  bool merge_exchanges = true; // MEEP_B200_MERGE_EXCHANGES=0: one exchange per field type
+  bool defer_known = false;
+  bool defer_ok[meep::NUM_FIELD_TYPES] = {}; // global decision: D/B connections may be merged
+  bool deferred_exchange[meep::NUM_FIELD_TYPES] = {}; // D/B connections ride with the E/H ones
   bool connections_valid = false; // fields::chunk_connections_valid at the last step_db
 
   // Brackets every interposed entry point.  On the outermost entry it validates the mirror

@@ -202,9 +202,46 @@ void fields::step_boundaries(field_type ft) {
   connect_chunks(); // re-connect if !chunk_connections_valid (host tables, reference code)
   if (!was_valid) E.invalidate_plans();
 
+  // Exchange merging.  The not-owned D (B) values are read by nothing before the E (H) exchange
+  // unless update_eh needs neighbouring D (B) points (off-diagonal chi1inv, chi2/chi3: the g1/g2
+  // reads of src/step_generic.cpp:580-581,592-593).  When no chunk of this process does, the D
+  // (B) connections are carried out together with the E (H) ones: half as many launches and —
+  // across GPUs — half as many (latency-bound) transfers per time step, same final arrays.
+  const field_type partner = ft == D_stuff ? E_stuff : (ft == B_stuff ? H_stuff : ft);
+  if (!was_valid || changed_materials || !E.defer_known) {
+    // (re)decide, together with all other processes — these three conditions are the same on
+    // every rank, as the reference itself requires for sync_chunk_connections()
+    for (field_type fdb : {D_stuff, B_stuff}) {
+      const field_type feh = fdb == D_stuff ? E_stuff : H_stuff;
+      bool ok = E.merge_exchanges && !fluxes;
+      for (int i = 0; i < num_chunks && ok; i++) {
+        if (!chunks[i]->is_mine()) continue;
+        const structure_chunk *sc = chunks[i]->s;
+        FOR_FT_COMPONENTS(feh, ec) {
+          const direction d_ec = component_direction(ec);
+          const direction d_1 = cycle_direction(chunks[i]->gv.dim, d_ec, 1);
+          const direction d_2 = cycle_direction(chunks[i]->gv.dim, d_ec, 2);
+          if (sc->chi1inv[ec][d_1] || sc->chi1inv[ec][d_2] || sc->chi2[ec] || sc->chi3[ec]) ok = false;
+        }
+      }
+      if (count_processors() > 1) ok = and_to_all(ok);
+      if (ok != E.defer_ok[fdb]) E.invalidate_plans();
+      E.defer_ok[fdb] = ok;
+    }
+    E.defer_known = true;
+  }
+  const bool defer = E.in_step && partner != ft && E.defer_ok[ft];
+  const bool take_partner = E.in_step && (ft == E_stuff || ft == H_stuff) &&
+                            E.deferred_exchange[ft == E_stuff ? D_stuff : B_stuff];
+
   am_now_working_on(Boundaries);
-  run_phase(E, this, PH_BND, ft, true, [&]() {
+  run_phase(E, this, PH_BND, ft, E.in_step, [&]() {
     Recorder &R = E.rec();
+    if (E.in_step && partner != ft) {
+      // the decision is remade with this recording: re-record the partner phase against it
+      E.deferred_exchange[ft] = defer;
+      E.free_phase(E.phase(PH_BND, partner));
+    }
     for (int i = 0; i < num_chunks; i++) {
       if (!chunks[i]->is_mine()) continue;
       // Do the metals first!  (fields_chunk::zero_metal, src/boundaries.cpp:310-313)
@@ -230,6 +267,10 @@ void fields::step_boundaries(field_type ft) {
       for (realnum *p : v)
         out.push_back(E.dev_addr(p));
     };
+    std::vector<field_type> fts;
+    if (take_partner) fts.push_back(ft == E_stuff ? D_stuff : B_stuff);
+    if (!(E.in_step && partner != ft && defer)) fts.push_back(ft);
+    for (field_type ft : fts)
     for (int j = 0; j < num_chunks; j++)
       for (int i = 0; i < num_chunks; i++) {
         const chunk_pair pair{j, i};
