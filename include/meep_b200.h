@@ -84,6 +84,21 @@ typedef struct {
   mb200_pml_t pmlw;
 } mb200_edhb_job_t;
 
+/* ---- step_beta (src/meep_internals.hpp:103-105, src/step_generic.cpp:255-333), called from
+ *      fields_chunk::step_db for 2-D cells with an exp(i beta z) dependence (src/step_db.cpp:161-175):
+ *      f += betadt * g (with the conductivity / PML / f_u variants).  pml.siginv = siginv,
+ *      pmlu.siginv = siginvu (sig/kap unused; siginv == NULL means NO_DIRECTION). */
+typedef struct {
+  mb200_box_t box;
+  void *f;
+  const void *g;
+  double betadt;
+  mb200_pml_t pml, pmlu;
+  void *fu;
+  const void *cndinv;
+  void *fcnd;
+} mb200_beta_job_t;
+
 /* ---- lorentzian_susceptibility::update_P (src/susceptibility.cpp:188-262), one job per
  *      (component, cmp).  Constants are computed by the caller in realnum arithmetic exactly as
  *      lines 192-195 do.  s1/w1 (and s2/w2) NULL => isotropic / 2x2 cases. */
@@ -227,7 +242,8 @@ enum {
   MB200_K_DFT = 7,
   MB200_K_FLUX = 8,
   MB200_K_STEP3 = 9,
-  MB200_NUM_KINDS = 10
+  MB200_K_BETA = 10,
+  MB200_NUM_KINDS = 11
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -283,6 +299,7 @@ int mb200_update_dft(mb200_ctx *ctx, int dtype, const mb200_dft_job_t *jobs, int
                      const void *phases, int nphases);
 int mb200_dft_flux(mb200_ctx *ctx, int dtype, const mb200_flux_job_t *jobs, int njobs);
 int mb200_step3(mb200_ctx *ctx, int dtype, const mb200_step3_job_t *jobs, int njobs);
+int mb200_step_beta(mb200_ctx *ctx, int dtype, const mb200_beta_job_t *jobs, int njobs);
 
 /* ---- inter-process chunk exchange (one process per GPU).  Replaces the transport half of
  *      fields::step_boundaries — comms_manager::send_real_async / receive_real_async over

@@ -11,8 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "meep_b200", "lib")
 
 F64, F32 = 0, 1
-(K_CURL, K_EDHB, K_LORENTZ, K_FMP, K_SOURCE, K_HALO, K_ZERO, K_DFT, K_FLUX, K_STEP3) = range(10)
-NUM_KINDS = 10
+(K_CURL, K_EDHB, K_LORENTZ, K_FMP, K_SOURCE, K_HALO, K_ZERO, K_DFT, K_FLUX, K_STEP3, K_BETA) = range(11)
+NUM_KINDS = 11
 MAX_P = 8
 
 
@@ -96,12 +96,17 @@ class Step3Job(C.Structure):
                 ("dt", C.c_double), ("ix_lo", C.c_int32), ("ix_hi", C.c_int32), ("c", Step3Comp * 3)]
 
 
+class BetaJob(C.Structure):
+    _fields_ = [("box", Box), ("f", C.c_void_p), ("g", C.c_void_p), ("betadt", C.c_double),
+                ("pml", Pml), ("pmlu", Pml), ("fu", C.c_void_p), ("cndinv", C.c_void_p), ("fcnd", C.c_void_p)]
+
+
 class Xfer(C.Structure):
     _fields_ = [("peer", C.c_int32), ("reserved", C.c_int32), ("buf", C.c_void_p), ("count", C.c_int64)]
 
 
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,
-             K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job}
+             K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job, K_BETA: BetaJob}
 
 
 def declare(lib):
@@ -139,6 +144,7 @@ def declare(lib):
         "mb200_update_dft": (i, [vp, i, vp, i, vp, i]),
         "mb200_dft_flux": (i, [vp, i, vp, i]),
         "mb200_step3": (i, [vp, i, vp, i]),
+        "mb200_step_beta": (i, [vp, i, vp, i]),
         "mb200_comm_unique_id": (i, [vp]),
         "mb200_comm_create": (i, [vp, i, i, vp, P(vp)]),
         "mb200_comm_destroy": (None, [vp]),

@@ -109,6 +109,10 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       flux_kernel<T><<<grid, block, 0, s>>>((const mb200_flux_job_t *)p->d_jobs, p->d_prefix,
                                             p->njobs);
       break;
+    case MB200_K_BETA:
+      beta_kernel<T><<<grid, block, 0, s>>>((const mb200_beta_job_t *)p->d_jobs, p->d_prefix,
+                                            p->njobs);
+      break;
     case MB200_K_STEP3:
       if (g_param_jobs) {
         launch_step3_params<T>((const mb200_step3_job_t *)p->h_jobs.data(), p->h_prefix.data(),
@@ -381,6 +385,9 @@ int mb200_dft_flux(mb200_ctx *c, int dtype, const mb200_flux_job_t *jobs, int nj
 }
 int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_STEP3, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
 }
 
 int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag) {

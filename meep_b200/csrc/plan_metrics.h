@@ -19,6 +19,7 @@ inline size_t job_size_of(int kind) {
     case MB200_K_DFT: return sizeof(mb200_dft_job_t);
     case MB200_K_FLUX: return sizeof(mb200_flux_job_t);
     case MB200_K_STEP3: return sizeof(mb200_step3_job_t);
+    case MB200_K_BETA: return sizeof(mb200_beta_job_t);
     default: return 0;
   }
 }
@@ -101,6 +102,15 @@ inline void job_metrics(int kind, int dtype, const void *jobs, int j, int64_t *t
       *tiles = ceil_div(J.npts, kFluxPts);
       *points = (double)J.npts;
       *bytes = 4 * R * J.nomega * *points;
+      break;
+    }
+    case MB200_K_BETA: {
+      const mb200_beta_job_t &J = ((const mb200_beta_job_t *)jobs)[j];
+      *tiles = box_tiles(J.box);
+      *points = box_points(J.box);
+      int arrays = 2 + 1 + (J.cndinv ? 1 : 0) + (J.pmlu.siginv ? 2 : 0) +
+                   (J.cndinv && J.pml.siginv ? 2 : 0);
+      *bytes = R * arrays * *points;
       break;
     }
     case MB200_K_STEP3: {

@@ -154,6 +154,25 @@ MB200_HD T curl_point_any(const JOB &J, int variant, int64_t i, int k, int ku, T
 }
 
 // ------------------------------------------------------------------------------------------------
+// step_beta (src/step_generic.cpp:255-333): the eight specialised loops as one body
+template <typename T> MB200_HD void beta_point(const mb200_beta_job_t &J, int64_t i, int k, int ku) {
+  T *f = (T *)J.f;
+  const T *g = (const T *)J.g;
+  T df = (T)J.betadt * ldro(g + i);
+  if (J.cndinv) df = df * ldro((const T *)J.cndinv + i);
+  if (J.pml.siginv) {
+    if (J.cndinv) ((T *)J.fcnd)[i] += df;
+    df = df * ldro((const T *)J.pml.siginv + k);
+  }
+  if (J.pmlu.siginv) {
+    ((T *)J.fu)[i] += df;
+    f[i] += ldro((const T *)J.pmlu.siginv + ku) * df;
+  }
+  else
+    f[i] += df;
+}
+
+// ------------------------------------------------------------------------------------------------
 // step_update_EDHB (src/step_generic.cpp:566-785).  Callers have applied the swap of line 573.
 // calc_nonlinear_u: lines 542-547.
 template <typename T> MB200_HD T calc_nonlinear_u(T Dsqr, T Di, T chi1inv, T chi2, T chi3) {

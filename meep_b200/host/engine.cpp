@@ -606,6 +606,7 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_plain.data(), s3_plain.size()));
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_gen.data(), s3_gen.size()));
       push(ph, MB200_K_CURL, make_plan(*this, MB200_K_CURL, rest.data(), rest.size()));
+      push(ph, MB200_K_BETA, make_plan(*this, MB200_K_BETA, R.beta.data(), R.beta.size()));
       break;
     }
     case PH_SRC: {

@@ -63,6 +63,7 @@ struct Phase {
 // job recorder used while a phase is being (re)built
 struct Recorder {
   std::vector<mb200_curl_job_t> curl;
+  std::vector<mb200_beta_job_t> beta; // 2-D exp(i beta z) terms, run after the curl jobs
   std::vector<mb200_edhb_job_t> edhb;
   std::vector<mb200_lorentz_job_t> lorentz;
   std::vector<mb200_fmp_job_t> fmp;

@@ -184,8 +184,6 @@ bool fields_chunk::step_db(field_type ft) {
 
   if (gv.dim == Dcyl)
     meep::abort("meep_b200: cylindrical coordinates are not supported on the device path yet");
-  if (gv.dim == D2 && beta != 0)
-    meep::abort("meep_b200: 2d beta != 0 is not supported on the device path yet");
   if (bfast_scaled_k[0] || bfast_scaled_k[1] || bfast_scaled_k[2])
     meep::abort("meep_b200: BFAST is not supported on the device path yet");
 
@@ -271,6 +269,35 @@ bool fields_chunk::step_db(field_type ft) {
       }
     }
   }
+  /* In 2d with beta != 0, add beta terms (see the reference's comment at
+     src/step_db.cpp:148-160); one mb200_beta_job_t per STEP_BETA call (lines 161-175). */
+  if (gv.dim == D2 && beta != 0) DOCMP for (direction d_c = X; d_c <= Y; d_c = direction(d_c + 1)) {
+      component cc = direction_component(first_field_component(ft), d_c);
+      component c_g = direction_component(ft == D_stuff ? Hx : Ex, d_c == X ? Y : X);
+      realnum *the_f = f[cc][cmp];
+      const realnum *g = f[c_g][1 - cmp] ? f[c_g][1 - cmp] : f[c_g][cmp];
+      if (!the_f || !g) continue; // step_beta returns immediately without g (src/step_generic.cpp:259)
+      const direction dsig0 = cycle_direction(gv.dim, d_c, 1);
+      const direction dsig = s->sigsize[dsig0] > 1 ? dsig0 : NO_DIRECTION;
+      const direction dsigu0 = cycle_direction(gv.dim, d_c, 2);
+      const direction dsigu = s->sigsize[dsigu0] > 1 ? dsigu0 : NO_DIRECTION;
+      const realnum betadt = 2 * pi * beta * dt * (d_c == X ? +1 : -1) *
+                             (f[c_g][1 - cmp] ? (ft == D_stuff ? -1 : +1) * (2 * cmp - 1) : 1);
+      const ivec is = gv.little_owned_corner0(cc), ie = gv.big_corner();
+      mb200_beta_job_t J;
+      memset(&J, 0, sizeof(J));
+      J.box = make_box(gv, is, ie);
+      J.f = E->dev(the_f);
+      J.g = E->dev(g);
+      J.betadt = betadt;
+      if (dsig != NO_DIRECTION) J.pml = make_pml(gv, is, dsig, NULL, NULL, E->dev(s->siginv[dsig]));
+      if (dsigu != NO_DIRECTION) J.pmlu = make_pml(gv, is, dsigu, NULL, NULL, E->dev(s->siginv[dsigu]));
+      J.fu = E->dev(f_u[cc][cmp]);
+      J.cndinv = E->dev(s->condinv[cc][d_c]);
+      J.fcnd = E->dev(f_cond[cc][cmp]);
+      if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.beta.push_back(J);
+    }
+
   return allocated_u;
 }
 

@@ -73,6 +73,49 @@ void FN(oracle_step_curl)(const mb200_curl_job_t *J) {
       }
 }
 
+/* reference src/step_generic.cpp:255-333 (step_beta) */
+void FN(oracle_step_beta)(const mb200_beta_job_t *J) {
+  REAL *f = (REAL *)J->f, *fu = (REAL *)J->fu, *fcnd = (REAL *)J->fcnd;
+  const REAL *g = (const REAL *)J->g, *cndinv = (const REAL *)J->cndinv;
+  const REAL *siginv = (const REAL *)J->pml.siginv, *siginvu = (const REAL *)J->pmlu.siginv;
+  const REAL betadt = (REAL)J->betadt;
+  if (!g) return;
+  for (int i1 = 0; i1 < J->box.n[0]; ++i1)
+    for (int i2 = 0; i2 < J->box.n[1]; ++i2)
+      for (int i3 = 0; i3 < J->box.n[2]; ++i3) {
+        const int64_t i = J->box.idx0 + i1 * J->box.s[0] + i2 * J->box.s[1] + i3 * J->box.s[2];
+        if (siginv) {
+          const int k = FN(kidx)(&J->pml, i1, i2, i3);
+          if (siginvu) {
+            const int ku = FN(kidx)(&J->pmlu, i1, i2, i3);
+            REAL df;
+            if (cndinv) {
+              REAL dfcnd = betadt * g[i] * cndinv[i];
+              fcnd[i] += dfcnd;
+              fu[i] += (df = dfcnd * siginv[k]);
+            }
+            else fu[i] += (df = betadt * g[i] * siginv[k]);
+            f[i] += siginvu[ku] * df;
+          }
+          else if (cndinv) {
+            REAL dfcnd = betadt * g[i] * cndinv[i];
+            fcnd[i] += dfcnd;
+            f[i] += dfcnd * siginv[k];
+          }
+          else f[i] += betadt * g[i] * siginv[k];
+        }
+        else if (siginvu) {
+          const int ku = FN(kidx)(&J->pmlu, i1, i2, i3);
+          REAL df;
+          if (cndinv) fu[i] += (df = betadt * g[i] * cndinv[i]);
+          else fu[i] += (df = betadt * g[i]);
+          f[i] += siginvu[ku] * df;
+        }
+        else if (cndinv) f[i] += betadt * g[i] * cndinv[i];
+        else f[i] += betadt * g[i];
+      }
+}
+
 /* reference src/step_generic.cpp:542-547 */
 static REAL FN(nonlinear_u)(REAL Dsqr, REAL Di, REAL chi1inv, REAL chi2, REAL chi3) {
   REAL c2 = Di * chi2 * (chi1inv * chi1inv);

@@ -108,6 +108,36 @@ static void gen_curl(const std::string &dir, const grid_volume &gv, const char *
   }
 }
 
+// ---- step_beta -----------------------------------------------------------------------------------
+static void gen_beta(const std::string &dir, const grid_volume &gv, const char *tag) {
+  const size_t n = gv.ntot();
+  const component cc = Dx;
+  const ivec is = gv.little_owned_corner0(cc), ie = gv.big_corner();
+  const direction dsig0 = Y, dsigu0 = X; // any two in-plane directions exercise both k lookups
+  for (int variant = 0; variant < 8; ++variant) {
+    const bool PML = variant & 4, FU = variant & 2, CND = variant & 1;
+    char nm[64];
+    snprintf(nm, sizeof nm, "beta_%s_v%d", tag, variant);
+    open_case(dir, nm);
+    realnum *f = rand_array(n), *g = rand_array(n);
+    realnum *fu = FU ? rand_array(n) : NULL, *fcnd = (CND && PML) ? rand_array(n) : NULL;
+    realnum *cndinv = CND ? rand_array(n, 0.5, 1) : NULL;
+    const int ns = 2 * gv.num_direction(dsig0) + 2, nsu = 2 * gv.num_direction(dsigu0) + 2;
+    realnum *siginv = rand_array(ns, 0.3, 1), *siginvu = rand_array(nsu, 0.3, 1);
+    const realnum betadt = 0.0371;
+    const direction dsig = PML ? dsig0 : NO_DIRECTION, dsigu = FU ? dsigu0 : NO_DIRECTION;
+    dump_r("in.f", f, n); dump_r("in.g", g, n); dump_r("in.fu", fu, n); dump_r("in.fcnd", fcnd, n);
+    dump_r("in.cndinv", cndinv, n); dump_r("in.siginv", siginv, ns); dump_r("in.siginvu", siginvu, nsu);
+    dump_box("box", make_box(gv, is, ie));
+    dump_pml("pml", make_pml(gv, is, dsig, NULL, NULL, siginv), PML);
+    dump_pml("pmlu", make_pml(gv, is, dsigu, NULL, NULL, siginvu), FU);
+    dump_d("scalars", {(double)betadt});
+    STEP_BETA(f, cc, g, gv, is, ie, betadt, dsig, siginv, fu, dsigu, siginvu, cndinv, fcnd);
+    dump_r("out.f", f, n); dump_r("out.fu", fu, n); dump_r("out.fcnd", fcnd, n);
+    fclose(g_out);
+  }
+}
+
 // ---- step_update_EDHB --------------------------------------------------------------------------
 static void gen_edhb(const std::string &dir, const grid_volume &gv, const char *tag) {
   const size_t n = gv.ntot();
@@ -276,6 +306,7 @@ int main(int argc, char **argv) {
   grid_volume g2 = voltwo(0.7, 0.5, 10);     // 7 x 5 cells
   gen_curl(dir, g3, "3d");
   gen_curl(dir, g2, "2d");
+  gen_beta(dir, g2, "2d");
   gen_edhb(dir, g3, "3d");
   gen_edhb(dir, g2, "2d");
   gen_lorentz(dir, g3, "3d");

@@ -229,6 +229,51 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
+  else if (cs == "2d_mirror_sym" || cs == "3d_rotate_sym") {
+    // symmetry-reduced cells (reference tests/symmetry.cpp): connections with -1 / complex phases
+    // between a chunk and its own mirror / rotated image
+    if (cs == "2d_mirror_sym") {
+      g_L = 2.0;
+      grid_volume gv = voltwo(2.0, 1.6, a);
+      const symmetry S = mirror(X, gv) + mirror(Y, gv);
+      structure s(gv, one, pml(0.4), S, num_chunks);
+      fields f(&s);
+      f.add_point_source(Ez, 0.7, 2.5, 0.0, 4.0, gv.center());
+      f.add_point_source(Hz, 0.6, 2.0, 0.0, 4.0, vec(0.7, 0.55));
+      for (int i = 0; i < nsteps; ++i) f.step();
+      probes(f, gv);
+      dump_fields(f);
+    }
+    else {
+      g_L = 1.2;
+      grid_volume gv = vol3d(1.2, 1.2, 1.0, a);
+      const symmetry S = rotate4(Z, gv);
+      structure s(gv, one, no_pml(), S, num_chunks);
+      fields f(&s);
+      f.add_point_source(Ez, 0.7, 2.5, 0.0, 4.0, gv.center());
+      f.add_point_source(Hz, 0.6, 2.0, 0.0, 4.0, gv.center());
+      f.use_bloch(vec(0.0, 0.0, 0.2));
+      for (int i = 0; i < nsteps; ++i) f.step();
+      probes(f, gv);
+      dump_fields(f);
+    }
+  }
+  else if (cs == "2d_beta" || cs == "2d_beta_real") {
+    // 2-D cell with an exp(i beta z) dependence (fields ctor argument beta; Python's kz_2d):
+    // step_beta couples the TE and TM families (src/step_db.cpp:148-175)
+    g_L = 2.4;
+    grid_volume gv = voltwo(2.4, 2.0, a);
+    structure s(gv, eps_box, pml(0.5), identity(), num_chunks);
+    s.set_conductivity(Dx, cond_slab);
+    fields f(&s, 0.0, 0.37);
+    if (cs == "2d_beta_real") f.use_real_fields();
+    gaussian_src_time src(0.4, 0.3);
+    f.add_point_source(Ez, src, gv.center());
+    f.add_point_source(Hz, src, vec(1.0, 0.8));
+    for (int i = 0; i < nsteps; ++i) f.step();
+    probes(f, gv);
+    dump_fields(f);
+  }
   else if (cs == "2d_bend_flux") {
     // BASELINE config 1 restated (tests/bend-flux-ll.cpp:47-61,137-187): 2-D Ez
     // waveguide bend, eps = 12, PML, two DFT flux planes; scaled to 8 x 16 for test time

@@ -68,6 +68,13 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
             lorentz_thread<T>(J, t, tid);
         break;
       }
+      case MB200_K_BETA: {
+        const mb200_beta_job_t &J = ((const mb200_beta_job_t *)p->jobs.data())[j];
+        for (int64_t t = 0; t < ntiles; ++t)
+          for (int tid = 0; tid < kThreads; ++tid)
+            beta_thread<T>(J, t, tid);
+        break;
+      }
       case MB200_K_STEP3: {
         const mb200_step3_job_t &J = ((const mb200_step3_job_t *)p->jobs.data())[j];
         const bool plain = step3_is_plain(J);
@@ -272,6 +279,9 @@ int mb200_dft_flux(mb200_ctx *c, int dtype, const mb200_flux_job_t *jobs, int nj
 }
 int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_STEP3, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
 }
 
 // the emulator has no device interconnect: the host engine moves "device" comm blocks (plain

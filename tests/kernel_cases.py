@@ -41,7 +41,8 @@ class HostMem:
         names = {capi.K_CURL: "oracle_step_curl", capi.K_EDHB: "oracle_step_update_EDHB",
                  capi.K_LORENTZ: "oracle_lorentzian_update_P", capi.K_FMP: "oracle_subtract_P",
                  capi.K_SOURCE: "oracle_step_source", capi.K_HALO: "oracle_step_boundaries",
-                 capi.K_DFT: "oracle_update_dft", capi.K_FLUX: "oracle_dft_flux"}
+                 capi.K_DFT: "oracle_update_dft", capi.K_FLUX: "oracle_dft_flux",
+                 capi.K_BETA: "oracle_step_beta"}
         fn = getattr(self.lib, names[kind] + "_" + self.prec)
         fn.restype = None
         for j in jobs:
@@ -126,6 +127,19 @@ def replay_curl(rec, mem):
     return {k: mem.get(P[k], g(k)) for k in ("f", "fu", "fcnd") if g(k) is not None}
 
 
+def replay_beta(rec, mem):
+    g = lambda k: rec.get("in." + k)
+    P = {k: mem.put(g(k)) for k in ("f", "g", "fu", "fcnd", "cndinv", "siginv", "siginvu")}
+    j = capi.BetaJob()
+    j.box = mk_box(rec["box"])
+    j.f, j.g, j.betadt = P["f"], P["g"], rec["scalars"][0]
+    j.pml = mk_pml(rec["pml"], None, None, P["siginv"])
+    j.pmlu = mk_pml(rec["pmlu"], None, None, P["siginvu"])
+    j.fu, j.cndinv, j.fcnd = P["fu"], P["cndinv"], P["fcnd"]
+    mem.run(capi.K_BETA, [j])
+    return {k: mem.get(P[k], g(k)) for k in ("f", "fu", "fcnd") if g(k) is not None}
+
+
 def replay_edhb(rec, mem):
     g = lambda k: rec.get("in." + k)
     P = {k: mem.put(g(k)) for k in ("f", "g", "g1", "g2", "u", "u1", "u2", "chi2", "chi3", "fw", "sigw", "kapw")}
@@ -189,7 +203,7 @@ def replay_dft(rec, mem):
     return {"k%d.dft" % k: mem.get(ptrs[k], rec["k%d.in.dft" % k]) for k in range(n)}
 
 
-REPLAY = {"curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
+REPLAY = {"beta": replay_beta, "curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
 
 
 def check_golden(prefix, prec, mem_factory):

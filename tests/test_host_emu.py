@@ -26,6 +26,10 @@ CASES = [  # (case, steps, num_chunks)
     ("offdiag_2d", 60, 0),
     ("cond_chi3_3d", 30, 0),
     ("dft_fields_3d", 30, 0),
+    ("2d_beta", 60, 0),
+    ("2d_beta_real", 60, 2),
+    ("2d_mirror_sym", 60, 0),
+    ("3d_rotate_sym", 40, 2),
 ]
 
 

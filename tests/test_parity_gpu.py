@@ -33,6 +33,10 @@ CASES = [  # (case, steps, num_chunks)
     ("offdiag_2d", 100, 0),
     ("cond_chi3_3d", 60, 0),
     ("dft_fields_3d", 60, 2),
+    ("2d_beta", 100, 0),
+    ("2d_beta_real", 100, 3),
+    ("2d_mirror_sym", 100, 2),
+    ("3d_rotate_sym", 60, 0),
 ]
 
 
