@@ -151,9 +151,33 @@ void fields::connect_the_chunks() {
   };
   std::vector<Slot> slots((size_t)NUM_FIELD_TYPES * NUM_CONNECT_PHASE_TYPES * num_chunks);
 
+  // A chunk of another process matters only if one of its not-owned points can be owned by one
+  // of OUR chunks.  Without periodic boundaries or symmetries a not-owned point is at most one
+  // pixel outside its chunk, so a bounding-box test against our chunks prunes the rest (in an
+  // N-process run this keeps the work per process O(own surface) instead of O(total surface)).
+  bool can_prune = S.multiplicity() == 1;
+  LOOP_OVER_DIRECTIONS(gv.dim, d) {
+    if (boundaries[High][d] == Periodic || boundaries[Low][d] == Periodic) can_prune = false;
+  }
+  auto touches_mine = [&](const grid_volume &vi) {
+    const ivec lo = vi.little_corner() - one_ivec(vi.dim) * 2, hi = vi.big_corner() + one_ivec(vi.dim) * 2;
+    for (int j = 0; j < num_chunks; j++) {
+      if (!chunks[j]->is_mine()) continue;
+      const ivec jl = chunks[j]->gv.little_corner(), jh = chunks[j]->gv.big_corner();
+      bool overlap = true;
+      LOOP_OVER_DIRECTIONS(vi.dim, d) {
+        if (hi.in_direction(d) < jl.in_direction(d) || lo.in_direction(d) > jh.in_direction(d))
+          overlap = false;
+      }
+      if (overlap) return true;
+    }
+    return false;
+  };
+
   for (int i = 0; i < num_chunks; i++) {
     const grid_volume &vi = chunks[i]->gv;
     const bool i_is_mine = chunks[i]->is_mine();
+    if (!i_is_mine && can_prune && !touches_mine(vi)) continue;
     std::fill(slots.begin(), slots.end(), Slot());
     std::vector<char> touched(slots.size(), 0);
     std::vector<size_t> touched_list;
