@@ -109,7 +109,19 @@ typedef struct {
   const void *w1, *s1, *w2, *s2;
   int64_t is, is1, is2;
   double gamma1inv, gamma1, omega0dtsqr, omega0dtsqr_denom;
+  /* optional zero-block skipping (isotropic jobs on the standard 3-D layout only).  The arrays
+   * are viewed as blocks of MB200_ZBLOCK consecutive elements; szero[b] != 0 says sigma is
+   * identically zero in block b (set by mb200_block_zero_flags when sigma is uploaded),
+   * pzero[b] != 0 says P and P_prev are.  A block with both flags set is skipped — the update
+   * would read zeros and write zeros (src/susceptibility.cpp:252-257 with s = p = pp = 0) —
+   * otherwise it is updated and pzero[b] is recomputed from the values written.  A dispersive
+   * object that fills a few percent of the cell (BASELINE config 3) then costs a few percent of
+   * the polarisation traffic the reference pays on every chunk (src/susceptibility.cpp:66-75). */
+  uint8_t *pzero;
+  const uint8_t *szero;
+  int64_t ntot;
 } mb200_lorentz_job_t;
+#define MB200_ZBLOCK 1024
 
 /* ---- f_minus_p initialisation: memcpy D -> f_minus_p (src/update_eh.cpp:114-120) followed by
  *      lorentzian_susceptibility::subtract_P for each polarisation (src/susceptibility.cpp:264-281):
@@ -122,6 +134,7 @@ typedef struct {
   int32_t np;
   int32_t reserved;
   int64_t ntot;
+  const uint8_t *pzero[MB200_MAX_P]; /* optional: pzero[k][b] != 0 => p[k] is zero in block b */
 } mb200_fmp_job_t;
 
 /* ---- fields_chunk::step_source (src/step.cpp:295-318) [mode 0] and the integrated-source dipole
@@ -153,6 +166,10 @@ typedef struct {
   const uint64_t *dst;
   const void *phase;
   int64_t n_phase, n_negate, n_copy;
+  /* optional, same length as dst: address of the zero-block flag byte (see
+   * mb200_lorentz_job_t.pzero) that covers dst[k]; cleared when a non-zero value is stored, so
+   * that polarisation values arriving from a neighbouring chunk keep the flags exact */
+  const uint64_t *dst_flag;
 } mb200_halo_job_t;
 
 /* ---- fields_chunk::zero_metal (src/boundaries.cpp:310-313): *ptrs[k] = 0. */
@@ -243,7 +260,8 @@ enum {
   MB200_K_FLUX = 8,
   MB200_K_STEP3 = 9,
   MB200_K_BETA = 10,
-  MB200_NUM_KINDS = 11
+  MB200_K_EXCHANGE = 11, /* not a plan kind: profiling slot of mb200_comm_exchange */
+  MB200_NUM_KINDS = 12
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -320,6 +338,9 @@ int mb200_comm_create(mb200_ctx *ctx, int rank, int nranks, const void *id128, m
 void mb200_comm_destroy(mb200_comm *comm);
 int mb200_comm_exchange(mb200_ctx *ctx, mb200_comm *comm, int dtype, const mb200_xfer_t *sends,
                         int nsend, const mb200_xfer_t *recvs, int nrecv);
+
+/* ---- flags[b] = 1 if arr[b*MB200_ZBLOCK .. ) is identically zero, else 0 (n elements) */
+int mb200_block_zero_flags(mb200_ctx *ctx, int dtype, const void *arr, int64_t n, uint8_t *flags);
 
 /* ---- finiteness probe (replaces the per-step host read in fields::step, src/step.cpp:137-138):
  *      sets *flag (device int32) to 1 if any of the n listed array elements is NaN/Inf. */

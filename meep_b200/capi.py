@@ -12,7 +12,8 @@ LIBDIR = os.path.join(ROOT, "meep_b200", "lib")
 
 F64, F32 = 0, 1
 (K_CURL, K_EDHB, K_LORENTZ, K_FMP, K_SOURCE, K_HALO, K_ZERO, K_DFT, K_FLUX, K_STEP3, K_BETA) = range(11)
-NUM_KINDS = 11
+K_EXCHANGE = 11
+NUM_KINDS = 12
 MAX_P = 8
 
 
@@ -44,12 +45,13 @@ class LorentzJob(C.Structure):
                 ("w1", C.c_void_p), ("s1", C.c_void_p), ("w2", C.c_void_p), ("s2", C.c_void_p),
                 ("is_", C.c_int64), ("is1", C.c_int64), ("is2", C.c_int64),
                 ("gamma1inv", C.c_double), ("gamma1", C.c_double), ("omega0dtsqr", C.c_double),
-                ("omega0dtsqr_denom", C.c_double)]
+                ("omega0dtsqr_denom", C.c_double), ("pzero", C.c_void_p), ("szero", C.c_void_p),
+                ("ntot", C.c_int64)]
 
 
 class FmpJob(C.Structure):
     _fields_ = [("fmp", C.c_void_p), ("d", C.c_void_p), ("p", C.c_void_p * MAX_P),
-                ("np", C.c_int32), ("reserved", C.c_int32), ("ntot", C.c_int64)]
+                ("np", C.c_int32), ("reserved", C.c_int32), ("ntot", C.c_int64), ("pzero", C.c_void_p * MAX_P)]
 
 
 class SrcJob(C.Structure):
@@ -60,7 +62,8 @@ class SrcJob(C.Structure):
 
 class HaloJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("phase", C.c_void_p),
-                ("n_phase", C.c_int64), ("n_negate", C.c_int64), ("n_copy", C.c_int64)]
+                ("n_phase", C.c_int64), ("n_negate", C.c_int64), ("n_copy", C.c_int64),
+                ("dst_flag", C.c_void_p)]
 
 
 class ZeroJob(C.Structure):
@@ -149,6 +152,7 @@ def declare(lib):
         "mb200_comm_create": (i, [vp, i, i, vp, P(vp)]),
         "mb200_comm_destroy": (None, [vp]),
         "mb200_comm_exchange": (i, [vp, vp, i, vp, i, vp, i]),
+        "mb200_block_zero_flags": (i, [vp, i, vp, i64, vp]),
         "mb200_check_finite": (i, [vp, i, vp, i64, vp]),
         "mb200_timer_start": (i, [vp]),
         "mb200_timer_stop": (i, [vp, P(d)]),

@@ -82,6 +82,11 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
                                             p->njobs);
       break;
     case MB200_K_LORENTZ:
+      if (p->all_plain) { // (for this kind: every job uses the zero-block variant)
+        lorentz_blocked_kernel<T><<<grid, block, 0, s>>>((const mb200_lorentz_job_t *)p->d_jobs,
+                                                         p->d_prefix, p->njobs);
+        break;
+      }
       lorentz_kernel<T><<<grid, block, 0, s>>>((const mb200_lorentz_job_t *)p->d_jobs, p->d_prefix,
                                                p->njobs);
       break;
@@ -264,6 +269,16 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
   if (kind == MB200_K_STEP3)
     for (int j = 0; j < njobs; ++j)
       if (!step3_is_plain(((const mb200_step3_job_t *)jobs)[j])) p->all_plain = false;
+  if (kind == MB200_K_LORENTZ) {
+    int nblocked = 0;
+    for (int j = 0; j < njobs; ++j)
+      if (lorentz_blocked_ok(((const mb200_lorentz_job_t *)jobs)[j])) ++nblocked;
+    if (nblocked != 0 && nblocked != njobs) {
+      delete p;
+      return fail("mb200_plan_create: a Lorentz plan must not mix zero-block jobs with plain ones");
+    }
+    p->all_plain = njobs > 0 && nblocked == njobs;
+  }
   std::vector<int64_t> prefix(njobs + 1, 0);
   for (int j = 0; j < njobs; ++j) {
     int64_t t;
@@ -390,6 +405,19 @@ int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int n
   return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
 }
 
+int mb200_block_zero_flags(mb200_ctx *c, int dtype, const void *arr, int64_t n, uint8_t *flags) {
+  if (n <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const unsigned grid = (unsigned)ceil_div(n, MB200_ZBLOCK);
+  if (dtype == MB200_F64)
+    block_zero_flags_kernel<double><<<grid, kThreads, 0, c->stream>>>((const double *)arr, n, flags);
+  else
+    block_zero_flags_kernel<float><<<grid, kThreads, 0, c->stream>>>((const float *)arr, n, flags);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
 int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag) {
   if (n <= 0) return 0;
   CUDA_TRY(cudaSetDevice(c->device));
@@ -488,6 +516,17 @@ int mb200_comm_exchange(mb200_ctx *c, mb200_comm *m, int dtype, const mb200_xfer
   if (nsend == 0 && nrecv == 0) return 0;
   CUDA_TRY(cudaSetDevice(c->device));
   const int dt = dtype == MB200_F64 ? ncclFloat64 : ncclFloat32;
+  ProfRec rec;
+  if (c->profiling) {
+    rec.kind = MB200_K_EXCHANGE;
+    rec.bytes = 0;
+    const double R = dtype == MB200_F64 ? 8.0 : 4.0;
+    for (int k = 0; k < nsend; ++k) rec.bytes += R * (double)sends[k].count;
+    for (int k = 0; k < nrecv; ++k) rec.bytes += R * (double)recvs[k].count;
+    CUDA_TRY(cudaEventCreate(&rec.a));
+    CUDA_TRY(cudaEventCreate(&rec.b));
+    CUDA_TRY(cudaEventRecord(rec.a, c->stream));
+  }
   NCCL_TRY(g_nccl.GroupStart());
   for (int k = 0; k < nrecv; ++k)
     NCCL_TRY(g_nccl.Recv(recvs[k].buf, (size_t)recvs[k].count, dt, recvs[k].peer, m->comm, c->stream));
@@ -495,6 +534,10 @@ int mb200_comm_exchange(mb200_ctx *c, mb200_comm *m, int dtype, const mb200_xfer
     NCCL_TRY(g_nccl.Send(sends[k].buf, (size_t)sends[k].count, dt, sends[k].peer, m->comm, c->stream));
   NCCL_TRY(g_nccl.GroupEnd());
   c->launches += 1;
+  if (c->profiling) {
+    CUDA_TRY(cudaEventRecord(rec.b, c->stream));
+    c->recs.push_back(rec);
+  }
   return 0;
 }
 

@@ -204,6 +204,31 @@ template <typename T> MB200_HD void beta_thread(const mb200_beta_job_t &J, int64
     beta_point<T>(J, i, k, ku);
 }
 
+// ---- zero-block variant of the isotropic Lorentz update (see mb200_lorentz_job_t) ------------------
+// usable when the job runs over the standard 3-D layout: s = {(n2+1)(n3+1)-like, row, 1}
+MB200_HD bool lorentz_blocked_ok(const mb200_lorentz_job_t &J) {
+  return J.pzero && J.szero && !J.s1 && J.ntot > 0 && J.box.s[2] == 1 && J.box.s[1] > 0 &&
+         J.box.s[0] > 0 && J.box.s[0] % J.box.s[1] == 0;
+}
+MB200_HD bool lorentz_owned(const mb200_lorentz_job_t &J, int64_t idx) {
+  const int64_t s0 = J.box.s[0], s1 = J.box.s[1];
+  const int64_t a1 = idx / s0, r = idx - a1 * s0, a2 = r / s1, a3 = r - a2 * s1;
+  const int64_t l1 = J.box.idx0 / s0, lr = J.box.idx0 - l1 * s0, l2 = lr / s1, l3 = lr - l2 * s1;
+  return a1 >= l1 && a1 < l1 + J.box.n[0] && a2 >= l2 && a2 < l2 + J.box.n[1] && a3 >= l3 &&
+         a3 < l3 + J.box.n[2];
+}
+// one element; returns true if the (new) p and pp are both zero
+template <typename T> MB200_HD bool lorentz_blocked_point(const mb200_lorentz_job_t &J, int64_t idx) {
+  T *p = (T *)J.p, *pp = (T *)J.pp;
+  if (!lorentz_owned(J, idx)) return p[idx] == T(0) && pp[idx] == T(0);
+  const T pcur = p[idx];
+  const T pn = (T)J.gamma1inv * (pcur * (2 - (T)J.omega0dtsqr_denom) - (T)J.gamma1 * pp[idx] +
+                                 (T)J.omega0dtsqr * (ldro((const T *)J.s + idx) * ldro((const T *)J.w + idx)));
+  p[idx] = pn;
+  pp[idx] = pcur;
+  return pn == T(0) && pcur == T(0);
+}
+
 #ifdef __CUDACC__
 
 // ---- job lookup: tile_prefix[j] <= tile < tile_prefix[j+1] -------------------------------------
@@ -281,6 +306,37 @@ __global__ void __launch_bounds__(kThreads)
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   beta_thread<T>(J, tile, threadIdx.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    lorentz_blocked_kernel(const mb200_lorentz_job_t *__restrict__ jobs,
+                           const int64_t *__restrict__ tile_prefix, int njobs) {
+  __shared__ mb200_lorentz_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  if (J.szero[tile] && J.pzero[tile]) return; // sigma = P = P_prev = 0 here: nothing changes
+  const int64_t base = tile * MB200_ZBLOCK + threadIdx.x;
+  bool zero = true;
+#pragma unroll
+  for (int r = 0; r < MB200_ZBLOCK / kThreads; ++r) {
+    const int64_t idx = base + (int64_t)r * kThreads;
+    if (idx < J.ntot) zero = lorentz_blocked_point<T>(J, idx) && zero;
+  }
+  const int allzero = __syncthreads_and(zero ? 1 : 0);
+  if (threadIdx.x == 0) J.pzero[tile] = allzero ? 1 : 0;
+}
+
+template <typename T>
+__global__ void block_zero_flags_kernel(const T *__restrict__ arr, int64_t n, uint8_t *flags) {
+  const int64_t base = (int64_t)blockIdx.x * MB200_ZBLOCK + threadIdx.x;
+  bool zero = true;
+  for (int r = 0; r < MB200_ZBLOCK / kThreads; ++r) {
+    const int64_t idx = base + (int64_t)r * kThreads;
+    if (idx < n && arr[idx] != T(0)) zero = false;
+  }
+  const int allzero = __syncthreads_and(zero ? 1 : 0);
+  if (threadIdx.x == 0) flags[blockIdx.x] = allzero ? 1 : 0;
 }
 
 // ---- 1-D jobs ----------------------------------------------------------------------------------

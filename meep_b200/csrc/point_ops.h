@@ -297,9 +297,10 @@ template <typename T> MB200_HD void fmp_point(const mb200_fmp_job_t &J, int64_t 
   T *fmp = (T *)J.fmp;
   T v = J.d ? ldro((const T *)J.d + i) : fmp[i];
   T pv[MB200_MAX_P];
+  const int64_t zb = i / MB200_ZBLOCK;
 #pragma unroll
   for (int k = 0; k < MB200_MAX_P; ++k) // all loads first (they are independent)
-    pv[k] = k < J.np ? ldro((const T *)J.p[k] + i) : T(0);
+    pv[k] = (k < J.np && !(J.pzero[k] && J.pzero[k][zb])) ? ldro((const T *)J.p[k] + i) : T(0);
 #pragma unroll
   for (int k = 0; k < MB200_MAX_P; ++k)
     if (k < J.np) v -= pv[k];
@@ -336,13 +337,19 @@ template <typename T> MB200_HD void halo_transfer(const mb200_halo_job_t &J, int
     T *dr = (T *)(uintptr_t)J.dst[2 * n], *di = (T *)(uintptr_t)J.dst[2 * n + 1];
     const T pr = ((const T *)J.phase)[2 * n], pi = ((const T *)J.phase)[2 * n + 1];
     const T vr = *sr, vi = *si;
-    *dr = pr * vr - pi * vi;
-    *di = pr * vi + pi * vr;
+    const T outr = pr * vr - pi * vi, outi = pr * vi + pi * vr;
+    *dr = outr;
+    *di = outi;
+    if (J.dst_flag) {
+      if (outr != T(0)) *(uint8_t *)(uintptr_t)J.dst_flag[2 * n] = 0;
+      if (outi != T(0)) *(uint8_t *)(uintptr_t)J.dst_flag[2 * n + 1] = 0;
+    }
   }
   else {
     const int64_t m = n + J.n_phase; // list position (phase entries occupy 2*n_phase slots)
     const T v = *(const T *)(uintptr_t)J.src[m];
     *(T *)(uintptr_t)J.dst[m] = (n < J.n_phase + J.n_negate) ? -v : v;
+    if (J.dst_flag && v != T(0)) *(uint8_t *)(uintptr_t)J.dst_flag[m] = 0;
   }
 }
 MB200_HD int64_t halo_count(const mb200_halo_job_t &J) {

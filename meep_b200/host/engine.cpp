@@ -87,6 +87,7 @@ Engine::Engine(fields *) {
   eager = env_int("MEEP_B200_EAGER", 0) != 0;
   verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
   merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
+  zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;
@@ -100,6 +101,10 @@ Engine::~Engine() {
     mb200_free(ctx, kv.second.dev);
   arrs_.clear();
   if (probe_flag_) mb200_free(ctx, probe_flag_);
+  for (auto &kv : pzero_)
+    mb200_free(ctx, kv.second.dev);
+  for (auto &kv : szero_)
+    mb200_free(ctx, kv.second.dev);
   if (comm) mb200_comm_destroy(comm);
   mb200_destroy(ctx);
 }
@@ -342,7 +347,78 @@ void Engine::scan(fields *f) {
   }
 }
 
+uint8_t *Engine::pzero_flags(const void *host_P, size_t ntot, bool known_zero) {
+  if (!zero_skip || !host_P) return nullptr;
+  auto it = pzero_.find((uintptr_t)host_P);
+  if (it != pzero_.end() && it->second.ntot == ntot) return it->second.dev;
+  if (it != pzero_.end()) {
+    mb200_free(ctx, it->second.dev);
+    pzero_.erase(it);
+  }
+  Flags fl;
+  fl.ntot = ntot;
+  fl.nblocks = (ntot + MB200_ZBLOCK - 1) / MB200_ZBLOCK;
+  void *d = nullptr;
+  check(mb200_malloc(ctx, fl.nblocks, &d), "malloc(pzero)");
+  check(mb200_memset(ctx, d, known_zero ? 1 : 0, fl.nblocks), "memset(pzero)");
+  fl.dev = (uint8_t *)d;
+  pzero_[(uintptr_t)host_P] = fl;
+  return fl.dev;
+}
+
+void Engine::pzero_drop(const void *host_P) {
+  auto it = pzero_.find((uintptr_t)host_P);
+  if (it == pzero_.end()) return;
+  mb200_free(ctx, it->second.dev);
+  pzero_.erase(it);
+  invalidate_plans(); // f_minus_p jobs may hold the flag pointer
+}
+
+uint8_t *Engine::pzero_lookup(const void *host_elem) const {
+  const uintptr_t a = (uintptr_t)host_elem;
+  auto it = pzero_.upper_bound(a);
+  if (it == pzero_.begin()) return nullptr;
+  --it;
+  if (a >= it->first && a < it->first + it->second.ntot * sizeof(realnum)) return it->second.dev;
+  return nullptr;
+}
+
+uint64_t Engine::pzero_flag_addr(const void *host_elem) const {
+  const uintptr_t a = (uintptr_t)host_elem;
+  auto it = pzero_.upper_bound(a);
+  if (it == pzero_.begin()) return 0;
+  --it;
+  if (a < it->first || a >= it->first + it->second.ntot * sizeof(realnum)) return 0;
+  const size_t idx = (a - it->first) / sizeof(realnum);
+  return (uint64_t)(uintptr_t)(it->second.dev + idx / MB200_ZBLOCK);
+}
+
+const uint8_t *Engine::szero_flags(const void *host_sigma, size_t ntot) {
+  if (!zero_skip || !host_sigma) return nullptr;
+  Flags &fl = szero_[(uintptr_t)host_sigma];
+  if (fl.dev && fl.ntot != ntot) {
+    mb200_free(ctx, fl.dev);
+    fl = Flags();
+  }
+  if (!fl.dev) {
+    fl.ntot = ntot;
+    fl.nblocks = (ntot + MB200_ZBLOCK - 1) / MB200_ZBLOCK;
+    void *d = nullptr;
+    check(mb200_malloc(ctx, fl.nblocks, &d), "malloc(szero)");
+    fl.dev = (uint8_t *)d;
+    fl.fresh = false;
+  }
+  if (!fl.fresh) {
+    check(mb200_block_zero_flags(ctx, dtype, dev(host_sigma), (int64_t)ntot, fl.dev), "block_zero_flags");
+    fl.fresh = true;
+  }
+  return fl.dev;
+}
+
 void Engine::upload_fields() {
+  // host values replace the device ones: nothing is known about zero blocks any more
+  for (auto &kv : pzero_)
+    check(mb200_memset(ctx, kv.second.dev, 0, kv.second.nblocks), "memset(pzero)");
   for (auto &kv : arrs_)
     if (kv.second.is_field) {
       check(mb200_h2d(ctx, kv.second.dev, (const void *)kv.first, kv.second.bytes), "h2d");
@@ -361,6 +437,8 @@ void Engine::download_fields() {
 }
 
 void Engine::upload_materials() {
+  for (auto &kv : szero_)
+    kv.second.fresh = false; // recomputed on next use
   for (auto &kv : arrs_)
     if (!kv.second.is_field) {
       check(mb200_h2d(ctx, kv.second.dev, (const void *)kv.first, kv.second.bytes), "h2d");
@@ -647,10 +725,15 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
       push(ph, MB200_K_EDHB, make_plan(*this, MB200_K_EDHB, R.edhb.data(), R.edhb.size()));
       break;
     }
-    case PH_POLS:
-      push(ph, MB200_K_LORENTZ,
-           make_plan(*this, MB200_K_LORENTZ, R.lorentz.data(), R.lorentz.size()));
+    case PH_POLS: {
+      // zero-block jobs and plain jobs use different kernels (one plan each)
+      std::vector<mb200_lorentz_job_t> blocked, plainj;
+      for (const mb200_lorentz_job_t &j : R.lorentz)
+        (j.pzero ? blocked : plainj).push_back(j);
+      push(ph, MB200_K_LORENTZ, make_plan(*this, MB200_K_LORENTZ, blocked.data(), blocked.size()));
+      push(ph, MB200_K_LORENTZ, make_plan(*this, MB200_K_LORENTZ, plainj.data(), plainj.size()));
       break;
+    }
     case PH_DFT:
       for (auto &kv : R.dft) {
         mb200_plan *p = make_plan(*this, MB200_K_DFT, kv.second.data(), kv.second.size());

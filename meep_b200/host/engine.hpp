@@ -153,6 +153,14 @@ public:
   void ensure_from(const void *host, size_t bytes, const void *src_host);
   void forget(const void *host);
   void scan(meep::fields *f);          // (re)register everything reachable from f
+  // zero-block flags (include/meep_b200.h: mb200_lorentz_job_t): one byte per MB200_ZBLOCK
+  // elements of a polarisation array pair (P, P_prev) / of a susceptibility sigma array
+  uint8_t *pzero_flags(const void *host_P, size_t ntot, bool known_zero); // create on first use
+  void pzero_drop(const void *host_P);
+  uint8_t *pzero_lookup(const void *host_elem) const; // flag array covering a P element (or NULL)
+  uint64_t pzero_flag_addr(const void *host_elem) const;
+  const uint8_t *szero_flags(const void *host_sigma, size_t ntot);
+  bool zero_skip = true; // MEEP_B200_ZERO_SKIP=0 disables
   void upload_fields();
   void download_fields();
   void upload_materials();
@@ -197,6 +205,12 @@ public:
 
 private:
   std::map<uintptr_t, Arr> arrs_; // keyed by host base address
+  struct Flags {
+    uint8_t *dev = nullptr;
+    size_t ntot = 0, nblocks = 0;
+    bool fresh = false; // szero: computed since the last material upload
+  };
+  std::map<uintptr_t, Flags> pzero_, szero_; // keyed by the host address of the array
   std::vector<void *> rec_aux_; // side tables uploaded while recording the current phase
   bool pending_invalidate_ = false;
   Phase phases_[PH_COUNT][meep::NUM_FIELD_TYPES];

@@ -330,6 +330,23 @@ void fields::step_boundaries(field_type ft) {
           }
           hj.src = (const uint64_t *)E.aux_upload(src.data(), src.size() * 8);
           hj.dst = (const uint64_t *)E.aux_upload(dst.data(), dst.size() * 8);
+          if (i_mine && (ft == PE_stuff || ft == PH_stuff) && E.zero_skip) {
+            // polarisation values arriving from a neighbour: keep the zero-block flags exact
+            const std::vector<realnum *> &in = chunks[i]->connections_in.at(key);
+            std::vector<uint64_t> fl(in.size());
+            bool any = false;
+            for (size_t k = 0; k < in.size(); ++k) {
+              fl[k] = E.pzero_flag_addr(in[k]);
+              any = any || fl[k];
+            }
+            if (any) {
+              // (elements without flags point at a scratch byte)
+              uint64_t scratch = (uint64_t)(uintptr_t)E.aux_alloc(8);
+              for (size_t k = 0; k < fl.size(); ++k)
+                if (!fl[k]) fl[k] = scratch;
+              hj.dst_flag = (const uint64_t *)E.aux_upload(fl.data(), fl.size() * 8);
+            }
+          }
           ((j_mine || i_mine) && j_mine == i_mine ? R.halo : (j_mine ? R.halo : R.unpack)).push_back(hj);
           off += n;
         }

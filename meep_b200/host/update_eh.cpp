@@ -145,7 +145,9 @@ bool fields_chunk::update_eh(field_type ft, bool skip_w_components) {
               R.fmp.push_back(J);
               J.d = nullptr;
               J.np = 0;
+              memset(J.pzero, 0, sizeof(J.pzero));
             }
+            J.pzero[J.np] = E->pzero_lookup(d->P[ec][cmp]);
             J.p[J.np++] = E->dev(d->P[ec][cmp]);
           }
         }

@@ -134,6 +134,14 @@ void lorentzian_susceptibility::update_P(realnum *W[NUM_FIELD_COMPONENTS][2],
         J.gamma1 = gamma1;
         J.omega0dtsqr = omega0dtsqr;
         J.omega0dtsqr_denom = omega0dtsqr_denom;
+        J.ntot = (int64_t)gv.ntot();
+        if (!s1 && gv.dim == D3) { // isotropic, standard 3-D layout: zero-block skipping
+          // (flags start as "unknown"; the kernel establishes them with its first update)
+          J.pzero = E->pzero_flags(p, gv.ntot(), false);
+          J.szero = J.pzero ? E->szero_flags(s, gv.ntot()) : NULL;
+          if (!J.szero) J.pzero = NULL;
+        }
+        if (!J.pzero) E->pzero_drop(p); // this array is updated by the plain kernel: no flags
         if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.lorentz.push_back(J);
       }
     }

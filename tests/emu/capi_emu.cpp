@@ -63,6 +63,16 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
       }
       case MB200_K_LORENTZ: {
         const mb200_lorentz_job_t &J = ((const mb200_lorentz_job_t *)p->jobs.data())[j];
+        if (lorentz_blocked_ok(J)) {
+          for (int64_t t = 0; t < ntiles; ++t) {
+            if (J.szero[t] && J.pzero[t]) continue;
+            bool zero = true;
+            for (int64_t idx = t * MB200_ZBLOCK; idx < (t + 1) * MB200_ZBLOCK && idx < J.ntot; ++idx)
+              zero = lorentz_blocked_point<T>(J, idx) && zero;
+            J.pzero[t] = zero ? 1 : 0;
+          }
+          break;
+        }
         for (int64_t t = 0; t < ntiles; ++t)
           for (int tid = 0; tid < kThreads; ++tid)
             lorentz_thread<T>(J, t, tid);
@@ -301,6 +311,17 @@ void mb200_comm_destroy(mb200_comm *m) { delete m; }
 int mb200_comm_exchange(mb200_ctx *, mb200_comm *, int, const mb200_xfer_t *, int, const mb200_xfer_t *,
                         int) {
   return fail("emu: mb200_comm_exchange is not available (the host engine uses its socket runtime)");
+}
+
+int mb200_block_zero_flags(mb200_ctx *c, int dtype, const void *arr, int64_t n, uint8_t *flags) {
+  for (int64_t b = 0; b * MB200_ZBLOCK < n; ++b) {
+    bool zero = true;
+    for (int64_t i = b * MB200_ZBLOCK; i < (b + 1) * MB200_ZBLOCK && i < n; ++i)
+      if ((dtype == MB200_F64 ? ((const double *)arr)[i] : (double)((const float *)arr)[i]) != 0) zero = false;
+    flags[b] = zero ? 1 : 0;
+  }
+  c->launches += 1;
+  return 0;
 }
 
 int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag) {
