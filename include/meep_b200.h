@@ -339,6 +339,20 @@ void mb200_comm_destroy(mb200_comm *comm);
 int mb200_comm_exchange(mb200_ctx *ctx, mb200_comm *comm, int dtype, const mb200_xfer_t *sends,
                         int nsend, const mb200_xfer_t *recvs, int nrecv);
 
+/* ---- peer-memory exchange (processes on one NVLink/NVSwitch node).  Instead of handing the comm
+ *      blocks to a library, the receiving process exports its block arena with CUDA IPC, the
+ *      sending process maps it, and the SAME halo kernel that gathers the outgoing values stores
+ *      them straight into the neighbour's HBM over NVLink (its dst addresses are peer
+ *      addresses).  Ordering between the two GPUs uses sequence words in the arenas:
+ *      mb200_flag_signal publishes a value (after a system-scope fence, in stream order),
+ *      mb200_flag_wait makes the stream wait until the word reaches a value (bounded spin; on
+ *      time-out an error is latched and reported by the next mb200_sync). */
+int mb200_ipc_export(mb200_ctx *ctx, void *devptr, void *handle64);
+int mb200_ipc_import(mb200_ctx *ctx, const void *handle64, void **out);
+int mb200_ipc_close(mb200_ctx *ctx, void *imported);
+int mb200_flag_signal(mb200_ctx *ctx, uint64_t *flag, uint64_t value);
+int mb200_flag_wait(mb200_ctx *ctx, const uint64_t *flag, uint64_t value);
+
 /* ---- flags[b] = 1 if arr[b*MB200_ZBLOCK .. ) is identically zero, else 0 (n elements) */
 int mb200_block_zero_flags(mb200_ctx *ctx, int dtype, const void *arr, int64_t n, uint8_t *flags);
 

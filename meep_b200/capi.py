@@ -152,6 +152,11 @@ def declare(lib):
         "mb200_comm_create": (i, [vp, i, i, vp, P(vp)]),
         "mb200_comm_destroy": (None, [vp]),
         "mb200_comm_exchange": (i, [vp, vp, i, vp, i, vp, i]),
+        "mb200_ipc_export": (i, [vp, vp, vp]),
+        "mb200_ipc_import": (i, [vp, vp, P(vp)]),
+        "mb200_ipc_close": (i, [vp, vp]),
+        "mb200_flag_signal": (i, [vp, vp, C.c_uint64]),
+        "mb200_flag_wait": (i, [vp, vp, C.c_uint64]),
         "mb200_block_zero_flags": (i, [vp, i, vp, i64, vp]),
         "mb200_check_finite": (i, [vp, i, vp, i64, vp]),
         "mb200_timer_start": (i, [vp]),

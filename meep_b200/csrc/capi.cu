@@ -50,6 +50,7 @@ struct mb200_ctx {
   double prof_ms[MB200_NUM_KINDS], prof_bytes[MB200_NUM_KINDS];
   void *run_buf;
   size_t run_cap;
+  int *d_err; // latched device-side error word (flag-wait time-out)
 };
 
 struct mb200_plan {
@@ -166,6 +167,8 @@ int mb200_init(int device, mb200_ctx **out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&c->t0));
   CUDA_TRY(cudaEventCreate(&c->t1));
+  CUDA_TRY(cudaMalloc((void **)&c->d_err, sizeof(int)));
+  CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
   *out = c;
   return 0;
 }
@@ -179,6 +182,7 @@ void mb200_destroy(mb200_ctx *c) {
     cudaEventDestroy(r.b);
   }
   if (c->run_buf) cudaFree(c->run_buf);
+  if (c->d_err) cudaFree(c->d_err);
   cudaEventDestroy(c->t0);
   cudaEventDestroy(c->t1);
   cudaStreamDestroy(c->stream);
@@ -188,6 +192,9 @@ void mb200_destroy(mb200_ctx *c) {
 int mb200_sync(mb200_ctx *c) {
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  int err = 0;
+  CUDA_TRY(cudaMemcpy(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) return fail("a device-side wait for a neighbouring GPU timed out (peer exchange)");
   return 0;
 }
 
@@ -533,6 +540,80 @@ int mb200_comm_exchange(mb200_ctx *c, mb200_comm *m, int dtype, const mb200_xfer
   for (int k = 0; k < nsend; ++k)
     NCCL_TRY(g_nccl.Send(sends[k].buf, (size_t)sends[k].count, dt, sends[k].peer, m->comm, c->stream));
   NCCL_TRY(g_nccl.GroupEnd());
+  c->launches += 1;
+  if (c->profiling) {
+    CUDA_TRY(cudaEventRecord(rec.b, c->stream));
+    c->recs.push_back(rec);
+  }
+  return 0;
+}
+
+// ---- peer-memory exchange ----------------------------------------------------------------------
+__global__ void flag_signal_kernel(volatile uint64_t *flag, uint64_t value) {
+  __threadfence_system(); // everything this stream stored before (incl. into peer HBM) is visible
+  *flag = value;
+}
+__global__ void flag_wait_kernel(const volatile uint64_t *flag, uint64_t value, int *err,
+                                 long long max_iters) {
+  // bounded spin: a lost neighbour must not hang the GPU
+  for (long long it = 0; it < max_iters; ++it) {
+    if (*flag >= value) {
+      __threadfence_system();
+      return;
+    }
+    __nanosleep(100);
+  }
+  *err = 1;
+}
+
+int mb200_ipc_export(mb200_ctx *c, void *devptr, void *handle64) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, devptr));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int mb200_ipc_import(mb200_ctx *c, const void *handle64, void **out) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int mb200_ipc_close(mb200_ctx *c, void *imported) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaIpcCloseMemHandle(imported));
+  return 0;
+}
+int mb200_flag_signal(mb200_ctx *c, uint64_t *flag, uint64_t value) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  flag_signal_kernel<<<1, 1, 0, c->stream>>>(flag, value);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+int mb200_flag_wait(mb200_ctx *c, const uint64_t *flag, uint64_t value) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  // MEEP_B200_PEER_TIMEOUT_S (default 60): how long a GPU waits for its neighbour's data
+  static long long max_iters = 0;
+  if (!max_iters) {
+    const char *e = getenv("MEEP_B200_PEER_TIMEOUT_S");
+    double secs = e ? atof(e) : 60.0;
+    if (!(secs > 0)) secs = 60.0;
+    max_iters = (long long)(secs * 5e6); // ~200 ns per probe (100 ns sleep + a system-scope load)
+  }
+  ProfRec rec;
+  if (c->profiling) {
+    rec.kind = MB200_K_EXCHANGE;
+    rec.bytes = 0;
+    CUDA_TRY(cudaEventCreate(&rec.a));
+    CUDA_TRY(cudaEventCreate(&rec.b));
+    CUDA_TRY(cudaEventRecord(rec.a, c->stream));
+  }
+  flag_wait_kernel<<<1, 1, 0, c->stream>>>(flag, value, c->d_err, max_iters);
+  CUDA_TRY(cudaGetLastError());
   c->launches += 1;
   if (c->profiling) {
     CUDA_TRY(cudaEventRecord(rec.b, c->stream));

@@ -106,6 +106,7 @@ template <typename T> MB200_HD void curl_thread(const mb200_curl_job_t &J, int64
 }
 
 constexpr int kBatch = 4; // loop-1 planes whose loads are issued together
+constexpr int kZBlocksPerCta = 16; // zero-block Lorentz kernel: blocks walked by one CTA
 
 // step_update_EDHB.  Diagonal, linear jobs (the common case when the update could not be fused
 // into the D/B pass: f_minus_p present, 1-D/2-D grids, tiled update_eh) take a batched path that
@@ -315,16 +316,21 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ mb200_lorentz_job_t J;
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
-  if (J.szero[tile] && J.pzero[tile]) return; // sigma = P = P_prev = 0 here: nothing changes
-  const int64_t base = tile * MB200_ZBLOCK + threadIdx.x;
-  bool zero = true;
+  // a CTA walks kZBlocksPerCta consecutive blocks, so that skipped blocks cost a flag test and
+  // not a CTA launch
+  const int64_t nblocks = (J.ntot + MB200_ZBLOCK - 1) / MB200_ZBLOCK;
+  for (int64_t b = tile * kZBlocksPerCta; b < (tile + 1) * kZBlocksPerCta && b < nblocks; ++b) {
+    if (J.szero[b] && J.pzero[b]) continue; // sigma = P = P_prev = 0 here: nothing changes
+    const int64_t base = b * MB200_ZBLOCK + threadIdx.x;
+    bool zero = true;
 #pragma unroll
-  for (int r = 0; r < MB200_ZBLOCK / kThreads; ++r) {
-    const int64_t idx = base + (int64_t)r * kThreads;
-    if (idx < J.ntot) zero = lorentz_blocked_point<T>(J, idx) && zero;
+    for (int r = 0; r < MB200_ZBLOCK / kThreads; ++r) {
+      const int64_t idx = base + (int64_t)r * kThreads;
+      if (idx < J.ntot) zero = lorentz_blocked_point<T>(J, idx) && zero;
+    }
+    const int allzero = __syncthreads_and(zero ? 1 : 0);
+    if (threadIdx.x == 0) J.pzero[b] = allzero ? 1 : 0;
   }
-  const int allzero = __syncthreads_and(zero ? 1 : 0);
-  if (threadIdx.x == 0) J.pzero[tile] = allzero ? 1 : 0;
 }
 
 template <typename T>

@@ -54,7 +54,8 @@ inline void job_metrics(int kind, int dtype, const void *jobs, int j, int64_t *t
     }
     case MB200_K_LORENTZ: {
       const mb200_lorentz_job_t &J = ((const mb200_lorentz_job_t *)jobs)[j];
-      *tiles = lorentz_blocked_ok(J) ? ceil_div(J.ntot, MB200_ZBLOCK) : box_tiles(J.box);
+      *tiles = lorentz_blocked_ok(J) ? ceil_div(ceil_div(J.ntot, MB200_ZBLOCK), kZBlocksPerCta)
+                                     : box_tiles(J.box);
       *points = box_points(J.box);
       int arrays = 4 + 2 + (J.s1 ? 2 : 0) + (J.s2 ? 2 : 0);
       *bytes = R * arrays * *points;

@@ -121,6 +121,7 @@ void fields::find_metals() {
 
 void fields::connect_the_chunks() {
   const double t_start = wall_time();
+  if (meep_b200::Engine *e = meep_b200::Engine::find(this)) e->connect_epoch++;
   // (see the reference's comment at src/boundaries.cpp:369-377)
   std::vector<int> B_redundant(num_chunks * 2 * 5);
   for (int i = 0; i < num_chunks; ++i)

@@ -83,11 +83,13 @@ Engine::Engine(fields *) {
   int device = env_int("MEEP_B200_DEVICE", env_int("LOCAL_RANK", 0));
   if (device >= mb200_device_count()) device = device % mb200_device_count();
   check(mb200_init(device, &ctx), "mb200_init");
+  emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   fuse = env_int("MEEP_B200_FUSE", 1) != 0;
   eager = env_int("MEEP_B200_EAGER", 0) != 0;
   verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
   merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
+  p2p = env_int("MEEP_B200_P2P", 1) != 0 && !emulated;
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;
@@ -97,6 +99,7 @@ Engine::~Engine() {
   if (current_ == this) current_ = nullptr;
   recording_ = false;
   invalidate_plans();
+  drop_links();
   for (auto &kv : arrs_)
     mb200_free(ctx, kv.second.dev);
   arrs_.clear();
@@ -182,6 +185,107 @@ void *Engine::aux_alloc(size_t bytes) {
   return d;
 }
 
+// ---- peer-memory links ----------------------------------------------------------------------------
+
+int Engine::find_link(int ft, int rank) const {
+  for (size_t k = 0; k < links.size(); ++k)
+    if (links[k].ft == ft && links[k].rank == rank) return (int)k;
+  return -1;
+}
+
+// Collective over all processes whenever any link exists anywhere (the callers guarantee this:
+// links exist on both ends or on neither).
+void Engine::drop_links() {
+  if (links.empty()) return;
+  // neighbours may still be storing into my arenas, and I into theirs: drain the device, meet the
+  // other processes, unmap, meet again, free.
+  mb200_sync(ctx);
+  comm_barrier();
+  for (P2PLink &p : links)
+    if (p.theirs) mb200_ipc_close(ctx, p.theirs);
+  comm_barrier();
+  for (P2PLink &p : links)
+    if (p.mine) mb200_free(ctx, p.mine);
+  links.clear();
+}
+
+void Engine::rebuild_links(const std::map<std::pair<int, int>, std::pair<size_t, size_t> > &counts) {
+  // boundary phases recorded against the old arenas are stale
+  for (int ft = 0; ft < NUM_FIELD_TYPES; ++ft)
+    free_phase(phases_[PH_BND][ft]);
+  // "does anybody have links" must be answered identically everywhere: links are symmetric, and
+  // every process runs this function at the same point of the schedule
+  int any_old = links.empty() ? 0 : 1;
+  comm_allreduce(&any_old, sizeof(int), 1, [](void *acc, const void *in, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+      ((int *)acc)[i] = ((int *)acc)[i] > ((const int *)in)[i] ? ((int *)acc)[i] : ((const int *)in)[i];
+  }, true);
+  if (any_old) {
+    mb200_sync(ctx);
+    comm_barrier();
+    for (P2PLink &p : links)
+      if (p.theirs) mb200_ipc_close(ctx, p.theirs);
+    comm_barrier();
+    for (P2PLink &p : links)
+      if (p.mine) mb200_free(ctx, p.mine);
+    links.clear();
+  }
+  links_epoch = connect_epoch;
+  const size_t Rsz = sizeof(meep::realnum);
+  int ok = 1;
+  std::vector<char> handles(counts.size() * 64), peer_handles(counts.size() * 64);
+  size_t k = 0;
+  for (const auto &kv : counts) {
+    P2PLink p;
+    p.ft = kv.first.first;
+    p.rank = kv.first.second;
+    p.send_count = kv.second.first;
+    p.recv_count = kv.second.second;
+    const size_t bytes = kArenaHeader + p.recv_count * Rsz;
+    if (mb200_malloc(ctx, bytes, &p.mine) != 0 || mb200_memset(ctx, p.mine, 0, bytes) != 0 ||
+        mb200_ipc_export(ctx, p.mine, &handles[64 * k]) != 0)
+      ok = 0;
+    links.push_back(p);
+    ++k;
+  }
+  if (mb200_sync(ctx) != 0) ok = 0; // the zeroed headers must be in place before anybody signals
+  // swap the handles (std::map order = (ft, peer): both ends list their common links by ft order)
+  std::vector<HostMsg> sends, recvs;
+  for (size_t i = 0; i < links.size(); ++i) {
+    sends.push_back(HostMsg{links[i].rank, &handles[64 * i], 64});
+    recvs.push_back(HostMsg{links[i].rank, &peer_handles[64 * i], 64});
+  }
+  comm_sendrecv_all(sends, recvs);
+  for (size_t i = 0; i < links.size() && ok; ++i)
+    if (mb200_ipc_import(ctx, &peer_handles[64 * i], &links[i].theirs) != 0) ok = 0;
+  comm_allreduce(&ok, sizeof(int), 1, [](void *acc, const void *in, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+      ((int *)acc)[i] = ((int *)acc)[i] < ((const int *)in)[i] ? ((int *)acc)[i] : ((const int *)in)[i];
+  }, true);
+  if (!ok) {
+    // no peer mapping between some pair of GPUs: everybody falls back to the NCCL exchange
+    if (verbose || comm_rank() == 0)
+      fprintf(stderr, "meep_b200: peer-memory exchange unavailable (%s); using NCCL send/recv\n",
+              mb200_last_error());
+    for (P2PLink &p : links)
+      if (p.theirs) mb200_ipc_close(ctx, p.theirs);
+    comm_barrier();
+    for (P2PLink &p : links)
+      if (p.mine) mb200_free(ctx, p.mine);
+    links.clear();
+    p2p = false;
+    return;
+  }
+  comm_barrier();
+  if (verbose) {
+    size_t tot = 0;
+    for (const P2PLink &p : links)
+      tot += p.recv_count * Rsz;
+    fprintf(stderr, "meep_b200[%d]: %zu peer-memory links, %.1f MB of arenas\n", comm_rank(), links.size(),
+            tot / 1e6);
+  }
+}
+
 // One communicator per Engine; the 128-byte id is made on rank 0 and broadcast over the socket
 // runtime (comm.hpp).  Collective: every rank reaches this from its first step_boundaries.
 void Engine::ensure_comm() {
@@ -194,6 +298,7 @@ void Engine::ensure_comm() {
 }
 
 void Engine::free_phase(Phase &ph) {
+  ph.links.clear();
   for (Launch &l : ph.launches)
     if (l.plan) mb200_plan_destroy(ctx, l.plan);
   ph.launches.clear();
@@ -701,6 +806,19 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
     }
     case PH_BND:
       push(ph, MB200_K_ZERO, make_plan(*this, MB200_K_ZERO, R.zero.data(), R.zero.size()));
+      if (!R.links.empty()) { // peer-memory mode: the pack jobs store straight into the neighbours' HBM
+        ph.links = R.links;
+        Launch pre, mid, post;
+        pre.kind = KIND_P2P_PRE;
+        mid.kind = KIND_P2P_MID;
+        post.kind = KIND_P2P_POST;
+        ph.launches.push_back(pre);
+        push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.halo.data(), R.halo.size()));
+        ph.launches.push_back(mid);
+        push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.unpack.data(), R.unpack.size()));
+        ph.launches.push_back(post);
+        break;
+      }
       push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.halo.data(), R.halo.size()));
       if (!R.sends.empty() || !R.recvs.empty()) {
         Launch l;
@@ -753,7 +871,9 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
                                   "update_pols", "update_dfts"};
     fprintf(stderr, "meep_b200: recorded %s:", names[id]);
     for (const Launch &l : ph.launches)
-      if (l.kind == KIND_EXCHANGE)
+      if (l.kind >= KIND_P2P_PRE)
+        fprintf(stderr, " [p2p sync %d]", l.kind - KIND_P2P_PRE);
+      else if (l.kind == KIND_EXCHANGE)
         fprintf(stderr, " [exchange: %zu sends, %zu recvs]", l.sends.size(), l.recvs.size());
       else
         fprintf(stderr, " [kind %d: %.0f points, %.3f MB]", l.kind, mb200_plan_points(l.plan),
@@ -781,6 +901,32 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
 
 void Engine::run(Phase &ph, fields *f) {
   for (Launch &l : ph.launches) {
+    if (l.kind == KIND_P2P_PRE) {
+      // what I stored into the neighbour's arena last time must have been consumed
+      for (int k : ph.links) {
+        P2PLink &p = links[k];
+        p.seq += 1;
+        if (p.send_count)
+          check(mb200_flag_wait(ctx, (const uint64_t *)((char *)p.mine + 8), p.seq - 1), "flag_wait");
+      }
+      continue;
+    }
+    if (l.kind == KIND_P2P_MID) {
+      for (int k : ph.links)
+        if (links[k].send_count)
+          check(mb200_flag_signal(ctx, (uint64_t *)links[k].theirs, links[k].seq), "flag_signal");
+      for (int k : ph.links)
+        if (links[k].recv_count)
+          check(mb200_flag_wait(ctx, (const uint64_t *)links[k].mine, links[k].seq), "flag_wait");
+      continue;
+    }
+    if (l.kind == KIND_P2P_POST) {
+      for (int k : ph.links)
+        if (links[k].recv_count)
+          check(mb200_flag_signal(ctx, (uint64_t *)((char *)links[k].theirs + 8), links[k].seq),
+                "flag_signal");
+      continue;
+    }
     if (l.kind == KIND_EXCHANGE) {
       if (emulated) {
         // emulator: "device" buffers are host memory; move them through the socket runtime

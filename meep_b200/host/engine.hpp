@@ -51,13 +51,27 @@ struct Launch {
   // EXCHANGE (kind == KIND_EXCHANGE): comm blocks sent to / received from other processes
   std::vector<mb200_xfer_t> sends, recvs;
 };
-enum { KIND_EXCHANGE = 100 };
+enum { KIND_EXCHANGE = 100, KIND_P2P_PRE = 101, KIND_P2P_MID = 102, KIND_P2P_POST = 103 };
+
+// Peer-memory exchange: one link per (field type, neighbour process).  `mine` lives in MY HBM and
+// is written by the neighbour's pack kernel over NVLink; `theirs` is the neighbour's arena for me
+// (CUDA IPC mapping).  Arena layout: 64-byte header ([0] "packed" sequence word, [8] "consumed"
+// sequence word, both written by the OTHER side), then the comm blocks of every chunk pair
+// between the two processes in the global pair order.
+struct P2PLink {
+  int ft = 0, rank = -1;
+  void *mine = nullptr, *theirs = nullptr;
+  size_t recv_count = 0, send_count = 0; // realnums
+  uint64_t seq = 0;                      // exchanges done over this link
+};
+constexpr size_t kArenaHeader = 64;
 
 struct Phase {
   bool valid = false;
   bool one_shot = false; // recorded while the array set was changing: run once, then re-record
   std::vector<Launch> launches;
   std::vector<void *> aux; // device side tables (index lists, ...) owned by this phase
+  std::vector<int> links; // peer-memory exchange: indices into Engine::links (empty: none / NCCL)
 };
 
 // job recorder used while a phase is being (re)built
@@ -74,6 +88,7 @@ struct Recorder {
   std::vector<mb200_halo_job_t> halo;   // same-process pairs + packing of outgoing comm blocks
   std::vector<mb200_halo_job_t> unpack; // scatter of received comm blocks
   std::vector<mb200_xfer_t> sends, recvs;
+  std::vector<int> links;
   std::vector<mb200_zero_job_t> zero;
   std::map<int, std::vector<mb200_dft_job_t> > dft; // by decimation factor
   std::map<int, std::vector<meep::dft_chunk *> > dft_chunks;
@@ -181,6 +196,14 @@ public:
   mb200_ctx *ctx = nullptr;
   mb200_comm *comm = nullptr; // inter-process exchange (created on first use when WORLD_SIZE > 1)
   bool emulated = false;      // the C ABI is served by the test-only emulator
+  bool p2p = true;            // MEEP_B200_P2P=0: move comm blocks with NCCL instead of peer stores
+  // peer-memory links (see P2PLink).  (Re)built collectively by the first in-step
+  // step_boundaries after the chunks were (re)connected; counts[(ft, peer)] = (send, recv).
+  std::vector<P2PLink> links;
+  int connect_epoch = 0, links_epoch = -1;
+  void rebuild_links(const std::map<std::pair<int, int>, std::pair<size_t, size_t> > &counts);
+  void drop_links(); // collective when links exist
+  int find_link(int ft, int rank) const;
   void ensure_comm();
   // plain device buffer owned by the phase being recorded
   void *aux_alloc(size_t bytes);

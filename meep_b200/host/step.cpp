@@ -8,6 +8,9 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
+#include <map>
+#include <vector>
 
 #include "engine.hpp"
 #include "loop_desc.hpp"
@@ -202,6 +205,26 @@ void fields::step_boundaries(field_type ft) {
   connect_chunks(); // re-connect if !chunk_connections_valid (host tables, reference code)
   if (!was_valid) E.invalidate_plans();
 
+  // Peer-memory links follow the chunk connections (connect.cpp bumps connect_epoch); all
+  // processes reach the first in-step exchange after a (collective) re-connection together.
+  if (E.in_step && E.p2p && count_processors() > 1 && E.links_epoch != E.connect_epoch) {
+    std::map<std::pair<int, int>, std::pair<size_t, size_t> > counts;
+    FOR_FIELD_TYPES(ft2) {
+      for (int j = 0; j < num_chunks; j++)
+        for (int i = 0; i < num_chunks; i++) {
+          const bool j_mine = chunks[j]->is_mine(), i_mine = chunks[i]->is_mine();
+          if (j_mine == i_mine) continue;
+          const size_t tot = comm_size_tot(ft2, chunk_pair{j, i});
+          if (!tot) continue;
+          std::pair<size_t, size_t> &c =
+              counts[std::make_pair((int)ft2, j_mine ? chunks[i]->n_proc() : chunks[j]->n_proc())];
+          (j_mine ? c.first : c.second) += tot;
+        }
+    }
+    E.rebuild_links(counts);
+  }
+  const bool use_links = E.in_step && E.p2p && count_processors() > 1;
+
   // Exchange merging.  The not-owned D (B) values are read by nothing before the E (H) exchange
   // unless update_eh needs neighbouring D (B) points (off-diagonal chi1inv, chi2/chi3: the g1/g2
   // reads of src/step_generic.cpp:580-581,592-593).  When no chunk of this process does, the D
@@ -267,6 +290,7 @@ void fields::step_boundaries(field_type ft) {
       for (realnum *p : v)
         out.push_back(E.dev_addr(p));
     };
+    std::map<int, size_t> link_send_off, link_recv_off;
     std::vector<field_type> fts;
     if (take_partner) fts.push_back(ft == E_stuff ? D_stuff : B_stuff);
     if (!(E.in_step && partner != ft && defer)) fts.push_back(ft);
@@ -279,7 +303,21 @@ void fields::step_boundaries(field_type ft) {
         const bool j_mine = chunks[j]->is_mine(), i_mine = chunks[i]->is_mine();
         if (!j_mine && !i_mine) continue;
         uint64_t block = 0; // device comm block for a cross-process pair
-        if (j_mine != i_mine) {
+        if (j_mine != i_mine && use_links) {
+          // the block is a slice of the arena in the RECEIVER's memory: packed straight into the
+          // neighbour's HBM / unpacked from mine
+          const int peer = j_mine ? chunks[i]->n_proc() : chunks[j]->n_proc();
+          const int lk = E.find_link((int)ft, peer);
+          if (lk < 0) meep::abort("meep_b200: no peer-memory link for a cross-process chunk pair");
+          size_t &off = (j_mine ? link_send_off : link_recv_off)[lk];
+          const P2PLink &L = E.links[lk];
+          if (off + tot > (j_mine ? L.send_count : L.recv_count))
+            meep::abort("meep_b200: peer-memory arena overflow (stale links)");
+          block = (uint64_t)(uintptr_t)((char *)(j_mine ? L.theirs : L.mine) + kArenaHeader) + off * Rsz;
+          off += tot;
+          if (std::find(R.links.begin(), R.links.end(), lk) == R.links.end()) R.links.push_back(lk);
+        }
+        else if (j_mine != i_mine) {
           block = (uint64_t)(uintptr_t)E.aux_alloc(tot * Rsz);
           mb200_xfer_t x;
           x.peer = j_mine ? chunks[i]->n_proc() : chunks[j]->n_proc();

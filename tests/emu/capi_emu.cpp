@@ -64,7 +64,8 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
       case MB200_K_LORENTZ: {
         const mb200_lorentz_job_t &J = ((const mb200_lorentz_job_t *)p->jobs.data())[j];
         if (lorentz_blocked_ok(J)) {
-          for (int64_t t = 0; t < ntiles; ++t) {
+          const int64_t nblocks = (J.ntot + MB200_ZBLOCK - 1) / MB200_ZBLOCK;
+          for (int64_t t = 0; t < nblocks; ++t) {
             if (J.szero[t] && J.pzero[t]) continue;
             bool zero = true;
             for (int64_t idx = t * MB200_ZBLOCK; idx < (t + 1) * MB200_ZBLOCK && idx < J.ntot; ++idx)
@@ -322,6 +323,17 @@ int mb200_block_zero_flags(mb200_ctx *c, int dtype, const void *arr, int64_t n, 
   }
   c->launches += 1;
   return 0;
+}
+
+int mb200_ipc_export(mb200_ctx *, void *, void *) { return fail("emu: no CUDA IPC"); }
+int mb200_ipc_import(mb200_ctx *, const void *, void **) { return fail("emu: no CUDA IPC"); }
+int mb200_ipc_close(mb200_ctx *, void *) { return fail("emu: no CUDA IPC"); }
+int mb200_flag_signal(mb200_ctx *, uint64_t *flag, uint64_t value) {
+  *flag = value;
+  return 0;
+}
+int mb200_flag_wait(mb200_ctx *, const uint64_t *flag, uint64_t value) {
+  return *flag >= value ? 0 : fail("emu: flag not reached");
 }
 
 int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag) {
