@@ -97,7 +97,38 @@ typedef struct {
   void *fu;
   const void *cndinv;
   void *fcnd;
+  /* cylindrical i*m/r terms (src/step_db.cpp:178-280) are the same eight loops with a factor that
+   * depends on the radial loop index: cyl != 0 -> factor = betadt / (r_is2 + 2 * i2), betadt
+   * holding the reference's `the_m` and r_is2 the reference's loop_is2. */
+  int32_t cyl, r_is2;
 } mb200_beta_job_t;
+
+/* ---- cylindrical helper array (src/step_db.cpp:93-116): out = running sum over r of
+ *      1/r d(r f_p)/dr, so that the unmodified step_curl produces the Z-component update.
+ *      One thread per z column, serial in r (the reference's summation order). */
+typedef struct {
+  void *out;
+  const void *fp;
+  int64_t nr, sr; /* gv.nr(), gv.nz() + 1 */
+  double ir0;
+} mb200_cylint_job_t;
+
+/* ---- r = 0 row of a cylindrical chunk with origin_r == 0 (src/step_db.cpp:285-377):
+ *      mode 0 (m == 0, Dz):         dfcnd = fp[i] * c                       (c = 4 Courant)
+ *      mode 1 (|m| == 1, Dp or Br): dfcnd = c * (fp[i] - fp[i-sd] - mult * fm[i])   (c = sd Courant)
+ *      followed by the conductivity / PML / u updates of lines 308-320 = 358-370.
+ *      f = the reference's `the_f` (f_u[cc] when fu != NULL), fu = then f[cc]. */
+typedef struct {
+  mb200_box_t box;
+  void *f, *fu;
+  const void *fp, *fm;
+  int64_t sd;
+  double c, mult, dt;
+  int32_t mode, reserved;
+  const void *cnd, *cndinv;
+  void *fcnd;
+  mb200_pml_t pml, pmlu;
+} mb200_cylr0_job_t;
 
 /* ---- lorentzian_susceptibility::update_P (src/susceptibility.cpp:188-262), one job per
  *      (component, cmp).  Constants are computed by the caller in realnum arithmetic exactly as
@@ -261,7 +292,9 @@ enum {
   MB200_K_STEP3 = 9,
   MB200_K_BETA = 10,
   MB200_K_EXCHANGE = 11, /* not a plan kind: profiling slot of mb200_comm_exchange */
-  MB200_NUM_KINDS = 12
+  MB200_K_CYLINT = 12,
+  MB200_K_CYLR0 = 13,
+  MB200_NUM_KINDS = 14
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -318,6 +351,9 @@ int mb200_update_dft(mb200_ctx *ctx, int dtype, const mb200_dft_job_t *jobs, int
 int mb200_dft_flux(mb200_ctx *ctx, int dtype, const mb200_flux_job_t *jobs, int njobs);
 int mb200_step3(mb200_ctx *ctx, int dtype, const mb200_step3_job_t *jobs, int njobs);
 int mb200_step_beta(mb200_ctx *ctx, int dtype, const mb200_beta_job_t *jobs, int njobs);
+/* cylindrical coordinates: src/step_db.cpp:93-116 and 285-377 */
+int mb200_cyl_rderiv_int(mb200_ctx *ctx, int dtype, const mb200_cylint_job_t *jobs, int njobs);
+int mb200_cyl_origin(mb200_ctx *ctx, int dtype, const mb200_cylr0_job_t *jobs, int njobs);
 
 /* ---- inter-process chunk exchange (one process per GPU).  Replaces the transport half of
  *      fields::step_boundaries — comms_manager::send_real_async / receive_real_async over

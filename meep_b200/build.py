@@ -183,7 +183,7 @@ def build_drivers(prec, arms=("ref", "b200", "emu")):
 # exercise the stepping path and need none of the absent libraries (libctl, HDF5, MPI, Harminv)
 REFERENCE_TESTS = ["known_results", "three_d", "two_dimensional", "one_dimensional", "flux", "symmetry",
                    "harmonics", "pml", "physical", "integrate", "stress_tensor", "near2far",
-                   "2D_convergence"]
+                   "2D_convergence", "cylindrical", "bragg_transmission"]
 
 
 def build_reference_tests(prec, arms=("ref", "b200", "emu"), names=None):

@@ -13,7 +13,9 @@ LIBDIR = os.path.join(ROOT, "meep_b200", "lib")
 F64, F32 = 0, 1
 (K_CURL, K_EDHB, K_LORENTZ, K_FMP, K_SOURCE, K_HALO, K_ZERO, K_DFT, K_FLUX, K_STEP3, K_BETA) = range(11)
 K_EXCHANGE = 11
-NUM_KINDS = 12
+K_CYLINT = 12
+K_CYLR0 = 13
+NUM_KINDS = 14
 MAX_P = 8
 
 
@@ -101,7 +103,20 @@ class Step3Job(C.Structure):
 
 class BetaJob(C.Structure):
     _fields_ = [("box", Box), ("f", C.c_void_p), ("g", C.c_void_p), ("betadt", C.c_double),
-                ("pml", Pml), ("pmlu", Pml), ("fu", C.c_void_p), ("cndinv", C.c_void_p), ("fcnd", C.c_void_p)]
+                ("pml", Pml), ("pmlu", Pml), ("fu", C.c_void_p), ("cndinv", C.c_void_p), ("fcnd", C.c_void_p),
+                ("cyl", C.c_int32), ("r_is2", C.c_int32)]
+
+
+class CylIntJob(C.Structure):
+    _fields_ = [("out", C.c_void_p), ("fp", C.c_void_p), ("nr", C.c_int64), ("sr", C.c_int64),
+                ("ir0", C.c_double)]
+
+
+class CylR0Job(C.Structure):
+    _fields_ = [("box", Box), ("f", C.c_void_p), ("fu", C.c_void_p), ("fp", C.c_void_p), ("fm", C.c_void_p),
+                ("sd", C.c_int64), ("c", C.c_double), ("mult", C.c_double), ("dt", C.c_double),
+                ("mode", C.c_int32), ("reserved", C.c_int32), ("cnd", C.c_void_p), ("cndinv", C.c_void_p),
+                ("fcnd", C.c_void_p), ("pml", Pml), ("pmlu", Pml)]
 
 
 class Xfer(C.Structure):
@@ -109,7 +124,8 @@ class Xfer(C.Structure):
 
 
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,
-             K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job, K_BETA: BetaJob}
+             K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job, K_BETA: BetaJob,
+             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job}
 
 
 def declare(lib):
@@ -148,6 +164,8 @@ def declare(lib):
         "mb200_dft_flux": (i, [vp, i, vp, i]),
         "mb200_step3": (i, [vp, i, vp, i]),
         "mb200_step_beta": (i, [vp, i, vp, i]),
+        "mb200_cyl_rderiv_int": (i, [vp, i, vp, i]),
+        "mb200_cyl_origin": (i, [vp, i, vp, i]),
         "mb200_comm_unique_id": (i, [vp]),
         "mb200_comm_create": (i, [vp, i, i, vp, P(vp)]),
         "mb200_comm_destroy": (None, [vp]),

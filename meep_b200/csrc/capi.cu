@@ -119,6 +119,14 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       beta_kernel<T><<<grid, block, 0, s>>>((const mb200_beta_job_t *)p->d_jobs, p->d_prefix,
                                             p->njobs);
       break;
+    case MB200_K_CYLINT:
+      cylint_kernel<T><<<grid, block, 0, s>>>((const mb200_cylint_job_t *)p->d_jobs, p->d_prefix,
+                                              p->njobs);
+      break;
+    case MB200_K_CYLR0:
+      cylr0_kernel<T><<<grid, block, 0, s>>>((const mb200_cylr0_job_t *)p->d_jobs, p->d_prefix,
+                                             p->njobs);
+      break;
     case MB200_K_STEP3:
       if (g_param_jobs) {
         launch_step3_params<T>((const mb200_step3_job_t *)p->h_jobs.data(), p->h_prefix.data(),
@@ -410,6 +418,12 @@ int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njob
 }
 int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_cyl_rderiv_int(mb200_ctx *c, int dtype, const mb200_cylint_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_CYLINT, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_cyl_origin(mb200_ctx *c, int dtype, const mb200_cylr0_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_CYLR0, dtype, jobs, njobs, nullptr, 0);
 }
 
 int mb200_block_zero_flags(mb200_ctx *c, int dtype, const void *arr, int64_t n, uint8_t *flags) {

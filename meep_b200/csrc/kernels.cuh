@@ -201,8 +201,25 @@ template <typename T> MB200_HD void beta_thread(const mb200_beta_job_t &J, int64
   int k = pml_k(J.pml, i1_0, i2, i3), ku = pml_k(J.pmlu, i1_0, i2, i3);
   const int64_t s1 = J.box.s[0];
   const int dk = J.pml.ks[0], dku = J.pmlu.ks[0];
+  const T fac = J.cyl ? (T)J.betadt / (T)(J.r_is2 + 2 * i2) : (T)J.betadt;
   for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1, k += dk, ku += dku)
-    beta_point<T>(J, i, k, ku);
+    beta_point<T>(J, i, k, ku, fac);
+}
+
+template <typename T> MB200_HD void cylr0_thread(const mb200_cylr0_job_t &J, int64_t tile, int tid) {
+  int i1_0, i1_end, i2, i3;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  int64_t i = box_index(J.box, i1_0, i2, i3);
+  int k = pml_k(J.pml, i1_0, i2, i3), ku = pml_k(J.pmlu, i1_0, i2, i3);
+  const int64_t s1 = J.box.s[0];
+  const int dk = J.pml.ks[0], dku = J.pmlu.ks[0];
+  for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1, k += dk, ku += dku)
+    cylr0_point<T>(J, i, k, ku);
+}
+
+template <typename T> MB200_HD void cylint_thread(const mb200_cylint_job_t &J, int64_t tile, int tid) {
+  const int64_t iz = tile * kThreads + tid;
+  if (iz < J.sr) cylint_column<T>(J, iz);
 }
 
 // ---- zero-block variant of the isotropic Lorentz update (see mb200_lorentz_job_t) ------------------
@@ -296,6 +313,26 @@ __global__ void __launch_bounds__(kThreads)
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   lorentz_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- cylindrical coordinates --------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    cylint_kernel(const mb200_cylint_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                  int njobs) {
+  __shared__ mb200_cylint_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  cylint_thread<T>(J, tile, threadIdx.x);
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    cylr0_kernel(const mb200_cylr0_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                 int njobs) {
+  __shared__ mb200_cylr0_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  cylr0_thread<T>(J, tile, threadIdx.x);
 }
 
 // ---- step_beta ---------------------------------------------------------------------------------

@@ -155,10 +155,12 @@ MB200_HD T curl_point_any(const JOB &J, int variant, int64_t i, int k, int ku, T
 
 // ------------------------------------------------------------------------------------------------
 // step_beta (src/step_generic.cpp:255-333): the eight specialised loops as one body
-template <typename T> MB200_HD void beta_point(const mb200_beta_job_t &J, int64_t i, int k, int ku) {
+// (fac = betadt, or the_m / r for the cylindrical i*m/r terms of src/step_db.cpp:178-280)
+template <typename T>
+MB200_HD void beta_point(const mb200_beta_job_t &J, int64_t i, int k, int ku, T fac) {
   T *f = (T *)J.f;
   const T *g = (const T *)J.g;
-  T df = (T)J.betadt * ldro(g + i);
+  T df = fac * ldro(g + i);
   if (J.cndinv) df = df * ldro((const T *)J.cndinv + i);
   if (J.pml.siginv) {
     if (J.cndinv) ((T *)J.fcnd)[i] += df;
@@ -170,6 +172,53 @@ template <typename T> MB200_HD void beta_point(const mb200_beta_job_t &J, int64_
   }
   else
     f[i] += df;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cylindrical r = 0 row (src/step_db.cpp:300-321 and 350-371): one body for both loops
+template <typename T> MB200_HD void cylr0_point(const mb200_cylr0_job_t &J, int64_t i, int k, int ku) {
+  T *the_f = (T *)J.f, *fu = (T *)J.fu, *fcnd = (T *)J.fcnd;
+  const T *fp = (const T *)J.fp, *fm = (const T *)J.fm;
+  const T fprev = the_f[i];
+  T dfcnd;
+  if (J.mode == 0)
+    dfcnd = (T)((double)ldro(fp + i) * J.c);
+  else
+    dfcnd = (T)(J.c * (double)(ldro(fp + i) - ldro(fp + i - J.sd) - (T)J.mult * ldro(fm + i)));
+  if (fcnd) {
+    const T dt2 = (T)(J.dt * 0.5);
+    const T fcnd_prev = fcnd[i];
+    fcnd[i] = ((1 - dt2 * ldro((const T *)J.cnd + i)) * fcnd[i] + dfcnd) * ldro((const T *)J.cndinv + i);
+    dfcnd = fcnd[i] - fcnd_prev;
+  }
+  const T *kap = (const T *)J.pml.kap, *sig = (const T *)J.pml.sig, *siginv = (const T *)J.pml.siginv;
+  the_f[i] = ((kap ? ldro(kap + k) - ldro(sig + k) : T(1)) * the_f[i] + dfcnd) *
+             (siginv ? ldro(siginv + k) : T(1));
+  if (fu) {
+    const T *kapu = (const T *)J.pmlu.kap, *sigu = (const T *)J.pmlu.sig,
+            *siginvu = (const T *)J.pmlu.siginv;
+    fu[i] = ldro(siginvu + ku) *
+            ((kapu ? ldro(kapu + ku) - ldro(sigu + ku) : T(1)) * fu[i] + the_f[i] - fprev);
+  }
+}
+
+// cylindrical helper array (src/step_db.cpp:104-116): one z column, serial in r
+template <typename T> MB200_HD void cylint_column(const mb200_cylint_job_t &J, int64_t iz) {
+  T *out = (T *)J.out;
+  const T *fp = (const T *)J.fp;
+  const T ir0 = (T)J.ir0;
+  const int64_t sr = J.sr;
+  T acc = 0;
+  out[iz] = 0;
+  T prev = ldro(fp + iz);
+  for (int64_t ir = 1; ir <= J.nr; ++ir) {
+    const T rinv = (T)(1.0 / ((double)((T)ir + ir0) - 0.5));
+    const int64_t idx = ir * sr + iz;
+    const T cur = ldro(fp + idx);
+    acc = acc + rinv * (cur * ((T)ir + ir0) - prev * ((T)(ir - 1) + ir0));
+    out[idx] = acc;
+    prev = cur;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

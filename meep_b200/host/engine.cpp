@@ -587,7 +587,10 @@ void Engine::leave(fields *f, bool modified) {
   // step does not rescan
   last_fingerprint = fingerprint(f);
   current_ = nullptr;
-  if (!in_step) {
+  // solve_cw (src/cw_fields.cpp:25-73) gathers / scatters the host arrays directly around every
+  // fields::step(): in that mode the host copy is the master between calls
+  // (cw_mode is set by fields::step)
+  if (!in_step || cw_mode) {
     // The caller is reference/user code running a piece of the schedule by itself (e.g.
     // synchronize_magnetic_fields, initialize_field): it works on the host arrays right
     // before and after this call, so hand them back and assume it will modify them.
@@ -786,10 +789,13 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
         else
           s3_plain.push_back(j);
       }
+      push(ph, MB200_K_CYLINT, make_plan(*this, MB200_K_CYLINT, R.cylint.data(), R.cylint.size()));
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_plain.data(), s3_plain.size()));
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_gen.data(), s3_gen.size()));
       push(ph, MB200_K_CURL, make_plan(*this, MB200_K_CURL, rest.data(), rest.size()));
       push(ph, MB200_K_BETA, make_plan(*this, MB200_K_BETA, R.beta.data(), R.beta.size()));
+      push(ph, MB200_K_CYLR0, make_plan(*this, MB200_K_CYLR0, R.cylr0.data(), R.cylr0.size()));
+      push(ph, MB200_K_ZERO, make_plan(*this, MB200_K_ZERO, R.cylzero.data(), R.cylzero.size()));
       break;
     }
     case PH_SRC: {

@@ -78,6 +78,10 @@ struct Phase {
 struct Recorder {
   std::vector<mb200_curl_job_t> curl;
   std::vector<mb200_beta_job_t> beta; // 2-D exp(i beta z) terms, run after the curl jobs
+  // cylindrical coordinates: helper arrays (before the curl jobs), r = 0 rows and zeroed rows (after)
+  std::vector<mb200_cylint_job_t> cylint;
+  std::vector<mb200_cylr0_job_t> cylr0;
+  std::vector<mb200_zero_job_t> cylzero;
   std::vector<mb200_edhb_job_t> edhb;
   std::vector<mb200_lorentz_job_t> lorentz;
   std::vector<mb200_fmp_job_t> fmp;
@@ -196,6 +200,7 @@ public:
   mb200_ctx *ctx = nullptr;
   mb200_comm *comm = nullptr; // inter-process exchange (created on first use when WORLD_SIZE > 1)
   bool emulated = false;      // the C ABI is served by the test-only emulator
+  bool cw_mode = false;       // inside solve_cw: the host arrays are the master between steps
   bool p2p = true;            // MEEP_B200_P2P=0: move comm blocks with NCCL instead of peer stores
   // peer-memory links (see P2PLink).  (Re)built collectively by the first in-step
   // step_boundaries after the chunks were (re)connected; counts[(ft, peer)] = (send, recv).

@@ -56,6 +56,9 @@ void fields::step() {
       chunks[i]->s->update_condinv();
     }
     E.in_step = true;
+    E.cw_mode = false;
+    for (int i = 0; i < num_chunks; i++)
+      if (chunks[i]->is_mine() && chunks[i]->doing_solve_cw) E.cw_mode = true;
     Scope scope(E, this);
 
     phase_material();

@@ -182,8 +182,9 @@ bool fields_chunk::step_db(field_type ft) {
   bool allocated_u = false;
   const size_t nbytes = gv.ntot() * sizeof(realnum);
 
-  if (gv.dim == Dcyl)
-    meep::abort("meep_b200: cylindrical coordinates are not supported on the device path yet");
+  // cylindrical: the helper array of src/step_db.cpp:93-116 is device scratch, one per real /
+  // imaginary part (the jobs of both parts run in the same launch)
+  void *rderiv_int[2] = {nullptr, nullptr};
   if (bfast_scaled_k[0] || bfast_scaled_k[1] || bfast_scaled_k[2])
     meep::abort("meep_b200: BFAST is not supported on the device path yet");
 
@@ -230,13 +231,42 @@ bool fields_chunk::step_db(field_type ft) {
             stride_m = -stride_m;
           }
 
+          void *g1_dev = E->dev(f_p), *g2_dev = E->dev(f_m);
+          if (gv.dim == Dcyl) switch (d_c) { // (src/step_db.cpp:86-122)
+              case meep::R:
+                g1_dev = nullptr; // im/r Fz term will be handled separately
+                break;
+              case P: break; // curl works normally for phi component
+              case Z: {
+                g2_dev = nullptr; // im/r Fr term will be handled separately
+                /* the z component needs 1/r d(r Fp)/dr: as in the reference, step_curl is given
+                   the running sum over r of that quantity instead of Fp (see its comment at
+                   src/step_db.cpp:93-103) */
+                if (!rderiv_int[cmp]) {
+                  rderiv_int[cmp] = E->aux_alloc(nbytes);
+                  mb200_cylint_job_t CJ;
+                  memset(&CJ, 0, sizeof(CJ));
+                  CJ.out = rderiv_int[cmp];
+                  CJ.fp = E->dev(f_p);
+                  CJ.nr = gv.nr();
+                  CJ.sr = gv.nz() + 1;
+                  const realnum ir0 = gv.origin_r() * gv.a + 0.5 * gv.iyee_shift(c_p).in_direction(meep::R);
+                  CJ.ir0 = ir0;
+                  R.cylint.push_back(CJ);
+                }
+                g1_dev = rderiv_int[cmp];
+                break;
+              }
+              default: meep::abort("bug - non-cylindrical field component in Dcyl");
+            }
+
           const ivec is = sub_gv.little_owned_corner0(cc), ie = sub_gv.big_corner();
           mb200_curl_job_t J;
           memset(&J, 0, sizeof(J));
           J.box = make_box(gv, is, ie);
           J.f = E->dev(the_f);
-          J.g1 = E->dev(f_p);
-          J.g2 = E->dev(f_m);
+          J.g1 = g1_dev;
+          J.g2 = g2_dev;
           J.s1 = stride_p;
           J.s2 = stride_m;
           J.dtdx = (realnum)Courant;
@@ -256,7 +286,7 @@ bool fields_chunk::step_db(field_type ft) {
           J.cnd = E->dev(s->conductivity[cc][d_c]);
           J.cndinv = E->dev(s->condinv[cc][d_c]);
           J.fcnd = E->dev(f_cond[cc][cmp]);
-          if (!J.g1) continue; // no curl term at all (cannot happen for allocated components)
+          if (!J.g1) continue; // no curl term at all (step_curl returns at once: step_generic.cpp:72-77)
           if (J.box.n[0] <= 0 || J.box.n[1] <= 0 || J.box.n[2] <= 0) continue;
           R.curl.push_back(J);
         }
@@ -296,6 +326,136 @@ bool fields_chunk::step_db(field_type ft) {
       J.cndinv = E->dev(s->condinv[cc][d_c]);
       J.fcnd = E->dev(f_cond[cc][cmp]);
       if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.beta.push_back(J);
+    }
+
+  // in cylindrical coordinates, we now have to add the i*m/r terms (src/step_db.cpp:177-280):
+  // the eight loops there are the eight loops of step_beta with a factor the_m / r
+  if (gv.dim == Dcyl && m != 0) DOCMP FOR_FT_COMPONENTS(ft, cc) {
+      const direction d_c = component_direction(cc);
+      if (f[cc][cmp] && (d_c == meep::R || d_c == Z)) {
+        const component c_g = d_c == meep::R ? plus_component[cc] : minus_component[cc];
+        const realnum *g = f[c_g][1 - cmp];
+        if (!g) meep::abort("meep_b200: cylindrical fields with m != 0 must be complex");
+        const direction dsig = cycle_direction(gv.dim, d_c, 1);
+        const direction dsigu = cycle_direction(gv.dim, d_c, 2);
+        const ivec is = gv.little_owned_corner0(cc), ie = gv.big_corner();
+        const realnum the_m =
+            2 * m * (1 - 2 * cmp) * (1 - 2 * (ft == B_stuff)) * (1 - 2 * (d_c == meep::R)) * Courant;
+        mb200_beta_job_t J;
+        memset(&J, 0, sizeof(J));
+        J.box = make_box(gv, is, ie);
+        J.f = E->dev(f[cc][cmp]);
+        J.g = E->dev(g);
+        J.betadt = the_m;
+        J.cyl = 1;
+        J.r_is2 = is.yucky_val(1);
+        if (s->sigsize[dsig] > 1) J.pml = make_pml(gv, is, dsig, NULL, NULL, E->dev(s->siginv[dsig]));
+        if (s->sigsize[dsigu] > 1)
+          J.pmlu = make_pml(gv, is, dsigu, NULL, NULL, E->dev(s->siginv[dsigu]));
+        J.fu = E->dev(f_u[cc][cmp]);
+        J.cndinv = E->dev(s->condinv[cc][d_c]);
+        J.fcnd = E->dev(f_cond[cc][cmp]);
+        if (J.pmlu.siginv && !J.fu) meep::abort("meep_b200: cylindrical m/r term: missing f_u");
+        if (J.pml.siginv && J.cndinv && !J.fcnd) meep::abort("meep_b200: cylindrical m/r term: missing f_cond");
+        if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.beta.push_back(J);
+      }
+    }
+
+  // deal with the r=0 boundary conditions for m=0 and m=1 (src/step_db.cpp:282-462)
+  if (gv.dim == Dcyl && gv.origin_r() == 0.0) DOCMP {
+      const int nz = gv.nz();
+      auto zero_z = [&](realnum *array, int row) { // ZERO_Z(array + row * (nz + 1))
+        if (!array) return;
+        std::vector<uint64_t> zp(nz + 1);
+        const uint64_t base = E->dev_addr(array + (size_t)row * (nz + 1));
+        for (int k = 0; k <= nz; ++k)
+          zp[k] = base + (uint64_t)k * sizeof(realnum);
+        mb200_zero_job_t zj;
+        zj.ptrs = (const uint64_t *)E->aux_upload(zp.data(), zp.size() * 8);
+        zj.n = (int64_t)zp.size();
+        R.cylzero.push_back(zj);
+      };
+      auto zero3 = [&](component c, int row) {
+        zero_z(f[c][cmp], row);
+        zero_z(f_cond[c][cmp], row);
+        zero_z(f_u[c][cmp], row);
+      };
+      // the common tail of the two r = 0 loops (lines 300-321 and 350-371)
+      auto origin_job = [&](component cc, direction d_c, int mode, const realnum *fp, const realnum *fm,
+                            int sd, double c, double mult) {
+        const direction dsig = cycle_direction(gv.dim, d_c, 1);
+        const direction dsigu = cycle_direction(gv.dim, d_c, 2);
+        const bool have_sig = s->sigsize[dsig] > 1, have_sigu = s->sigsize[dsigu] > 1;
+        realnum *fu = have_sigu && f_u[cc][cmp] ? f[cc][cmp] : 0;
+        realnum *the_f = fu ? f_u[cc][cmp] : f[cc][cmp];
+        ivec is = gv.little_owned_corner(cc);
+        ivec ie = gv.big_owned_corner(cc);
+        ie.set_direction(meep::R, 0);
+        mb200_cylr0_job_t J;
+        memset(&J, 0, sizeof(J));
+        J.box = make_box(gv, is, ie);
+        J.f = E->dev(the_f);
+        J.fu = E->dev(fu);
+        J.fp = E->dev(fp);
+        J.fm = fm ? E->dev(fm) : nullptr;
+        J.sd = sd;
+        J.c = c;
+        J.mult = mult;
+        J.dt = dt;
+        J.mode = mode;
+        J.fcnd = E->dev(f_cond[cc][cmp]);
+        J.cnd = E->dev(s->conductivity[cc][d_c]);
+        J.cndinv = E->dev(s->condinv[cc][d_c]);
+        if (J.fcnd && (!J.cnd || !J.cndinv)) meep::abort("meep_b200: r=0 update: f_cond without conductivity");
+        if (have_sig)
+          J.pml = make_pml(gv, is, dsig, E->dev(s->sig[dsig]), E->dev(s->kap[dsig]), E->dev(s->siginv[dsig]));
+        if (have_sigu)
+          J.pmlu = make_pml(gv, is, dsigu, E->dev(s->sig[dsigu]), E->dev(s->kap[dsigu]),
+                            E->dev(s->siginv[dsigu]));
+        if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.cylr0.push_back(J);
+      };
+      if (m == 0 && ft == D_stuff && f[Dz][cmp]) {
+        // d(Dz)/dt = (1/r) * d(r*Hp)/dr
+        origin_job(Dz, Z, 0, f[Hp][cmp], NULL, 0, Courant * 4, 0);
+        zero3(Dp, 0);
+      }
+      else if (m == 0 && ft == B_stuff && f[Br][cmp]) { zero3(Br, 0); }
+      else if (fabs(m) == 1) {
+        // D_stuff: d(Dp)/dt = d(Hr)/dz - d(Hz)/dr
+        // B_stuff: d(Br)/dt = d(Ep)/dz - i*m*Ez/r
+        component cc = ft == D_stuff ? Dp : Br;
+        if (!f[cc][cmp]) continue;
+        const realnum *f_p = f[ft == D_stuff ? Hr : Ep][cmp];
+        if (ft != D_stuff && !f[Ez][1 - cmp])
+          meep::abort("meep_b200: cylindrical fields with m != 0 must be complex");
+        const realnum *f_m = ft == D_stuff ? f[Hz][cmp] : (f[Ez][1 - cmp] + (nz + 1));
+        const int sd = ft == D_stuff ? +1 : -1;
+        const realnum f_m_mult = ft == D_stuff ? 2 : (1 - 2 * cmp) * m;
+        origin_job(cc, component_direction(cc), 1, f_p, f_m, sd, sd * Courant, f_m_mult);
+        if (ft == D_stuff) zero3(Dz, 0);
+      }
+      else if (m != 0) { // m != {0,+1,-1}
+        // (see the reference's comments at src/step_db.cpp:389-405 and 433-439)
+        int nrows = 1;
+        if (zero_fields_near_cylorigin) {
+          const double rmax = fabs(m) - int(gv.origin_r() * gv.a + 0.5);
+          nrows = 0;
+          for (int r = 0; r <= gv.nr() && r < rmax; r++)
+            nrows++;
+        }
+        for (int r = 0; r < nrows; r++) {
+          if (ft == D_stuff) {
+            zero3(Dr, r);
+            zero3(Dp, r);
+            zero3(Dz, r);
+          }
+          else {
+            zero3(Br, r);
+            zero3(Bp, r);
+            zero3(Bz, r);
+          }
+        }
+      }
     }
 
   return allocated_u;

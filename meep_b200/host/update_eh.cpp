@@ -280,6 +280,30 @@ bool fields_chunk::update_eh(field_type ft, bool skip_w_components) {
             }
           }
           if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.edhb.push_back(J);
+
+          if (gv.dim == Dcyl) { // the r = 0 row (src/update_eh.cpp:197-209)
+            const ivec is0 = gvs_eh[ft][i].little_owned_corner(ec);
+            if (is0.r() == 0) {
+              ivec ie0 = gvs_eh[ft][i].big_corner();
+              ie0.set_direction(meep::R, 0);
+              /* NULL off-diagonal terms: they must be zero at r=0 for an axisymmetric structure */
+              mb200_edhb_job_t J0;
+              memset(&J0, 0, sizeof(J0));
+              J0.box = make_box(gv, is0, ie0);
+              J0.f = E->dev(f[ec][cmp]);
+              J0.g = E->dev(dmp[dc][cmp]);
+              J0.u = E->dev(s->chi1inv[ec][d_ec]);
+              J0.s = s_ec;
+              J0.s1 = s_1;
+              J0.s2 = s_2;
+              J0.chi2 = E->dev(s->chi2[ec]);
+              J0.chi3 = E->dev(s->chi3[ec]);
+              J0.fw = E->dev(f_w[ec][cmp]);
+              if (dsigw != NO_DIRECTION)
+                J0.pmlw = make_pml(gv, is0, dsigw, E->dev(s->sig[dsigw]), E->dev(s->kap[dsigw]), NULL);
+              if (J0.box.n[0] > 0 && J0.box.n[1] > 0 && J0.box.n[2] > 0) R.edhb.push_back(J0);
+            }
+          }
         }
       }
     }

@@ -78,12 +78,15 @@ void FN(oracle_step_beta)(const mb200_beta_job_t *J) {
   REAL *f = (REAL *)J->f, *fu = (REAL *)J->fu, *fcnd = (REAL *)J->fcnd;
   const REAL *g = (const REAL *)J->g, *cndinv = (const REAL *)J->cndinv;
   const REAL *siginv = (const REAL *)J->pml.siginv, *siginvu = (const REAL *)J->pmlu.siginv;
-  const REAL betadt = (REAL)J->betadt;
+  const REAL the_m = (REAL)J->betadt;
   if (!g) return;
   for (int i1 = 0; i1 < J->box.n[0]; ++i1)
     for (int i2 = 0; i2 < J->box.n[1]; ++i2)
       for (int i3 = 0; i3 < J->box.n[2]; ++i3) {
         const int64_t i = J->box.idx0 + i1 * J->box.s[0] + i2 * J->box.s[1] + i3 * J->box.s[2];
+        /* the cylindrical i*m/r loops of reference src/step_db.cpp:203-280 are these same eight
+         * loops with rinv = the_m / (loop_is2 + 2 * loop_i2) in place of betadt */
+        const REAL betadt = J->cyl ? the_m / (J->r_is2 + 2 * i2) : the_m;
         if (siginv) {
           const int k = FN(kidx)(&J->pml, i1, i2, i3);
           if (siginvu) {
@@ -113,6 +116,58 @@ void FN(oracle_step_beta)(const mb200_beta_job_t *J) {
         }
         else if (cndinv) f[i] += betadt * g[i] * cndinv[i];
         else f[i] += betadt * g[i];
+      }
+}
+
+/* reference src/boundaries.cpp:310-313 (fields_chunk::zero_metal); also the ZERO_Z rows of
+ * src/step_db.cpp:283,322-327,372-376,406-461 */
+void FN(oracle_zero_metal)(const mb200_zero_job_t *J) {
+  for (int64_t i = 0; i < J->n; ++i)
+    *(REAL *)(uintptr_t)J->ptrs[i] = 0;
+}
+
+/* reference src/step_db.cpp:104-116: running sum over r of 1/r d(r f_p)/dr */
+void FN(oracle_cyl_rderiv_int)(const mb200_cylint_job_t *J) {
+  REAL *out = (REAL *)J->out;
+  const REAL *f_p = (const REAL *)J->fp;
+  const REAL ir0 = (REAL)J->ir0;
+  const int64_t sr = J->sr;
+  for (int64_t iz = 0; iz < sr; ++iz)
+    out[iz] = 0;
+  for (int64_t ir = 1; ir <= J->nr; ++ir) {
+    REAL rinv = 1.0 / ((ir + ir0) - 0.5);
+    for (int64_t iz = 0; iz < sr; ++iz) {
+      int64_t idx = ir * sr + iz;
+      out[idx] = out[idx - sr] + rinv * (f_p[idx] * (ir + ir0) - f_p[idx - sr] * ((ir - 1) + ir0));
+    }
+  }
+}
+
+/* reference src/step_db.cpp:285-321 (m == 0, Dz at r = 0) and 329-371 (|m| == 1, Dp / Br) */
+void FN(oracle_cyl_origin)(const mb200_cylr0_job_t *J) {
+  REAL *the_f = (REAL *)J->f, *fu = (REAL *)J->fu, *fcnd = (REAL *)J->fcnd;
+  const REAL *f_p = (const REAL *)J->fp, *f_m = (const REAL *)J->fm;
+  const REAL *cnd = (const REAL *)J->cnd, *cndinv = (const REAL *)J->cndinv;
+  const REAL *sig = (const REAL *)J->pml.sig, *kap = (const REAL *)J->pml.kap,
+             *siginv = (const REAL *)J->pml.siginv;
+  const REAL *sigu = (const REAL *)J->pmlu.sig, *kapu = (const REAL *)J->pmlu.kap,
+             *siginvu = (const REAL *)J->pmlu.siginv;
+  const REAL dt2 = J->dt * 0.5, f_m_mult = (REAL)J->mult;
+  const int64_t sd = J->sd;
+  for (int i1 = 0; i1 < J->box.n[0]; ++i1)
+    for (int i2 = 0; i2 < J->box.n[1]; ++i2)
+      for (int i3 = 0; i3 < J->box.n[2]; ++i3) {
+        const int64_t i = J->box.idx0 + i1 * J->box.s[0] + i2 * J->box.s[1] + i3 * J->box.s[2];
+        REAL fprev = the_f[i];
+        REAL dfcnd = J->mode == 0 ? f_p[i] * J->c : J->c * (f_p[i] - f_p[i - sd] - f_m_mult * f_m[i]);
+        if (fcnd) {
+          REAL fcnd_prev = fcnd[i];
+          fcnd[i] = ((1 - dt2 * cnd[i]) * fcnd[i] + dfcnd) * cndinv[i];
+          dfcnd = fcnd[i] - fcnd_prev;
+        }
+        const int k = FN(kidx)(&J->pml, i1, i2, i3), ku = FN(kidx)(&J->pmlu, i1, i2, i3);
+        the_f[i] = ((kap ? kap[k] - sig[k] : 1) * the_f[i] + dfcnd) * (siginv ? siginv[k] : 1);
+        if (fu) fu[i] = siginvu[ku] * ((kapu ? kapu[ku] - sigu[ku] : 1) * fu[i] + the_f[i] - fprev);
       }
 }
 

@@ -297,6 +297,108 @@ static void gen_dft(const std::string &dir, bool three_d, bool complex_fields, c
   fclose(g_out);
 }
 
+// ---- cylindrical step_db ---------------------------------------------------------------------------
+// The cylindrical terms (src/step_db.cpp:86-122, 177-462) are inline in fields_chunk::step_db, so
+// the golden vector is one whole fields::step_db(ft) of a one-chunk Dcyl cell with random arrays.
+// fields::step_db is private: reach it through an explicit-instantiation accessor (no header is
+// modified).  The record also holds the job parameters, derived with the reference's own tables
+// (plus_component, gv.stride, little_owned_corner0, ...) so that the replay only wires arrays.
+namespace {
+typedef void (fields::*step_db_fn)(field_type);
+template <step_db_fn F> struct step_db_access {
+  friend step_db_fn get_step_db() { return F; }
+};
+step_db_fn get_step_db();
+template struct step_db_access<&fields::step_db>;
+} // namespace
+
+static double one_eps(const vec &) { return 1.0; }
+
+static void gen_cyl(const std::string &dir, double m, field_type ft, const char *tag) {
+  grid_volume gv = volcyl(0.6, 0.5, 10); // 6 x 5 cells, origin at r = 0
+  structure s(gv, one_eps, no_pml(), identity(), 1);
+  fields f(&s, m);
+  f.require_component(Ep);
+  f.require_component(Hp);
+  fields_chunk *fc = f.chunks[0];
+  const size_t n = fc->gv.ntot();
+  open_case(dir, std::string("cyl_") + tag);
+  // random state (H aliases B without mu: fill every distinct array once)
+  std::vector<realnum *> seen;
+  FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
+    realnum *a = fc->f[c][cmp];
+    if (!a) continue;
+    bool dup = false;
+    for (realnum *q : seen) dup = dup || q == a;
+    if (dup) continue;
+    seen.push_back(a);
+    for (size_t i = 0; i < n; ++i)
+      a[i] = (realnum)(2 * urand() - 1);
+  }
+  char nm[64];
+  FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) if (fc->f[c][cmp]) {
+    snprintf(nm, sizeof nm, "in.f.%d.%d", (int)c, cmp);
+    dump_r(nm, fc->f[c][cmp], n);
+  }
+  const grid_volume &g = fc->gv;
+  const double Courant = fc->Courant, dt = fc->dt;
+  const int nz = g.nz();
+  dump_d("dims", {(double)g.nr(), (double)nz, m, Courant, dt, (double)(ft == D_stuff)});
+  int k = 0, km = 0;
+  FOR_FT_COMPONENTS(ft, cc) for (int cmp = 0; cmp < 2; ++cmp) if (fc->f[cc][cmp]) {
+    const direction d_c = component_direction(cc);
+    // the step plan (private tables of fields_chunk, src/fields.cpp:428-456) for (r, phi, z):
+    // d(F_a)/dt takes +d/d(b) of the component along c and -d/d(c) of the component along b,
+    // (a, b, c) a cyclic permutation of (R, P, Z)
+    const direction cyc[3] = {R, P, Z};
+    const int ia = d_c == R ? 0 : (d_c == P ? 1 : 2);
+    const direction d_b = cyc[(ia + 1) % 3], d_cc = cyc[(ia + 2) % 3];
+    const component base = ft == D_stuff ? Hr : Er;
+    const component c_p = direction_component(base, d_cc), c_m = direction_component(base, d_b);
+    const bool have_p = fc->f[c_p][0] != NULL, have_m = fc->f[c_m][0] != NULL;
+    const direction dd_p = d_b, dd_m = d_cc;
+    ptrdiff_t stride_p = have_p ? g.stride(dd_p) : 0;
+    ptrdiff_t stride_m = have_m ? g.stride(dd_m) : 0;
+    if (ft == D_stuff) { stride_p = -stride_p; stride_m = -stride_m; }
+    int gp = have_p ? (int)c_p : -1, gm = have_m ? (int)c_m : -1, rderiv = 0;
+    double ir0 = 0;
+    if (d_c == R) gp = -1;
+    if (d_c == Z) {
+      gm = -1;
+      rderiv = 1;
+      ir0 = (realnum)(g.origin_r() * g.a + 0.5 * g.iyee_shift(c_p).in_direction(R));
+    }
+    const ivec is = g.little_owned_corner0(cc), ie = g.big_corner();
+    const mb200_box_t b = make_box(g, is, ie);
+    snprintf(nm, sizeof nm, "job.curl.%d", k++);
+    dump_d(nm, {(double)cc, (double)cmp, (double)gp, (double)gm, (double)stride_p, (double)stride_m,
+                (double)rderiv, ir0, (double)b.idx0, (double)b.s[0], (double)b.s[1], (double)b.s[2],
+                (double)b.n[0], (double)b.n[1], (double)b.n[2]});
+    if (m != 0 && (d_c == R || d_c == Z)) {
+      const component c_g = d_c == R ? c_p : c_m;
+      const realnum the_m =
+          2 * m * (1 - 2 * cmp) * (1 - 2 * (ft == B_stuff)) * (1 - 2 * (d_c == R)) * Courant;
+      snprintf(nm, sizeof nm, "job.mr.%d", km++);
+      dump_d(nm, {(double)cc, (double)cmp, (double)c_g, (double)the_m, (double)is.yucky_val(1),
+                  (double)b.idx0, (double)b.s[0], (double)b.s[1], (double)b.s[2], (double)b.n[0],
+                  (double)b.n[1], (double)b.n[2]});
+    }
+  }
+  // the r = 0 row boxes (src/step_db.cpp:297-299, 347-349)
+  FOR_FT_COMPONENTS(ft, cc) {
+    ivec is = g.little_owned_corner(cc), ie = g.big_owned_corner(cc);
+    ie.set_direction(R, 0);
+    snprintf(nm, sizeof nm, "box.r0.%d", (int)cc);
+    dump_box(nm, make_box(g, is, ie));
+  }
+  (f.*get_step_db())(ft); // THE REFERENCE CALL
+  FOR_FT_COMPONENTS(ft, cc) for (int cmp = 0; cmp < 2; ++cmp) if (fc->f[cc][cmp]) {
+    snprintf(nm, sizeof nm, "out.f.%d.%d", (int)cc, cmp);
+    dump_r(nm, fc->f[cc][cmp], n);
+  }
+  fclose(g_out);
+}
+
 int main(int argc, char **argv) {
   initialize mpi(argc, argv);
   verbosity = 0;
@@ -312,5 +414,11 @@ int main(int argc, char **argv) {
   gen_lorentz(dir, g3, "3d");
   gen_dft(dir, true, false, "3d_real");
   gen_dft(dir, false, true, "2d_complex");
+  gen_cyl(dir, 0, D_stuff, "m0_D");
+  gen_cyl(dir, 0, B_stuff, "m0_B");
+  gen_cyl(dir, 1, D_stuff, "m1_D");
+  gen_cyl(dir, -1, B_stuff, "mneg1_B");
+  gen_cyl(dir, 2, D_stuff, "m2_D");
+  gen_cyl(dir, 3, B_stuff, "m3_B");
   return 0;
 }

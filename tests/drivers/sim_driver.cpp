@@ -274,6 +274,51 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
+  else if (cs.rfind("cyl_", 0) == 0) {
+    // cylindrical coordinates (src/step_db.cpp:86-122,177-462; src/update_eh.cpp:197-209):
+    // cyl_m0 / cyl_m1 / cyl_mneg1 / cyl_m2 (fields zeroed near r=0) / cyl_m3_nozero (r=0 boundary
+    // condition only, smaller Courant factor) / cyl_m1_cond (conductivity + PML => f_cond) /
+    // cyl_m1_flux (DFT flux through an r = const surface and a z = const disc)
+    g_L = 2.0;
+    const double rsize = 2.0, zsize = 2.6;
+    grid_volume gv = volcyl(rsize, zsize, a);
+    struct rod : public material_function { // eps = 9 rod of radius 0.7 between z = 0.8 and 1.8
+      virtual double chi1p1(field_type, const vec &r) {
+        return (r.r() < 0.7 && r.z() > 0.8 && r.z() < 1.8) ? 9.0 : 1.0;
+      }
+      virtual double conductivity(component, const vec &r) { return cond && r.z() > 1.3 ? 0.6 : 0.0; }
+      virtual bool has_conductivity(component c) { return cond && is_D(c); }
+      virtual bool has_mu() { return false; }
+      bool cond = false;
+    } mat;
+    double m = 0;
+    bool zero_near = true;
+    double courant = 0.5;
+    if (cs == "cyl_m0") m = 0;
+    else if (cs == "cyl_m1" || cs == "cyl_m1_cond" || cs == "cyl_m1_flux") m = 1;
+    else if (cs == "cyl_mneg1") m = -1;
+    else if (cs == "cyl_m2") m = 2;
+    else if (cs == "cyl_m3_nozero") { m = 3; zero_near = false; courant = 0.25; }
+    else { fprintf(stderr, "unknown case %s\n", cs.c_str()); return 2; }
+    mat.cond = (cs == "cyl_m1_cond");
+    structure s(gv, mat, pml(0.5), identity(), num_chunks, courant);
+    fields f(&s, m, 0.0, zero_near);
+    gaussian_src_time src(0.35, 0.3);
+    f.add_point_source(Ep, src, veccyl(0.45, 1.2));
+    f.add_point_source(Ez, src, veccyl(0.85, 0.9));
+    f.add_point_source(Hr, src, veccyl(0.3, 1.5));
+    std::vector<dft_flux> fluxes;
+    if (cs == "cyl_m1_flux") {
+      volume side(veccyl(1.2, 0.7), veccyl(1.2, 1.9));
+      volume top(veccyl(0.0, 1.9), veccyl(1.2, 1.9));
+      fluxes.push_back(f.add_dft_flux_plane(side, 0.2, 0.5, 7));
+      fluxes.push_back(f.add_dft_flux_plane(top, 0.2, 0.5, 7));
+    }
+    for (int i = 0; i < nsteps; ++i) f.step();
+    for (size_t k = 0; k < fluxes.size(); ++k)
+      dump_flux(k == 0 ? "flux.side" : "flux.top", fluxes[k]);
+    dump_fields(f);
+  }
   else if (cs == "2d_bend_flux") {
     // BASELINE config 1 restated (tests/bend-flux-ll.cpp:47-61,137-187): 2-D Ez
     // waveguide bend, eps = 12, PML, two DFT flux planes; scaled to 8 x 16 for test time

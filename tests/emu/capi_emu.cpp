@@ -86,6 +86,20 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
             beta_thread<T>(J, t, tid);
         break;
       }
+      case MB200_K_CYLINT: {
+        const mb200_cylint_job_t &J = ((const mb200_cylint_job_t *)p->jobs.data())[j];
+        for (int64_t t = 0; t < ntiles; ++t)
+          for (int tid = 0; tid < kThreads; ++tid)
+            cylint_thread<T>(J, t, tid);
+        break;
+      }
+      case MB200_K_CYLR0: {
+        const mb200_cylr0_job_t &J = ((const mb200_cylr0_job_t *)p->jobs.data())[j];
+        for (int64_t t = 0; t < ntiles; ++t)
+          for (int tid = 0; tid < kThreads; ++tid)
+            cylr0_thread<T>(J, t, tid);
+        break;
+      }
       case MB200_K_STEP3: {
         const mb200_step3_job_t &J = ((const mb200_step3_job_t *)p->jobs.data())[j];
         const bool plain = step3_is_plain(J);
@@ -293,6 +307,12 @@ int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njob
 }
 int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_cyl_rderiv_int(mb200_ctx *c, int dtype, const mb200_cylint_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_CYLINT, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_cyl_origin(mb200_ctx *c, int dtype, const mb200_cylr0_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_CYLR0, dtype, jobs, njobs, nullptr, 0);
 }
 
 // the emulator has no device interconnect: the host engine moves "device" comm blocks (plain

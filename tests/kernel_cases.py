@@ -42,7 +42,8 @@ class HostMem:
                  capi.K_LORENTZ: "oracle_lorentzian_update_P", capi.K_FMP: "oracle_subtract_P",
                  capi.K_SOURCE: "oracle_step_source", capi.K_HALO: "oracle_step_boundaries",
                  capi.K_DFT: "oracle_update_dft", capi.K_FLUX: "oracle_dft_flux",
-                 capi.K_BETA: "oracle_step_beta"}
+                 capi.K_BETA: "oracle_step_beta", capi.K_CYLINT: "oracle_cyl_rderiv_int",
+                 capi.K_CYLR0: "oracle_cyl_origin", capi.K_ZERO: "oracle_zero_metal"}
         fn = getattr(self.lib, names[kind] + "_" + self.prec)
         fn.restype = None
         for j in jobs:
@@ -203,7 +204,106 @@ def replay_dft(rec, mem):
     return {"k%d.dft" % k: mem.get(ptrs[k], rec["k%d.in.dft" % k]) for k in range(n)}
 
 
-REPLAY = {"beta": replay_beta, "curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
+# component numbers of src/meep/vec.hpp:31-52
+(Er, Ep, Ez, Hr, Hp, Hz, Dr, Dp, Dz, Br, Bp, Bz) = (2, 3, 4, 7, 8, 9, 12, 13, 14, 17, 18, 19)
+
+
+def replay_cyl(rec, mem):
+    """one whole cylindrical fields::step_db(ft) (src/step_db.cpp:40-462, no PML / conductivity) out of
+    C-ABI jobs: helper-array scan, curl jobs, i*m/r jobs, the r = 0 row, zeroed rows"""
+    nr, nz, m, courant, dt, is_d = rec["dims"]
+    nr, nz, is_d = int(nr), int(nz), bool(is_d)
+    real = REAL[mem.prec]
+    like, P = {}, {}
+    for k, v in rec.items():
+        if k.startswith("in.f."):
+            c, cmp = (int(x) for x in k.split(".")[2:])
+            like[(c, cmp)] = v
+            P[(c, cmp)] = mem.put(v)
+    n = len(next(iter(like.values())))
+    # 1. helper arrays + curl jobs
+    ints, curls = [], []
+    k = 0
+    while "job.curl.%d" % k in rec:
+        v = rec["job.curl.%d" % k]
+        k += 1
+        cc, cmp, gp, gm, sp, sm, rderiv = (int(x) for x in v[:7])
+        g1 = P[(gp, cmp)] if gp >= 0 else None
+        g2 = P[(gm, cmp)] if gm >= 0 else None
+        if rderiv:
+            ij = capi.CylIntJob()
+            ij.out, ij.fp, ij.nr, ij.sr, ij.ir0 = mem.put(np.zeros(n, real)), g1, nr, nz + 1, v[7]
+            ints.append(ij)
+            g1 = ij.out
+        j = capi.CurlJob()
+        j.box = mk_box(v[8:15])
+        j.f, j.g1, j.g2, j.s1, j.s2 = P[(cc, cmp)], g1, g2, sp, sm
+        j.dtdx, j.dt = float(real(courant)), float(real(dt))
+        if not j.g1:
+            j.g1, j.g2, j.s1, j.s2, j.dtdx = j.g2, j.g1, j.s2, j.s1, -j.dtdx
+        if j.g1:
+            curls.append(j)
+    if ints:
+        mem.run(capi.K_CYLINT, ints)
+    mem.run(capi.K_CURL, curls)
+    # 2. i*m/r terms
+    mrs = []
+    k = 0
+    while "job.mr.%d" % k in rec:
+        v = rec["job.mr.%d" % k]
+        k += 1
+        cc, cmp, cg = (int(x) for x in v[:3])
+        j = capi.BetaJob()
+        j.box = mk_box(v[5:12])
+        j.f, j.g, j.betadt, j.cyl, j.r_is2 = P[(cc, cmp)], P[(cg, 1 - cmp)], v[3], 1, int(v[4])
+        mrs.append(j)
+    if mrs:
+        mem.run(capi.K_BETA, mrs)
+    # 3. r = 0 boundary conditions (src/step_db.cpp:282-462)
+    r0, zero_rows = [], []  # zero_rows: (component, cmp, row)
+    R = np.dtype(real).itemsize
+    for cmp in (0, 1):
+        def origin(cc, mode, fp, fm, fm_off, sd, c, mult):
+            j = capi.CylR0Job()
+            j.box = mk_box(rec["box.r0.%d" % cc])
+            j.f, j.fp, j.sd, j.c, j.mult, j.dt, j.mode = P[(cc, cmp)], fp, sd, c, mult, dt, mode
+            j.fm = (fm + fm_off * R) if fm else None
+            r0.append(j)
+        if m == 0 and is_d:
+            origin(Dz, 0, P[(Hp, cmp)], None, 0, 0, courant * 4, 0)
+            zero_rows.append((Dp, cmp, 0))
+        elif m == 0:
+            zero_rows.append((Br, cmp, 0))
+        elif abs(m) == 1:
+            if is_d:
+                origin(Dp, 1, P[(Hr, cmp)], P[(Hz, cmp)], 0, +1, courant, 2)
+                zero_rows.append((Dz, cmp, 0))
+            else:
+                origin(Br, 1, P[(Ep, cmp)], P[(Ez, 1 - cmp)], nz + 1, -1, -courant, (1 - 2 * cmp) * m)
+        else:
+            rows = [r for r in range(nr + 1) if r < abs(m)]  # zero_fields_near_cylorigin, origin_r = 0
+            for r in rows:
+                for c in ((Dr, Dp, Dz) if is_d else (Br, Bp, Bz)):
+                    zero_rows.append((c, cmp, r))
+    if r0:
+        mem.run(capi.K_CYLR0, r0)
+    zj = []
+    for c, cmp, row in zero_rows:
+        ptrs = np.array([P[(c, cmp)] + (row * (nz + 1) + k) * R for k in range(nz + 1)], np.uint64)
+        j = capi.ZeroJob()
+        j.ptrs, j.n = mem.put(ptrs), len(ptrs)
+        zj.append(j)
+    if zj:
+        mem.run(capi.K_ZERO, zj)
+    out = {}
+    for key in rec:
+        if key.startswith("out.f."):
+            c, cmp = (int(x) for x in key.split(".")[2:])
+            out["f.%d.%d" % (c, cmp)] = mem.get(P[(c, cmp)], like[(c, cmp)])
+    return out
+
+
+REPLAY = {"cyl": replay_cyl, "beta": replay_beta, "curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
 
 
 def check_golden(prefix, prec, mem_factory):

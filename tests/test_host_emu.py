@@ -30,6 +30,12 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_beta_real", 60, 2),
     ("2d_mirror_sym", 60, 0),
     ("3d_rotate_sym", 40, 2),
+    ("cyl_m0", 60, 0),
+    ("cyl_m1", 60, 2),
+    ("cyl_m2", 60, 0),
+    ("cyl_m3_nozero", 60, 0),
+    ("cyl_m1_cond", 60, 3),
+    ("cyl_m1_flux", 80, 0),
 ]
 
 
@@ -65,7 +71,7 @@ def test_eager_mirror_mode():
 
 
 @pytest.mark.parametrize("name", ["known_results", "three_d", "one_dimensional", "physical", "integrate",
-                                  "stress_tensor"])
+                                  "stress_tensor", "cylindrical", "symmetry", "bragg_transmission"])
 def test_reference_test_program_passes_through_the_dropin(name):
     """the reference's own C++ test programs, compiled from /root/reference/tests unmodified and
     linked with the (emulated) drop-in in front of libmeep"""
@@ -86,6 +92,7 @@ MP_CASES = [  # (case, steps, num_chunks, world_size)
     ("lorentz_3d", 15, 4, 2),
     ("2d_bend_flux", 100, 4, 3),
     ("c4_aniso_ring", 12, 2, 2),
+    ("cyl_m1", 40, 4, 2),
 ]
 
 

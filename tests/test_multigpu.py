@@ -1,6 +1,7 @@
 """N > 1 on real GPUs: the cell sharded over 2 processes / 2 B200s (one process per GPU, launched
-with torchrun-style environment), comm blocks moved device-to-device with NCCL, compared array by
-array with the single-process reference run."""
+with torchrun-style environment), comm blocks packed straight into the neighbour GPU's HBM over
+NVLink (CUDA IPC peer memory; MEEP_B200_P2P=0: NCCL send/recv), compared array by array with the
+single-process reference run."""
 import pytest
 
 from meep_b200 import capi
@@ -17,11 +18,16 @@ def _ngpu():
 
 
 @pytest.mark.parametrize("case,steps,chunks,world", [("c2_3d_pml", 40, 2, 2), ("3d_bloch", 40, 4, 2),
-                                                     ("lorentz_3d", 30, 2, 2), ("c4_aniso_ring", 20, 4, 2)])
-def test_two_gpu_sharded_run_matches_reference(case, steps, chunks, world):
+                                                     ("lorentz_3d", 30, 2, 2), ("c4_aniso_ring", 20, 4, 2),
+                                                     ("cyl_m1", 60, 4, 2)])
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_two_gpu_sharded_run_matches_reference(case, steps, chunks, world, transport):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
+    if transport == "nccl" and case not in ("c2_3d_pml", "3d_bloch"):
+        pytest.skip("NCCL fallback: two cases are enough")
     ref = run_case("ref", "f64", case, steps, chunks)
-    got = run_case_mp("b200", "f64", case, steps, chunks, world)
+    got = run_case_mp("b200", "f64", case, steps, chunks, world,
+                      env={"MEEP_B200_P2P": "1" if transport == "peer" else "0"})
     rep = compare(got, ref, TOL["f64"])
     print(case, "worst group rel-L2 %.2e" % max(rep.values()))

@@ -37,6 +37,13 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_beta_real", 100, 3),
     ("2d_mirror_sym", 100, 2),
     ("3d_rotate_sym", 60, 0),
+    ("cyl_m0", 150, 0),
+    ("cyl_m1", 150, 3),
+    ("cyl_mneg1", 100, 0),
+    ("cyl_m2", 150, 2),
+    ("cyl_m3_nozero", 150, 0),
+    ("cyl_m1_cond", 150, 0),
+    ("cyl_m1_flux", 200, 2),
 ]
 
 
@@ -51,7 +58,8 @@ def test_b200_matches_reference_f64(case, steps, chunks):
 
 @pytest.mark.parametrize("case,steps,chunks", [("c2_3d_pml", 200, 0), ("lorentz_3d", 60, 0),
                                                ("2d_bend_flux", 300, 0), ("3d_bloch", 60, 0),
-                                               ("c4_aniso_ring", 40, 0), ("dft_fields_3d", 40, 0)])
+                                               ("c4_aniso_ring", 40, 0), ("dft_fields_3d", 40, 0),
+                                               ("cyl_m1_flux", 100, 0)])
 def test_b200_matches_reference_f32(case, steps, chunks):
     ref = run_case("ref", "f32", case, steps, chunks)
     got = run_case("b200", "f32", case, steps, chunks)
@@ -74,7 +82,8 @@ def test_chunk_count_invariance_on_device():
 
 
 REFTESTS = ["known_results", "three_d", "two_dimensional", "one_dimensional", "physical", "integrate",
-            "stress_tensor", "harmonics", "2D_convergence"]
+            "stress_tensor", "harmonics", "2D_convergence", "cylindrical", "flux", "symmetry", "near2far",
+            "bragg_transmission"]
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
