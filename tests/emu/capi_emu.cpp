@@ -13,6 +13,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+#include <map>
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <vector>
 
 #include "../../meep_b200/csrc/plan_metrics.h"
@@ -182,14 +187,33 @@ int mb200_init(int device, mb200_ctx **out) {
 void mb200_destroy(mb200_ctx *c) { delete c; }
 int mb200_sync(mb200_ctx *) { return 0; }
 
+// "Device" memory is page-granular host memory so that an allocation can later be turned into a
+// shared mapping in place (the stand-in for CUDA IPC, see mb200_ipc_export below).
+struct EmuAlloc {
+  size_t size;
+  int fd; // memfd once exported, else -1
+};
+static std::map<void *, EmuAlloc> g_allocs;
+static std::map<void *, size_t> g_imports;
+
 int mb200_malloc(mb200_ctx *c, size_t bytes, void **out) {
-  *out = malloc(bytes ? bytes : 8);
-  if (!*out) return fail("emu: out of memory");
-  memset(*out, 0xA5, bytes ? bytes : 8); // poison: device memory is uninitialised
+  const size_t sz = ((bytes ? bytes : 8) + 4095) & ~(size_t)4095;
+  if (posix_memalign(out, 4096, sz) != 0 || !*out) return fail("emu: out of memory");
+  memset(*out, 0xA5, sz); // poison: device memory is uninitialised
+  g_allocs[*out] = EmuAlloc{sz, -1};
   c->bytes_allocated += bytes;
   return 0;
 }
 int mb200_free(mb200_ctx *, void *p) {
+  auto it = g_allocs.find(p);
+  if (it != g_allocs.end()) {
+    if (it->second.fd >= 0) {
+      // give the pages back to private anonymous memory before the allocator reuses them
+      mmap(p, it->second.size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED, -1, 0);
+      close(it->second.fd);
+    }
+    g_allocs.erase(it);
+  }
   free(p);
   return 0;
 }
@@ -345,15 +369,65 @@ int mb200_block_zero_flags(mb200_ctx *c, int dtype, const void *arr, int64_t n, 
   return 0;
 }
 
-int mb200_ipc_export(mb200_ctx *, void *, void *) { return fail("emu: no CUDA IPC"); }
-int mb200_ipc_import(mb200_ctx *, const void *, void **) { return fail("emu: no CUDA IPC"); }
-int mb200_ipc_close(mb200_ctx *, void *) { return fail("emu: no CUDA IPC"); }
+// Stand-in for CUDA IPC between emulated devices (= processes): the allocation is re-mapped in
+// place as a shared memfd mapping; the handle names it as /proc/<pid>/fd/<fd>.
+struct EmuHandle {
+  int32_t pid, fd;
+  uint64_t size;
+};
+int mb200_ipc_export(mb200_ctx *, void *devptr, void *handle64) {
+  auto it = g_allocs.find(devptr);
+  if (it == g_allocs.end()) return fail("emu: ipc_export of an unknown allocation");
+  EmuAlloc &a = it->second;
+  if (a.fd < 0) {
+    int fd = memfd_create("mb200_emu_arena", 0);
+    if (fd < 0 || ftruncate(fd, (off_t)a.size) != 0) return fail("emu: memfd_create failed");
+    if (pwrite(fd, devptr, a.size, 0) != (ssize_t)a.size) return fail("emu: pwrite failed");
+    if (mmap(devptr, a.size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0) != devptr)
+      return fail("emu: could not re-map the allocation as shared memory");
+    a.fd = fd;
+  }
+  EmuHandle h = {(int32_t)getpid(), (int32_t)a.fd, (uint64_t)a.size};
+  memset(handle64, 0, 64);
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+int mb200_ipc_import(mb200_ctx *, const void *handle64, void **out) {
+  EmuHandle h;
+  memcpy(&h, handle64, sizeof(h));
+  char path[64];
+  snprintf(path, sizeof path, "/proc/%d/fd/%d", (int)h.pid, (int)h.fd);
+  int fd = open(path, O_RDWR);
+  if (fd < 0) return fail("emu: cannot open the peer's arena");
+  void *p = mmap(nullptr, h.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return fail("emu: cannot map the peer's arena");
+  g_imports[p] = h.size;
+  *out = p;
+  return 0;
+}
+int mb200_ipc_close(mb200_ctx *, void *imported) {
+  auto it = g_imports.find(imported);
+  if (it == g_imports.end()) return fail("emu: ipc_close of an unknown mapping");
+  munmap(imported, it->second);
+  g_imports.erase(it);
+  return 0;
+}
 int mb200_flag_signal(mb200_ctx *, uint64_t *flag, uint64_t value) {
-  *flag = value;
+  __atomic_store_n(flag, value, __ATOMIC_RELEASE);
   return 0;
 }
 int mb200_flag_wait(mb200_ctx *, const uint64_t *flag, uint64_t value) {
-  return *flag >= value ? 0 : fail("emu: flag not reached");
+  // the emulated stream is the calling thread: wait here (bounded, like the device-side spin)
+  const char *e = getenv("MEEP_B200_PEER_TIMEOUT_S");
+  const double limit = e && atof(e) > 0 ? atof(e) : 60.0;
+  const auto t0 = std::chrono::steady_clock::now();
+  while (__atomic_load_n(flag, __ATOMIC_ACQUIRE) < value) {
+    sched_yield();
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > limit)
+      return fail("emu: a wait for a neighbouring device timed out (peer exchange)");
+  }
+  return 0;
 }
 
 int mb200_check_finite(mb200_ctx *c, int dtype, const uint64_t *ptrs, int64_t n, int32_t *flag) {

@@ -93,6 +93,8 @@ MP_CASES = [  # (case, steps, num_chunks, world_size)
     ("2d_bend_flux", 100, 4, 3),
     ("c4_aniso_ring", 12, 2, 2),
     ("cyl_m1", 40, 4, 2),
+    ("c2_3d_pml", 20, 8, 4),
+    ("3d_xperiodic_ypml", 20, 6, 3),
 ]
 
 
@@ -100,9 +102,19 @@ MP_CASES = [  # (case, steps, num_chunks, world_size)
 def test_sharded_multi_process_run_matches_single_process_reference(case, steps, chunks, world):
     """chunks distributed over `world` processes by the reference's own split_by_cost /
     is_mine() logic; rank, size and the small host reductions come from the MPI-free runtime
-    (meep_b200/host/mympi_b200.cpp, TCP on 127.0.0.1), comm blocks are packed/unpacked by halo
-    jobs and moved between the processes; every array of every rank must match the
-    single-process reference run."""
+    (meep_b200/host/mympi_b200.cpp, TCP on 127.0.0.1), comm blocks are packed by halo jobs straight
+    into the neighbour's arena (peer-memory protocol of DESIGN §5; the emulator maps the arenas as
+    shared memory where the CUDA build uses CUDA IPC) and unpacked after the sequence-word
+    handshake; every array of every rank must match the single-process reference run."""
     ref = run_case("ref", "f64", case, steps, chunks)
     got = run_case_mp("emu", "f64", case, steps, chunks, world)
+    compare(got, ref, TOL["f64"])
+
+
+@pytest.mark.parametrize("case,steps,chunks,world", [("c2_3d_pml", 20, 4, 4), ("2d_bend_flux", 60, 5, 3)])
+def test_sharded_run_with_the_fallback_transport(case, steps, chunks, world):
+    """MEEP_B200_P2P=0: comm blocks travel as separate transfers (NCCL on GPUs, the socket runtime
+    under the emulator) between a pack and an unpack launch"""
+    ref = run_case("ref", "f64", case, steps, chunks)
+    got = run_case_mp("emu", "f64", case, steps, chunks, world, env={"MEEP_B200_P2P": "0"})
     compare(got, ref, TOL["f64"])
