@@ -294,7 +294,9 @@ enum {
   MB200_K_EXCHANGE = 11, /* not a plan kind: profiling slot of mb200_comm_exchange */
   MB200_K_CYLINT = 12,
   MB200_K_CYLR0 = 13,
-  MB200_NUM_KINDS = 14
+  MB200_K_STEP3_GENERAL = 14, /* not a plan kind: profiling slot of MB200_K_STEP3 plans that run the
+                                 general (PML) fused kernel; slot 9 then holds the fast-path plans */
+  MB200_NUM_KINDS = 15
 };
 
 /* ---- context ------------------------------------------------------------------------------- */

@@ -15,7 +15,8 @@ F64, F32 = 0, 1
 K_EXCHANGE = 11
 K_CYLINT = 12
 K_CYLR0 = 13
-NUM_KINDS = 14
+K_STEP3_GENERAL = 14
+NUM_KINDS = 15
 MAX_P = 8
 
 

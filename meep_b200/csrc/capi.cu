@@ -354,7 +354,7 @@ int mb200_plan_run(mb200_ctx *c, mb200_plan *p, const void *run_data, size_t run
   }
   ProfRec rec;
   if (c->profiling) {
-    rec.kind = p->kind;
+    rec.kind = (p->kind == MB200_K_STEP3 && !p->all_plain) ? MB200_K_STEP3_GENERAL : p->kind;
     rec.bytes = p->bytes;
     CUDA_TRY(cudaEventCreate(&rec.a));
     CUDA_TRY(cudaEventCreate(&rec.b));
