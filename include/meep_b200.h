@@ -103,6 +103,26 @@ typedef struct {
   int32_t cyl, r_is2;
 } mb200_beta_job_t;
 
+/* ---- step_bfast (src/meep_internals.hpp:107-112, src/step_generic.cpp:335-530): the BFAST
+ *      correction for Bloch-periodic oblique incidence, called from fields_chunk::step_db right
+ *      after step_curl of the same component (src/step_db.cpp:129-143):
+ *        F' = k1 (g1[i+s1] + g1[i]) - k2 (g2[i+s2] + g2[i]) - F ;  f += (F' - F) [cndinv][siginv]...
+ *      g1 != NULL (the caller applies the swap of lines 342-346, k1/k2 included).  The reference's
+ *      variant without PML, f_u, conductivity AND g2 stores F' = k1 (g1[i+s1] + g1[i]) without
+ *      subtracting the old F (line 372); reproduced. */
+typedef struct {
+  mb200_box_t box;
+  void *f;
+  const void *g1, *g2;
+  int64_t s1, s2;
+  double k1, k2;
+  mb200_pml_t pml, pmlu; /* only siginv is used */
+  void *fu;
+  const void *cnd, *cndinv; /* cnd != NULL selects the conductivity variants (its values are unused) */
+  void *fcnd;
+  void *F; /* f_bfast */
+} mb200_bfast_job_t;
+
 /* ---- cylindrical helper array (src/step_db.cpp:93-116): out = running sum over r of
  *      1/r d(r f_p)/dr, so that the unmodified step_curl produces the Z-component update.
  *      One thread per z column, serial in r (the reference's summation order). */
@@ -296,7 +316,8 @@ enum {
   MB200_K_CYLR0 = 13,
   MB200_K_STEP3_GENERAL = 14, /* not a plan kind: profiling slot of MB200_K_STEP3 plans that run the
                                  general (PML) fused kernel; slot 9 then holds the fast-path plans */
-  MB200_NUM_KINDS = 15
+  MB200_K_BFAST = 15,
+  MB200_NUM_KINDS = 16
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -353,6 +374,7 @@ int mb200_update_dft(mb200_ctx *ctx, int dtype, const mb200_dft_job_t *jobs, int
 int mb200_dft_flux(mb200_ctx *ctx, int dtype, const mb200_flux_job_t *jobs, int njobs);
 int mb200_step3(mb200_ctx *ctx, int dtype, const mb200_step3_job_t *jobs, int njobs);
 int mb200_step_beta(mb200_ctx *ctx, int dtype, const mb200_beta_job_t *jobs, int njobs);
+int mb200_step_bfast(mb200_ctx *ctx, int dtype, const mb200_bfast_job_t *jobs, int njobs);
 /* cylindrical coordinates: src/step_db.cpp:93-116 and 285-377 */
 int mb200_cyl_rderiv_int(mb200_ctx *ctx, int dtype, const mb200_cylint_job_t *jobs, int njobs);
 int mb200_cyl_origin(mb200_ctx *ctx, int dtype, const mb200_cylr0_job_t *jobs, int njobs);

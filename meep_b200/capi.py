@@ -16,7 +16,8 @@ K_EXCHANGE = 11
 K_CYLINT = 12
 K_CYLR0 = 13
 K_STEP3_GENERAL = 14
-NUM_KINDS = 15
+K_BFAST = 15
+NUM_KINDS = 16
 MAX_P = 8
 
 
@@ -108,6 +109,13 @@ class BetaJob(C.Structure):
                 ("cyl", C.c_int32), ("r_is2", C.c_int32)]
 
 
+class BfastJob(C.Structure):
+    _fields_ = [("box", Box), ("f", C.c_void_p), ("g1", C.c_void_p), ("g2", C.c_void_p), ("s1", C.c_int64),
+                ("s2", C.c_int64), ("k1", C.c_double), ("k2", C.c_double), ("pml", Pml), ("pmlu", Pml),
+                ("fu", C.c_void_p), ("cnd", C.c_void_p), ("cndinv", C.c_void_p), ("fcnd", C.c_void_p),
+                ("F", C.c_void_p)]
+
+
 class CylIntJob(C.Structure):
     _fields_ = [("out", C.c_void_p), ("fp", C.c_void_p), ("nr", C.c_int64), ("sr", C.c_int64),
                 ("ir0", C.c_double)]
@@ -126,7 +134,7 @@ class Xfer(C.Structure):
 
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,
              K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job, K_BETA: BetaJob,
-             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job}
+             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job, K_BFAST: BfastJob}
 
 
 def declare(lib):
@@ -165,6 +173,7 @@ def declare(lib):
         "mb200_dft_flux": (i, [vp, i, vp, i]),
         "mb200_step3": (i, [vp, i, vp, i]),
         "mb200_step_beta": (i, [vp, i, vp, i]),
+        "mb200_step_bfast": (i, [vp, i, vp, i]),
         "mb200_cyl_rderiv_int": (i, [vp, i, vp, i]),
         "mb200_cyl_origin": (i, [vp, i, vp, i]),
         "mb200_comm_unique_id": (i, [vp]),

@@ -206,6 +206,17 @@ template <typename T> MB200_HD void beta_thread(const mb200_beta_job_t &J, int64
     beta_point<T>(J, i, k, ku, fac);
 }
 
+template <typename T> MB200_HD void bfast_thread(const mb200_bfast_job_t &J, int64_t tile, int tid) {
+  int i1_0, i1_end, i2, i3;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  int64_t i = box_index(J.box, i1_0, i2, i3);
+  int k = pml_k(J.pml, i1_0, i2, i3), ku = pml_k(J.pmlu, i1_0, i2, i3);
+  const int64_t s1 = J.box.s[0];
+  const int dk = J.pml.ks[0], dku = J.pmlu.ks[0];
+  for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1, k += dk, ku += dku)
+    bfast_point<T>(J, i, k, ku);
+}
+
 template <typename T> MB200_HD void cylr0_thread(const mb200_cylr0_job_t &J, int64_t tile, int tid) {
   int i1_0, i1_end, i2, i3;
   if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
@@ -313,6 +324,17 @@ __global__ void __launch_bounds__(kThreads)
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   lorentz_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- step_bfast ----------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    bfast_kernel(const mb200_bfast_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                 int njobs) {
+  __shared__ mb200_bfast_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  bfast_thread<T>(J, tile, threadIdx.x);
 }
 
 // ---- cylindrical coordinates --------------------------------------------------------------------

@@ -175,6 +175,35 @@ MB200_HD void beta_point(const mb200_beta_job_t &J, int64_t i, int k, int ku, T 
 }
 
 // ------------------------------------------------------------------------------------------------
+// step_bfast (src/step_generic.cpp:335-530): the sixteen specialised loops as one body
+template <typename T> MB200_HD void bfast_point(const mb200_bfast_job_t &J, int64_t i, int k, int ku) {
+  T *f = (T *)J.f, *F = (T *)J.F;
+  const T *g1 = (const T *)J.g1, *g2 = (const T *)J.g2;
+  const T k1 = (T)J.k1, k2 = (T)J.k2;
+  const T F_prev = F[i];
+  T Fn;
+  if (g2)
+    Fn = (k1 * (ldro(g1 + i + J.s1) + ldro(g1 + i)) - k2 * (ldro(g2 + i + J.s2) + ldro(g2 + i))) - F_prev;
+  else if (!J.pml.siginv && !J.pmlu.siginv && !J.cnd)
+    Fn = k1 * (ldro(g1 + i + J.s1) + ldro(g1 + i)); // (line 372: this variant does not subtract F)
+  else
+    Fn = k1 * (ldro(g1 + i + J.s1) + ldro(g1 + i)) - F_prev;
+  F[i] = Fn;
+  T df = Fn - F_prev;
+  if (J.cnd) df = df * ldro((const T *)J.cndinv + i);
+  if (J.pml.siginv) {
+    if (J.cnd) ((T *)J.fcnd)[i] += df;
+    df = df * ldro((const T *)J.pml.siginv + k);
+  }
+  if (J.pmlu.siginv) {
+    ((T *)J.fu)[i] += df;
+    f[i] += ldro((const T *)J.pmlu.siginv + ku) * df;
+  }
+  else
+    f[i] += df;
+}
+
+// ------------------------------------------------------------------------------------------------
 // cylindrical r = 0 row (src/step_db.cpp:300-321 and 350-371): one body for both loops
 template <typename T> MB200_HD void cylr0_point(const mb200_cylr0_job_t &J, int64_t i, int k, int ku) {
   T *the_f = (T *)J.f, *fu = (T *)J.fu, *fcnd = (T *)J.fcnd;

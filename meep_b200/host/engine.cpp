@@ -348,6 +348,7 @@ uint64_t Engine::fingerprint(fields *f) const {
       hash_mix(h, (uint64_t)(uintptr_t)fc->f_u[c][cmp]);
       hash_mix(h, (uint64_t)(uintptr_t)fc->f_w[c][cmp]);
       hash_mix(h, (uint64_t)(uintptr_t)fc->f_cond[c][cmp]);
+      hash_mix(h, (uint64_t)(uintptr_t)fc->f_bfast[c][cmp]);
       hash_mix(h, (uint64_t)(uintptr_t)fc->f_minus_p[c][cmp]);
       hash_mix(h, (uint64_t)(uintptr_t)fc->f_w_prev[c][cmp]);
     }
@@ -399,13 +400,12 @@ void Engine::scan(fields *f) {
       ensure(fc->f_u[c][cmp], nb, true);
       ensure(fc->f_w[c][cmp], nb, true);
       ensure(fc->f_cond[c][cmp], nb, true);
+      ensure(fc->f_bfast[c][cmp], nb, true);
       // f_minus_p is scratch that is fully rewritten before every use: no upload needed
       ensure(fc->f_minus_p[c][cmp], nb, true, 1);
       if (fc->f_w_prev[c][cmp])
         meep::abort("meep_b200: susceptibilities that need W_prev (multilevel atoms) are not "
                     "supported on the device path");
-      if (fc->f_bfast[c][cmp])
-        meep::abort("meep_b200: BFAST fields are not supported on the device path");
     }
     const structure_chunk *s = fc->s;
     FOR_COMPONENTS(c) {
@@ -793,6 +793,7 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_plain.data(), s3_plain.size()));
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_gen.data(), s3_gen.size()));
       push(ph, MB200_K_CURL, make_plan(*this, MB200_K_CURL, rest.data(), rest.size()));
+      push(ph, MB200_K_BFAST, make_plan(*this, MB200_K_BFAST, R.bfast.data(), R.bfast.size()));
       push(ph, MB200_K_BETA, make_plan(*this, MB200_K_BETA, R.beta.data(), R.beta.size()));
       push(ph, MB200_K_CYLR0, make_plan(*this, MB200_K_CYLR0, R.cylr0.data(), R.cylr0.size()));
       push(ph, MB200_K_ZERO, make_plan(*this, MB200_K_ZERO, R.cylzero.data(), R.cylzero.size()));

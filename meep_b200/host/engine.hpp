@@ -79,6 +79,7 @@ struct Recorder {
   std::vector<mb200_curl_job_t> curl;
   std::vector<mb200_beta_job_t> beta; // 2-D exp(i beta z) terms, run after the curl jobs
   // cylindrical coordinates: helper arrays (before the curl jobs), r = 0 rows and zeroed rows (after)
+  std::vector<mb200_bfast_job_t> bfast; // BFAST corrections, after the curl jobs
   std::vector<mb200_cylint_job_t> cylint;
   std::vector<mb200_cylr0_job_t> cylr0;
   std::vector<mb200_zero_job_t> cylzero;

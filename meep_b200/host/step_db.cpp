@@ -185,8 +185,7 @@ bool fields_chunk::step_db(field_type ft) {
   // cylindrical: the helper array of src/step_db.cpp:93-116 is device scratch, one per real /
   // imaginary part (the jobs of both parts run in the same launch)
   void *rderiv_int[2] = {nullptr, nullptr};
-  if (bfast_scaled_k[0] || bfast_scaled_k[1] || bfast_scaled_k[2])
-    meep::abort("meep_b200: BFAST is not supported on the device path yet");
+  const bool use_bfast = bfast_scaled_k[0] || bfast_scaled_k[1] || bfast_scaled_k[2];
 
   for (const auto &sub_gv : gvs_tiled) {
     DOCMP {
@@ -224,6 +223,11 @@ bool fields_chunk::step_db(field_type ft) {
             memcpy(f_u[cc][cmp], the_f, nbytes); // (host copy is refreshed on the next download)
             E->ensure_from(f_u[cc][cmp], nbytes, the_f);
             allocated_u = true;
+          }
+          if (use_bfast && !f_bfast[cc][cmp]) {
+            f_bfast[cc][cmp] = new realnum[gv.ntot()];
+            memset(f_bfast[cc][cmp], 0, nbytes);
+            E->ensure_from(f_bfast[cc][cmp], nbytes, NULL);
           }
 
           if (ft == D_stuff) { // strides are opposite sign for H curl
@@ -289,11 +293,43 @@ bool fields_chunk::step_db(field_type ft) {
           if (!J.g1) continue; // no curl term at all (step_curl returns at once: step_generic.cpp:72-77)
           if (J.box.n[0] <= 0 || J.box.n[1] <= 0 || J.box.n[2] <= 0) continue;
           R.curl.push_back(J);
+
+          if (use_bfast) { // STEP_BFAST right after STEP_CURL of the same component (lines 129-143)
+            realnum k1 = have_m ? bfast_scaled_k[component_index(c_m)] : 0; // puts k1 in direction of g2
+            realnum k2 = have_p ? bfast_scaled_k[component_index(c_p)] : 0; // puts k2 in direction of g1
+            if (ft == D_stuff) {
+              k1 = -k1;
+              k2 = -k2;
+            }
+            mb200_bfast_job_t BJ;
+            memset(&BJ, 0, sizeof(BJ));
+            BJ.box = J.box;
+            BJ.f = J.f;
+            BJ.g1 = g1_dev;
+            BJ.g2 = g2_dev;
+            BJ.s1 = stride_p;
+            BJ.s2 = stride_m;
+            BJ.k1 = k1;
+            BJ.k2 = k2;
+            if (!BJ.g1) { // swap g1 and g2, and k1/k2 with them (src/step_generic.cpp:342-346)
+              std::swap(BJ.g1, BJ.g2);
+              std::swap(BJ.s1, BJ.s2);
+              std::swap(BJ.k1, BJ.k2);
+            }
+            BJ.pml = J.pml;
+            BJ.pmlu = J.pmlu;
+            BJ.fu = J.fu;
+            BJ.cnd = J.cnd;
+            BJ.cndinv = J.cndinv;
+            BJ.fcnd = J.fcnd;
+            BJ.F = E->dev(f_bfast[cc][cmp]);
+            R.bfast.push_back(BJ);
+          }
         }
       }
       grp.count = (int)R.curl.size() - grp.first;
       if (gvs_tiled.size() == 1 && grp.count > 0) {
-        if (grp.count == 3 && gv.dim == D3 && E->fuse && E->in_step)
+        if (grp.count == 3 && gv.dim == D3 && E->fuse && E->in_step && !use_bfast)
           plan_eh_fusion_impl(this, ft, cmp, grp, E, doing_solve_cw);
         R.curl_groups.push_back(grp);
       }

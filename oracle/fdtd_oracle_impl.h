@@ -119,6 +119,57 @@ void FN(oracle_step_beta)(const mb200_beta_job_t *J) {
       }
 }
 
+/* reference src/step_generic.cpp:335-530 (step_bfast); g1 != NULL on entry (the caller applies the
+ * swap of lines 342-346) */
+void FN(oracle_step_bfast)(const mb200_bfast_job_t *J) {
+  REAL *f = (REAL *)J->f, *fu = (REAL *)J->fu, *fcnd = (REAL *)J->fcnd, *F = (REAL *)J->F;
+  const REAL *g1 = (const REAL *)J->g1, *g2 = (const REAL *)J->g2;
+  const REAL *cnd = (const REAL *)J->cnd, *cndinv = (const REAL *)J->cndinv;
+  const REAL *siginv = (const REAL *)J->pml.siginv, *siginvu = (const REAL *)J->pmlu.siginv;
+  const REAL k1 = (REAL)J->k1, k2 = (REAL)J->k2;
+  const int64_t s1 = J->s1, s2 = J->s2;
+  for (int i1 = 0; i1 < J->box.n[0]; ++i1)
+    for (int i2 = 0; i2 < J->box.n[1]; ++i2)
+      for (int i3 = 0; i3 < J->box.n[2]; ++i3) {
+        const int64_t i = J->box.idx0 + i1 * J->box.s[0] + i2 * J->box.s[1] + i3 * J->box.s[2];
+        const int k = FN(kidx)(&J->pml, i1, i2, i3), ku = FN(kidx)(&J->pmlu, i1, i2, i3);
+        REAL F_prev = F[i];
+        if (g2) F[i] = (k1 * (g1[i + s1] + g1[i]) - k2 * (g2[i + s2] + g2[i])) - F[i];
+        else if (!siginv && !siginvu && !cnd) F[i] = k1 * (g1[i + s1] + g1[i]); /* line 372 */
+        else F[i] = k1 * (g1[i + s1] + g1[i]) - F[i];
+        if (!siginv) {
+          if (!siginvu) {
+            if (cnd) f[i] += (F[i] - F_prev) * cndinv[i];
+            else f[i] += (F[i] - F_prev);
+          }
+          else {
+            REAL df;
+            if (cnd) fu[i] += (df = (F[i] - F_prev) * cndinv[i]);
+            else fu[i] += (df = (F[i] - F_prev));
+            f[i] += siginvu[ku] * df;
+          }
+        }
+        else if (!siginvu) {
+          if (cnd) {
+            REAL dfcnd = (F[i] - F_prev) * cndinv[i];
+            fcnd[i] += dfcnd;
+            f[i] += dfcnd * siginv[k];
+          }
+          else f[i] += (F[i] - F_prev) * siginv[k];
+        }
+        else {
+          REAL df;
+          if (cnd) {
+            REAL dfcnd = (F[i] - F_prev) * cndinv[i];
+            fcnd[i] += dfcnd;
+            fu[i] += (df = dfcnd * siginv[k]);
+          }
+          else fu[i] += (df = (F[i] - F_prev) * siginv[k]);
+          f[i] += siginvu[ku] * df;
+        }
+      }
+}
+
 /* reference src/boundaries.cpp:310-313 (fields_chunk::zero_metal); also the ZERO_Z rows of
  * src/step_db.cpp:283,322-327,372-376,406-461 */
 void FN(oracle_zero_metal)(const mb200_zero_job_t *J) {

@@ -108,6 +108,44 @@ static void gen_curl(const std::string &dir, const grid_volume &gv, const char *
   }
 }
 
+// ---- step_bfast ----------------------------------------------------------------------------------
+static void gen_bfast(const std::string &dir, const grid_volume &gv, const char *tag) {
+  const size_t n = gv.ntot();
+  const component cc = gv.dim == D3 ? Dx : Dz;
+  direction d1, d2;
+  if (gv.dim == D3) { d1 = Y; d2 = Z; } else { d1 = X; d2 = Y; }
+  const ivec is = gv.little_owned_corner0(cc), ie = gv.big_corner();
+  const direction dsig0 = gv.dim == D3 ? Y : X, dsigu0 = gv.dim == D3 ? Z : Y;
+  for (int variant = 0; variant < 16; ++variant) {
+    const bool PML = variant & 8, FU = variant & 4, CND = variant & 2, G2 = variant & 1;
+    char nm[64];
+    snprintf(nm, sizeof nm, "bfast_%s_v%02d", tag, variant);
+    open_case(dir, nm);
+    realnum *f = rand_array(n), *g1 = rand_array(n), *g2 = G2 ? rand_array(n) : NULL, *F = rand_array(n);
+    realnum *fu = FU ? rand_array(n) : NULL, *fcnd = (CND && PML) ? rand_array(n) : NULL;
+    realnum *cnd = CND ? rand_array(n, 0, 2) : NULL, *cndinv = CND ? rand_array(n, 0.5, 1) : NULL;
+    const int ns = 2 * gv.num_direction(dsig0) + 2, nsu = 2 * gv.num_direction(dsigu0) + 2;
+    realnum *sig = rand_array(ns, 0, 0.5), *kap = rand_array(ns, 1, 2), *siginv = rand_array(ns, 0.3, 1);
+    realnum *sigu = rand_array(nsu, 0, 0.5), *kapu = rand_array(nsu, 1, 2), *siginvu = rand_array(nsu, 0.3, 1);
+    const ptrdiff_t s1 = -gv.stride(d1), s2 = -gv.stride(d2);
+    const realnum dtdx = 0.5, dt = 0.05, k1 = 0.173, k2 = -0.291;
+    const direction dsig = PML ? dsig0 : NO_DIRECTION, dsigu = FU ? dsigu0 : NO_DIRECTION;
+    dump_r("in.f", f, n); dump_r("in.g1", g1, n); dump_r("in.g2", g2, n); dump_r("in.F", F, n);
+    dump_r("in.fu", fu, n); dump_r("in.fcnd", fcnd, n); dump_r("in.cnd", cnd, n);
+    dump_r("in.cndinv", cndinv, n);
+    dump_r("in.siginv", siginv, ns); dump_r("in.siginvu", siginvu, nsu);
+    dump_box("box", make_box(gv, is, ie));
+    dump_pml("pml", make_pml(gv, is, dsig, sig, kap, siginv), PML);
+    dump_pml("pmlu", make_pml(gv, is, dsigu, sigu, kapu, siginvu), FU);
+    dump_d("scalars", {(double)s1, (double)s2, (double)k1, (double)k2});
+    // THE REFERENCE CALL
+    STEP_BFAST(f, cc, g1, g2, s1, s2, gv, is, ie, dtdx, dsig, sig, kap, siginv, fu, dsigu, sigu, kapu,
+               siginvu, dt, cnd, cndinv, fcnd, F, k1, k2);
+    dump_r("out.f", f, n); dump_r("out.fu", fu, n); dump_r("out.fcnd", fcnd, n); dump_r("out.F", F, n);
+    fclose(g_out);
+  }
+}
+
 // ---- step_beta -----------------------------------------------------------------------------------
 static void gen_beta(const std::string &dir, const grid_volume &gv, const char *tag) {
   const size_t n = gv.ntot();
@@ -420,5 +458,7 @@ int main(int argc, char **argv) {
   gen_cyl(dir, -1, B_stuff, "mneg1_B");
   gen_cyl(dir, 2, D_stuff, "m2_D");
   gen_cyl(dir, 3, B_stuff, "m3_B");
+  gen_bfast(dir, g3, "3d");
+  gen_bfast(dir, g2, "2d");
   return 0;
 }

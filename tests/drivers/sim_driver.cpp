@@ -71,6 +71,7 @@ static void dump_fields(fields &f) {
       DUMP(f_u, "f_u")
       DUMP(f_w, "f_w")
       DUMP(f_cond, "f_cond")
+      DUMP(f_bfast, "f_bfast")
 #undef DUMP
     }
     FOR_FIELD_TYPES(ft) {
@@ -214,6 +215,24 @@ int main(int argc, char **argv) {
     fields f(&s);
     f.add_point_source(Ez, 0.2, 3.0, 0.0, 2.0, gv.center(), complex<double>(0, -2 * pi * 0.2));
     f.use_bloch(vec(0.3, 0.5, 0.8));
+    for (int i = 0; i < nsteps; ++i) f.step();
+    probes(f, gv);
+    dump_fields(f);
+  }
+  else if (cs == "3d_bfast" || cs == "2d_bfast") {
+    // BFAST (src/step_db.cpp:129-143, step_bfast): oblique-incidence Bloch-periodic cell, PML along
+    // y (f_u / PML-in-f variants), a conducting slab (cnd / f_cond variants), complex fields
+    g_L = 1.0;
+    grid_volume gv = cs == "3d_bfast" ? vol3d(1.0, 3.0, 1.0, a) : voltwo(1.0, 3.0, a);
+    structure s(gv, eps_box, pml(1.0, Y), identity(), num_chunks, 0.4);
+    s.set_conductivity(Dz, cond_slab);
+    s.set_conductivity(Dx, cond_slab);
+    std::vector<double> bk = {0.2, 0.0, cs == "3d_bfast" ? 0.1 : 0.0};
+    fields f(&s, 0.0, 0.0, true, 0, 0, bk);
+    f.add_point_source(Ez, 0.4, 3.0, 0.0, 2.0, gv.center(), complex<double>(0, -2 * pi * 0.2));
+    f.add_point_source(Hz, 0.4, 3.0, 0.0, 2.0, gv.center(), 1.0);
+    f.use_bloch(X, 0.0);
+    if (cs == "3d_bfast") f.use_bloch(Z, 0.0);
     for (int i = 0; i < nsteps; ++i) f.step();
     probes(f, gv);
     dump_fields(f);

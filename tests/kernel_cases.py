@@ -43,7 +43,8 @@ class HostMem:
                  capi.K_SOURCE: "oracle_step_source", capi.K_HALO: "oracle_step_boundaries",
                  capi.K_DFT: "oracle_update_dft", capi.K_FLUX: "oracle_dft_flux",
                  capi.K_BETA: "oracle_step_beta", capi.K_CYLINT: "oracle_cyl_rderiv_int",
-                 capi.K_CYLR0: "oracle_cyl_origin", capi.K_ZERO: "oracle_zero_metal"}
+                 capi.K_CYLR0: "oracle_cyl_origin", capi.K_ZERO: "oracle_zero_metal",
+                 capi.K_BFAST: "oracle_step_bfast"}
         fn = getattr(self.lib, names[kind] + "_" + self.prec)
         fn.restype = None
         for j in jobs:
@@ -139,6 +140,21 @@ def replay_beta(rec, mem):
     j.fu, j.cndinv, j.fcnd = P["fu"], P["cndinv"], P["fcnd"]
     mem.run(capi.K_BETA, [j])
     return {k: mem.get(P[k], g(k)) for k in ("f", "fu", "fcnd") if g(k) is not None}
+
+
+def replay_bfast(rec, mem):
+    g = lambda k: rec.get("in." + k)
+    P = {k: mem.put(g(k)) for k in ("f", "g1", "g2", "F", "fu", "fcnd", "cnd", "cndinv", "siginv", "siginvu")}
+    j = capi.BfastJob()
+    j.box = mk_box(rec["box"])
+    j.f, j.g1, j.g2, j.F = P["f"], P["g1"], P["g2"], P["F"]
+    s1, s2, k1, k2 = rec["scalars"]
+    j.s1, j.s2, j.k1, j.k2 = int(s1), int(s2), k1, k2
+    j.pml = mk_pml(rec["pml"], None, None, P["siginv"])
+    j.pmlu = mk_pml(rec["pmlu"], None, None, P["siginvu"])
+    j.fu, j.cnd, j.cndinv, j.fcnd = P["fu"], P["cnd"], P["cndinv"], P["fcnd"]
+    mem.run(capi.K_BFAST, [j])
+    return {k: mem.get(P[k], g(k)) for k in ("f", "fu", "fcnd", "F") if g(k) is not None}
 
 
 def replay_edhb(rec, mem):
@@ -303,7 +319,7 @@ def replay_cyl(rec, mem):
     return out
 
 
-REPLAY = {"cyl": replay_cyl, "beta": replay_beta, "curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
+REPLAY = {"cyl": replay_cyl, "bfast": replay_bfast, "beta": replay_beta, "curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
 
 
 def check_golden(prefix, prec, mem_factory):
