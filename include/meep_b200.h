@@ -213,6 +213,13 @@ typedef struct {
  *      first 2*n_phase entries are (re,im) pairs multiplied by phase[k] (complex<realnum>),
  *      next n_negate entries are negated, the last n_copy are copied. */
 typedef struct {
+  uint64_t src0, dst0; /* device addresses of the first element */
+  int64_t dsrc, ddst;  /* byte strides */
+  int32_t n;           /* elements */
+  int32_t negate;      /* 1: NEGATE class, 0: COPY class */
+} mb200_halo_run_t;
+
+typedef struct {
   const uint64_t *src;
   const uint64_t *dst;
   const void *phase;
@@ -221,6 +228,13 @@ typedef struct {
    * mb200_lorentz_job_t.pzero) that covers dst[k]; cleared when a non-zero value is stored, so
    * that polarisation values arriving from a neighbouring chunk keep the flags exact */
   const uint64_t *dst_flag;
+  /* optional run-length form of the NEGATE || COPY entries (chunk faces are regular planes, so
+   * the address lists are runs of constant stride): when nrun > 0 the n_negate + n_copy
+   * transfers are the elements of runs[0..nrun) and src/dst hold only the 2*n_phase PHASE
+   * entries (may be NULL when n_phase == 0); dst_flag must be NULL.  16 bytes of addresses per
+   * transfer become 40 bytes per run. */
+  const mb200_halo_run_t *runs;
+  int64_t nrun;
 } mb200_halo_job_t;
 
 /* ---- fields_chunk::zero_metal (src/boundaries.cpp:310-313): *ptrs[k] = 0. */

@@ -64,10 +64,15 @@ class SrcJob(C.Structure):
                 ("scalar_slot", C.c_int32), ("mode", C.c_int32)]
 
 
+class HaloRun(C.Structure):
+    _fields_ = [("src0", C.c_uint64), ("dst0", C.c_uint64), ("dsrc", C.c_int64), ("ddst", C.c_int64),
+                ("n", C.c_int32), ("negate", C.c_int32)]
+
+
 class HaloJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("phase", C.c_void_p),
                 ("n_phase", C.c_int64), ("n_negate", C.c_int64), ("n_copy", C.c_int64),
-                ("dst_flag", C.c_void_p)]
+                ("dst_flag", C.c_void_p), ("runs", C.c_void_p), ("nrun", C.c_int64)]
 
 
 class ZeroJob(C.Structure):

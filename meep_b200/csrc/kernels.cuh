@@ -206,6 +206,27 @@ template <typename T> MB200_HD void beta_thread(const mb200_beta_job_t &J, int64
     beta_point<T>(J, i, k, ku, fac);
 }
 
+// list form: one thread per transfer.  Run-length form: the tiles after the PHASE tiles hold
+// kHaloRunsPerTile runs each, one warp per run, lanes striding through its elements.
+constexpr int kHaloRunsPerTile = kThreads / 32;
+MB200_HD int64_t halo_list_tiles(const mb200_halo_job_t &J) {
+  const int64_t n = J.nrun > 0 ? J.n_phase : J.n_phase + J.n_negate + J.n_copy;
+  return (n + kThreads - 1) / kThreads;
+}
+template <typename T> MB200_HD void halo_thread(const mb200_halo_job_t &J, int64_t tile, int tid) {
+  const int64_t lt = halo_list_tiles(J);
+  if (tile < lt) {
+    const int64_t n = tile * kThreads + tid;
+    if (n < (J.nrun > 0 ? J.n_phase : halo_count(J))) halo_transfer<T>(J, n);
+    return;
+  }
+  const int64_t r = (tile - lt) * kHaloRunsPerTile + tid / 32;
+  if (r >= J.nrun) return;
+  const mb200_halo_run_t run = J.runs[r];
+  for (int e = tid % 32; e < run.n; e += 32)
+    halo_run_transfer<T>(run, e);
+}
+
 template <typename T> MB200_HD void bfast_thread(const mb200_bfast_job_t &J, int64_t tile, int tid) {
   int i1_0, i1_end, i2, i3;
   if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
@@ -439,8 +460,7 @@ __global__ void __launch_bounds__(kThreads)
   __shared__ mb200_halo_job_t J;
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
-  const int64_t n = tile * kThreads + threadIdx.x;
-  if (n < halo_count(J)) halo_transfer<T>(J, n);
+  halo_thread<T>(J, tile, threadIdx.x);
 }
 
 template <typename T>

@@ -80,10 +80,13 @@ inline void job_metrics(int kind, int dtype, const void *jobs, int j, int64_t *t
     }
     case MB200_K_HALO: {
       const mb200_halo_job_t &J = ((const mb200_halo_job_t *)jobs)[j];
-      const int64_t n = J.n_phase + J.n_negate + J.n_copy;
-      *tiles = ceil_div(n, kThreads);
+      *tiles = halo_list_tiles(J) + ceil_div(J.nrun, kHaloRunsPerTile);
       *points = (double)(2 * J.n_phase + J.n_negate + J.n_copy);
-      *bytes = (16 + 2 * R) * *points;
+      if (J.nrun > 0)
+        *bytes = (16 + 2 * R) * 2.0 * J.n_phase + 2 * R * (double)(J.n_negate + J.n_copy) +
+                 (double)sizeof(mb200_halo_run_t) * J.nrun;
+      else
+        *bytes = (16 + 2 * R) * *points;
       break;
     }
     case MB200_K_ZERO: {

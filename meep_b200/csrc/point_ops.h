@@ -433,6 +433,11 @@ template <typename T> MB200_HD void halo_transfer(const mb200_halo_job_t &J, int
 MB200_HD int64_t halo_count(const mb200_halo_job_t &J) {
   return J.n_phase + J.n_negate + J.n_copy;
 }
+// element e of run r (run-length form of the NEGATE || COPY entries)
+template <typename T> MB200_HD void halo_run_transfer(const mb200_halo_run_t &r, int e) {
+  const T v = *(const T *)(uintptr_t)(r.src0 + (int64_t)e * r.dsrc);
+  *(T *)(uintptr_t)(r.dst0 + (int64_t)e * r.ddst) = r.negate ? -v : v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // dft_chunk::update_dft (src/dft.cpp:266-308)

@@ -90,6 +90,7 @@ Engine::Engine(fields *) {
   merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   p2p = env_int("MEEP_B200_P2P", 1) != 0;
+  halo_runs = env_int("MEEP_B200_HALO_RUNS", 1) != 0;
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;

@@ -201,6 +201,7 @@ public:
   mb200_ctx *ctx = nullptr;
   mb200_comm *comm = nullptr; // inter-process exchange (created on first use when WORLD_SIZE > 1)
   bool emulated = false;      // the C ABI is served by the test-only emulator
+  bool halo_runs = true;      // MEEP_B200_HALO_RUNS=0: plain address lists for every halo job
   bool cw_mode = false;       // inside solve_cw: the host arrays are the master between steps
   bool p2p = true;            // MEEP_B200_P2P=0: move comm blocks with NCCL instead of peer stores
   // peer-memory links (see P2PLink).  (Re)built collectively by the first in-step

@@ -369,9 +369,45 @@ void fields::step_boundaries(field_type ft) {
             else
               hj.n_copy = (int64_t)n;
           }
+          bool need_flags = false;
+          if (i_mine && (ft == PE_stuff || ft == PH_stuff) && E.zero_skip)
+            for (realnum *p : chunks[i]->connections_in.at(key))
+              if (E.pzero_flag_addr(p)) need_flags = true;
+          // NEGATE / COPY transfers between regular chunk faces: runs of constant stride
+          // (40 bytes per run instead of 16 bytes of addresses per value)
+          if (hj.n_phase == 0 && !need_flags && E.halo_runs && n >= 64) {
+            std::vector<mb200_halo_run_t> runs;
+            size_t k = 0;
+            while (k < n) {
+              mb200_halo_run_t r;
+              r.src0 = src[k];
+              r.dst0 = dst[k];
+              r.dsrc = r.ddst = 0;
+              r.negate = hj.n_negate > 0 ? 1 : 0; // (pack jobs copy; the sign is applied on arrival)
+              size_t len = 1;
+              if (k + 1 < n) {
+                r.dsrc = (int64_t)(src[k + 1] - src[k]);
+                r.ddst = (int64_t)(dst[k + 1] - dst[k]);
+                len = 2;
+                while (k + len < n && len < (size_t)1 << 30 &&
+                       (int64_t)(src[k + len] - src[k + len - 1]) == r.dsrc &&
+                       (int64_t)(dst[k + len] - dst[k + len - 1]) == r.ddst)
+                  ++len;
+              }
+              r.n = (int32_t)len;
+              runs.push_back(r);
+              k += len;
+            }
+            if (runs.size() * 8 <= n) { // worth it: at least 8 values per run on average
+              hj.runs = (const mb200_halo_run_t *)E.aux_upload(runs.data(), runs.size() * sizeof(runs[0]));
+              hj.nrun = (int64_t)runs.size();
+              src.clear();
+              dst.clear();
+            }
+          }
           hj.src = (const uint64_t *)E.aux_upload(src.data(), src.size() * 8);
           hj.dst = (const uint64_t *)E.aux_upload(dst.data(), dst.size() * 8);
-          if (i_mine && (ft == PE_stuff || ft == PH_stuff) && E.zero_skip) {
+          if (need_flags) {
             // polarisation values arriving from a neighbour: keep the zero-block flags exact
             const std::vector<realnum *> &in = chunks[i]->connections_in.at(key);
             std::vector<uint64_t> fl(in.size());

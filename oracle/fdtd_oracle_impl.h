@@ -369,7 +369,7 @@ void FN(oracle_step_source)(const mb200_src_job_t *J, const double *scalars) {
 
 /* reference src/step.cpp:172-223 (gather into a block, then scatter with phase/negate/copy) */
 void FN(oracle_step_boundaries)(const mb200_halo_job_t *J) {
-  const int64_t nlist = 2 * J->n_phase + J->n_negate + J->n_copy;
+  const int64_t nlist = 2 * J->n_phase + (J->nrun > 0 ? 0 : J->n_negate + J->n_copy);
   REAL *block = (REAL *)malloc(sizeof(REAL) * (size_t)(nlist ? nlist : 1));
   for (int64_t n = 0; n < nlist; ++n)
     block[n] = *(const REAL *)(uintptr_t)J->src[n];
@@ -381,6 +381,24 @@ void FN(oracle_step_boundaries)(const mb200_halo_job_t *J) {
     *(REAL *)(uintptr_t)J->dst[2 * n + 1] = pr * vi + pi * vr;
   }
   o = 2 * J->n_phase;
+  if (J->nrun > 0) { /* the same NEGATE || COPY transfers, listed as constant-stride runs */
+    free(block);
+    int64_t total = 0;
+    for (int64_t r = 0; r < J->nrun; ++r)
+      total += J->runs[r].n;
+    block = (REAL *)malloc(sizeof(REAL) * (size_t)(total ? total : 1));
+    int64_t q = 0;
+    for (int64_t r = 0; r < J->nrun; ++r) /* gather everything first, as the comm block does */
+      for (int e = 0; e < J->runs[r].n; ++e)
+        block[q++] = *(const REAL *)(uintptr_t)(J->runs[r].src0 + (int64_t)e * J->runs[r].dsrc);
+    q = 0;
+    for (int64_t r = 0; r < J->nrun; ++r)
+      for (int e = 0; e < J->runs[r].n; ++e, ++q)
+        *(REAL *)(uintptr_t)(J->runs[r].dst0 + (int64_t)e * J->runs[r].ddst) =
+            J->runs[r].negate ? -block[q] : block[q];
+    free(block);
+    return;
+  }
   for (int64_t n = 0; n < J->n_negate; ++n)
     *(REAL *)(uintptr_t)J->dst[o + n] = -block[o + n];
   o += J->n_negate;

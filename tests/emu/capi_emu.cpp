@@ -135,8 +135,9 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
       }
       case MB200_K_HALO: {
         const mb200_halo_job_t &J = ((const mb200_halo_job_t *)p->jobs.data())[j];
-        for (int64_t n = 0; n < halo_count(J); ++n)
-          halo_transfer<T>(J, n);
+        for (int64_t t = 0; t < ntiles; ++t)
+          for (int tid = 0; tid < kThreads; ++tid)
+            halo_thread<T>(J, t, tid);
         break;
       }
       case MB200_K_ZERO: {
