@@ -69,6 +69,10 @@ struct mb200_plan {
 // instead of staging them in shared memory (experiment; see profiles/ for the comparison)
 static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("MEEP_B200_PARAMJOBS")) != 0;
 
+// MEEP_B200_SPLIT_PML=0 runs the PML chunks with the three-components-per-thread general kernel
+// instead of the one-component-per-thread form (A/B switch; see profiles/)
+static const bool g_split_general = !(getenv("MEEP_B200_SPLIT_PML") && atoi(getenv("MEEP_B200_SPLIT_PML")) == 0);
+
 template <typename T>
 static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
   const dim3 grid((unsigned)p->tiles), block(kThreads);
@@ -138,7 +142,7 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
         break;
       }
       launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
-                      p->all_plain, s);
+                      p->all_plain, g_split_general, s);
       break;
   }
   return cudaGetLastError();

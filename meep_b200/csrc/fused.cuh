@@ -172,21 +172,21 @@ template <typename T>
 MB200_HD void step3_load(const mb200_step3_comp_t &C, int64_t i, int ix, int iy, int iz,
                          Step3Vals<T> &v) {
   const T *g1 = (const T *)C.g1, *g2 = (const T *)C.g2;
-  v.f = ((const T *)C.f)[i];
+  v.f = ldmut((const T *)C.f + i);
   v.a1 = ldro(g1 + i + C.s1);
   v.c1 = ldro(g1 + i);
   v.c2 = ldro(g2 + i);
   v.a2 = ldro(g2 + i + C.s2);
   if (C.pmlu.sig) {
     const int ku = pml_k(C.pmlu, ix, iy, iz);
-    v.fu = ((const T *)C.fu)[i];
+    v.fu = ldmut((const T *)C.fu + i);
     v.kmsu = ldro((const T *)C.pmlu.kap + ku) - ldro((const T *)C.pmlu.sig + ku);
     v.sinvu = ldro((const T *)C.pmlu.siginv + ku);
   }
   if (C.cnd) {
     v.cnd = ldro((const T *)C.cnd + i);
     v.cndinv = ldro((const T *)C.cndinv + i);
-    if (C.pml.sig) v.fcnd = ((const T *)C.fcnd)[i];
+    if (C.pml.sig) v.fcnd = ldmut((const T *)C.fcnd + i);
   }
   if (C.pml.sig) {
     const int k = pml_k(C.pml, ix, iy, iz);
@@ -197,8 +197,8 @@ MB200_HD void step3_load(const mb200_step3_comp_t &C, int64_t i, int ix, int iy,
     v.u = C.u ? ldro((const T *)C.u + i) : T(1);
     if (C.pmlw.sig) {
       const int kw = pml_k(C.pmlw, ix, iy, iz);
-      v.fw = ((const T *)C.fw)[i];
-      v.e = ((const T *)C.e)[i];
+      v.fw = ldmut((const T *)C.fw + i);
+      v.e = ldmut((const T *)C.e + i);
       v.kapw = ldro((const T *)C.pmlw.kap + kw);
       v.sigw = ldro((const T *)C.pmlw.sig + kw);
     }
@@ -220,28 +220,28 @@ MB200_HD void step3_compute_store(const mb200_step3_comp_t &C, int64_t i, bool m
   }
   else if (CND) {
     const T fcn = ((1 - dt2 * v.cnd) * v.fcnd - curl) * v.cndinv;
-    ((T *)C.fcnd)[i] = fcn;
+    stout((T *)C.fcnd + i, fcn);
     xn = (v.kms * x + (fcn - v.fcnd)) * v.sinv;
   }
   else
     xn = (v.kms * x - curl) * v.sinv;
   T fn;
   if (FU) {
-    ((T *)C.fu)[i] = xn;
+    stout((T *)C.fu + i, xn);
     fn = v.sinvu * (v.kmsu * v.f + xn - v.fu);
   }
   else
     fn = xn;
-  ((T *)C.f)[i] = fn;
+  stout((T *)C.f + i, fn);
   if (C.e) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
     const T d = metal ? T(0) : fn;
     const T val = C.u ? d * v.u : d;
     if (C.pmlw.sig) {
-      ((T *)C.fw)[i] = val;
-      ((T *)C.e)[i] = v.e + ((v.kapw + v.sigw) * val - (v.kapw - v.sigw) * v.fw);
+      stout((T *)C.fw + i, val);
+      stout((T *)C.e + i, v.e + ((v.kapw + v.sigw) * val - (v.kapw - v.sigw) * v.fw));
     }
     else
-      ((T *)C.e)[i] = val;
+      stout((T *)C.e + i, val);
   }
 }
 
@@ -280,7 +280,185 @@ MB200_HD void step3_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
   }
 }
 
+// One component per thread (general kernel, split form).  The three components of a chunk are
+// independent of each other inside one D/B(+E/H) pass — each reads only arrays of the other field
+// type and writes its own f / f_u / f_cond / e / f_w — so the PML chunks can also be walked with
+// one component per thread and three times as many CTAs: a third of the operands per thread
+// (descriptor fields stay in registers across the march instead of being re-read from shared
+// memory; twice the resident warps).
+template <typename T>
+MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int tid) {
+  const mb200_box_t box = step3_box(J);
+  int ix0, ix_end, iy, iz;
+  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
+  const mb200_step3_comp_t &C = J.c[c];
+  if (!C.f || iy < C.lo[1] || iy > C.hi[1] || iz < C.lo[2] || iz > C.hi[2]) return;
+  int64_t i = box_index(box, ix0, iy, iz);
+  const int64_t sx = box.s[0];
+  ix0 += box.reserved; // loop index -> array index along direction 0
+  ix_end += box.reserved;
+  if (ix0 < C.lo[0]) {
+    i += (int64_t)(C.lo[0] - ix0) * sx;
+    ix0 = C.lo[0];
+  }
+  if (ix_end > C.hi[0] + 1) ix_end = C.hi[0] + 1;
+  if (ix0 >= ix_end) return;
+
+  // everything the march needs, taken out of the (shared-memory) descriptor once: array cursors
+  // at the first point, table cursors, flags
+  const bool FU = C.pmlu.sig != nullptr, PML = C.pml.sig != nullptr, CND = C.cnd != nullptr;
+  const bool EPI = C.e != nullptr, FW = EPI && C.pmlw.sig != nullptr, HASU = EPI && C.u != nullptr;
+  const T dtdx = (T)C.dtdx, dt2 = (T)J.dt * T(0.5);
+  T *pf = (T *)C.f + i;
+  const T *g1 = (const T *)C.g1 + i, *g2 = (const T *)C.g2 + i;
+  const int64_t s1 = C.s1, s2 = C.s2;
+  T *pfu = FU ? (T *)C.fu + i : nullptr;
+  T *pfcnd = (CND && PML) ? (T *)C.fcnd + i : nullptr;
+  const T *pcnd = CND ? (const T *)C.cnd + i : nullptr;
+  const T *pcndinv = CND ? (const T *)C.cndinv + i : nullptr;
+  T *pe = EPI ? (T *)C.e + i : nullptr;
+  T *pfw = FW ? (T *)C.fw + i : nullptr;
+  const T *pu = HASU ? (const T *)C.u + i : nullptr;
+  // 1-D PML tables: cursor at ix0 and step per x-plane (0 unless the PML direction is x; then the
+  // table values are the same for the whole march and are read once)
+  const int dk = PML ? C.pml.ks[0] : 0, dku = FU ? C.pmlu.ks[0] : 0, dkw = FW ? C.pmlw.ks[0] : 0;
+  const T *tsig = nullptr, *tkap = nullptr, *tsinv = nullptr;
+  const T *tsigu = nullptr, *tkapu = nullptr, *tsinvu = nullptr, *tsigw = nullptr, *tkapw = nullptr;
+  T kms = 0, sinv = 0, kmsu = 0, sinvu = 0, kapw = 0, sigw = 0;
+  if (PML) {
+    const int k = pml_k(C.pml, ix0, iy, iz);
+    tsig = (const T *)C.pml.sig + k;
+    tkap = (const T *)C.pml.kap + k;
+    tsinv = (const T *)C.pml.siginv + k;
+    kms = ldro(tkap) - ldro(tsig);
+    sinv = ldro(tsinv);
+  }
+  if (FU) {
+    const int ku = pml_k(C.pmlu, ix0, iy, iz);
+    tsigu = (const T *)C.pmlu.sig + ku;
+    tkapu = (const T *)C.pmlu.kap + ku;
+    tsinvu = (const T *)C.pmlu.siginv + ku;
+    kmsu = ldro(tkapu) - ldro(tsigu);
+    sinvu = ldro(tsinvu);
+  }
+  if (FW) {
+    const int kw = pml_k(C.pmlw, ix0, iy, iz);
+    tsigw = (const T *)C.pmlw.sig + kw;
+    tkapw = (const T *)C.pmlw.kap + kw;
+    kapw = ldro(tkapw);
+    sigw = ldro(tsigw);
+  }
+  const bool metal_yz = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
+                        iz == C.metal_hi[2];
+  const int mlo = C.metal_lo[0], mhi = C.metal_hi[0];
+
+  for (int ix = ix0; ix < ix_end; ++ix) {
+    // ---- all loads of this point (as step3_load) ----
+    const T f = ldmut(pf);
+    const T a1 = ldro(g1 + s1), c1 = ldro(g1), c2 = ldro(g2), a2 = ldro(g2 + s2);
+    T fu = 0, fcnd = 0, cnd = 0, cndinv = 0, u = 1, fw = 0, e = 0;
+    if (FU) fu = ldmut(pfu);
+    if (CND) {
+      cnd = ldro(pcnd);
+      cndinv = ldro(pcndinv);
+      if (PML) fcnd = ldmut(pfcnd);
+    }
+    if (HASU) u = ldro(pu);
+    if (FW) {
+      fw = ldmut(pfw);
+      e = ldmut(pe);
+    }
+    if (dk) {
+      kms = ldro(tkap) - ldro(tsig);
+      sinv = ldro(tsinv);
+    }
+    if (dku) {
+      kmsu = ldro(tkapu) - ldro(tsigu);
+      sinvu = ldro(tsinvu);
+    }
+    if (dkw) {
+      kapw = ldro(tkapw);
+      sigw = ldro(tsigw);
+    }
+    // ---- arithmetic and stores (as step3_compute_store) ----
+    T dg = a1 - c1;
+    dg = dg + c2 - a2;
+    const T curl = dtdx * dg;
+    const T x = FU ? fu : f;
+    T xn;
+    if (!PML) {
+      if (CND) xn = ((1 - dt2 * cnd) * x - curl) * cndinv;
+      else xn = x - curl;
+    }
+    else if (CND) {
+      const T fcn = ((1 - dt2 * cnd) * fcnd - curl) * cndinv;
+      stout(pfcnd, fcn);
+      xn = (kms * x + (fcn - fcnd)) * sinv;
+    }
+    else
+      xn = (kms * x - curl) * sinv;
+    T fn;
+    if (FU) {
+      stout(pfu, xn);
+      fn = sinvu * (kmsu * f + xn - fu);
+    }
+    else
+      fn = xn;
+    stout(pf, fn);
+    if (EPI) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
+      const bool metal = metal_yz || ix == mlo || ix == mhi;
+      const T d = metal ? T(0) : fn;
+      const T val = HASU ? d * u : d;
+      if (FW) {
+        stout(pfw, val);
+        stout(pe, e + ((kapw + sigw) * val - (kapw - sigw) * fw));
+      }
+      else
+        stout(pe, val);
+    }
+    // ---- advance the cursors by one x-plane ----
+    pf += sx;
+    g1 += sx;
+    g2 += sx;
+    if (FU) pfu += sx;
+    if (CND) {
+      pcnd += sx;
+      pcndinv += sx;
+      if (PML) pfcnd += sx;
+    }
+    if (EPI) pe += sx;
+    if (FW) pfw += sx;
+    if (HASU) pu += sx;
+    if (dk) {
+      tsig += dk;
+      tkap += dk;
+      tsinv += dk;
+    }
+    if (dku) {
+      tsigu += dku;
+      tkapu += dku;
+      tsinvu += dku;
+    }
+    if (dkw) {
+      tsigw += dkw;
+      tkapw += dkw;
+    }
+  }
+}
+
 #ifdef __CUDACC__
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 3)
+    step3c_kernel(const mb200_step3_job_t *__restrict__ jobs,
+                  const int64_t *__restrict__ tile_prefix, int njobs) {
+  __shared__ mb200_step3_job_t J;
+  int64_t tile;
+  // consecutive CTAs take the three components of the same tile: the curl operands they share
+  // are fetched from DRAM once and found in L2 by the other two
+  stage_job_at(&J, jobs, tile_prefix, njobs, (int64_t)(blockIdx.x / 3), &tile);
+  step3c_thread<T>(J, (int)(blockIdx.x % 3), tile, threadIdx.x);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -351,9 +529,11 @@ static void launch_step3_params(const mb200_step3_job_t *h_jobs, const int64_t *
 
 template <typename T>
 static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
-                         int64_t tiles, bool all_plain, cudaStream_t s) {
+                         int64_t tiles, bool all_plain, bool split, cudaStream_t s) {
   if (all_plain)
     step3_plain_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
+  else if (split)
+    step3c_kernel<T><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
   else
     step3_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
 }

@@ -294,13 +294,12 @@ __device__ __forceinline__ int find_job(const int64_t *__restrict__ tile_prefix,
 }
 
 template <typename JOB>
-__device__ __forceinline__ void stage_job(JOB *sm, const JOB *__restrict__ jobs,
-                                          const int64_t *__restrict__ tile_prefix, int njobs,
-                                          int64_t *tile_in_job) {
+__device__ __forceinline__ void stage_job_at(JOB *sm, const JOB *__restrict__ jobs,
+                                             const int64_t *__restrict__ tile_prefix, int njobs,
+                                             int64_t tile, int64_t *tile_in_job) {
   __shared__ int s_job;
   __shared__ int64_t s_tile;
   if (threadIdx.x == 0) {
-    const int64_t tile = blockIdx.x;
     const int j = find_job(tile_prefix, njobs, tile);
     s_job = j;
     s_tile = tile - __ldg(tile_prefix + j);
@@ -312,6 +311,12 @@ __device__ __forceinline__ void stage_job(JOB *sm, const JOB *__restrict__ jobs,
     dst[k] = __ldg(src + k);
   __syncthreads();
   *tile_in_job = s_tile;
+}
+template <typename JOB>
+__device__ __forceinline__ void stage_job(JOB *sm, const JOB *__restrict__ jobs,
+                                          const int64_t *__restrict__ tile_prefix, int njobs,
+                                          int64_t *tile_in_job) {
+  stage_job_at(sm, jobs, tile_prefix, njobs, (int64_t)blockIdx.x, tile_in_job);
 }
 
 // ---- step_curl ---------------------------------------------------------------------------------

@@ -33,6 +33,25 @@ template <typename T> MB200_HD T ldro(const T *p) {
 #endif
 }
 
+// Loads / stores of the arrays a kernel updates.  Job descriptors hand us generic pointers; every
+// array lives in global memory (mb200_malloc), and saying so (ld.global / st.global instead of
+// generic LD / ST) lets the compiler keep CTA-uniform descriptor fields, which sit in shared
+// memory, in registers across the stores of a marching loop instead of re-reading them.
+template <typename T> MB200_HD T ldmut(const T *p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+template <typename T> MB200_HD void stout(T *p, T v) {
+#if defined(__CUDA_ARCH__)
+  __stcg(p, v);
+#else
+  *p = v;
+#endif
+}
+
 // index of loop point (i1,i2,i3) in a box
 MB200_HD int64_t box_index(const mb200_box_t &b, int i1, int i2, int i3) {
   return b.idx0 + (int64_t)i1 * b.s[0] + (int64_t)i2 * b.s[1] + (int64_t)i3 * b.s[2];

@@ -115,10 +115,18 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
       case MB200_K_STEP3: {
         const mb200_step3_job_t &J = ((const mb200_step3_job_t *)p->jobs.data())[j];
         const bool plain = step3_is_plain(J);
-        for (int64_t t = 0; t < ntiles; ++t)
+        static const bool split = !(getenv("MEEP_B200_SPLIT_PML") && atoi(getenv("MEEP_B200_SPLIT_PML")) == 0);
+        for (int64_t t = 0; t < ntiles; ++t) {
+          if (!plain && split) {
+            for (int c = 0; c < 3; ++c)
+              for (int tid = 0; tid < kThreads; ++tid)
+                step3c_thread<T>(J, c, t, tid);
+            continue;
+          }
           for (int tid = 0; tid < kThreads; ++tid)
             if (plain) step3_plain_thread<T>(J, t, tid);
             else step3_thread<T>(J, t, tid);
+        }
         break;
       }
       case MB200_K_FMP: {
