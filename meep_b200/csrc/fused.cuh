@@ -286,29 +286,18 @@ MB200_HD void step3_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
 // one component per thread and three times as many CTAs: a third of the operands per thread
 // (descriptor fields stay in registers across the march instead of being re-read from shared
 // memory; twice the resident warps).
-template <typename T>
-MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int tid) {
-  const mb200_box_t box = step3_box(J);
-  int ix0, ix_end, iy, iz;
-  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
-  const mb200_step3_comp_t &C = J.c[c];
-  if (!C.f || iy < C.lo[1] || iy > C.hi[1] || iz < C.lo[2] || iz > C.hi[2]) return;
-  int64_t i = box_index(box, ix0, iy, iz);
-  const int64_t sx = box.s[0];
-  ix0 += box.reserved; // loop index -> array index along direction 0
-  ix_end += box.reserved;
-  if (ix0 < C.lo[0]) {
-    i += (int64_t)(C.lo[0] - ix0) * sx;
-    ix0 = C.lo[0];
-  }
-  if (ix_end > C.hi[0] + 1) ix_end = C.hi[0] + 1;
-  if (ix0 >= ix_end) return;
-
-  // everything the march needs, taken out of the (shared-memory) descriptor once: array cursors
-  // at the first point, table cursors, flags
-  const bool FU = C.pmlu.sig != nullptr, PML = C.pml.sig != nullptr, CND = C.cnd != nullptr;
-  const bool EPI = C.e != nullptr, FW = EPI && C.pmlw.sig != nullptr, HASU = EPI && C.u != nullptr;
+// The march of one thread, specialised at compile time on which auxiliary levels exist (the
+// general kernel spends most of its issue slots on predicates and dead operands otherwise):
+// PML = PML-in-f (dsig), FU = f_u level (dsigu), CND = conductivity, EPI = 0 no E/H epilogue,
+// 1 diagonal update_eh, 2 diagonal update_eh through the f_w ODE.
+template <typename T, bool PML, bool FU, bool CND, int EPI>
+MB200_HD void step3c_march(const mb200_step3_job_t &J, const mb200_step3_comp_t &C, int64_t i,
+                           int64_t sx, int ix0, int ix_end, int iy, int iz) {
+  constexpr bool FW = EPI == 2;
+  const bool HASU = EPI != 0 && C.u != nullptr;
   const T dtdx = (T)C.dtdx, dt2 = (T)J.dt * T(0.5);
+  // everything the march needs, taken out of the (shared-memory) descriptor once: array cursors
+  // at the first point, table cursors
   T *pf = (T *)C.f + i;
   const T *g1 = (const T *)C.g1 + i, *g2 = (const T *)C.g2 + i;
   const int64_t s1 = C.s1, s2 = C.s2;
@@ -348,9 +337,14 @@ MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int
     kapw = ldro(tkapw);
     sigw = ldro(tsigw);
   }
-  const bool metal_yz = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
-                        iz == C.metal_hi[2];
-  const int mlo = C.metal_lo[0], mhi = C.metal_hi[0];
+  bool metal_yz = false;
+  int mlo = -1, mhi = -1;
+  if (EPI) {
+    metal_yz = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
+               iz == C.metal_hi[2];
+    mlo = C.metal_lo[0];
+    mhi = C.metal_hi[0];
+  }
 
   for (int ix = ix0; ix < ix_end; ++ix) {
     // ---- all loads of this point (as step3_load) ----
@@ -368,15 +362,15 @@ MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int
       fw = ldmut(pfw);
       e = ldmut(pe);
     }
-    if (dk) {
+    if (PML && dk) {
       kms = ldro(tkap) - ldro(tsig);
       sinv = ldro(tsinv);
     }
-    if (dku) {
+    if (FU && dku) {
       kmsu = ldro(tkapu) - ldro(tsigu);
       sinvu = ldro(tsinvu);
     }
-    if (dkw) {
+    if (FW && dkw) {
       kapw = ldro(tkapw);
       sigw = ldro(tsigw);
     }
@@ -429,20 +423,53 @@ MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int
     if (EPI) pe += sx;
     if (FW) pfw += sx;
     if (HASU) pu += sx;
-    if (dk) {
+    if (PML) {
       tsig += dk;
       tkap += dk;
       tsinv += dk;
     }
-    if (dku) {
+    if (FU) {
       tsigu += dku;
       tkapu += dku;
       tsinvu += dku;
     }
-    if (dkw) {
+    if (FW) {
       tsigw += dkw;
       tkapw += dkw;
     }
+  }
+}
+
+template <typename T>
+MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int tid) {
+  const mb200_box_t box = step3_box(J);
+  int ix0, ix_end, iy, iz;
+  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
+  const mb200_step3_comp_t &C = J.c[c];
+  if (!C.f || iy < C.lo[1] || iy > C.hi[1] || iz < C.lo[2] || iz > C.hi[2]) return;
+  int64_t i = box_index(box, ix0, iy, iz);
+  const int64_t sx = box.s[0];
+  ix0 += box.reserved; // loop index -> array index along direction 0
+  ix_end += box.reserved;
+  if (ix0 < C.lo[0]) {
+    i += (int64_t)(C.lo[0] - ix0) * sx;
+    ix0 = C.lo[0];
+  }
+  if (ix_end > C.hi[0] + 1) ix_end = C.hi[0] + 1;
+  if (ix0 >= ix_end) return;
+  const int epi = C.e ? (C.pmlw.sig ? 2 : 1) : 0;
+  const int variant = (C.pml.sig ? 12 : 0) + (C.pmlu.sig ? 6 : 0) + (C.cnd ? 3 : 0) + epi;
+  switch (variant) { // CTA-uniform
+#define MB200_S3C(v)                                                                               \
+  case v:                                                                                          \
+    step3c_march<T, ((v) / 12) != 0, (((v) / 6) % 2) != 0, (((v) / 3) % 2) != 0, (v) % 3>(         \
+        J, C, i, sx, ix0, ix_end, iy, iz);                                                         \
+    break;
+    MB200_S3C(0) MB200_S3C(1) MB200_S3C(2) MB200_S3C(3) MB200_S3C(4) MB200_S3C(5)
+    MB200_S3C(6) MB200_S3C(7) MB200_S3C(8) MB200_S3C(9) MB200_S3C(10) MB200_S3C(11)
+    MB200_S3C(12) MB200_S3C(13) MB200_S3C(14) MB200_S3C(15) MB200_S3C(16) MB200_S3C(17)
+    MB200_S3C(18) MB200_S3C(19) MB200_S3C(20) MB200_S3C(21) MB200_S3C(22) MB200_S3C(23)
+#undef MB200_S3C
   }
 }
 
