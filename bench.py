@@ -288,7 +288,7 @@ def main():
     lib.mb200_profile_enable(ctx, 0)
     prof = {}
     kinds = ["curl", "edhb", "lorentz", "fmp", "source", "halo", "zero", "dft", "flux", "step3", "beta", "exchange",
-             "cylint", "cylr0", "step3_pml", "bfast"]
+             "cylint", "cylr0", "step3_pml", "bfast", "average"]
     for k, name in enumerate(kinds):
         n_, ms_, by_ = C.c_int64(), C.c_double(), C.c_double()
         lib.mb200_profile_get(ctx, k, C.byref(n_), C.byref(ms_), C.byref(by_))
@@ -315,6 +315,17 @@ def main():
                                    "frac": alg_step / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
                                    "bytes_per_cell": alg_step / (cells / ranks_per_problem)},
                     "kernels": prof}
+
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of
+    # this very configuration (null for any other size / workload / precision)
+    if roofline and dom[0] == "step3" and args.workload == "c2" and args.n == 512 and args.prec == "f64" \
+            and world == 1:
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1n_ncu_traffic_c2_512.json")) as fh:
+                roofline["traffic"] = json.load(fh)["step3_plain_traffic_bytes_per_launch"]
+                roofline["traffic_source"] = "profiles/r1n_ncu_traffic_c2_512.json (ncu --set full, dram__bytes_read+write)"
+        except (OSError, KeyError, ValueError):
+            pass
 
     nproblems = world // ranks_per_problem
     if roofline and world > 1:

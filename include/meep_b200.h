@@ -123,6 +123,14 @@ typedef struct {
   void *F; /* f_bfast */
 } mb200_bfast_job_t;
 
+/* ---- fields_chunk::average_with_backup (src/energy_and_flux.cpp:139-147), the last stage of
+ *      fields::synchronize_magnetic_fields: f[i] = 0.5 * (f[i] + backup[i]) over a whole array */
+typedef struct {
+  void *f;
+  const void *backup;
+  int64_t n;
+} mb200_average_job_t;
+
 /* ---- cylindrical helper array (src/step_db.cpp:93-116): out = running sum over r of
  *      1/r d(r f_p)/dr, so that the unmodified step_curl produces the Z-component update.
  *      One thread per z column, serial in r (the reference's summation order). */
@@ -331,7 +339,8 @@ enum {
   MB200_K_STEP3_GENERAL = 14, /* not a plan kind: profiling slot of MB200_K_STEP3 plans that run the
                                  general (PML) fused kernel; slot 9 then holds the fast-path plans */
   MB200_K_BFAST = 15,
-  MB200_NUM_KINDS = 16
+  MB200_K_AVERAGE = 16,
+  MB200_NUM_KINDS = 17
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -389,6 +398,7 @@ int mb200_dft_flux(mb200_ctx *ctx, int dtype, const mb200_flux_job_t *jobs, int 
 int mb200_step3(mb200_ctx *ctx, int dtype, const mb200_step3_job_t *jobs, int njobs);
 int mb200_step_beta(mb200_ctx *ctx, int dtype, const mb200_beta_job_t *jobs, int njobs);
 int mb200_step_bfast(mb200_ctx *ctx, int dtype, const mb200_bfast_job_t *jobs, int njobs);
+int mb200_average_with_backup(mb200_ctx *ctx, int dtype, const mb200_average_job_t *jobs, int njobs);
 /* cylindrical coordinates: src/step_db.cpp:93-116 and 285-377 */
 int mb200_cyl_rderiv_int(mb200_ctx *ctx, int dtype, const mb200_cylint_job_t *jobs, int njobs);
 int mb200_cyl_origin(mb200_ctx *ctx, int dtype, const mb200_cylr0_job_t *jobs, int njobs);

@@ -17,7 +17,8 @@ K_CYLINT = 12
 K_CYLR0 = 13
 K_STEP3_GENERAL = 14
 K_BFAST = 15
-NUM_KINDS = 16
+K_AVERAGE = 16
+NUM_KINDS = 17
 MAX_P = 8
 
 
@@ -121,6 +122,10 @@ class BfastJob(C.Structure):
                 ("F", C.c_void_p)]
 
 
+class AverageJob(C.Structure):
+    _fields_ = [("f", C.c_void_p), ("backup", C.c_void_p), ("n", C.c_int64)]
+
+
 class CylIntJob(C.Structure):
     _fields_ = [("out", C.c_void_p), ("fp", C.c_void_p), ("nr", C.c_int64), ("sr", C.c_int64),
                 ("ir0", C.c_double)]
@@ -139,7 +144,7 @@ class Xfer(C.Structure):
 
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,
              K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job, K_BETA: BetaJob,
-             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job, K_BFAST: BfastJob}
+             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job, K_BFAST: BfastJob, K_AVERAGE: AverageJob}
 
 
 def declare(lib):
@@ -179,6 +184,7 @@ def declare(lib):
         "mb200_step3": (i, [vp, i, vp, i]),
         "mb200_step_beta": (i, [vp, i, vp, i]),
         "mb200_step_bfast": (i, [vp, i, vp, i]),
+        "mb200_average_with_backup": (i, [vp, i, vp, i]),
         "mb200_cyl_rderiv_int": (i, [vp, i, vp, i]),
         "mb200_cyl_origin": (i, [vp, i, vp, i]),
         "mb200_comm_unique_id": (i, [vp]),

@@ -227,6 +227,15 @@ template <typename T> MB200_HD void halo_thread(const mb200_halo_job_t &J, int64
     halo_run_transfer<T>(run, e);
 }
 
+template <typename T> MB200_HD void average_thread(const mb200_average_job_t &J, int64_t tile, int tid) {
+  T *f = (T *)J.f;
+  const T *b = (const T *)J.backup;
+  for (int k = 0; k < kItems1D; ++k) {
+    const int64_t i = (tile * kItems1D + k) * kThreads + tid;
+    if (i < J.n) f[i] = (T)(0.5 * (f[i] + b[i]));
+  }
+}
+
 template <typename T> MB200_HD void bfast_thread(const mb200_bfast_job_t &J, int64_t tile, int tid) {
   int i1_0, i1_end, i2, i3;
   if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
@@ -350,6 +359,17 @@ __global__ void __launch_bounds__(kThreads)
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   lorentz_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- average_with_backup ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    average_kernel(const mb200_average_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                   int njobs) {
+  __shared__ mb200_average_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  average_thread<T>(J, tile, threadIdx.x);
 }
 
 // ---- step_bfast ----------------------------------------------------------------------------------

@@ -101,6 +101,7 @@ Engine::~Engine() {
   recording_ = false;
   invalidate_plans();
   drop_links();
+  drop_backups();
   for (auto &kv : arrs_)
     mb200_free(ctx, kv.second.dev);
   arrs_.clear();
@@ -139,6 +140,10 @@ void *Engine::ensure(const void *host, size_t bytes, bool is_field, int init) {
     }
     mb200_free(ctx, it->second.dev); // same address, different size: the host re-allocated
     arrs_.erase(it);
+    if (backups.count(host)) {
+      mb200_free(ctx, backups[host]);
+      backups.erase(host);
+    }
     invalidate_plans();
   }
   Arr arr;
@@ -167,6 +172,10 @@ void Engine::forget(const void *host) {
   invalidate_plans();
   mb200_free(ctx, it->second.dev);
   arrs_.erase(it);
+  if (backups.count(host)) {
+    mb200_free(ctx, backups[host]);
+    backups.erase(host);
+  }
 }
 
 void *Engine::aux_upload(const void *host, size_t bytes) {
@@ -184,6 +193,31 @@ void *Engine::aux_alloc(size_t bytes) {
   check(mb200_malloc(ctx, bytes ? bytes : 8, &d), "mb200_malloc(aux)");
   rec_aux_.push_back(d);
   return d;
+}
+
+// ---- device-side backups (synchronize_magnetic_fields) ----------------------------------------------
+
+void Engine::backup_array(const void *host) {
+  if (!host) return;
+  auto it = arrs_.find((uintptr_t)host);
+  if (it == arrs_.end()) meep::abort("meep_b200: backup of an array that has no device mirror");
+  void *&b = backups[host];
+  if (!b) check(mb200_malloc(ctx, it->second.bytes, &b), "mb200_malloc(backup)");
+  check(mb200_d2d(ctx, b, it->second.dev, it->second.bytes), "mb200_d2d(backup)");
+}
+
+void Engine::restore_array(const void *host) {
+  auto b = backups.find(host);
+  if (!host || b == backups.end()) return;
+  auto it = arrs_.find((uintptr_t)host);
+  if (it == arrs_.end()) return;
+  check(mb200_d2d(ctx, it->second.dev, b->second, it->second.bytes), "mb200_d2d(restore)");
+}
+
+void Engine::drop_backups() {
+  for (auto &kv : backups)
+    mb200_free(ctx, kv.second);
+  backups.clear();
 }
 
 // ---- peer-memory links ----------------------------------------------------------------------------
@@ -591,7 +625,7 @@ void Engine::leave(fields *f, bool modified) {
   // solve_cw (src/cw_fields.cpp:25-73) gathers / scatters the host arrays directly around every
   // fields::step(): in that mode the host copy is the master between calls
   // (cw_mode is set by fields::step)
-  if (!in_step || cw_mode) {
+  if ((!in_step && !keep_on_device) || cw_mode) {
     // The caller is reference/user code running a piece of the schedule by itself (e.g.
     // synchronize_magnetic_fields, initialize_field): it works on the host arrays right
     // before and after this call, so hand them back and assume it will modify them.

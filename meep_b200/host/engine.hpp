@@ -202,6 +202,13 @@ public:
   mb200_comm *comm = nullptr; // inter-process exchange (created on first use when WORLD_SIZE > 1)
   bool emulated = false;      // the C ABI is served by the test-only emulator
   bool halo_runs = true;      // MEEP_B200_HALO_RUNS=0: plain address lists for every halo job
+  // device-side copies made by fields::synchronize_magnetic_fields (host array -> backup buffer)
+  std::map<const void *, void *> backups;
+  void backup_array(const void *host);
+  void restore_array(const void *host);
+  bool has_backup(const void *host) const { return backups.count(host) != 0; }
+  void drop_backups();
+  int keep_on_device = 0;     // > 0: a stand-alone phase call leaves the arrays in HBM (no hand-back)
   bool cw_mode = false;       // inside solve_cw: the host arrays are the master between steps
   bool p2p = true;            // MEEP_B200_P2P=0: move comm blocks with NCCL instead of peer stores
   // peer-memory links (see P2PLink).  (Re)built collectively by the first in-step

@@ -103,8 +103,6 @@ void fields::loop_in_chunks(field_chunkloop chunkloop, void *chunkloop_data, con
   }
 MB200_WRITER_HOOK(zero_fields)
 MB200_WRITER_HOOK(use_real_fields)
-MB200_WRITER_HOOK(synchronize_magnetic_fields)
-MB200_WRITER_HOOK(restore_magnetic_fields)
 MB200_WRITER_HOOK(remove_susceptibilities)
 #undef MB200_WRITER_HOOK
 

@@ -237,6 +237,29 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
+  else if (cs == "3d_sync_magnetic") {
+    // fields::synchronize_magnetic_fields / restore_magnetic_fields (src/energy_and_flux.cpp:149-178)
+    // around an energy evaluation, stepping on afterwards, and a dump in the synchronised state
+    g_L = 2.0;
+    grid_volume gv = vol3d(2.0, 2.0, 2.0, a);
+    structure s(gv, eps_box, pml(0.5), identity(), num_chunks);
+    fields f(&s);
+    f.use_real_fields();
+    f.add_point_source(Ez, 0.3, 3.0, 0.0, 2.0, gv.center() + vec(0.05, 0.05, 0.05));
+    f.add_point_source(Hx, 0.3, 3.0, 0.0, 2.0, gv.center());
+    std::vector<double> en;
+    for (int i = 0; i < nsteps; ++i) {
+      f.step();
+      if (i % 7 == 3) {
+        en.push_back(f.field_energy());
+        en.push_back(f.magnetic_energy_in_box(gv.surroundings()));
+      }
+    }
+    dump("energy", en.data(), sizeof(double), en.size());
+    f.synchronize_magnetic_fields();
+    dump_fields(f);
+    f.restore_magnetic_fields();
+  }
   else if (cs == "3d_xperiodic_ypml") {
     g_L = 1.0;
     grid_volume gv = vol3d(1.0, 3.0, 1.0, a);

@@ -30,6 +30,7 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_beta_real", 60, 2),
     ("2d_mirror_sym", 60, 0),
     ("3d_rotate_sym", 40, 2),
+    ("3d_sync_magnetic", 30, 0),
     ("3d_bfast", 40, 0),
     ("2d_bfast", 80, 3),
     ("cyl_m0", 60, 0),
