@@ -71,7 +71,7 @@ static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("M
 
 // MEEP_B200_SPLIT_PML=0 runs the PML chunks with the three-components-per-thread general kernel
 // instead of the one-component-per-thread form (A/B switch; see profiles/)
-static const bool g_split_general = !(getenv("MEEP_B200_SPLIT_PML") && atoi(getenv("MEEP_B200_SPLIT_PML")) == 0);
+static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 1;
 
 template <typename T>
 static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {

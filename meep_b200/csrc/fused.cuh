@@ -475,8 +475,8 @@ MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int
 
 #ifdef __CUDACC__
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 3)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     step3c_kernel(const mb200_step3_job_t *__restrict__ jobs,
                   const int64_t *__restrict__ tile_prefix, int njobs) {
   __shared__ mb200_step3_job_t J;
@@ -556,11 +556,13 @@ static void launch_step3_params(const mb200_step3_job_t *h_jobs, const int64_t *
 
 template <typename T>
 static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
-                         int64_t tiles, bool all_plain, bool split, cudaStream_t s) {
+                         int64_t tiles, bool all_plain, int split, cudaStream_t s) {
   if (all_plain)
     step3_plain_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
+  else if (split == 4) // MEEP_B200_SPLIT_PML=4: 64 registers, 4 CTAs per SM
+    step3c_kernel<T, 4><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
   else if (split)
-    step3c_kernel<T><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
+    step3c_kernel<T, 3><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
   else
     step3_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
 }

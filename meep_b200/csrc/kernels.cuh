@@ -208,7 +208,8 @@ template <typename T> MB200_HD void beta_thread(const mb200_beta_job_t &J, int64
 
 // list form: one thread per transfer.  Run-length form: the tiles after the PHASE tiles hold
 // kHaloRunsPerTile runs each, one warp per run, lanes striding through its elements.
-constexpr int kHaloRunsPerTile = kThreads / 32;
+constexpr int kHaloRunsPerWarp = 4; // amortises the per-CTA job staging over more values
+constexpr int kHaloRunsPerTile = (kThreads / 32) * kHaloRunsPerWarp;
 MB200_HD int64_t halo_list_tiles(const mb200_halo_job_t &J) {
   const int64_t n = J.nrun > 0 ? J.n_phase : J.n_phase + J.n_negate + J.n_copy;
   return (n + kThreads - 1) / kThreads;
@@ -220,11 +221,12 @@ template <typename T> MB200_HD void halo_thread(const mb200_halo_job_t &J, int64
     if (n < (J.nrun > 0 ? J.n_phase : halo_count(J))) halo_transfer<T>(J, n);
     return;
   }
-  const int64_t r = (tile - lt) * kHaloRunsPerTile + tid / 32;
-  if (r >= J.nrun) return;
-  const mb200_halo_run_t run = J.runs[r];
-  for (int e = tid % 32; e < run.n; e += 32)
-    halo_run_transfer<T>(run, e);
+  const int64_t r0 = (tile - lt) * kHaloRunsPerTile + (tid / 32) * kHaloRunsPerWarp;
+  for (int64_t r = r0; r < r0 + kHaloRunsPerWarp && r < J.nrun; ++r) {
+    const mb200_halo_run_t run = J.runs[r];
+    for (int e = tid % 32; e < run.n; e += 32)
+      halo_run_transfer<T>(run, e);
+  }
 }
 
 template <typename T> MB200_HD void average_thread(const mb200_average_job_t &J, int64_t tile, int tid) {

@@ -91,6 +91,8 @@ Engine::Engine(fields *) {
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   p2p = env_int("MEEP_B200_P2P", 1) != 0;
   halo_runs = env_int("MEEP_B200_HALO_RUNS", 1) != 0;
+  pml_t1 = env_int("MEEP_B200_PML_T1", 4);
+  if (pml_t1 < 1 || pml_t1 > 64) pml_t1 = 4;
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;
@@ -818,7 +820,7 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
         }
         if (!plain) {
           mb200_step3_job_t g = j;
-          g.reserved = 4; // thin PML slabs: shorter marches, more CTAs in flight
+          g.reserved = pml_t1; // thin PML slabs: shorter marches, more CTAs in flight
           s3_gen.push_back(g);
         }
         else
