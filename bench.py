@@ -100,6 +100,18 @@ def run_reference(args):
     return r
 
 
+def workload_text(workload, nx, ny, nz, world):
+    """config.workload: the same text for the device arm and the reference arm"""
+    return {
+        "c2": "c2: 3D dielectric box %dx%dx%d, PML(1.0) on all faces, non-dispersive, Gaussian Ez dipole, "
+              "res 10, Courant 0.5, real fields (BASELINE.json configs[1]%s)"
+              % (nx, ny, nz, "" if world == 1 else "; configs[4] scaling form"),
+        "c3": "c3: Drude + 5 Lorentz Au sphere %dx%dx%d, PML(1.0), 100-frequency DFT flux box "
+              "(BASELINE.json configs[2], scaled to fit one GPU in double)" % (nx, ny, nz),
+        "c4": "c4: anisotropic subpixel-smoothed Si ring %dx%dx%d, off-diagonal chi1inv, PML(1.0) "
+              "(BASELINE.json configs[3], scaled)" % (nx, ny, nz)}[workload]
+
+
 def cpu_baseline_obj(r):
     return {"value": r["cells_per_s"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference",
             "sample": "same workload at %d^3 (%d chunks), %d timed steps after %d warm-up, OpenMP on all host "
@@ -144,12 +156,18 @@ def main():
         if rank != 0:
             return 0
         r = run_reference(args)
+        # the device arm's config at this GPU count; each step is a bounded sample of it
+        n_dev = max(args.gpus, 1)
+        nx = args.n * n_dev if (n_dev > 1 and args.scaling == "weak" and not args.replicas) else args.n
+        nz = args.n // 4 if args.workload == "c4" else args.n
         line = {"impl": "reference", "metric": "Yee cell-updates/s", "value": r["cells_per_s"],
                 "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"],
-                "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True,
+                "scaling": args.scaling if n_dev > 1 and not args.replicas else "weak",
                 "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
-                "config": {"workload": "c2: 3D dielectric box + PML, Gaussian dipole (bounded sample %d^3 of "
-                                       "the 512^3 config)" % r["n"], "n": r["n"], "num_chunks": r["num_chunks"]},
+                "config": {"workload": workload_text(args.workload, nx, args.n, nz, n_dev), "n": args.n,
+                           "cell": [nx, args.n, nz], "sample_n": r["n"], "sample_num_chunks": r["num_chunks"],
+                           "parallelism": "host CPU, OpenMP on %d cores" % r["cores"]},
                 "cpu_baseline": cpu_baseline_obj(r),
                 "e2e": {"value": r["cells_per_s"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
@@ -335,14 +353,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": args.scaling if sharded else "weak", "vs_baseline": None,
             "dtype": args.prec, "data": "synthetic",
-            "config": {"workload": {
-                "c2": "c2: 3D dielectric box %dx%dx%d, PML(1.0) on all faces, non-dispersive, Gaussian Ez dipole, "
-                      "res 10, Courant 0.5, real fields (BASELINE.json configs[1]%s)"
-                      % (nx, args.n, nz, "" if world == 1 else "; configs[4] scaling form"),
-                "c3": "c3: Drude + 5 Lorentz Au sphere %dx%dx%d, PML(1.0), 100-frequency DFT flux box "
-                      "(BASELINE.json configs[2], scaled to fit one GPU in double)" % (nx, args.n, nz),
-                "c4": "c4: anisotropic subpixel-smoothed Si ring %dx%dx%d, off-diagonal chi1inv, PML(1.0) "
-                      "(BASELINE.json configs[3], scaled)" % (nx, args.n, nz)}[args.workload],
+            "config": {"workload": workload_text(args.workload, nx, args.n, nz, world),
                        "n": args.n, "cell": [nx, args.n, nz], "num_chunks": drv.mb200_bench_num_chunks(h),
                        "parallelism": ("sharded: split_by_cost over %d ranks, device-to-device halo exchange" % world)
                        if sharded else ("replicas only" if world > 1 else "single GPU"),

@@ -1,0 +1,49 @@
+"""bench.py contract checks that need no GPU: the reference arm's JSON line (bounded CPU sample of
+the device arm's workload) and its behaviour under a torchrun-style multi-process launch."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from parity_util import ROOT
+
+BENCH = os.path.join(ROOT, "bench.py")
+REF_EXE = os.path.join(ROOT, "meep_b200", "lib", "bench_ref_f64")
+KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+        "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"}
+
+
+def _run(extra, env=None):
+    r = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--steps", "2", "--warmup", "3",
+                        "--cpu-n", "32"] + extra, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="reference bench driver not built")
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    out = _run([]).strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    assert KEYS <= set(d)
+    assert d["impl"] == "reference" and d["metric"] == "Yee cell-updates/s" and d["unit"] == "cell-updates/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # same workload text as the device arm prints for the default configuration
+    assert "512x512x512" in d["config"]["workload"] and "BASELINE.json configs[1]" in d["config"]["workload"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_EXE), reason="reference bench driver not built")
+def test_reference_arm_under_a_two_rank_launch_only_rank_zero_reports():
+    outs = []
+    for rank in (0, 1):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT="29713")
+        outs.append(_run(["--gpus", "2"], env=env).strip())
+    assert outs[1] == ""
+    d = json.loads(outs[0])
+    assert d["n_gpus"] == 2 and "1024x512x512" in d["config"]["workload"]
