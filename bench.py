@@ -100,6 +100,17 @@ def run_reference(args):
     return r
 
 
+def dist_max(x, world, device):
+    """max over ranks of a host scalar (device timings are reduced with this; bench contract)"""
+    if world <= 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def workload_text(workload, nx, ny, nz, world):
     """config.workload: the same text for the device arm and the reference arm"""
     return {
@@ -232,11 +243,7 @@ def main():
             dist.barrier()
 
     def max_over_ranks(x):
-        if world > 1:
-            t = torch.tensor([x], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item())
-        return x
+        return dist_max(x, world, "cuda")
 
     # warm-up: first step uploads all arrays, allocates PML aux fields, builds connection
     # tables (reference host code) and all launch plans

@@ -47,3 +47,28 @@ def test_reference_arm_under_a_two_rank_launch_only_rank_zero_reports():
     assert outs[1] == ""
     d = json.loads(outs[0])
     assert d["n_gpus"] == 2 and "1024x512x512" in d["config"]["workload"]
+
+
+def test_max_over_ranks_reduction_with_gloo_world_size_2(tmp_path):
+    """the timing reduction bench.py uses (max over ranks), exercised over gloo on the CPU"""
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import os, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "import torch.distributed as dist\n"
+        "import bench\n"
+        "dist.init_process_group('gloo')\n"
+        "r = dist.get_rank()\n"
+        "v = bench.dist_max(10.0 + 5.0 * r, dist.get_world_size(), 'cpu')\n"
+        "dist.barrier()\n"
+        "assert v == 15.0, v\n"
+        "print('ok', r)\n" % ROOT)
+    procs = []
+    for rank in (0, 1):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT="29714")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0 and "ok" in out, out[-2000:]
