@@ -559,8 +559,12 @@ static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, i
                          int64_t tiles, bool all_plain, int split, cudaStream_t s) {
   if (all_plain)
     step3_plain_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
-  else if (split == 4) // MEEP_B200_SPLIT_PML=4: 64 registers, 4 CTAs per SM
+  else if (split == 4) // MEEP_B200_SPLIT_PML=4|5|6: CTAs per SM (64 / 51 / 42 registers)
     step3c_kernel<T, 4><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
+  else if (split == 5)
+    step3c_kernel<T, 5><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
+  else if (split == 6)
+    step3c_kernel<T, 6><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
   else if (split)
     step3c_kernel<T, 3><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
   else

@@ -224,8 +224,18 @@ template <typename T> MB200_HD void halo_thread(const mb200_halo_job_t &J, int64
   const int64_t r0 = (tile - lt) * kHaloRunsPerTile + (tid / 32) * kHaloRunsPerWarp;
   for (int64_t r = r0; r < r0 + kHaloRunsPerWarp && r < J.nrun; ++r) {
     const mb200_halo_run_t run = J.runs[r];
-    for (int e = tid % 32; e < run.n; e += 32)
-      halo_run_transfer<T>(run, e);
+    // four loads in flight per lane before the first store
+    for (int e = tid % 32; e < run.n; e += 128) {
+      T v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (e + 32 * q < run.n)
+          v[q] = ldmut((const T *)(uintptr_t)(run.src0 + (int64_t)(e + 32 * q) * run.dsrc));
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (e + 32 * q < run.n)
+          stout((T *)(uintptr_t)(run.dst0 + (int64_t)(e + 32 * q) * run.ddst), run.negate ? -v[q] : v[q]);
+    }
   }
 }
 
