@@ -70,8 +70,10 @@ struct mb200_plan {
 static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("MEEP_B200_PARAMJOBS")) != 0;
 
 // MEEP_B200_SPLIT_PML=0 runs the PML chunks with the three-components-per-thread general kernel
-// instead of the one-component-per-thread form (A/B switch; see profiles/)
-static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 1;
+// instead of the one-component-per-thread form; 3..6 = CTAs per SM of the latter (default 4: 64
+// registers).  Measured at 512^3 (profiles/r1q_*): 0 -> 1.52 ms, 3 -> 1.25, 4 -> 1.04, 5 -> 1.18,
+// 6 -> 1.36 ms per step (16 planes per CTA).
+static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 4;
 
 template <typename T>
 static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {

@@ -91,8 +91,10 @@ Engine::Engine(fields *) {
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   p2p = env_int("MEEP_B200_P2P", 1) != 0;
   halo_runs = env_int("MEEP_B200_HALO_RUNS", 1) != 0;
-  pml_t1 = env_int("MEEP_B200_PML_T1", 4);
-  if (pml_t1 < 1 || pml_t1 > 64) pml_t1 = 4;
+  plain_t1 = env_int("MEEP_B200_PLAIN_T1", 0);
+  if (plain_t1 < 0 || plain_t1 > 64) plain_t1 = 0;
+  pml_t1 = env_int("MEEP_B200_PML_T1", 16);
+  if (pml_t1 < 1 || pml_t1 > 64) pml_t1 = 16;
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   nan_check_every = env_int("MEEP_B200_NAN_CHECK_EVERY", 16);
   if (nan_check_every < 1) nan_check_every = 1;
@@ -823,8 +825,11 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
           g.reserved = pml_t1; // thin PML slabs: shorter marches, more CTAs in flight
           s3_gen.push_back(g);
         }
-        else
-          s3_plain.push_back(j);
+        else {
+          mb200_step3_job_t g = j;
+          if (plain_t1 > 0) g.reserved = plain_t1;
+          s3_plain.push_back(g);
+        }
       }
       push(ph, MB200_K_CYLINT, make_plan(*this, MB200_K_CYLINT, R.cylint.data(), R.cylint.size()));
       push(ph, MB200_K_STEP3, make_plan(*this, MB200_K_STEP3, s3_plain.data(), s3_plain.size()));
