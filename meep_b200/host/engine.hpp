@@ -201,7 +201,7 @@ public:
   mb200_ctx *ctx = nullptr;
   mb200_comm *comm = nullptr; // inter-process exchange (created on first use when WORLD_SIZE > 1)
   bool emulated = false;      // the C ABI is served by the test-only emulator
-  int plain_t1 = 0;           // MEEP_B200_PLAIN_T1: same for the fast-path kernel (0: kernel default, 8)
+  int plain_t1 = 16;          // MEEP_B200_PLAIN_T1: same for the fast-path kernel (0: kernel default, 8)
   int pml_t1 = 16;            // MEEP_B200_PML_T1: x-planes marched per CTA in PML chunks
   bool halo_runs = true;      // MEEP_B200_HALO_RUNS=0: plain address lists for every halo job
   // device-side copies made by fields::synchronize_magnetic_fields (host array -> backup buffer)
