@@ -476,6 +476,31 @@ int main(int argc, char **argv) {
     dump_flux("flux.box", fl);
     dump_fields(f);
   }
+  else if (cs == "lorentz_aniso_sigma") {
+    // Lorentzian with an anisotropic (off-diagonal) sigma tensor: the OFFDIAG terms of update_P
+    // (src/susceptibility.cpp:214-247) and the exchange of not-owned W values between chunks
+    // (WE_stuff connections, src/boundaries.cpp:396-404)
+    g_L = 2.0;
+    grid_volume gv = vol3d(2.0, 2.0, 1.6, a);
+    struct aniso_sigma : public material_function {
+      virtual void sigma_row(component c, double sigrow[3], const vec &r) {
+        const bool in = sphere(r) > 0;
+        const int k = component_index(c);
+        const double m[3][3] = {{1.0, 0.3, 0.1}, {0.3, 0.8, 0.2}, {0.1, 0.2, 1.2}};
+        for (int j = 0; j < 3; ++j)
+          sigrow[j] = in ? m[k][j] : 0.0;
+      }
+    } sig;
+    structure s(gv, eps_box, pml(0.4), identity(), num_chunks);
+    s.add_susceptibility(sig, E_stuff, lorentzian_susceptibility(0.9, 0.05));
+    fields f(&s);
+    gaussian_src_time src(0.6, 0.5);
+    f.add_point_source(Ez, src, vec(0.7, 1.0, 0.8));
+    f.add_point_source(Ex, src, vec(1.2, 0.9, 0.7));
+    for (int i = 0; i < nsteps; ++i) f.step();
+    probes(f, gv);
+    dump_fields(f);
+  }
   else if (cs == "c4_aniso_ring" || cs == "aniso_smooth") {
     // BASELINE config 4 (scaled twin): subpixel-smoothed Si ring -> off-diagonal chi1inv
     g_L = 2.4;

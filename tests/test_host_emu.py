@@ -30,6 +30,7 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_beta_real", 60, 2),
     ("2d_mirror_sym", 60, 0),
     ("3d_rotate_sym", 40, 2),
+    ("lorentz_aniso_sigma", 30, 4),
     ("3d_sync_magnetic", 30, 0),
     ("3d_bfast", 40, 0),
     ("2d_bfast", 80, 3),
@@ -97,6 +98,7 @@ MP_CASES = [  # (case, steps, num_chunks, world_size)
     ("c4_aniso_ring", 12, 2, 2),
     ("cyl_m1", 40, 4, 2),
     ("c2_3d_pml", 20, 8, 4),
+    ("lorentz_aniso_sigma", 30, 4, 2),
     ("3d_xperiodic_ypml", 20, 6, 3),
 ]
 
