@@ -177,6 +177,14 @@ void FN(oracle_zero_metal)(const mb200_zero_job_t *J) {
     *(REAL *)(uintptr_t)J->ptrs[i] = 0;
 }
 
+/* reference src/energy_and_flux.cpp:139-147 (fields_chunk::average_with_backup) */
+void FN(oracle_average_with_backup)(const mb200_average_job_t *J) {
+  REAL *fc = (REAL *)J->f;
+  const REAL *backup = (const REAL *)J->backup;
+  for (int64_t i = 0; i < J->n; i++)
+    fc[i] = 0.5 * (fc[i] + backup[i]);
+}
+
 /* reference src/step_db.cpp:104-116: running sum over r of 1/r d(r f_p)/dr */
 void FN(oracle_cyl_rderiv_int)(const mb200_cylint_job_t *J) {
   REAL *out = (REAL *)J->out;

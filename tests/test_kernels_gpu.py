@@ -204,6 +204,49 @@ def test_halo_zero_source_fmp_flux(prec):
 
     assert rel_err(halo(DevMem(prec)), halo(HostMem(prec))) <= KTOL[prec]
 
+    # the same NEGATE || COPY transfers in run-length form (constant-stride runs, one warp per run)
+    def halo_runs(mem):
+        ps, pd = mem.put(src_arr), mem.put(dst_arr)
+        runs = (capi.HaloRun * 7)()
+        spec = [(0, 3, 10, 2, 300, 1), (1000, 1, 1200, 5, 129, 0), (2000, 7, 2500, 1, 33, 0),
+                (2400, -2, 3000, 3, 64, 1), (3500, 1, 3600, 1, 1, 0), (3700, 2, 4000, -1, 130, 0),
+                (4200, 1, 4300, 1, 500, 1)]
+        total = 0
+        for k, (s0, ds, d0, dd, cnt, neg) in enumerate(spec):
+            runs[k].src0, runs[k].dst0 = ps + s0 * R, pd + d0 * R
+            runs[k].dsrc, runs[k].ddst, runs[k].n, runs[k].negate = ds * R, dd * R, cnt, neg
+            total += cnt
+        j = capi.HaloJob()
+        j.runs = mem.put(np.frombuffer(bytes(runs), dtype=np.uint8).copy())
+        j.nrun = len(spec)
+        j.n_negate = sum(c for (_, _, _, _, c, neg) in spec if neg)
+        j.n_copy = total - j.n_negate
+        mem.run(capi.K_HALO, [j])
+        out = mem.get(pd, dst_arr)
+        mem.close()
+        return out
+
+    want = dst_arr.copy()
+    for (s0, ds, d0, dd, cnt, neg) in [(0, 3, 10, 2, 300, 1), (1000, 1, 1200, 5, 129, 0), (2000, 7, 2500, 1, 33, 0),
+                                       (2400, -2, 3000, 3, 64, 1), (3500, 1, 3600, 1, 1, 0),
+                                       (3700, 2, 4000, -1, 130, 0), (4200, 1, 4300, 1, 500, 1)]:
+        for e in range(cnt):
+            want[d0 + e * dd] = -src_arr[s0 + e * ds] if neg else src_arr[s0 + e * ds]
+    assert np.array_equal(halo_runs(HostMem(prec)), want)
+    assert np.array_equal(halo_runs(DevMem(prec)), want)
+
+    # average_with_backup
+    def average(mem):
+        pf = mem.put(dst_arr)
+        j = capi.AverageJob()
+        j.f, j.backup, j.n = pf, mem.put(src_arr), n
+        mem.run(capi.K_AVERAGE, [j])
+        out = mem.get(pf, dst_arr)
+        mem.close()
+        return out
+
+    assert np.array_equal(average(DevMem(prec)), average(HostMem(prec)))
+
     # zero_metal
     mem = DevMem(prec)
     pd = mem.put(dst_arr)
