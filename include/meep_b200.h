@@ -123,6 +123,26 @@ typedef struct {
   void *F; /* f_bfast */
 } mb200_bfast_job_t;
 
+/* ---- gyrotropic_susceptibility::update_P (src/meep.hpp:304-338, src/susceptibility.cpp:445-584):
+ *      three polarisation components at the Yee position of one driving-field component.
+ *      Arrays and tensors are given in the rotated frame (d0, d1, d2) = (direction of the field
+ *      component, the next two cyclic directions): p[k] / pp[k] = P, P_prev along d_k,
+ *      w[0] = the field itself, w[1], w[2] = the other two components (may be NULL),
+ *      gt[a][b] = gyro_tensor[d_a][d_b], inv[a][b] = inv[d_a][d_b] (the reference's precomputed
+ *      3x3 inverse).  model 0: GYROTROPIC_LORENTZIAN / GYROTROPIC_DRUDE (lines 454-510; c[0] = diag,
+ *      c[1] = gamma1, c[2] = omega0dtsqr, c[3] = pt), model 1: GYROTROPIC_SATURATED (lines 512-578;
+ *      c[0] = omega2pidt, c[1] = g2pidt, c[2] = alpha, c[3] = dt2pi). */
+typedef struct {
+  mb200_box_t box;
+  void *p[3], *pp[3];
+  const void *w[3];
+  const void *s;
+  int64_t is, is1, is2;
+  double c[4];
+  double gt[3][3], inv[3][3];
+  int32_t model, reserved;
+} mb200_gyro_job_t;
+
 /* ---- fields_chunk::average_with_backup (src/energy_and_flux.cpp:139-147), the last stage of
  *      fields::synchronize_magnetic_fields: f[i] = 0.5 * (f[i] + backup[i]) over a whole array */
 typedef struct {
@@ -340,7 +360,8 @@ enum {
                                  general (PML) fused kernel; slot 9 then holds the fast-path plans */
   MB200_K_BFAST = 15,
   MB200_K_AVERAGE = 16,
-  MB200_NUM_KINDS = 17
+  MB200_K_GYRO = 17,
+  MB200_NUM_KINDS = 18
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -388,6 +409,7 @@ int mb200_step_update_EDHB(mb200_ctx *ctx, int dtype, const mb200_edhb_job_t *jo
 int mb200_lorentzian_update_P(mb200_ctx *ctx, int dtype, const mb200_lorentz_job_t *jobs,
                               int njobs);
 int mb200_subtract_P(mb200_ctx *ctx, int dtype, const mb200_fmp_job_t *jobs, int njobs);
+int mb200_gyrotropic_update_P(mb200_ctx *ctx, int dtype, const mb200_gyro_job_t *jobs, int njobs);
 int mb200_step_source(mb200_ctx *ctx, int dtype, const mb200_src_job_t *jobs, int njobs,
                       const double *scalars, int nslots);
 int mb200_step_boundaries(mb200_ctx *ctx, int dtype, const mb200_halo_job_t *jobs, int njobs);

@@ -18,7 +18,8 @@ K_CYLR0 = 13
 K_STEP3_GENERAL = 14
 K_BFAST = 15
 K_AVERAGE = 16
-NUM_KINDS = 17
+K_GYRO = 17
+NUM_KINDS = 18
 MAX_P = 8
 
 
@@ -122,6 +123,13 @@ class BfastJob(C.Structure):
                 ("F", C.c_void_p)]
 
 
+class GyroJob(C.Structure):
+    _fields_ = [("box", Box), ("p", C.c_void_p * 3), ("pp", C.c_void_p * 3), ("w", C.c_void_p * 3),
+                ("s", C.c_void_p), ("is_", C.c_int64), ("is1", C.c_int64), ("is2", C.c_int64),
+                ("c", C.c_double * 4), ("gt", (C.c_double * 3) * 3), ("inv", (C.c_double * 3) * 3),
+                ("model", C.c_int32), ("reserved", C.c_int32)]
+
+
 class AverageJob(C.Structure):
     _fields_ = [("f", C.c_void_p), ("backup", C.c_void_p), ("n", C.c_int64)]
 
@@ -144,7 +152,7 @@ class Xfer(C.Structure):
 
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,
              K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job, K_BETA: BetaJob,
-             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job, K_BFAST: BfastJob, K_AVERAGE: AverageJob}
+             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job, K_BFAST: BfastJob, K_AVERAGE: AverageJob, K_GYRO: GyroJob}
 
 
 def declare(lib):
@@ -185,6 +193,7 @@ def declare(lib):
         "mb200_step_beta": (i, [vp, i, vp, i]),
         "mb200_step_bfast": (i, [vp, i, vp, i]),
         "mb200_average_with_backup": (i, [vp, i, vp, i]),
+        "mb200_gyrotropic_update_P": (i, [vp, i, vp, i]),
         "mb200_cyl_rderiv_int": (i, [vp, i, vp, i]),
         "mb200_cyl_origin": (i, [vp, i, vp, i]),
         "mb200_comm_unique_id": (i, [vp]),

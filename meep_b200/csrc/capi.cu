@@ -125,6 +125,9 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       beta_kernel<T><<<grid, block, 0, s>>>((const mb200_beta_job_t *)p->d_jobs, p->d_prefix,
                                             p->njobs);
       break;
+    case MB200_K_GYRO:
+      gyro_kernel<T><<<grid, block, 0, s>>>((const mb200_gyro_job_t *)p->d_jobs, p->d_prefix, p->njobs);
+      break;
     case MB200_K_AVERAGE:
       average_kernel<T><<<grid, block, 0, s>>>((const mb200_average_job_t *)p->d_jobs, p->d_prefix,
                                                p->njobs);
@@ -432,6 +435,9 @@ int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njob
 }
 int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_gyrotropic_update_P(mb200_ctx *c, int dtype, const mb200_gyro_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_GYRO, dtype, jobs, njobs, nullptr, 0);
 }
 int mb200_average_with_backup(mb200_ctx *c, int dtype, const mb200_average_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_AVERAGE, dtype, jobs, njobs, nullptr, 0);

@@ -239,6 +239,15 @@ template <typename T> MB200_HD void halo_thread(const mb200_halo_job_t &J, int64
   }
 }
 
+template <typename T> MB200_HD void gyro_thread(const mb200_gyro_job_t &J, int64_t tile, int tid) {
+  int i1_0, i1_end, i2, i3;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  int64_t i = box_index(J.box, i1_0, i2, i3);
+  const int64_t s1 = J.box.s[0];
+  for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1)
+    gyro_point<T>(J, i);
+}
+
 template <typename T> MB200_HD void average_thread(const mb200_average_job_t &J, int64_t tile, int tid) {
   T *f = (T *)J.f;
   const T *b = (const T *)J.backup;
@@ -371,6 +380,17 @@ __global__ void __launch_bounds__(kThreads)
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   lorentz_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- gyrotropic update_P ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    gyro_kernel(const mb200_gyro_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                int njobs) {
+  __shared__ mb200_gyro_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  gyro_thread<T>(J, tile, threadIdx.x);
 }
 
 // ---- average_with_backup ---------------------------------------------------------------------------

@@ -194,6 +194,48 @@ MB200_HD void beta_point(const mb200_beta_job_t &J, int64_t i, int k, int ku, T 
 }
 
 // ------------------------------------------------------------------------------------------------
+// gyrotropic_susceptibility::update_P (src/susceptibility.cpp:445-584), one loop point
+// OFFDIAGW (line 443)
+template <typename T> MB200_HD T offdiagw(const T *g, int64_t i, int64_t sx, int64_t s) {
+  return T(0.25) * (ldro(g + i) + ldro(g + i - sx) + ldro(g + i + s) + ldro(g + (i + s) - sx));
+}
+template <typename T> MB200_HD void gyro_point(const mb200_gyro_job_t &J, int64_t i) {
+  T *p0 = (T *)J.p[0], *p1 = (T *)J.p[1], *p2 = (T *)J.p[2];
+  T *pp0 = (T *)J.pp[0], *pp1 = (T *)J.pp[1], *pp2 = (T *)J.pp[2];
+  const T *w0 = (const T *)J.w[0], *w1 = (const T *)J.w[1], *w2 = (const T *)J.w[2];
+  const T si = ldro((const T *)J.s + i);
+  const T P0 = p0[i], P1 = p1[i], P2 = p2[i], Q0 = pp0[i], Q1 = pp1[i], Q2 = pp2[i];
+  const T g01 = (T)J.gt[0][1], g02 = (T)J.gt[0][2], g10 = (T)J.gt[1][0], g12 = (T)J.gt[1][2],
+          g20 = (T)J.gt[2][0], g21 = (T)J.gt[2][1];
+  T r0, r1, r2;
+  if (J.model == 0) {
+    const T diag = (T)J.c[0], gamma1 = (T)J.c[1], omega0dtsqr = (T)J.c[2], pt = (T)J.c[3];
+    r0 = diag * P0 - gamma1 * Q0 + omega0dtsqr * si * ldro(w0 + i) - pt * g01 * Q1 - pt * g02 * Q2;
+    r1 = diag * P1 - gamma1 * Q1 + (w1 ? omega0dtsqr * si * offdiagw(w1, i, J.is1, J.is) : T(0)) -
+         pt * g10 * Q0 - pt * g12 * Q2;
+    r2 = diag * P2 - gamma1 * Q2 + (w2 ? omega0dtsqr * si * offdiagw(w2, i, J.is2, J.is) : T(0)) -
+         pt * g21 * Q1 - pt * g20 * Q0;
+  }
+  else {
+    const T omega2pidt = (T)J.c[0], g2pidt = (T)J.c[1], alpha = (T)J.c[2], dt2pi = (T)J.c[3];
+    const T q0 = -omega2pidt * P0 + T(0.5) * alpha * Q0 + dt2pi * si * ldro(w0 + i);
+    const T q1 = -omega2pidt * P1 + T(0.5) * alpha * Q1 +
+                 dt2pi * si * (w1 ? offdiagw(w1, i, J.is1, J.is) : T(0));
+    const T q2 = -omega2pidt * P2 + T(0.5) * alpha * Q2 +
+                 dt2pi * si * (w2 ? offdiagw(w2, i, J.is2, J.is) : T(0));
+    r0 = T(0.5) * Q0 - g2pidt * P0 + g01 * q1 + g02 * q2;
+    r1 = T(0.5) * Q1 - g2pidt * P1 + g12 * q2 + g10 * q0;
+    r2 = T(0.5) * Q2 - g2pidt * P2 + g20 * q0 + g21 * q1;
+  }
+  pp0[i] = P0;
+  pp1[i] = P1;
+  pp2[i] = P2;
+  p0[i] = (T)J.inv[0][0] * r0 + (T)J.inv[0][1] * r1 + (T)J.inv[0][2] * r2;
+  p1[i] = (T)J.inv[1][0] * r0 + (T)J.inv[1][1] * r1 + (T)J.inv[1][2] * r2;
+  p2[i] = (T)J.inv[2][0] * r0 + (T)J.inv[2][1] * r1 + (T)J.inv[2][2] * r2;
+}
+
+// ------------------------------------------------------------------------------------------------
 // step_bfast (src/step_generic.cpp:335-530): the sixteen specialised loops as one body
 template <typename T> MB200_HD void bfast_point(const mb200_bfast_job_t &J, int64_t i, int k, int ku) {
   T *f = (T *)J.f, *F = (T *)J.F;

@@ -468,12 +468,8 @@ void Engine::scan(fields *f) {
         FOR_COMPONENTS(c) FOR_DIRECTIONS(d) ensure(sus->sigma[c][d], nb, false);
       for (polarization_state *p = fc->pol[ft]; p; p = p->next)
         if (p->data) {
-          if (typeid(*p->s) != typeid(lorentzian_susceptibility))
-            meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) polarisations "
-                        "are supported on the device path");
-          lorentzian_data_layout *d = (lorentzian_data_layout *)p->data;
-          const size_t hdr = offsetof(lorentzian_data_layout, data);
-          if (d->sz_data > hdr) ensure(d->data, d->sz_data - hdr, true);
+          const std::pair<realnum *, size_t> blk = polarisation_block(p->s, p->data);
+          if (blk.second) ensure(blk.first, blk.second, true);
         }
     }
     for (dft_chunk *d = fc->dft_chunks; d; d = d->next_in_chunk)
@@ -899,6 +895,7 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
         (j.pzero ? blocked : plainj).push_back(j);
       push(ph, MB200_K_LORENTZ, make_plan(*this, MB200_K_LORENTZ, blocked.data(), blocked.size()));
       push(ph, MB200_K_LORENTZ, make_plan(*this, MB200_K_LORENTZ, plainj.data(), plainj.size()));
+      push(ph, MB200_K_GYRO, make_plan(*this, MB200_K_GYRO, R.gyro.data(), R.gyro.size()));
       break;
     }
     case PH_DFT:

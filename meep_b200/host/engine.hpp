@@ -18,6 +18,9 @@
 #include <cstdint>
 #include <functional>
 #include <map>
+#include <typeinfo>
+#include <utility>
+#include <stddef.h>
 #include <string>
 #include <vector>
 
@@ -79,6 +82,7 @@ struct Recorder {
   std::vector<mb200_curl_job_t> curl;
   std::vector<mb200_beta_job_t> beta; // 2-D exp(i beta z) terms, run after the curl jobs
   // cylindrical coordinates: helper arrays (before the curl jobs), r = 0 rows and zeroed rows (after)
+  std::vector<mb200_gyro_job_t> gyro;   // gyrotropic polarisations (update_pols phase)
   std::vector<mb200_bfast_job_t> bfast; // BFAST corrections, after the curl jobs
   std::vector<mb200_cylint_job_t> cylint;
   std::vector<mb200_cylr0_job_t> cylr0;
@@ -310,6 +314,34 @@ struct lorentzian_data_layout {
   realnum *P_prev[meep::NUM_FIELD_COMPONENTS][2];
   realnum data[1];
 };
+
+// likewise src/susceptibility.cpp:374-380 (gyrotropic_susceptibility)
+struct gyrotropy_data_layout {
+  size_t sz_data;
+  size_t ntot;
+  realnum *P[meep::NUM_FIELD_COMPONENTS][2][3];
+  realnum *P_prev[meep::NUM_FIELD_COMPONENTS][2][3];
+  realnum data[1];
+};
+
+// the polarisation block of a susceptibility the device path supports: {start, bytes} of its data
+// area (0 bytes: nothing allocated), aborting for the kinds that are not supported
+inline std::pair<realnum *, size_t> polarisation_block(const meep::susceptibility *s, void *data) {
+  if (!data) return std::make_pair((realnum *)nullptr, (size_t)0);
+  if (typeid(*s) == typeid(meep::lorentzian_susceptibility)) {
+    lorentzian_data_layout *d = (lorentzian_data_layout *)data;
+    const size_t hdr = offsetof(lorentzian_data_layout, data);
+    return std::make_pair(d->data, d->sz_data > hdr ? d->sz_data - hdr : 0);
+  }
+  if (typeid(*s) == typeid(meep::gyrotropic_susceptibility)) {
+    gyrotropy_data_layout *d = (gyrotropy_data_layout *)data;
+    const size_t hdr = offsetof(gyrotropy_data_layout, data);
+    return std::make_pair(d->data, d->sz_data > hdr ? d->sz_data - hdr : 0);
+  }
+  meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) and gyrotropic_susceptibility "
+              "polarisations are supported on the device path");
+  return std::make_pair((realnum *)nullptr, (size_t)0);
+}
 
 } // namespace meep_b200
 #endif

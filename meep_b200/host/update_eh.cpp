@@ -137,18 +137,23 @@ bool fields_chunk::update_eh(field_type ft, bool skip_w_components) {
       // subtract_P of every polarisation that has data (src/susceptibility.cpp:264-281)
       for (polarization_state *p = pol[ft]; p; p = p->next)
         if (p->data) {
-          if (typeid(*p->s) != typeid(lorentzian_susceptibility))
-            meep::abort("meep_b200: only lorentzian_susceptibility polarisations are supported");
-          const lorentzian_data_layout *d = (const lorentzian_data_layout *)p->data;
-          if (d->P[ec][cmp]) {
+          const realnum *P = nullptr;
+          if (typeid(*p->s) == typeid(lorentzian_susceptibility))
+            P = ((const lorentzian_data_layout *)p->data)->P[ec][cmp];
+          else if (typeid(*p->s) == typeid(gyrotropic_susceptibility)) // (src/susceptibility.cpp:586-602)
+            P = ((const gyrotropy_data_layout *)p->data)->P[ec][cmp][component_direction(ec)];
+          else
+            meep::abort("meep_b200: only lorentzian_susceptibility and gyrotropic_susceptibility "
+                        "polarisations are supported");
+          if (P) {
             if (J.np == MB200_MAX_P) { // flush and continue in place
               R.fmp.push_back(J);
               J.d = nullptr;
               J.np = 0;
               memset(J.pzero, 0, sizeof(J.pzero));
             }
-            J.pzero[J.np] = E->pzero_lookup(d->P[ec][cmp]);
-            J.p[J.np++] = E->dev(d->P[ec][cmp]);
+            J.pzero[J.np] = E->pzero_lookup(P);
+            J.p[J.np++] = E->dev(P);
           }
         }
       R.fmp.push_back(J);

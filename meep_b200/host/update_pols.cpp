@@ -41,9 +41,10 @@ bool fields_chunk::update_pols(field_type ft) {
   FOR_COMPONENTS(c) DOCMP2 { w[c][cmp] = f_w[c][cmp] ? f_w[c][cmp] : f[c][cmp]; }
 
   for (polarization_state *p = pol[ft]; p; p = p->next) {
-    if (typeid(*p->s) != typeid(lorentzian_susceptibility))
-      meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) polarisations are "
-                  "supported on the device path");
+    const bool gyro = typeid(*p->s) == typeid(gyrotropic_susceptibility);
+    if (!gyro && typeid(*p->s) != typeid(lorentzian_susceptibility))
+      meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) and "
+                  "gyrotropic_susceptibility polarisations are supported on the device path");
 
     // Lazily allocate internal polarization data (host block laid out by the reference;
     // the device twin starts at zero exactly like init_internal_data's memset):
@@ -51,16 +52,19 @@ bool fields_chunk::update_pols(field_type ft) {
       p->data = p->s->new_internal_data(f, gv);
       if (p->data) {
         p->s->init_internal_data(f, dt, gv, p->data);
-        lorentzian_data_layout *d = (lorentzian_data_layout *)p->data;
-        const size_t hdr = offsetof(lorentzian_data_layout, data);
-        if (d->sz_data > hdr) E->ensure_from(d->data, d->sz_data - hdr, NULL);
+        const std::pair<realnum *, size_t> blk = polarisation_block(p->s, p->data);
+        if (blk.second) E->ensure_from(blk.first, blk.second, NULL);
         allocated_fields = true;
       }
     }
 
     // Finally, timestep the polarizations (emits jobs):
-    static_cast<const lorentzian_susceptibility *>(p->s)->lorentzian_susceptibility::update_P(
-        w, f_w_prev, dt, gv, p->data);
+    if (gyro)
+      static_cast<const gyrotropic_susceptibility *>(p->s)->gyrotropic_susceptibility::update_P(
+          w, f_w_prev, dt, gv, p->data);
+    else
+      static_cast<const lorentzian_susceptibility *>(p->s)->lorentzian_susceptibility::update_P(
+          w, f_w_prev, dt, gv, p->data);
   }
 
   return allocated_fields;
@@ -154,6 +158,113 @@ void lorentzian_susceptibility::update_P(realnum *W[NUM_FIELD_COMPONENTS][2],
 void lorentzian_susceptibility::subtract_P(field_type, realnum *[NUM_FIELD_COMPONENTS][2],
                                            void *) const {
   meep::abort("meep_b200: lorentzian_susceptibility::subtract_P: this build has no CPU "
+              "time-stepping path");
+}
+
+// gyrotropic_susceptibility::update_P (reference src/susceptibility.cpp:445-584): same constants,
+// computed in realnum as there; one mb200_gyro_job_t per (component, cmp), arrays and tensors
+// handed over in the rotated frame (d0, d1, d2) of that component.
+void gyrotropic_susceptibility::update_P(realnum *W[NUM_FIELD_COMPONENTS][2],
+                                         realnum *W_prev[NUM_FIELD_COMPONENTS][2], realnum dt,
+                                         const grid_volume &gv, void *P_internal_data) const {
+  Engine *E = Engine::current();
+  if (!E || !E->recording())
+    meep::abort("meep_b200: gyrotropic_susceptibility::update_P outside a phase: this build has no CPU "
+                "time-stepping path");
+  if (!P_internal_data) return;
+  Recorder &R = E->rec();
+  gyrotropy_data_layout *d = (gyrotropy_data_layout *)P_internal_data;
+  const realnum omega2pidt = 2 * pi * omega_0 * dt;
+  const realnum g2pidt = 2 * pi * gamma * dt;
+  (void)W_prev; // unused;
+
+  realnum c4[4], gd, gx, gy, gz;
+  int model_id;
+  switch (model) {
+    case GYROTROPIC_LORENTZIAN:
+    case GYROTROPIC_DRUDE: {
+      const realnum omega0dtsqr = omega2pidt * omega2pidt;
+      const realnum gamma1 = (1 - g2pidt / 2);
+      const realnum diag = 2 - (model == GYROTROPIC_DRUDE ? 0 : omega0dtsqr);
+      const realnum pt = pi * dt;
+      gd = (1 + g2pidt / 2);
+      gx = pt * gyro_tensor[Y][Z];
+      gy = pt * gyro_tensor[Z][X];
+      gz = pt * gyro_tensor[X][Y];
+      c4[0] = diag;
+      c4[1] = gamma1;
+      c4[2] = omega0dtsqr;
+      c4[3] = pt;
+      model_id = 0;
+    } break;
+    case GYROTROPIC_SATURATED: {
+      const realnum dt2pi = 2 * pi * dt;
+      gd = 0.5;
+      gx = -0.5 * alpha * gyro_tensor[Y][Z];
+      gy = -0.5 * alpha * gyro_tensor[Z][X];
+      gz = -0.5 * alpha * gyro_tensor[X][Y];
+      c4[0] = omega2pidt;
+      c4[1] = g2pidt;
+      c4[2] = alpha;
+      c4[3] = dt2pi;
+      model_id = 1;
+    } break;
+    default: meep::abort("meep_b200: unknown gyrotropy model"); return;
+  }
+  // Precalculate 3x3 matrix inverse, exploiting skew symmetry (lines 466-474 = 519-527)
+  const realnum invdet = 1.0 / gd / (gd * gd + gx * gx + gy * gy + gz * gz);
+  const realnum inv[3][3] = {{invdet * (gd * gd + gx * gx), invdet * (gx * gy + gd * gz),
+                              invdet * (gx * gz - gd * gy)},
+                             {invdet * (gy * gx - gd * gz), invdet * (gd * gd + gy * gy),
+                              invdet * (gy * gz + gd * gx)},
+                             {invdet * (gz * gx + gd * gy), invdet * (gz * gy - gd * gx),
+                              invdet * (gd * gd + gz * gz)}};
+
+  FOR_COMPONENTS(c) DOCMP2 {
+    if (d->P[c][cmp][0]) {
+      const direction d0 = component_direction(c);
+      const realnum *w0 = W[c][cmp], *s = sigma[c][d0];
+      if (!w0 || !s || (d0 != X && d0 != Y && d0 != Z))
+        meep::abort("gyrotropic media require 3D Cartesian fields\n");
+      const direction d1 = cycle_direction(gv.dim, d0, 1);
+      const direction d2 = cycle_direction(gv.dim, d0, 2);
+      const realnum *w1 = W[direction_component(c, d1)][cmp];
+      const realnum *w2 = W[direction_component(c, d2)][cmp];
+      const direction ds[3] = {d0, d1, d2};
+      if (!d->P_prev[c][cmp][d1] || !d->P_prev[c][cmp][d2])
+        meep::abort("gyrotropic media require 3D Cartesian fields\n");
+      if (sigma[c][d1] || sigma[c][d2])
+        meep::abort("gyrotropic media do not support anisotropic sigma\n");
+      mb200_gyro_job_t J;
+      memset(&J, 0, sizeof(J));
+      J.box = make_box(gv, gv.little_owned_corner(c), gv.big_corner()); // LOOP_OVER_VOL_OWNED
+      for (int a = 0; a < 3; ++a) {
+        J.p[a] = E->dev(d->P[c][cmp][ds[a]]);
+        J.pp[a] = E->dev(d->P_prev[c][cmp][ds[a]]);
+        for (int b = 0; b < 3; ++b) {
+          J.gt[a][b] = gyro_tensor[ds[a]][ds[b]];
+          J.inv[a][b] = inv[ds[a]][ds[b]];
+        }
+      }
+      J.w[0] = E->dev(w0);
+      J.w[1] = E->dev(w1);
+      J.w[2] = E->dev(w2);
+      J.s = E->dev(s);
+      J.is = gv.stride(d0) * (is_magnetic(c) ? -1 : +1);
+      J.is1 = gv.stride(d1) * (is_magnetic(c) ? -1 : +1);
+      J.is2 = gv.stride(d2) * (is_magnetic(c) ? -1 : +1);
+      for (int k = 0; k < 4; ++k)
+        J.c[k] = c4[k];
+      J.model = model_id;
+      if (J.box.n[0] > 0 && J.box.n[1] > 0 && J.box.n[2] > 0) R.gyro.push_back(J);
+    }
+  }
+}
+
+// (folded into the f_minus_p job of update_eh.cpp, like the Lorentzian one)
+void gyrotropic_susceptibility::subtract_P(field_type, realnum *[NUM_FIELD_COMPONENTS][2],
+                                           void *) const {
+  meep::abort("meep_b200: gyrotropic_susceptibility::subtract_P: this build has no CPU "
               "time-stepping path");
 }
 

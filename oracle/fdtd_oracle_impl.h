@@ -177,6 +177,58 @@ void FN(oracle_zero_metal)(const mb200_zero_job_t *J) {
     *(REAL *)(uintptr_t)J->ptrs[i] = 0;
 }
 
+/* reference src/susceptibility.cpp:445-584 (gyrotropic_susceptibility::update_P), the loop body
+ * for one driving-field component in its rotated frame (see mb200_gyro_job_t) */
+#define OFFDIAGW(g, sx, s) (0.25 * (g[i] + g[i - sx] + g[i + s] + g[i + s - sx]))
+void FN(oracle_gyrotropic_update_P)(const mb200_gyro_job_t *J) {
+  REAL *p0 = (REAL *)J->p[0], *p1 = (REAL *)J->p[1], *p2 = (REAL *)J->p[2];
+  REAL *pp0 = (REAL *)J->pp[0], *pp1 = (REAL *)J->pp[1], *pp2 = (REAL *)J->pp[2];
+  const REAL *w0 = (const REAL *)J->w[0], *w1 = (const REAL *)J->w[1], *w2 = (const REAL *)J->w[2];
+  const REAL *s = (const REAL *)J->s;
+  const int64_t is = J->is, is1 = J->is1, is2 = J->is2;
+  REAL gt[3][3], inv[3][3];
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      gt[a][b] = (REAL)J->gt[a][b];
+      inv[a][b] = (REAL)J->inv[a][b];
+    }
+  for (int i1 = 0; i1 < J->box.n[0]; ++i1)
+    for (int i2 = 0; i2 < J->box.n[1]; ++i2)
+      for (int i3 = 0; i3 < J->box.n[2]; ++i3) {
+        const int64_t i = J->box.idx0 + i1 * J->box.s[0] + i2 * J->box.s[1] + i3 * J->box.s[2];
+        REAL r0, r1, r2;
+        if (J->model == 0) {
+          const REAL diag = (REAL)J->c[0], gamma1 = (REAL)J->c[1], omega0dtsqr = (REAL)J->c[2],
+                     pt = (REAL)J->c[3];
+          r0 = diag * p0[i] - gamma1 * pp0[i] + omega0dtsqr * s[i] * w0[i] - pt * gt[0][1] * pp1[i] -
+               pt * gt[0][2] * pp2[i];
+          r1 = diag * p1[i] - gamma1 * pp1[i] + (w1 ? omega0dtsqr * s[i] * OFFDIAGW(w1, is1, is) : 0) -
+               pt * gt[1][0] * pp0[i] - pt * gt[1][2] * pp2[i];
+          r2 = diag * p2[i] - gamma1 * pp2[i] + (w2 ? omega0dtsqr * s[i] * OFFDIAGW(w2, is2, is) : 0) -
+               pt * gt[2][1] * pp1[i] - pt * gt[2][0] * pp0[i];
+        }
+        else {
+          const REAL omega2pidt = (REAL)J->c[0], g2pidt = (REAL)J->c[1], alpha = (REAL)J->c[2],
+                     dt2pi = (REAL)J->c[3];
+          REAL q0 = -omega2pidt * p0[i] + 0.5 * alpha * pp0[i] + dt2pi * s[i] * w0[i];
+          REAL q1 = -omega2pidt * p1[i] + 0.5 * alpha * pp1[i] +
+                    dt2pi * s[i] * (w1 ? OFFDIAGW(w1, is1, is) : 0);
+          REAL q2 = -omega2pidt * p2[i] + 0.5 * alpha * pp2[i] +
+                    dt2pi * s[i] * (w2 ? OFFDIAGW(w2, is2, is) : 0);
+          r0 = 0.5 * pp0[i] - g2pidt * p0[i] + gt[0][1] * q1 + gt[0][2] * q2;
+          r1 = 0.5 * pp1[i] - g2pidt * p1[i] + gt[1][2] * q2 + gt[1][0] * q0;
+          r2 = 0.5 * pp2[i] - g2pidt * p2[i] + gt[2][0] * q0 + gt[2][1] * q1;
+        }
+        pp0[i] = p0[i];
+        pp1[i] = p1[i];
+        pp2[i] = p2[i];
+        p0[i] = inv[0][0] * r0 + inv[0][1] * r1 + inv[0][2] * r2;
+        p1[i] = inv[1][0] * r0 + inv[1][1] * r1 + inv[1][2] * r2;
+        p2[i] = inv[2][0] * r0 + inv[2][1] * r1 + inv[2][2] * r2;
+      }
+}
+#undef OFFDIAGW
+
 /* reference src/energy_and_flux.cpp:139-147 (fields_chunk::average_with_backup) */
 void FN(oracle_average_with_backup)(const mb200_average_job_t *J) {
   REAL *fc = (REAL *)J->f;

@@ -277,6 +277,101 @@ static void gen_lorentz(const std::string &dir, const grid_volume &gv, const cha
     }
 }
 
+// ---- gyrotropic_susceptibility::update_P -----------------------------------------------------------
+struct gyro_layout { // src/susceptibility.cpp:374-380
+  size_t sz_data, ntot;
+  realnum *P[NUM_FIELD_COMPONENTS][2][3];
+  realnum *P_prev[NUM_FIELD_COMPONENTS][2][3];
+  realnum data[1];
+};
+
+static void gen_gyro(const std::string &dir, const grid_volume &gv) {
+  const size_t n = gv.ntot();
+  const gyrotropy_model models[3] = {GYROTROPIC_LORENTZIAN, GYROTROPIC_DRUDE, GYROTROPIC_SATURATED};
+  const char *mname[3] = {"lorentz", "drude", "saturated"};
+  for (int im = 0; im < 3; ++im)
+    for (int nw = 1; nw <= 3; nw += 2) { // only the driving component present / all three
+      char nm[64];
+      snprintf(nm, sizeof nm, "gyro_%s_w%d", mname[im], nw);
+      open_case(dir, nm);
+      const vec bias(0.3, -0.2, 0.9);
+      const realnum omega_0 = 0.7, gamma = 0.13, alpha = 0.05, dt = 0.05;
+      gyrotropic_susceptibility sus(bias, omega_0, gamma, alpha, models[im]);
+      const component c = Ey;
+      const direction d0 = component_direction(c);
+      const direction d1 = cycle_direction(gv.dim, d0, 1), d2 = cycle_direction(gv.dim, d0, 2);
+      const direction ds[3] = {d0, d1, d2};
+      realnum *W[NUM_FIELD_COMPONENTS][2];
+      FOR_COMPONENTS(cc) { W[cc][0] = W[cc][1] = NULL; }
+      W[c][0] = rand_array(n);
+      if (nw == 3) {
+        W[direction_component(c, d1)][0] = rand_array(n);
+        W[direction_component(c, d2)][0] = rand_array(n);
+      }
+      sus.ntot = n;
+      sus.sigma[c][d0] = rand_array(n, 0, 1);
+      sus.trivial_sigma[c][d0] = false;
+      gyro_layout *data = (gyro_layout *)sus.new_internal_data(W, gv);
+      sus.init_internal_data(W, dt, gv, data);
+      if (!data->P[c][0][0]) { fprintf(stderr, "gen_gyro: no P allocated\n"); exit(3); }
+      for (int k = 0; k < 3; ++k)
+        for (size_t i = 0; i < n; ++i) {
+          data->P[c][0][k][i] = (realnum)(2 * urand() - 1);
+          data->P_prev[c][0][k][i] = (realnum)(2 * urand() - 1);
+        }
+      // the reference's constants (src/susceptibility.cpp:449-474, 512-527), in realnum arithmetic
+      const vec b = models[im] == GYROTROPIC_SATURATED ? bias / abs(bias) : bias;
+      realnum gt[3][3];
+      memset(gt, 0, sizeof gt);
+      gt[X][Y] = b.z(); gt[Y][X] = -b.z(); gt[Y][Z] = b.x(); gt[Z][Y] = -b.x(); gt[Z][X] = b.y(); gt[X][Z] = -b.y();
+      const realnum omega2pidt = 2 * pi * omega_0 * dt, g2pidt = 2 * pi * gamma * dt;
+      realnum c4[4], gd, gx, gy, gz;
+      if (models[im] != GYROTROPIC_SATURATED) {
+        const realnum omega0dtsqr = omega2pidt * omega2pidt;
+        const realnum gamma1 = (1 - g2pidt / 2);
+        const realnum diag = 2 - (models[im] == GYROTROPIC_DRUDE ? 0 : omega0dtsqr);
+        const realnum pt = pi * dt;
+        gd = (1 + g2pidt / 2); gx = pt * gt[Y][Z]; gy = pt * gt[Z][X]; gz = pt * gt[X][Y];
+        c4[0] = diag; c4[1] = gamma1; c4[2] = omega0dtsqr; c4[3] = pt;
+      }
+      else {
+        const realnum dt2pi = 2 * pi * dt;
+        gd = 0.5; gx = -0.5 * alpha * gt[Y][Z]; gy = -0.5 * alpha * gt[Z][X]; gz = -0.5 * alpha * gt[X][Y];
+        c4[0] = omega2pidt; c4[1] = g2pidt; c4[2] = alpha; c4[3] = dt2pi;
+      }
+      const realnum invdet = 1.0 / gd / (gd * gd + gx * gx + gy * gy + gz * gz);
+      const realnum inv[3][3] = {{invdet * (gd * gd + gx * gx), invdet * (gx * gy + gd * gz), invdet * (gx * gz - gd * gy)},
+                                 {invdet * (gy * gx - gd * gz), invdet * (gd * gd + gy * gy), invdet * (gy * gz + gd * gx)},
+                                 {invdet * (gz * gx + gd * gy), invdet * (gz * gy - gd * gx), invdet * (gd * gd + gz * gz)}};
+      std::vector<double> gtr, invr;
+      for (int a = 0; a < 3; ++a)
+        for (int bb = 0; bb < 3; ++bb) {
+          gtr.push_back(gt[ds[a]][ds[bb]]);
+          invr.push_back(inv[ds[a]][ds[bb]]);
+        }
+      for (int k = 0; k < 3; ++k) {
+        snprintf(nm, sizeof nm, "in.p%d", k); dump_r(nm, data->P[c][0][ds[k]], n);
+        snprintf(nm, sizeof nm, "in.pp%d", k); dump_r(nm, data->P_prev[c][0][ds[k]], n);
+      }
+      dump_r("in.w0", W[c][0], n);
+      dump_r("in.w1", W[direction_component(c, d1)][0], n);
+      dump_r("in.w2", W[direction_component(c, d2)][0], n);
+      dump_r("in.s", sus.sigma[c][d0], n);
+      dump_box("box", make_box(gv, gv.little_owned_corner(c), gv.big_corner()));
+      dump_d("scalars", {(double)gv.stride(d0), (double)gv.stride(d1), (double)gv.stride(d2), (double)c4[0],
+                         (double)c4[1], (double)c4[2], (double)c4[3], (double)(im == 2 ? 1 : 0)});
+      dump_d("gt", gtr);
+      dump_d("inv", invr);
+      sus.update_P(W, NULL, dt, gv, data); // THE REFERENCE CALL
+      for (int k = 0; k < 3; ++k) {
+        snprintf(nm, sizeof nm, "out.p%d", k); dump_r(nm, data->P[c][0][ds[k]], n);
+        snprintf(nm, sizeof nm, "out.pp%d", k); dump_r(nm, data->P_prev[c][0][ds[k]], n);
+      }
+      fclose(g_out);
+      sus.delete_internal_data(data);
+    }
+}
+
 // ---- dft_chunk::update_dft -----------------------------------------------------------------------
 static double one(const vec &) { return 1.0; }
 
@@ -460,5 +555,6 @@ int main(int argc, char **argv) {
   gen_cyl(dir, 3, B_stuff, "m3_B");
   gen_bfast(dir, g3, "3d");
   gen_bfast(dir, g2, "2d");
+  gen_gyro(dir, g3);
   return 0;
 }

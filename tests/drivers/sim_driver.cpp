@@ -77,7 +77,20 @@ static void dump_fields(fields &f) {
     FOR_FIELD_TYPES(ft) {
       int ip = 0;
       for (polarization_state *p = fc->pol[ft]; p; p = p->next, ++ip)
-        if (p->data) {
+        if (p->data && dynamic_cast<const gyrotropic_susceptibility *>(p->s)) {
+          struct gyro_layout { // src/susceptibility.cpp:374-380
+            size_t sz_data, ntot;
+            realnum *P[NUM_FIELD_COMPONENTS][2][3];
+            realnum *P_prev[NUM_FIELD_COMPONENTS][2][3];
+          } *d = (gyro_layout *)p->data;
+          FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) for (int k = 0; k < 3; ++k) if (d->P[c][cmp][k]) {
+            snprintf(nm, sizeof nm, "chunk%d.P%d.%s.%d.%d", i, ip, component_name(c), cmp, k);
+            dump(nm, d->P[c][cmp][k], sizeof(realnum), n);
+            snprintf(nm, sizeof nm, "chunk%d.Pprev%d.%s.%d.%d", i, ip, component_name(c), cmp, k);
+            dump(nm, d->P_prev[c][cmp][k], sizeof(realnum), n);
+          }
+        }
+        else if (p->data) {
           lorentzian_data_layout *d = (lorentzian_data_layout *)p->data;
           FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) if (d->P[c][cmp]) {
             snprintf(nm, sizeof nm, "chunk%d.P%d.%s.%d", i, ip, component_name(c), cmp);
@@ -474,6 +487,27 @@ int main(int argc, char **argv) {
     for (int i = 0; i < nsteps; ++i) f.step();
     probes(f, gv);
     dump_flux("flux.box", fl);
+    dump_fields(f);
+  }
+  else if (cs == "gyro_lorentz_3d" || cs == "gyro_drude_3d" || cs == "gyro_saturated_3d") {
+    // gyrotropic media (src/susceptibility.cpp:349-602): nine polarisation arrays per cell, coupled
+    // through the bias vector; needs the not-owned W values of neighbouring chunks
+    g_L = 2.0;
+    grid_volume gv = vol3d(2.0, 1.6, 2.0, a);
+    structure s(gv, eps_box, pml(0.4), identity(), num_chunks);
+    const vec bias(0.3, -0.2, 0.9);
+    if (cs == "gyro_saturated_3d")
+      s.add_susceptibility(sphere, E_stuff, gyrotropic_susceptibility(bias, 0.7, 0.02, 0.05, GYROTROPIC_SATURATED));
+    else
+      s.add_susceptibility(sphere, E_stuff,
+                           gyrotropic_susceptibility(bias, 0.8, 0.04, 0.0,
+                                                     cs == "gyro_drude_3d" ? GYROTROPIC_DRUDE : GYROTROPIC_LORENTZIAN));
+    fields f(&s);
+    gaussian_src_time src(0.6, 0.5);
+    f.add_point_source(Ez, src, vec(0.7, 0.8, 0.9));
+    f.add_point_source(Ex, src, vec(1.2, 0.9, 1.1));
+    for (int i = 0; i < nsteps; ++i) f.step();
+    probes(f, gv);
     dump_fields(f);
   }
   else if (cs == "lorentz_aniso_sigma") {

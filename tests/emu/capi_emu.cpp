@@ -91,6 +91,13 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
             beta_thread<T>(J, t, tid);
         break;
       }
+      case MB200_K_GYRO: {
+        const mb200_gyro_job_t &J = ((const mb200_gyro_job_t *)p->jobs.data())[j];
+        for (int64_t t = 0; t < ntiles; ++t)
+          for (int tid = 0; tid < kThreads; ++tid)
+            gyro_thread<T>(J, t, tid);
+        break;
+      }
       case MB200_K_AVERAGE: {
         const mb200_average_job_t &J = ((const mb200_average_job_t *)p->jobs.data())[j];
         for (int64_t t = 0; t < ntiles; ++t)
@@ -354,6 +361,9 @@ int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njob
 }
 int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_gyrotropic_update_P(mb200_ctx *c, int dtype, const mb200_gyro_job_t *jobs, int njobs) {
+  return one_shot(c, MB200_K_GYRO, dtype, jobs, njobs, nullptr, 0);
 }
 int mb200_average_with_backup(mb200_ctx *c, int dtype, const mb200_average_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_AVERAGE, dtype, jobs, njobs, nullptr, 0);

@@ -44,7 +44,8 @@ class HostMem:
                  capi.K_DFT: "oracle_update_dft", capi.K_FLUX: "oracle_dft_flux",
                  capi.K_BETA: "oracle_step_beta", capi.K_CYLINT: "oracle_cyl_rderiv_int",
                  capi.K_CYLR0: "oracle_cyl_origin", capi.K_ZERO: "oracle_zero_metal",
-                 capi.K_BFAST: "oracle_step_bfast", capi.K_AVERAGE: "oracle_average_with_backup"}
+                 capi.K_BFAST: "oracle_step_bfast", capi.K_AVERAGE: "oracle_average_with_backup",
+                 capi.K_GYRO: "oracle_gyrotropic_update_P"}
         fn = getattr(self.lib, names[kind] + "_" + self.prec)
         fn.restype = None
         for j in jobs:
@@ -155,6 +156,28 @@ def replay_bfast(rec, mem):
     j.fu, j.cnd, j.cndinv, j.fcnd = P["fu"], P["cnd"], P["cndinv"], P["fcnd"]
     mem.run(capi.K_BFAST, [j])
     return {k: mem.get(P[k], g(k)) for k in ("f", "fu", "fcnd", "F") if g(k) is not None}
+
+
+def replay_gyro(rec, mem):
+    g = lambda k: rec.get("in." + k)
+    names = ["p0", "p1", "p2", "pp0", "pp1", "pp2", "w0", "w1", "w2", "s"]
+    P = {k: mem.put(g(k)) for k in names}
+    j = capi.GyroJob()
+    j.box = mk_box(rec["box"])
+    for k in range(3):
+        j.p[k], j.pp[k], j.w[k] = P["p%d" % k], P["pp%d" % k], P["w%d" % k]
+    j.s = P["s"]
+    sc = rec["scalars"]
+    j.is_, j.is1, j.is2 = int(sc[0]), int(sc[1]), int(sc[2])
+    for k in range(4):
+        j.c[k] = sc[3 + k]
+    j.model = int(sc[7])
+    for a in range(3):
+        for b in range(3):
+            j.gt[a][b] = rec["gt"][3 * a + b]
+            j.inv[a][b] = rec["inv"][3 * a + b]
+    mem.run(capi.K_GYRO, [j])
+    return {k: mem.get(P[k], g(k)) for k in names[:6]}
 
 
 def replay_edhb(rec, mem):
@@ -319,7 +342,7 @@ def replay_cyl(rec, mem):
     return out
 
 
-REPLAY = {"cyl": replay_cyl, "bfast": replay_bfast, "beta": replay_beta, "curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
+REPLAY = {"gyro": replay_gyro, "cyl": replay_cyl, "bfast": replay_bfast, "beta": replay_beta, "curl": replay_curl, "edhb": replay_edhb, "lorentz": replay_lorentz, "dft": replay_dft}
 
 
 def check_golden(prefix, prec, mem_factory):

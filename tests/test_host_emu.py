@@ -30,6 +30,9 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_beta_real", 60, 2),
     ("2d_mirror_sym", 60, 0),
     ("3d_rotate_sym", 40, 2),
+    ("gyro_lorentz_3d", 30, 0),
+    ("gyro_drude_3d", 30, 3),
+    ("gyro_saturated_3d", 30, 0),
     ("lorentz_aniso_sigma", 30, 4),
     ("3d_sync_magnetic", 30, 0),
     ("3d_bfast", 40, 0),
@@ -99,6 +102,7 @@ MP_CASES = [  # (case, steps, num_chunks, world_size)
     ("cyl_m1", 40, 4, 2),
     ("c2_3d_pml", 20, 8, 4),
     ("lorentz_aniso_sigma", 30, 4, 2),
+    ("gyro_lorentz_3d", 30, 4, 2),
     ("3d_xperiodic_ypml", 20, 6, 3),
 ]
 

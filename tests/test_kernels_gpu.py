@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-@pytest.mark.parametrize("kind", ["curl", "beta", "edhb", "lorentz", "dft", "cyl", "bfast"])
+@pytest.mark.parametrize("kind", ["curl", "beta", "edhb", "lorentz", "dft", "cyl", "bfast", "gyro"])
 def test_cuda_matches_reference_golden(kind, prec):
     worst = check_golden(kind, prec, DevMem)
     print("CUDA vs reference golden: %s/%s worst rel err %.2e" % (kind, prec, worst))
