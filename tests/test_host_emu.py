@@ -127,3 +127,24 @@ def test_sharded_run_with_the_fallback_transport(case, steps, chunks, world):
     ref = run_case("ref", "f64", case, steps, chunks)
     got = run_case_mp("emu", "f64", case, steps, chunks, world, env={"MEEP_B200_P2P": "0"})
     compare(got, ref, TOL["f64"])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_process_runtime_reductions_and_broadcasts(world):
+    """the reference's src/mympi.cpp entry points (sum_to_all, and_to_all, partial_sum_to_all,
+    broadcast, ...) served by the MPI-free socket runtime, `world` cooperating processes"""
+    import socket
+    from parity_util import driver
+    exe = driver("comm_driver", "emu", "f64")
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for r, p in enumerate(procs):
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, "rank %d:\n%s" % (r, out[-2000:])
