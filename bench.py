@@ -313,7 +313,7 @@ def main():
     lib.mb200_profile_enable(ctx, 0)
     prof = {}
     kinds = ["curl", "edhb", "lorentz", "fmp", "source", "halo", "zero", "dft", "flux", "step3", "beta", "exchange",
-             "cylint", "cylr0", "step3_pml", "bfast", "average", "gyro"]
+             "cylint", "cylr0", "step3_pml", "bfast", "average", "gyro", "noise"]
     for k, name in enumerate(kinds):
         n_, ms_, by_ = C.c_int64(), C.c_double(), C.c_double()
         lib.mb200_profile_get(ctx, k, C.byref(n_), C.byref(ms_), C.byref(by_))

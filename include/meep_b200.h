@@ -143,6 +143,17 @@ typedef struct {
   int32_t model, reserved;
 } mb200_gyro_job_t;
 
+/* ---- noisy_lorentzian_susceptibility::update_P, the noise term (src/susceptibility.cpp:317-339):
+ *      p[i] += gaussian_random(0, amp sqrt(sigma[i])) over the owned points.  The random numbers
+ *      come from the reference's own generator on the host, drawn in the reference's loop order
+ *      (that is what makes runs reproducible against the CPU build); they are the plan's run data:
+ *      noise[slot + (i1 n2 + i2) n3 + i3] (double) is added to the point of loop indices (i1,i2,i3). */
+typedef struct {
+  mb200_box_t box;
+  void *p;
+  int64_t slot;
+} mb200_noise_job_t;
+
 /* ---- fields_chunk::average_with_backup (src/energy_and_flux.cpp:139-147), the last stage of
  *      fields::synchronize_magnetic_fields: f[i] = 0.5 * (f[i] + backup[i]) over a whole array */
 typedef struct {
@@ -361,7 +372,8 @@ enum {
   MB200_K_BFAST = 15,
   MB200_K_AVERAGE = 16,
   MB200_K_GYRO = 17,
-  MB200_NUM_KINDS = 18
+  MB200_K_NOISE = 18,
+  MB200_NUM_KINDS = 19
 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -394,6 +406,7 @@ int mb200_plan_create(mb200_ctx *ctx, int kind, int dtype, const void *jobs, int
 /* run_data: per-run side input, copied to the device before launch:
  *   MB200_K_SOURCE: interleaved complex<double> scalars[], run_bytes = 16*nslots
  *   MB200_K_DFT   : complex<realnum> phase table, run_bytes = 2*sizeof(realnum)*nphases
+ *   MB200_K_NOISE : double noise[], run_bytes = 8*(number of loop points of all jobs)
  *   others        : NULL / 0 */
 int mb200_plan_run(mb200_ctx *ctx, mb200_plan *plan, const void *run_data, size_t run_bytes);
 void mb200_plan_destroy(mb200_ctx *ctx, mb200_plan *plan);
@@ -409,6 +422,8 @@ int mb200_step_update_EDHB(mb200_ctx *ctx, int dtype, const mb200_edhb_job_t *jo
 int mb200_lorentzian_update_P(mb200_ctx *ctx, int dtype, const mb200_lorentz_job_t *jobs,
                               int njobs);
 int mb200_subtract_P(mb200_ctx *ctx, int dtype, const mb200_fmp_job_t *jobs, int njobs);
+int mb200_add_noise(mb200_ctx *ctx, int dtype, const mb200_noise_job_t *jobs, int njobs,
+                    const double *noise, int64_t nnoise);
 int mb200_gyrotropic_update_P(mb200_ctx *ctx, int dtype, const mb200_gyro_job_t *jobs, int njobs);
 int mb200_step_source(mb200_ctx *ctx, int dtype, const mb200_src_job_t *jobs, int njobs,
                       const double *scalars, int nslots);

@@ -19,7 +19,8 @@ K_STEP3_GENERAL = 14
 K_BFAST = 15
 K_AVERAGE = 16
 K_GYRO = 17
-NUM_KINDS = 18
+K_NOISE = 18
+NUM_KINDS = 19
 MAX_P = 8
 
 
@@ -130,6 +131,10 @@ class GyroJob(C.Structure):
                 ("model", C.c_int32), ("reserved", C.c_int32)]
 
 
+class NoiseJob(C.Structure):
+    _fields_ = [("box", Box), ("p", C.c_void_p), ("slot", C.c_int64)]
+
+
 class AverageJob(C.Structure):
     _fields_ = [("f", C.c_void_p), ("backup", C.c_void_p), ("n", C.c_int64)]
 
@@ -152,7 +157,7 @@ class Xfer(C.Structure):
 
 JOB_TYPES = {K_CURL: CurlJob, K_EDHB: EdhbJob, K_LORENTZ: LorentzJob, K_FMP: FmpJob, K_SOURCE: SrcJob,
              K_HALO: HaloJob, K_ZERO: ZeroJob, K_DFT: DftJob, K_FLUX: FluxJob, K_STEP3: Step3Job, K_BETA: BetaJob,
-             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job, K_BFAST: BfastJob, K_AVERAGE: AverageJob, K_GYRO: GyroJob}
+             K_CYLINT: CylIntJob, K_CYLR0: CylR0Job, K_BFAST: BfastJob, K_AVERAGE: AverageJob, K_GYRO: GyroJob, K_NOISE: NoiseJob}
 
 
 def declare(lib):
@@ -194,6 +199,7 @@ def declare(lib):
         "mb200_step_bfast": (i, [vp, i, vp, i]),
         "mb200_average_with_backup": (i, [vp, i, vp, i]),
         "mb200_gyrotropic_update_P": (i, [vp, i, vp, i]),
+        "mb200_add_noise": (i, [vp, i, vp, i, vp, C.c_int64]),
         "mb200_cyl_rderiv_int": (i, [vp, i, vp, i]),
         "mb200_cyl_origin": (i, [vp, i, vp, i]),
         "mb200_comm_unique_id": (i, [vp]),

@@ -125,6 +125,10 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       beta_kernel<T><<<grid, block, 0, s>>>((const mb200_beta_job_t *)p->d_jobs, p->d_prefix,
                                             p->njobs);
       break;
+    case MB200_K_NOISE:
+      noise_kernel<T><<<grid, block, 0, s>>>((const mb200_noise_job_t *)p->d_jobs, p->d_prefix, p->njobs,
+                                             (const double *)d_run);
+      break;
     case MB200_K_GYRO:
       gyro_kernel<T><<<grid, block, 0, s>>>((const mb200_gyro_job_t *)p->d_jobs, p->d_prefix, p->njobs);
       break;
@@ -357,7 +361,7 @@ int mb200_plan_run(mb200_ctx *c, mb200_plan *p, const void *run_data, size_t run
   if (!p) return fail("mb200_plan_run: plan == NULL");
   if (p->tiles == 0) return 0;
   CUDA_TRY(cudaSetDevice(c->device));
-  const bool needs_run = p->kind == MB200_K_SOURCE || p->kind == MB200_K_DFT;
+  const bool needs_run = p->kind == MB200_K_SOURCE || p->kind == MB200_K_DFT || p->kind == MB200_K_NOISE;
   if (needs_run) {
     if (!run_data || !run_bytes) return fail("mb200_plan_run: kind %d needs run_data", p->kind);
     if (run_bytes > c->run_cap) {
@@ -435,6 +439,10 @@ int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njob
 }
 int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_add_noise(mb200_ctx *c, int dtype, const mb200_noise_job_t *jobs, int njobs, const double *noise,
+                    int64_t nnoise) {
+  return one_shot(c, MB200_K_NOISE, dtype, jobs, njobs, noise, sizeof(double) * (size_t)nnoise);
 }
 int mb200_gyrotropic_update_P(mb200_ctx *c, int dtype, const mb200_gyro_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_GYRO, dtype, jobs, njobs, nullptr, 0);

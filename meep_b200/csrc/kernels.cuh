@@ -248,6 +248,18 @@ template <typename T> MB200_HD void gyro_thread(const mb200_gyro_job_t &J, int64
     gyro_point<T>(J, i);
 }
 
+template <typename T>
+MB200_HD void noise_thread(const mb200_noise_job_t &J, int64_t tile, int tid, const double *noise) {
+  int i1_0, i1_end, i2, i3;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  T *p = (T *)J.p;
+  for (int i1 = i1_0; i1 < i1_end; ++i1) {
+    const int64_t i = box_index(J.box, i1, i2, i3);
+    const int64_t k = J.slot + ((int64_t)i1 * J.box.n[1] + i2) * J.box.n[2] + i3;
+    p[i] = (T)((double)p[i] + noise[k]);
+  }
+}
+
 template <typename T> MB200_HD void average_thread(const mb200_average_job_t &J, int64_t tile, int tid) {
   T *f = (T *)J.f;
   const T *b = (const T *)J.backup;
@@ -391,6 +403,17 @@ __global__ void __launch_bounds__(kThreads)
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   gyro_thread<T>(J, tile, threadIdx.x);
+}
+
+// ---- noise term of noisy_lorentzian_susceptibility ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    noise_kernel(const mb200_noise_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                 int njobs, const double *__restrict__ noise) {
+  __shared__ mb200_noise_job_t J;
+  int64_t tile;
+  stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  noise_thread<T>(J, tile, threadIdx.x, noise);
 }
 
 // ---- average_with_backup ---------------------------------------------------------------------------

@@ -23,6 +23,7 @@ inline size_t job_size_of(int kind) {
     case MB200_K_BFAST: return sizeof(mb200_bfast_job_t);
     case MB200_K_AVERAGE: return sizeof(mb200_average_job_t);
     case MB200_K_GYRO: return sizeof(mb200_gyro_job_t);
+    case MB200_K_NOISE: return sizeof(mb200_noise_job_t);
     case MB200_K_CYLINT: return sizeof(mb200_cylint_job_t);
     case MB200_K_CYLR0: return sizeof(mb200_cylr0_job_t);
     default: return 0;
@@ -120,6 +121,13 @@ inline void job_metrics(int kind, int dtype, const void *jobs, int j, int64_t *t
       int arrays = 2 + 1 + (J.cndinv ? 1 : 0) + (J.pmlu.siginv ? 2 : 0) +
                    (J.cndinv && J.pml.siginv ? 2 : 0);
       *bytes = R * arrays * *points;
+      break;
+    }
+    case MB200_K_NOISE: {
+      const mb200_noise_job_t &J = ((const mb200_noise_job_t *)jobs)[j];
+      *tiles = box_tiles(J.box);
+      *points = box_points(J.box);
+      *bytes = (2 * R + 8) * *points;
       break;
     }
     case MB200_K_GYRO: {

@@ -896,6 +896,13 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
       push(ph, MB200_K_LORENTZ, make_plan(*this, MB200_K_LORENTZ, blocked.data(), blocked.size()));
       push(ph, MB200_K_LORENTZ, make_plan(*this, MB200_K_LORENTZ, plainj.data(), plainj.size()));
       push(ph, MB200_K_GYRO, make_plan(*this, MB200_K_GYRO, R.gyro.data(), R.gyro.size()));
+      if (mb200_plan *p = make_plan(*this, MB200_K_NOISE, R.noise.data(), R.noise.size())) {
+        Launch l;
+        l.kind = MB200_K_NOISE;
+        l.plan = p;
+        l.noise_gens = R.noise_gens;
+        ph.launches.push_back(l);
+      }
       break;
     }
     case PH_DFT:
@@ -990,6 +997,21 @@ void Engine::run(Phase &ph, fields *f) {
                                   l.recvs.data(), (int)l.recvs.size()),
               "mb200_comm_exchange");
       }
+      continue;
+    }
+    if (l.kind == MB200_K_NOISE) {
+      // the reference's generator, in the reference's order (chunk, susceptibility, component,
+      // loop point): src/susceptibility.cpp:326-337
+      std::vector<double> noise;
+      for (const NoiseGen &g : l.noise_gens)
+        for (int i1 = 0; i1 < g.box.n[0]; ++i1)
+          for (int i2 = 0; i2 < g.box.n[1]; ++i2)
+            for (int i3 = 0; i3 < g.box.n[2]; ++i3) {
+              const int64_t i = g.box.idx0 + i1 * g.box.s[0] + i2 * g.box.s[1] + i3 * g.box.s[2];
+              noise.push_back(meep::gaussian_random(0, (realnum)g.amp * sqrt(g.sigma[i])));
+            }
+      check(mb200_plan_run(ctx, l.plan, noise.data(), noise.size() * sizeof(double)), "run(noise)");
+      stats.h2d_bytes += noise.size() * sizeof(double);
       continue;
     }
     if (l.kind == MB200_K_SOURCE) {

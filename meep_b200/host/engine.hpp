@@ -41,10 +41,20 @@ enum PhaseId {
   PH_COUNT
 };
 
+// one noisy polarisation array: noise[k] = gaussian_random(0, amp * sqrt(sigma[idx(k)])) over the
+// loop box, drawn on the host before every launch (reference src/susceptibility.cpp:331-334)
+struct NoiseGen {
+  double amp;
+  const meep::realnum *sigma; // host array
+  mb200_box_t box;
+};
+
 // a recorded launch: plan + how to build its per-run side data
 struct Launch {
   int kind = -1;
   mb200_plan *plan = nullptr;
+  // NOISE: the generators whose numbers are concatenated at run time
+  std::vector<NoiseGen> noise_gens;
   // SOURCE: src_time objects whose current()/dipole() fill the scalar slots at run time
   std::vector<const meep::src_time *> src_times;
   bool src_dipole = false;
@@ -82,6 +92,10 @@ struct Recorder {
   std::vector<mb200_curl_job_t> curl;
   std::vector<mb200_beta_job_t> beta; // 2-D exp(i beta z) terms, run after the curl jobs
   // cylindrical coordinates: helper arrays (before the curl jobs), r = 0 rows and zeroed rows (after)
+  // noise terms of noisy_lorentzian_susceptibility: device jobs + what the host needs to draw the
+  // numbers each step (amp, host sigma array, loop box), in the reference's order
+  std::vector<mb200_noise_job_t> noise;
+  std::vector<NoiseGen> noise_gens;
   std::vector<mb200_gyro_job_t> gyro;   // gyrotropic polarisations (update_pols phase)
   std::vector<mb200_bfast_job_t> bfast; // BFAST corrections, after the curl jobs
   std::vector<mb200_cylint_job_t> cylint;
@@ -214,6 +228,7 @@ public:
   void restore_array(const void *host);
   bool has_backup(const void *host) const { return backups.count(host) != 0; }
   void drop_backups();
+  bool suppress_zero_skip = false; // set while recording the Lorentzian part of a noisy susceptibility
   int keep_on_device = 0;     // > 0: a stand-alone phase call leaves the arrays in HBM (no hand-back)
   bool cw_mode = false;       // inside solve_cw: the host arrays are the master between steps
   bool p2p = true;            // MEEP_B200_P2P=0: move comm blocks with NCCL instead of peer stores
@@ -328,7 +343,8 @@ struct gyrotropy_data_layout {
 // area (0 bytes: nothing allocated), aborting for the kinds that are not supported
 inline std::pair<realnum *, size_t> polarisation_block(const meep::susceptibility *s, void *data) {
   if (!data) return std::make_pair((realnum *)nullptr, (size_t)0);
-  if (typeid(*s) == typeid(meep::lorentzian_susceptibility)) {
+  if (typeid(*s) == typeid(meep::lorentzian_susceptibility) ||
+      typeid(*s) == typeid(meep::noisy_lorentzian_susceptibility)) {
     lorentzian_data_layout *d = (lorentzian_data_layout *)data;
     const size_t hdr = offsetof(lorentzian_data_layout, data);
     return std::make_pair(d->data, d->sz_data > hdr ? d->sz_data - hdr : 0);
@@ -338,8 +354,8 @@ inline std::pair<realnum *, size_t> polarisation_block(const meep::susceptibilit
     const size_t hdr = offsetof(gyrotropy_data_layout, data);
     return std::make_pair(d->data, d->sz_data > hdr ? d->sz_data - hdr : 0);
   }
-  meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) and gyrotropic_susceptibility "
-              "polarisations are supported on the device path");
+  meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude, also noisy) and "
+              "gyrotropic_susceptibility polarisations are supported on the device path");
   return std::make_pair((realnum *)nullptr, (size_t)0);
 }
 

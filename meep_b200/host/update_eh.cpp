@@ -138,7 +138,8 @@ bool fields_chunk::update_eh(field_type ft, bool skip_w_components) {
       for (polarization_state *p = pol[ft]; p; p = p->next)
         if (p->data) {
           const realnum *P = nullptr;
-          if (typeid(*p->s) == typeid(lorentzian_susceptibility))
+          if (typeid(*p->s) == typeid(lorentzian_susceptibility) ||
+              typeid(*p->s) == typeid(noisy_lorentzian_susceptibility))
             P = ((const lorentzian_data_layout *)p->data)->P[ec][cmp];
           else if (typeid(*p->s) == typeid(gyrotropic_susceptibility)) // (src/susceptibility.cpp:586-602)
             P = ((const gyrotropy_data_layout *)p->data)->P[ec][cmp][component_direction(ec)];

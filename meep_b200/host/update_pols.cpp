@@ -42,8 +42,9 @@ bool fields_chunk::update_pols(field_type ft) {
 
   for (polarization_state *p = pol[ft]; p; p = p->next) {
     const bool gyro = typeid(*p->s) == typeid(gyrotropic_susceptibility);
-    if (!gyro && typeid(*p->s) != typeid(lorentzian_susceptibility))
-      meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude) and "
+    const bool noisy = typeid(*p->s) == typeid(noisy_lorentzian_susceptibility);
+    if (!gyro && !noisy && typeid(*p->s) != typeid(lorentzian_susceptibility))
+      meep::abort("meep_b200: only lorentzian_susceptibility (Lorentz/Drude, also noisy) and "
                   "gyrotropic_susceptibility polarisations are supported on the device path");
 
     // Lazily allocate internal polarization data (host block laid out by the reference;
@@ -61,6 +62,9 @@ bool fields_chunk::update_pols(field_type ft) {
     // Finally, timestep the polarizations (emits jobs):
     if (gyro)
       static_cast<const gyrotropic_susceptibility *>(p->s)->gyrotropic_susceptibility::update_P(
+          w, f_w_prev, dt, gv, p->data);
+    else if (noisy)
+      static_cast<const noisy_lorentzian_susceptibility *>(p->s)->noisy_lorentzian_susceptibility::update_P(
           w, f_w_prev, dt, gv, p->data);
     else
       static_cast<const lorentzian_susceptibility *>(p->s)->lorentzian_susceptibility::update_P(
@@ -139,7 +143,7 @@ void lorentzian_susceptibility::update_P(realnum *W[NUM_FIELD_COMPONENTS][2],
         J.omega0dtsqr = omega0dtsqr;
         J.omega0dtsqr_denom = omega0dtsqr_denom;
         J.ntot = (int64_t)gv.ntot();
-        if (!s1 && gv.dim == D3) { // isotropic, standard 3-D layout: zero-block skipping
+        if (!s1 && gv.dim == D3 && !E->suppress_zero_skip) { // isotropic, standard 3-D layout: zero-block skipping
           // (flags start as "unknown"; the kernel establishes them with its first update)
           J.pzero = E->pzero_flags(p, gv.ntot(), false);
           J.szero = J.pzero ? E->szero_flags(s, gv.ntot()) : NULL;
@@ -159,6 +163,52 @@ void lorentzian_susceptibility::subtract_P(field_type, realnum *[NUM_FIELD_COMPO
                                            void *) const {
   meep::abort("meep_b200: lorentzian_susceptibility::subtract_P: this build has no CPU "
               "time-stepping path");
+}
+
+// noisy_lorentzian_susceptibility::update_P (reference src/susceptibility.cpp:317-339): the
+// Lorentzian update, then p[i] += gaussian_random(0, amp sqrt(sigma[i])).  The numbers are drawn
+// by the reference's generator on the host at every run (Engine::run), here only the jobs and the
+// generators are recorded.
+void noisy_lorentzian_susceptibility::update_P(realnum *W[NUM_FIELD_COMPONENTS][2],
+                                               realnum *W_prev[NUM_FIELD_COMPONENTS][2], realnum dt,
+                                               const grid_volume &gv, void *P_internal_data) const {
+  Engine *E = Engine::current();
+  if (!E || !E->recording())
+    meep::abort("meep_b200: noisy_lorentzian_susceptibility::update_P outside a phase: this build has no "
+                "CPU time-stepping path");
+  // (the noise makes P non-zero wherever sigma is: no zero-block bookkeeping for these arrays)
+  E->suppress_zero_skip = true;
+  lorentzian_susceptibility::update_P(W, W_prev, dt, gv, P_internal_data);
+  E->suppress_zero_skip = false;
+  if (!P_internal_data) return;
+  Recorder &R = E->rec();
+  lorentzian_data_layout *d = (lorentzian_data_layout *)P_internal_data;
+
+  const realnum g2pi = gamma * 2 * pi;
+  const realnum w2pi = omega_0 * 2 * pi;
+  const realnum amp = w2pi * noise_amp * sqrt(g2pi) * dt * dt / (1 + g2pi * dt / 2);
+
+  FOR_COMPONENTS(c) DOCMP2 {
+    if (d->P[c][cmp]) {
+      const realnum *s = sigma[c][component_direction(c)];
+      if (s) {
+        mb200_noise_job_t J;
+        memset(&J, 0, sizeof(J));
+        J.box = make_box(gv, gv.little_owned_corner(c), gv.big_corner()); // LOOP_OVER_VOL_OWNED
+        if (J.box.n[0] <= 0 || J.box.n[1] <= 0 || J.box.n[2] <= 0) continue;
+        J.p = E->dev(d->P[c][cmp]);
+        J.slot = 0;
+        for (const NoiseGen &g : R.noise_gens)
+          J.slot += (int64_t)g.box.n[0] * g.box.n[1] * g.box.n[2];
+        NoiseGen g;
+        g.amp = amp;
+        g.sigma = s;
+        g.box = J.box;
+        R.noise.push_back(J);
+        R.noise_gens.push_back(g);
+      }
+    }
+  }
 }
 
 // gyrotropic_susceptibility::update_P (reference src/susceptibility.cpp:445-584): same constants,

@@ -229,6 +229,19 @@ void FN(oracle_gyrotropic_update_P)(const mb200_gyro_job_t *J) {
 }
 #undef OFFDIAGW
 
+/* reference src/susceptibility.cpp:331-334: p[i] += gaussian_random(0, amp sqrt(s[i])), with the
+ * random numbers handed in (drawn by the caller in loop order) */
+void FN(oracle_add_noise)(const mb200_noise_job_t *J, const double *noise) {
+  REAL *p = (REAL *)J->p;
+  int64_t k = J->slot;
+  for (int i1 = 0; i1 < J->box.n[0]; ++i1)
+    for (int i2 = 0; i2 < J->box.n[1]; ++i2)
+      for (int i3 = 0; i3 < J->box.n[2]; ++i3) {
+        const int64_t i = J->box.idx0 + i1 * J->box.s[0] + i2 * J->box.s[1] + i3 * J->box.s[2];
+        p[i] += noise[k++];
+      }
+}
+
 /* reference src/energy_and_flux.cpp:139-147 (fields_chunk::average_with_backup) */
 void FN(oracle_average_with_backup)(const mb200_average_job_t *J) {
   REAL *fc = (REAL *)J->f;

@@ -510,6 +510,24 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
+  else if (cs == "noisy_lorentz_3d") {
+    // noisy_lorentzian_susceptibility (src/susceptibility.cpp:317-339): the polarisation is driven
+    // by the reference's own Gaussian random numbers, drawn on the host in the reference's loop
+    // order, so a seeded run is reproducible point by point
+    g_L = 1.6;
+    set_random_seed(20251017);
+    grid_volume gv = vol3d(1.6, 1.6, 1.2, a);
+    structure s(gv, eps_box, pml(0.3), identity(), num_chunks);
+    s.add_susceptibility(sphere, E_stuff, noisy_lorentzian_susceptibility(0.5, 0.9, 0.06));
+    s.add_susceptibility(eps_box, E_stuff, lorentzian_susceptibility(1.3, 0.1));
+    fields f(&s);
+    f.use_real_fields();
+    gaussian_src_time src(0.6, 0.5);
+    f.add_point_source(Ez, src, vec(0.6, 0.8, 0.6));
+    for (int i = 0; i < nsteps; ++i) f.step();
+    probes(f, gv);
+    dump_fields(f);
+  }
   else if (cs == "lorentz_aniso_sigma") {
     // Lorentzian with an anisotropic (off-diagonal) sigma tensor: the OFFDIAG terms of update_P
     // (src/susceptibility.cpp:214-247) and the exchange of not-owned W values between chunks

@@ -91,6 +91,13 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
             beta_thread<T>(J, t, tid);
         break;
       }
+      case MB200_K_NOISE: {
+        const mb200_noise_job_t &J = ((const mb200_noise_job_t *)p->jobs.data())[j];
+        for (int64_t t = 0; t < ntiles; ++t)
+          for (int tid = 0; tid < kThreads; ++tid)
+            noise_thread<T>(J, t, tid, (const double *)run);
+        break;
+      }
       case MB200_K_GYRO: {
         const mb200_gyro_job_t &J = ((const mb200_gyro_job_t *)p->jobs.data())[j];
         for (int64_t t = 0; t < ntiles; ++t)
@@ -361,6 +368,10 @@ int mb200_step3(mb200_ctx *c, int dtype, const mb200_step3_job_t *jobs, int njob
 }
 int mb200_step_beta(mb200_ctx *c, int dtype, const mb200_beta_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_BETA, dtype, jobs, njobs, nullptr, 0);
+}
+int mb200_add_noise(mb200_ctx *c, int dtype, const mb200_noise_job_t *jobs, int njobs, const double *noise,
+                    int64_t nnoise) {
+  return one_shot(c, MB200_K_NOISE, dtype, jobs, njobs, noise, sizeof(double) * (size_t)nnoise);
 }
 int mb200_gyrotropic_update_P(mb200_ctx *c, int dtype, const mb200_gyro_job_t *jobs, int njobs) {
   return one_shot(c, MB200_K_GYRO, dtype, jobs, njobs, nullptr, 0);

@@ -45,7 +45,7 @@ class HostMem:
                  capi.K_BETA: "oracle_step_beta", capi.K_CYLINT: "oracle_cyl_rderiv_int",
                  capi.K_CYLR0: "oracle_cyl_origin", capi.K_ZERO: "oracle_zero_metal",
                  capi.K_BFAST: "oracle_step_bfast", capi.K_AVERAGE: "oracle_average_with_backup",
-                 capi.K_GYRO: "oracle_gyrotropic_update_P"}
+                 capi.K_GYRO: "oracle_gyrotropic_update_P", capi.K_NOISE: "oracle_add_noise"}
         fn = getattr(self.lib, names[kind] + "_" + self.prec)
         fn.restype = None
         for j in jobs:

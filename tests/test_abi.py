@@ -35,10 +35,10 @@ def test_struct_layouts_match_the_header():
     names = ["mb200_box_t", "mb200_pml_t", "mb200_curl_job_t", "mb200_edhb_job_t", "mb200_lorentz_job_t",
              "mb200_fmp_job_t", "mb200_src_job_t", "mb200_halo_job_t", "mb200_zero_job_t", "mb200_dft_job_t",
              "mb200_flux_job_t", "mb200_step3_comp_t", "mb200_step3_job_t", "mb200_beta_job_t",
-             "mb200_cylint_job_t", "mb200_cylr0_job_t", "mb200_xfer_t", "mb200_bfast_job_t", "mb200_halo_run_t", "mb200_average_job_t", "mb200_gyro_job_t"]
+             "mb200_cylint_job_t", "mb200_cylr0_job_t", "mb200_xfer_t", "mb200_bfast_job_t", "mb200_halo_run_t", "mb200_average_job_t", "mb200_gyro_job_t", "mb200_noise_job_t"]
     types = [capi.Box, capi.Pml, capi.CurlJob, capi.EdhbJob, capi.LorentzJob, capi.FmpJob, capi.SrcJob,
              capi.HaloJob, capi.ZeroJob, capi.DftJob, capi.FluxJob, capi.Step3Comp, capi.Step3Job,
-             capi.BetaJob, capi.CylIntJob, capi.CylR0Job, capi.Xfer, capi.BfastJob, capi.HaloRun, capi.AverageJob, capi.GyroJob]
+             capi.BetaJob, capi.CylIntJob, capi.CylR0Job, capi.Xfer, capi.BfastJob, capi.HaloRun, capi.AverageJob, capi.GyroJob, capi.NoiseJob]
     prog = '#include <stdio.h>\n#include "meep_b200.h"\nint main(void){%s return 0;}\n' % "".join(
         'printf("%%zu\\n", sizeof(%s));' % n for n in names)
     d = os.path.join(ROOT, "tests", "_build")

@@ -30,6 +30,7 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_beta_real", 60, 2),
     ("2d_mirror_sym", 60, 0),
     ("3d_rotate_sym", 40, 2),
+    ("noisy_lorentz_3d", 30, 3),
     ("gyro_lorentz_3d", 30, 0),
     ("gyro_drude_3d", 30, 3),
     ("gyro_saturated_3d", 30, 0),

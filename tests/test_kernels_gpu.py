@@ -235,6 +235,25 @@ def test_halo_zero_source_fmp_flux(prec):
     assert np.array_equal(halo_runs(HostMem(prec)), want)
     assert np.array_equal(halo_runs(DevMem(prec)), want)
 
+    # noise term of noisy_lorentzian_susceptibility: two jobs sharing one run-data buffer
+    noise = rng.normal(0, 0.1, 6 * 7 * 9 + 5 * 4 * 3)
+
+    def add_noise(mem):
+        pa = mem.put(dst_arr)
+        j1, j2 = capi.NoiseJob(), capi.NoiseJob()
+        j1.box.idx0, j1.p, j1.slot = 11, pa, 0
+        j2.box.idx0, j2.p, j2.slot = 2000, pa, 6 * 7 * 9
+        for k, (nn, ss) in enumerate(zip((6, 7, 9), (100, 12, 1))):
+            j1.box.n[k], j1.box.s[k] = nn, ss
+        for k, (nn, ss) in enumerate(zip((5, 4, 3), (60, 13, 2))):
+            j2.box.n[k], j2.box.s[k] = nn, ss
+        mem.run(capi.K_NOISE, [j1, j2], noise)
+        out = mem.get(pa, dst_arr)
+        mem.close()
+        return out
+
+    assert np.array_equal(add_noise(DevMem(prec)), add_noise(HostMem(prec)))
+
     # average_with_backup
     def average(mem):
         pf = mem.put(dst_arr)

@@ -37,6 +37,7 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_beta_real", 100, 3),
     ("2d_mirror_sym", 100, 2),
     ("3d_rotate_sym", 60, 0),
+    ("noisy_lorentz_3d", 40, 0),
     ("gyro_lorentz_3d", 60, 0),
     ("gyro_drude_3d", 60, 3),
     ("gyro_saturated_3d", 60, 0),
