@@ -73,8 +73,6 @@ static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("M
 // instead of the one-component-per-thread form; 3..6 = CTAs per SM of the latter (default 4: 64
 // registers).  Measured at 512^3 (profiles/r1q_*): 0 -> 1.52 ms, 3 -> 1.25, 4 -> 1.04, 5 -> 1.18,
 // 6 -> 1.36 ms per step (16 planes per CTA).
-// MEEP_B200_PLAIN_UNROLL=2: the fast-path kernel loads two x-planes before its first store
-static const int g_plain_unroll = getenv("MEEP_B200_PLAIN_UNROLL") ? atoi(getenv("MEEP_B200_PLAIN_UNROLL")) : 1;
 static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 4;
 
 template <typename T>
@@ -157,7 +155,7 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
         break;
       }
       launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
-                      p->all_plain, g_split_general, g_plain_unroll, s);
+                      p->all_plain, g_split_general, s);
       break;
   }
   return cudaGetLastError();

@@ -147,68 +147,6 @@ MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int t
   }
 }
 
-// U = x-planes loaded before the first store (2 for single precision: a thread's loads are half
-// as wide there, so two planes keep the same number of bytes in flight)
-template <typename T, int U>
-MB200_HD void step3_plain_thread_u(const mb200_step3_job_t &J, int64_t tile, int tid) {
-  const mb200_box_t box = step3_box(J);
-  int ix0, ix_end, iy, iz;
-  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
-  int64_t i = box_index(box, ix0, iy, iz);
-  const int64_t sx = box.s[0];
-  ix0 += box.reserved;
-  ix_end += box.reserved;
-  bool myz[3], metal_yz[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const mb200_step3_comp_t &C = J.c[c];
-    myz[c] = iy >= C.lo[1] && iy <= C.hi[1] && iz >= C.lo[2] && iz <= C.hi[2];
-    metal_yz[c] = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
-                  iz == C.metal_hi[2];
-  }
-  for (int ix = ix0; ix < ix_end; ix += U, i += U * sx) {
-    T fv[U][3], a1[U][3], c1[U][3], c2[U][3], a2[U][3], uv[U][3];
-    bool m[U][3];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t iu = i + u * sx;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { // ---- all loads first
-        const mb200_step3_comp_t &C = J.c[c];
-        m[u][c] = myz[c] && ix + u < ix_end && ix + u >= C.lo[0] && ix + u <= C.hi[0];
-        if (m[u][c]) {
-          const T *g1 = (const T *)C.g1, *g2 = (const T *)C.g2;
-          fv[u][c] = ldmut((const T *)C.f + iu);
-          a1[u][c] = ldro(g1 + iu + C.s1);
-          c1[u][c] = ldro(g1 + iu);
-          c2[u][c] = ldro(g2 + iu);
-          a2[u][c] = ldro(g2 + iu + C.s2);
-          uv[u][c] = (C.e && C.u) ? ldro((const T *)C.u + iu) : T(1);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t iu = i + u * sx;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) { // ---- then arithmetic + stores
-        const mb200_step3_comp_t &C = J.c[c];
-        if (m[u][c]) {
-          T dg = a1[u][c] - c1[u][c];
-          dg = dg + c2[u][c] - a2[u][c];
-          const T d = fv[u][c] - (T)C.dtdx * dg;
-          stout((T *)C.f + iu, d);
-          if (C.e) {
-            const bool metal = metal_yz[c] || ix + u == C.metal_lo[0] || ix + u == C.metal_hi[0];
-            const T dd = metal ? T(0) : d;
-            stout((T *)C.e + iu, C.u ? dd * uv[u][c] : dd);
-          }
-        }
-      }
-    }
-  }
-}
-
 // ---- general path --------------------------------------------------------------------------------
 // Any mix of the 16 step_curl variants per component (PML in f, f_u level, conductivity with or
 // without f_cond) plus the diagonal update_eh with or without the f_w ODE.  The variants are
@@ -569,16 +507,6 @@ __global__ void __launch_bounds__(kThreads)
   step3_plain_thread<T>(J, tile, threadIdx.x);
 }
 
-template <typename T, int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-    step3_plain_u_kernel(const mb200_step3_job_t *__restrict__ jobs,
-                         const int64_t *__restrict__ tile_prefix, int njobs) {
-  __shared__ mb200_step3_job_t J;
-  int64_t tile;
-  stage_job(&J, jobs, tile_prefix, njobs, &tile);
-  step3_plain_thread_u<T, U>(J, tile, threadIdx.x);
-}
-
 // ---- job table in kernel-parameter (constant) space ---------------------------------------------
 // The job descriptor is CTA-uniform.  Staging it in shared memory costs an LDS (and a short-
 // scoreboard stall) for every pointer/flag use inside the marching loop; passed by value as a
@@ -628,12 +556,8 @@ static void launch_step3_params(const mb200_step3_job_t *h_jobs, const int64_t *
 
 template <typename T>
 static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
-                         int64_t tiles, bool all_plain, int split, int plain_unroll, cudaStream_t s) {
-  if (all_plain && plain_unroll == 2) // two planes in flight, registers as needed
-    step3_plain_u_kernel<T, 2, 1><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
-  else if (all_plain && plain_unroll == 24) // two planes in flight, 4 CTAs per SM (64 registers)
-    step3_plain_u_kernel<T, 2, 4><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
-  else if (all_plain)
+                         int64_t tiles, bool all_plain, int split, cudaStream_t s) {
+  if (all_plain)
     step3_plain_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
   else if (split == 4) // MEEP_B200_SPLIT_PML=4|5|6: CTAs per SM (64 / 51 / 42 registers)
     step3c_kernel<T, 4><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);

@@ -144,10 +144,8 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
                 step3c_thread<T>(J, c, t, tid);
             continue;
           }
-          static const int unroll = getenv("MEEP_B200_PLAIN_UNROLL") ? atoi(getenv("MEEP_B200_PLAIN_UNROLL")) : 1;
           for (int tid = 0; tid < kThreads; ++tid)
-            if (plain && unroll >= 2) step3_plain_thread_u<T, 2>(J, t, tid);
-            else if (plain) step3_plain_thread<T>(J, t, tid);
+            if (plain) step3_plain_thread<T>(J, t, tid);
             else step3_thread<T>(J, t, tid);
         }
         break;
