@@ -11,8 +11,11 @@
 // (sizes are read off the finished vectors); metal points found by walking only the boundary
 // planes of the owned volume.  Host code only — nothing here touches field values.
 #include <algorithm>
+#include <atomic>
+#include <deque>
 #include <stdlib.h>
 #include <map>
+#include <thread>
 #include <vector>
 
 #include "engine.hpp"
@@ -150,7 +153,6 @@ void fields::connect_the_chunks() {
     std::vector<std::complex<realnum> > *phases = nullptr;
     size_t count = 0; // realnums of this key when neither vector is ours to fill (never both NULL)
   };
-  std::vector<Slot> slots((size_t)NUM_FIELD_TYPES * NUM_CONNECT_PHASE_TYPES * num_chunks);
 
   // A chunk of another process matters only if one of its not-owned points can be owned by one
   // of OUR chunks.  Without periodic boundaries or symmetries a not-owned point is at most one
@@ -175,13 +177,31 @@ void fields::connect_the_chunks() {
     return false;
   };
 
-  for (int i = 0; i < num_chunks; i++) {
+  // One worker call per chunk i.  A worker only touches chunk i's own incoming tables; the
+  // outgoing tables (which belong to the OTHER chunk j of each pair) are staged in `res` and
+  // merged serially afterwards, so chunks can be processed by several host threads.
+  struct Staged {
+    size_t k; // slot index = ((field type, phase class), j)
+    std::vector<realnum *> out;
+  };
+  struct ChunkResult {
+    bool done = false;
+    std::deque<Staged> staged;       // in first-touch order
+    std::vector<size_t> touched_list; // slot indices in first-touch order
+    std::vector<size_t> sizes;        // comm size per touched slot
+  };
+  std::vector<ChunkResult> results(num_chunks);
+  const size_t nslots = (size_t)NUM_FIELD_TYPES * NUM_CONNECT_PHASE_TYPES * num_chunks;
+
+  auto process_chunk = [&](int i) {
     const grid_volume &vi = chunks[i]->gv;
     const bool i_is_mine = chunks[i]->is_mine();
-    if (!i_is_mine && can_prune && !touches_mine(vi)) continue;
-    std::fill(slots.begin(), slots.end(), Slot());
-    std::vector<char> touched(slots.size(), 0);
-    std::vector<size_t> touched_list;
+    if (!i_is_mine && can_prune && !touches_mine(vi)) return;
+    ChunkResult &res = results[i];
+    res.done = true;
+    std::vector<Slot> slots(nslots);
+    std::vector<char> touched(nslots, 0);
+    std::vector<size_t> &touched_list = res.touched_list;
     auto slot = [&](field_type f, connect_phase ip, int j) -> Slot & {
       const size_t k = ((size_t)f * NUM_CONNECT_PHASE_TYPES + (size_t)ip) * num_chunks + j;
       if (!touched[k]) {
@@ -193,7 +213,10 @@ void fields::connect_the_chunks() {
           s.in = &chunks[i]->connections_in[key];
           if (ip == CONNECT_PHASE) s.phases = &chunks[i]->connection_phases[key];
         }
-        if (chunks[j]->is_mine()) s.out = &chunks[j]->connections_out[key];
+        if (chunks[j]->is_mine()) {
+          res.staged.push_back(Staged{k, {}});
+          s.out = &res.staged.back().out;
+        }
       }
       return slots[k];
     };
@@ -296,16 +319,53 @@ void fields::connect_the_chunks() {
     // sizes of the comm blocks of every pair (j -> i) that was touched (src/boundaries.cpp:406-451)
     for (size_t k : touched_list) {
       const Slot &s = slots[k];
-      const size_t sz = s.in ? s.in->size() : (s.out ? s.out->size() : 0);
+      res.sizes.push_back(s.in ? s.in->size() : (s.out ? s.out->size() : 0));
+    }
+  };
+
+  // workers: chunks are independent (see above); MEEP_B200_HOST_THREADS overrides the count
+  {
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("MEEP_B200_HOST_THREADS")) nthreads = atoi(e);
+    const int local_ranks = getenv("LOCAL_WORLD_SIZE") ? atoi(getenv("LOCAL_WORLD_SIZE")) : count_processors();
+    if (!getenv("MEEP_B200_HOST_THREADS") && local_ranks > 1) nthreads /= local_ranks;
+    nthreads = std::max(1, std::min(nthreads, std::min(num_chunks, 16)));
+    std::atomic<int> next(0);
+    auto worker = [&]() {
+      for (int i = next.fetch_add(1); i < num_chunks; i = next.fetch_add(1))
+        process_chunk(i);
+    };
+    if (nthreads == 1)
+      worker();
+    else {
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back(worker);
+      for (std::thread &t : pool)
+        t.join();
+    }
+  }
+
+  // merge, in chunk order
+  for (int i = 0; i < num_chunks; i++) {
+    ChunkResult &res = results[i];
+    if (!res.done) continue;
+    std::vector<std::vector<realnum *> *> staged_of(nslots, nullptr);
+    for (Staged &st : res.staged)
+      staged_of[st.k] = &st.out;
+    for (size_t q = 0; q < res.touched_list.size(); ++q) {
+      const size_t k = res.touched_list[q], sz = res.sizes[q];
       const int j = (int)(k % num_chunks);
       const size_t fi = k / num_chunks;
       const comms_key key = {field_type(fi / NUM_CONNECT_PHASE_TYPES),
                              connect_phase(fi % NUM_CONNECT_PHASE_TYPES), {j, i}};
-      if (sz) comm_sizes[key] = sz;
+      if (sz) {
+        comm_sizes[key] = sz;
+        if (staged_of[k]) chunks[j]->connections_out[key] = std::move(*staged_of[k]);
+      }
       else { // nothing was connected under this key after all: leave no empty table behind
-        if (s.in) chunks[i]->connections_in.erase(key);
-        if (s.phases) chunks[i]->connection_phases.erase(key);
-        if (s.out) chunks[j]->connections_out.erase(key);
+        chunks[i]->connections_in.erase(key);
+        chunks[i]->connection_phases.erase(key);
       }
     }
   }

@@ -302,9 +302,13 @@ inline void run_phase(Engine &E, meep::fields *f, PhaseId id, int ft, bool cache
   if (cacheable) {
     Phase &ph = E.phase(id, ft);
     if (!ph.valid) {
+      const double t0 = E.verbose ? meep::wall_time() : 0;
       E.begin_record();
       record();
       E.end_record(ph, id, f);
+      if (E.verbose)
+        fprintf(stderr, "meep_b200: phase %d/%d recorded in %.3f s (host)\n", (int)id, ft,
+                meep::wall_time() - t0);
     }
     E.run(ph, f);
     if (ph.one_shot) E.free_phase(ph);
