@@ -149,3 +149,20 @@ def test_process_runtime_reductions_and_broadcasts(world):
     for r, p in enumerate(procs):
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, "rank %d:\n%s" % (r, out[-2000:])
+
+
+def test_ld_preload_over_a_program_linked_against_the_reference_only(tmp_path):
+    """INTEGRATION.md route A: an existing binary that knows nothing about the drop-in (linked
+    against the reference library alone) runs on the (emulated) device when the drop-in is
+    preloaded, and produces the reference's arrays"""
+    from parity_util import TBUILD, driver, read_dump
+    exe = driver("sim_driver", "ref", "f64")
+    pre = ":".join([os.path.join(TBUILD, "libmeep_b200_emu_f64.so"), os.path.join(TBUILD, "libmeepb200_emu.so")])
+    out = str(tmp_path / "pre.bin")
+    env = dict(os.environ, LD_PRELOAD=pre, MEEP_B200_VERBOSE="1", OMP_NUM_THREADS="2")
+    r = subprocess.run([exe, "3d_metal", "12", out, "2"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "meep_b200: recorded" in r.stdout  # the engine, not the CPU loops, did the stepping
+    ref = run_case("ref", "f64", "3d_metal", 12, 2)
+    compare(read_dump(out), ref, TOL["f64"])
