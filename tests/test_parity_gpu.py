@@ -105,3 +105,23 @@ def test_reference_test_program_passes_on_the_device(name, prec):
     env = dict(os.environ, OMP_NUM_THREADS="4")
     r = subprocess.run([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_ld_preload_over_a_program_linked_against_the_reference_only(tmp_path):
+    """INTEGRATION.md route A on the real device: a binary linked against the reference library
+    alone, with the drop-in preloaded"""
+    import os
+    import subprocess
+    from parity_util import ROOT, driver, read_dump
+    lib = os.path.join(ROOT, "meep_b200", "lib")
+    exe = driver("sim_driver", "ref", "f64")
+    out = str(tmp_path / "pre.bin")
+    env = dict(os.environ, LD_PRELOAD=":".join([os.path.join(lib, "libmeep_b200_f64.so"),
+                                                os.path.join(lib, "libmeepb200.so")]),
+               MEEP_B200_VERBOSE="1", OMP_NUM_THREADS="2")
+    r = subprocess.run([exe, "c2_3d_pml", "40", out, "0"], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "meep_b200: recorded" in r.stdout
+    ref = run_case("ref", "f64", "c2_3d_pml", 40, 0)
+    compare(read_dump(out), ref, TOL["f64"])
