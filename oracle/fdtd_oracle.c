@@ -8,12 +8,18 @@
  * include/meep_b200.h, but every pointer is a HOST pointer here, so the same job description
  * drives the oracle and the CUDA kernels on identical inputs.
  *
- * Pinning: tests/test_oracle.py checks every function against golden vectors produced by
- * calling the reference's own functions (meep::step_curl, step_update_EDHB,
- * lorentzian_susceptibility::update_P, dft_chunk::update_dft, ...) from the unmodified
- * reference build in oracle/_ref (generator: tests/drivers/gen_golden.cpp; fixtures:
- * tests/golden/).  The full reference build itself (oracle/_ref, which passes the reference's
- * tests/known_results.cpp 13/13) is the second, end-to-end oracle used by tests/test_parity_*.py.
+ * Pinning: tests/test_oracle.py checks the arithmetic kernels against golden vectors produced by
+ * calling the reference's own functions from the unmodified reference build in oracle/_ref
+ * (generator: tests/drivers/gen_golden.cpp; fixtures: tests/golden/): step_curl (32 variants),
+ * step_beta, step_bfast, step_update_EDHB, lorentzian_susceptibility::update_P,
+ * gyrotropic_susceptibility::update_P, dft_chunk::update_dft + dft_flux::flux, and one whole
+ * cylindrical fields::step_db (which pins the r-derivative scan, the i*m/r terms, the r = 0 rows
+ * and the zeroed rows).  The remaining functions are gathers / scatters / one-line updates
+ * (step_source, step_boundaries, subtract_P, zero_metal, average_with_backup, add_noise) whose
+ * reference form is a single statement; they are exercised against the full reference build
+ * itself (oracle/_ref, which passes the reference's tests/known_results.cpp 13/13) — the second,
+ * end-to-end oracle used by tests/test_host_emu.py and tests/test_parity_gpu.py on every array
+ * of 40+ simulations.
  */
 #include <complex.h>
 #include <math.h>
