@@ -21,20 +21,36 @@ using namespace meep_b200;
 
 namespace meep {
 
+// One half of a time step: the D/B family `db` is advanced from the curl of the other family,
+// then the E/H family `eh` is derived from it (with its W and polarisation exchanges in between).
+// fields::step() is two of these, B/H first; the order inside is the reference's
+// (src/step.cpp:62-121) and is what every parity test checks.
+namespace {
+struct HalfStep {
+  field_type db, eh, w, p;
+  time_sink t_update_db, t_bnd_db, t_update_eh, t_bnd_w, t_bnd_p, t_bnd_eh;
+};
+const HalfStep kHalves[2] = {
+    {B_stuff, H_stuff, WH_stuff, PH_stuff, FieldUpdateB, BoundarySteppingB, FieldUpdateH,
+     BoundarySteppingWH, BoundarySteppingPH, BoundarySteppingH},
+    {D_stuff, E_stuff, WE_stuff, PE_stuff, FieldUpdateD, BoundarySteppingD, FieldUpdateE,
+     BoundarySteppingWE, BoundarySteppingPE, BoundarySteppingE}};
+} // namespace
+
 void fields::step() {
   Engine &E = Engine::get(this);
 
-  // however many times the fields have been synched, we want to restore now
-  int save_synchronized_magnetic_fields = synchronized_magnetic_fields;
-  if (synchronized_magnetic_fields) {
-    synchronized_magnetic_fields = 1; // reset synchronization count
-    E.sync_host();                    // restore_component works on the host arrays
+  // Stepping happens on unsynchronised fields: undo any number of pending
+  // synchronize_magnetic_fields() calls now and redo one at the end (device-side, sync_magnetic.cpp)
+  const int sync_depth = synchronized_magnetic_fields;
+  if (sync_depth) {
+    synchronized_magnetic_fields = 1;
     restore_magnetic_fields();
-    E.mark_host_dirty();
   }
 
   am_now_working_on(Stepping);
 
+  // progress line (same text and cadence as the reference's)
   if (!t) {
     last_step_output_wall_time = wall_time();
     last_step_output_t = t;
@@ -42,94 +58,65 @@ void fields::step() {
   if (verbosity > 0 && wall_time() > last_step_output_wall_time + MEEP_MIN_OUTPUT_TIME) {
     master_printf("on time step %d (time=%g), %g s/step\n", t, time(),
                   (wall_time() - last_step_output_wall_time) / (t - last_step_output_t));
-    if (save_synchronized_magnetic_fields)
-      master_printf("  (doing expensive timestepping of synched fields)\n");
+    if (sync_depth) master_printf("  (doing expensive timestepping of synched fields)\n");
     last_step_output_wall_time = wall_time();
     last_step_output_t = t;
   }
 
   {
-    if (changed_materials) E.materials_dirty = true;
-    // update cached conductivity-inverse array, if needed (host; re-uploaded if it changed)
+    // host-side material state that the device mirrors: conductivity inverses are refreshed by
+    // reference code and re-uploaded when they changed
+    E.materials_dirty = E.materials_dirty || changed_materials;
+    E.cw_mode = false;
     for (int i = 0; i < num_chunks; i++) {
-      if (chunks[i]->is_mine() && chunks[i]->s->condinv_stale) E.materials_dirty = true;
+      const bool mine = chunks[i]->is_mine();
+      if (mine && chunks[i]->s->condinv_stale) E.materials_dirty = true;
+      if (mine && chunks[i]->doing_solve_cw) E.cw_mode = true;
       chunks[i]->s->update_condinv();
     }
     E.in_step = true;
-    E.cw_mode = false;
-    for (int i = 0; i < num_chunks; i++)
-      if (chunks[i]->is_mine() && chunks[i]->doing_solve_cw) E.cw_mode = true;
     Scope scope(E, this);
 
     phase_material();
 
-    calc_sources(time()); // for B sources
-    {
-      auto step_timer = with_timing_scope(FieldUpdateB);
-      step_db(B_stuff);
-    }
-    step_source(B_stuff);
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingB);
-      step_boundaries(B_stuff);
-    }
-    calc_sources(time() + 0.5 * dt); // for integrated H sources
-    {
-      auto step_timer = with_timing_scope(FieldUpdateH);
-      update_eh(H_stuff);
-    }
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingWH);
-      step_boundaries(WH_stuff);
-    }
-    update_pols(H_stuff);
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingPH);
-      step_boundaries(PH_stuff);
-    }
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingH);
-      step_boundaries(H_stuff);
-    }
-
-    if (fluxes) { // legacy flux planes integrate the host arrays
-      E.download_fields();
-      fluxes->update_half();
-    }
-
-    calc_sources(time() + 0.5 * dt); // for D sources
-    {
-      auto step_timer = with_timing_scope(FieldUpdateD);
-      step_db(D_stuff);
-    }
-    step_source(D_stuff);
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingD);
-      step_boundaries(D_stuff);
-    }
-    calc_sources(time() + dt); // for integrated E sources
-    {
-      auto step_timer = with_timing_scope(FieldUpdateE);
-      update_eh(E_stuff);
-    }
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingWE);
-      step_boundaries(WE_stuff);
-    }
-    update_pols(E_stuff);
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingPE);
-      step_boundaries(PE_stuff);
-    }
-    {
-      auto step_timer = with_timing_scope(BoundarySteppingE);
-      step_boundaries(E_stuff);
+    for (int h = 0; h < 2; ++h) {
+      const HalfStep &H = kHalves[h];
+      const double t_half = time() + 0.5 * dt * h;
+      calc_sources(t_half); // currents driving this family
+      {
+        auto timer = with_timing_scope(H.t_update_db);
+        step_db(H.db);
+      }
+      step_source(H.db);
+      {
+        auto timer = with_timing_scope(H.t_bnd_db);
+        step_boundaries(H.db);
+      }
+      calc_sources(t_half + 0.5 * dt); // integrated sources enter the E/H update
+      {
+        auto timer = with_timing_scope(H.t_update_eh);
+        update_eh(H.eh);
+      }
+      {
+        auto timer = with_timing_scope(H.t_bnd_w);
+        step_boundaries(H.w);
+      }
+      update_pols(H.eh);
+      {
+        auto timer = with_timing_scope(H.t_bnd_p);
+        step_boundaries(H.p);
+      }
+      {
+        auto timer = with_timing_scope(H.t_bnd_eh);
+        step_boundaries(H.eh);
+      }
+      if (fluxes) { // legacy flux planes integrate the host arrays
+        E.download_fields();
+        if (h == 0) fluxes->update_half();
+        else fluxes->update();
+      }
     }
 
-    if (fluxes) {
-      E.download_fields();
-      fluxes->update();
-    }
     t += 1;
     update_dfts();
     finished_working();
@@ -146,12 +133,9 @@ void fields::step() {
 
   if (E.eager) E.sync_host();
 
-  // re-synch magnetic fields if they were previously synchronized
-  if (save_synchronized_magnetic_fields) {
-    E.sync_host();
-    E.mark_host_dirty();
+  if (sync_depth) {
     synchronize_magnetic_fields();
-    synchronized_magnetic_fields = save_synchronized_magnetic_fields;
+    synchronized_magnetic_fields = sync_depth;
   }
 }
 

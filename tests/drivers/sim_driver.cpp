@@ -269,8 +269,13 @@ int main(int argc, char **argv) {
       }
     }
     dump("energy", en.data(), sizeof(double), en.size());
+    // stepping while synchronised (restore -> step -> re-synchronise inside fields::step, twice
+    // nested), then a dump in the synchronised state
     f.synchronize_magnetic_fields();
+    f.synchronize_magnetic_fields();
+    for (int i = 0; i < 5; ++i) f.step();
     dump_fields(f);
+    f.restore_magnetic_fields();
     f.restore_magnetic_fields();
   }
   else if (cs == "3d_xperiodic_ypml") {
