@@ -56,7 +56,12 @@ def test_emulated_dropin_matches_reference_f64(case, steps, chunks):
 
 
 @pytest.mark.parametrize("case,steps,chunks", [("c2_3d_pml", 20, 0), ("lorentz_3d", 20, 0),
-                                               ("2d_bend_flux", 100, 0), ("3d_bloch", 20, 0)])
+                                               ("2d_bend_flux", 100, 0), ("3d_bloch", 20, 0),
+                                               ("cyl_m1", 40, 0), ("cyl_m1_cond", 40, 0),
+                                               ("gyro_lorentz_3d", 30, 0), ("gyro_saturated_3d", 30, 0),
+                                               ("3d_bfast", 30, 0), ("lorentz_aniso_sigma", 30, 0),
+                                               ("noisy_lorentz_3d", 20, 0), ("3d_sync_magnetic", 20, 0),
+                                               ("cond_chi3_3d", 20, 0), ("c4_aniso_ring", 12, 0)])
 def test_emulated_dropin_matches_reference_f32(case, steps, chunks):
     ref = run_case("ref", "f32", case, steps, chunks)
     got = run_case("emu", "f32", case, steps, chunks)

@@ -67,7 +67,9 @@ def test_b200_matches_reference_f64(case, steps, chunks):
 @pytest.mark.parametrize("case,steps,chunks", [("c2_3d_pml", 200, 0), ("lorentz_3d", 60, 0),
                                                ("2d_bend_flux", 300, 0), ("3d_bloch", 60, 0),
                                                ("c4_aniso_ring", 40, 0), ("dft_fields_3d", 40, 0),
-                                               ("cyl_m1_flux", 100, 0)])
+                                               ("cyl_m1_flux", 100, 0), ("gyro_lorentz_3d", 40, 0),
+                                               ("3d_bfast", 40, 0), ("lorentz_aniso_sigma", 40, 0),
+                                               ("cond_chi3_3d", 40, 0)])
 def test_b200_matches_reference_f32(case, steps, chunks):
     ref = run_case("ref", "f32", case, steps, chunks)
     got = run_case("b200", "f32", case, steps, chunks)
