@@ -107,6 +107,16 @@ MP_CASES = [  # (case, steps, num_chunks, world_size)
     ("c4_aniso_ring", 12, 2, 2),
     ("cyl_m1", 40, 4, 2),
     ("c2_3d_pml", 20, 8, 4),
+    ("2d_mirror_sym", 40, 4, 2),
+    ("3d_rotate_sym", 30, 4, 3),
+    ("cyl_m1_flux", 60, 4, 2),
+    ("3d_bfast", 30, 4, 2),
+    ("2d_beta", 40, 6, 3),
+    ("dft_fields_3d", 30, 4, 2),
+    ("c3_au_sphere", 15, 8, 4),
+    ("cond_chi3_3d", 20, 4, 2),
+    ("3d_sync_magnetic", 20, 4, 2),
+    ("1d_polariton", 60, 4, 2),
     ("lorentz_aniso_sigma", 30, 4, 2),
     ("gyro_lorentz_3d", 30, 4, 2),
     ("3d_xperiodic_ypml", 20, 6, 3),
