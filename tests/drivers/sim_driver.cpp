@@ -250,6 +250,20 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
+  else if (cs == "3d_tiled") {
+    // loop tiling of step_db / update_eh (fields ctor loop_tile_base_db / _eh; split_into_tiles,
+    // src/step_db.cpp:47, src/update_eh.cpp:31-50): anisotropic medium so that update_eh tiles too
+    g_L = 2.0;
+    grid_volume gv = vol3d(2.0, 1.8, 1.6, a);
+    structure s(gv, eps_smooth, pml(0.4), identity(), num_chunks, 0.5, true, 1e-2, 2000);
+    fields f(&s, 0.0, 0.0, true, 6, 5);
+    f.use_real_fields();
+    gaussian_src_time src(0.4, 0.3);
+    f.add_point_source(Ez, src, vec(0.9, 0.8, 0.7));
+    for (int i = 0; i < nsteps; ++i) f.step();
+    probes(f, gv);
+    dump_fields(f);
+  }
   else if (cs == "3d_sync_magnetic") {
     // fields::synchronize_magnetic_fields / restore_magnetic_fields (src/energy_and_flux.cpp:149-178)
     // around an energy evaluation, stepping on afterwards, and a dump in the synchronised state
