@@ -250,6 +250,37 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
+  else if (cs == "3d_midrun_changes") {
+    // things user code does between steps: a source and a DFT monitor added mid-run, sources
+    // removed, fields::reset(), then stepping again (plans must follow; host writers must be seen)
+    g_L = 1.6;
+    grid_volume gv = vol3d(1.6, 1.6, 1.6, a);
+    structure s(gv, eps_box, pml(0.3), identity(), num_chunks);
+    s.add_susceptibility(sphere, E_stuff, lorentzian_susceptibility(0.8, 0.05));
+    fields f(&s);
+    f.use_real_fields();
+    gaussian_src_time src(0.5, 0.4);
+    f.add_point_source(Ez, src, vec(0.8, 0.8, 0.8));
+    const int q = nsteps / 4;
+    for (int i = 0; i < q; ++i) f.step();
+    continuous_src_time cw(0.45, 0.0, f.time());
+    f.add_point_source(Hy, cw, vec(0.6, 0.9, 0.7));
+    for (int i = 0; i < q; ++i) f.step();
+    volume box(vec(0.5, 0.5, 0.5), vec(1.1, 1.1, 1.1));
+    dft_flux fl = f.add_dft_flux_box(box, 0.3, 0.7, 5);
+    for (int i = 0; i < q; ++i) f.step();
+    dump_flux("flux.before_reset", fl);
+    f.remove_sources();
+    for (int i = 0; i < 3; ++i) f.step();
+    std::vector<double> e0 = {f.field_energy()};
+    f.reset();
+    f.add_point_source(Ex, src, vec(0.9, 0.7, 0.8));
+    for (int i = 0; i < q; ++i) f.step();
+    e0.push_back(f.field_energy());
+    dump("energy", e0.data(), sizeof(double), e0.size());
+    probes(f, gv);
+    dump_fields(f);
+  }
   else if (cs == "3d_tiled") {
     // loop tiling of step_db / update_eh (fields ctor loop_tile_base_db / _eh; split_into_tiles,
     // src/step_db.cpp:47, src/update_eh.cpp:31-50): anisotropic medium so that update_eh tiles too
