@@ -250,6 +250,24 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
+  else if (cs == "3d_phase_in" || cs == "3d_bloch_change") {
+    // fields::phase_in_material (material arrays rewritten on the host every step while phasing,
+    // src/step.cpp:141-166) / use_bloch changed mid-run (boundary phases and connections rebuilt)
+    g_L = 1.6;
+    grid_volume gv = vol3d(1.6, 1.6, 1.2, a);
+    structure s(gv, one, cs == "3d_phase_in" ? pml(0.3) : no_pml(), identity(), num_chunks);
+    structure s2(gv, eps_box, cs == "3d_phase_in" ? pml(0.3) : no_pml(), identity(), num_chunks);
+    fields f(&s);
+    gaussian_src_time src(0.5, 0.4);
+    f.add_point_source(Ez, src, vec(0.8, 0.8, 0.6));
+    if (cs == "3d_bloch_change") f.use_bloch(vec(0.1, 0.2, 0.0));
+    for (int i = 0; i < nsteps / 3; ++i) f.step();
+    if (cs == "3d_phase_in") f.phase_in_material(&s2, 0.5 * (nsteps / 3) * f.dt);
+    else f.use_bloch(vec(0.3, -0.1, 0.25));
+    for (int i = 0; i < 2 * (nsteps / 3); ++i) f.step();
+    probes(f, gv);
+    dump_fields(f);
+  }
   else if (cs == "3d_midrun_changes") {
     // things user code does between steps: a source and a DFT monitor added mid-run, sources
     // removed, fields::reset(), then stepping again (plans must follow; host writers must be seen)

@@ -35,6 +35,8 @@ CASES = [  # (case, steps, num_chunks)
     ("gyro_drude_3d", 30, 3),
     ("gyro_saturated_3d", 30, 0),
     ("lorentz_aniso_sigma", 30, 4),
+    ("3d_phase_in", 45, 2),
+    ("3d_bloch_change", 45, 3),
     ("3d_midrun_changes", 48, 2),
     ("3d_tiled", 30, 0),
     ("3d_sync_magnetic", 30, 0),

@@ -42,6 +42,8 @@ CASES = [  # (case, steps, num_chunks)
     ("gyro_drude_3d", 60, 3),
     ("gyro_saturated_3d", 60, 0),
     ("lorentz_aniso_sigma", 60, 0),
+    ("3d_phase_in", 60, 0),
+    ("3d_bloch_change", 60, 2),
     ("3d_midrun_changes", 80, 0),
     ("3d_tiled", 40, 0),
     ("3d_sync_magnetic", 60, 2),
