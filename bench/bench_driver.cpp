@@ -142,9 +142,10 @@ void *mb200_bench_create3d(const char *workload, int nx, int ny, int nz, int num
       b->gv = vol3d(nx / a, ny / a, nz / a, a);
       vacuum_material vac;
       b->s = new structure(b->gv, vac, pml(1.0), identity(), num_chunks, 0.5, false);
-      const double eV = 1 / 1.23984193;
-      // (the 13.32 eV pole is moved to 4.5 eV: at resolution 10 it would have omega_0 dt > 2)
-      const double frq[6] = {1e-3, 0.415 * eV, 0.830 * eV, 2.969 * eV, 4.304 * eV, 4.5 * eV};
+      // unit length 0.1 um (python/materials.py um_scale = 0.1), i.e. 10 nm pixels: with 1 um units the
+      // Drude term has omega_p dt = 2.0 at resolution 10 and the run diverges in the reference itself
+      const double eV = 0.1 / 1.23984193;
+      const double frq[6] = {1e-3, 0.415 * eV, 0.830 * eV, 2.969 * eV, 4.304 * eV, 13.32 * eV};
       const double gam[6] = {0.053 * eV, 0.241 * eV, 0.345 * eV, 0.870 * eV, 2.494 * eV, 2.214 * eV};
       const double wp = 9.03 * eV;
       const double fstr[6] = {0.760, 0.024, 0.010, 0.071, 0.601, 4.384};
@@ -154,12 +155,12 @@ void *mb200_bench_create3d(const char *workload, int nx, int ny, int nz, int num
       }
       b->f = new fields(b->s);
       b->f->use_real_fields();
-      gaussian_src_time src(1.5, 1.0);
+      gaussian_src_time src(0.4, 0.3);
       src.is_integrated = false;
       b->f->add_point_source(Ez, src, vec(0.15 * nx / a, g_cy, g_cz));
       volume box(vec(0.25 * nx / a, 0.25 * ny / a, 0.25 * nz / a),
                  vec(0.75 * nx / a, 0.75 * ny / a, 0.75 * nz / a));
-      b->flux = new dft_flux(b->f->add_dft_flux_box(box, 1.0, 2.0, 100));
+      b->flux = new dft_flux(b->f->add_dft_flux_box(box, 0.24, 0.56, 100));
       b->probe_pt = b->gv.center() + vec(0.35, 0.25, 0.15);
       b->cells = (double)nx * ny * nz;
     }

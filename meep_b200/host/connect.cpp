@@ -2,7 +2,7 @@
 // (reference src/boundaries.cpp:315-345 and 368-638).
 //
 // These build the tables that fields::step_boundaries consumes (connections_in/out,
-// connection_phases, comm_sizes, comms_sequence_for_field, zeroes).  The reference versions are
+// connection_phases, comm_sizes, zeroes).  The reference versions are
 // O(not-owned points x chunks) with several hash-map lookups per point and a full-volume scan for
 // metal points: 14 s at 256^3 / 27 chunks, ~1 min at 512^3, and they grow with the SQUARE of the
 // chunk count in a multi-GPU run.  Here the same tables (same contents, same order) are produced
@@ -26,33 +26,6 @@ using namespace std;
 namespace meep {
 
 namespace {
-
-// as optimize_comms_operations in the reference's anonymous namespace (src/boundaries.cpp:37-75)
-comms_sequence order_comms_operations(const std::vector<comms_operation> &operations) {
-  comms_sequence ret;
-  std::map<int, size_t> send_size_by_my_chunk_idx;
-  std::map<int, std::vector<comms_operation> > send_ops_by_my_chunk_idx;
-  for (const auto &op : operations) {
-    if (op.comm_direction == Incoming) {
-      ret.receive_ops.push_back(op);
-      continue;
-    }
-    if (op.other_proc_id != my_rank()) { send_size_by_my_chunk_idx[op.my_chunk_idx] += op.transfer_size; }
-    else { send_size_by_my_chunk_idx[op.my_chunk_idx] += 0; }
-    send_ops_by_my_chunk_idx[op.my_chunk_idx].push_back(op);
-  }
-  std::vector<std::pair<int, size_t> > send_op_sizes(send_size_by_my_chunk_idx.begin(),
-                                                     send_size_by_my_chunk_idx.end());
-  std::stable_sort(send_op_sizes.begin(), send_op_sizes.end(),
-                   [](const std::pair<int, size_t> &a, const std::pair<int, size_t> &b) -> bool {
-                     return a.second > b.second;
-                   });
-  for (const auto &size_pair : send_op_sizes) {
-    const auto &ops_vector = send_ops_by_my_chunk_idx[size_pair.first];
-    ret.send_ops.insert(std::end(ret.send_ops), std::begin(ops_vector), std::end(ops_vector));
-  }
-  return ret;
-}
 
 bool phase_isclose(std::complex<double> thephase, double realphase) {
   return fabs(thephase.imag()) < 1e-13 && fabs(thephase.real() - realphase) < 1e-13;
@@ -373,37 +346,10 @@ void fields::connect_the_chunks() {
   // (the host comm_blocks of the reference are not allocated: comm blocks live in HBM,
   //  fields::step_boundaries in step.cpp)
 
-  FOR_FIELD_TYPES(f) {
-    std::vector<comms_operation> operations;
-    std::vector<int> tagto(count_processors());
-    for (int j = 0; j < num_chunks; j++) {
-      for (int i = 0; i < num_chunks; i++) {
-        const chunk_pair pair{j, i};
-        const size_t comm_size = comm_size_tot(f, pair);
-        if (!comm_size) continue;
-        const int pair_idx = j + i * num_chunks;
-        if (chunks[j]->is_mine()) {
-          operations.push_back(comms_operation{/*my_chunk_idx=*/j,
-                                               /*other_chunk_idx=*/i,
-                                               /*other_proc_id=*/chunks[i]->n_proc(),
-                                               /*pair_idx=*/pair_idx,
-                                               /*transfer_size=*/comm_size,
-                                               /*comm_direction=*/Outgoing,
-                                               /*tag=*/tagto[chunks[i]->n_proc()]++});
-        }
-        if (chunks[i]->is_mine()) {
-          operations.push_back(comms_operation{/*my_chunk_idx=*/i,
-                                               /*other_chunk_idx=*/j,
-                                               /*other_proc_id=*/chunks[j]->n_proc(),
-                                               /*pair_idx=*/pair_idx,
-                                               /*transfer_size=*/comm_size,
-                                               /*comm_direction=*/Incoming,
-                                               /*tag=*/tagto[chunks[j]->n_proc()]++});
-        }
-      }
-    }
-    comms_sequence_for_field[f] = order_comms_operations(operations);
-  }
+  // comms_sequence_for_field (the reference's ordered list of MPI sends/receives, consumed only
+  // by its own fields::step_boundaries) has no reader in this build: our step_boundaries walks
+  // comm_sizes in a fixed global pair order and moves the blocks device-to-device.
+  FOR_FIELD_TYPES(f) { comms_sequence_for_field[f].clear(); }
   if (getenv("MEEP_B200_VERBOSE") && atoi(getenv("MEEP_B200_VERBOSE")))
     master_printf("meep_b200: connect_the_chunks: %d chunks, %.3f s\n", num_chunks,
                   wall_time() - t_start);

@@ -16,6 +16,7 @@ using namespace meep;
 namespace meep_b200 {
 
 Engine *Engine::current_ = nullptr;
+uint64_t Engine::source_generation = 0;
 
 static std::unordered_map<const fields *, Engine *> &table() {
   static std::unordered_map<const fields *, Engine *> t;
@@ -377,6 +378,7 @@ uint64_t Engine::fingerprint(fields *f) const {
   uint64_t h = 1469598103934665603ULL;
   hash_mix(h, (uint64_t)f->num_chunks);
   hash_mix(h, (uint64_t)f->is_real);
+  hash_mix(h, source_generation);
   for (int i = 0; i < f->num_chunks; ++i) {
     fields_chunk *fc = f->chunks[i];
     if (!fc->is_mine()) continue;
@@ -591,6 +593,15 @@ void Engine::sync_host() {
   if (state == DEVICE_NEWER) {
     download_fields();
     state = COHERENT;
+    // whoever reads the arrays on the host now must not be handed NaNs (or stale halos after a
+    // peer time-out) silently: the per-step probe is only read back every nan_check_every steps
+    check(mb200_sync(ctx), "device synchronisation");
+    if (probe_flag_ && probe_n_) {
+      int32_t flag = 0;
+      check(mb200_d2h(ctx, &flag, probe_flag_, 4), "d2h(flag)");
+      stats.d2h_bytes += 4;
+      if (flag) meep::abort("simulation fields are NaN or Inf");
+    }
   }
 }
 

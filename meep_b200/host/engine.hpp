@@ -147,6 +147,7 @@ public:
   static Engine *find(const meep::fields *f);   // NULL if none
   static void drop(const meep::fields *f);      // fields destroyed
   static Engine *current() { return current_; }
+  static uint64_t source_generation; // bumped by the interposed fields_chunk::add_source
   // the Engine whose mirror table contains host address p (NULL if none)
   static Engine *owner_of(const void *p);
   bool mirrors(const void *p) const;
@@ -236,6 +237,7 @@ public:
   // step_boundaries after the chunks were (re)connected; counts[(ft, peer)] = (send, recv).
   std::vector<P2PLink> links;
   int connect_epoch = 0, links_epoch = -1;
+  int plans_epoch = -1; // connect_epoch the cached plans were recorded against
   void rebuild_links(const std::map<std::pair<int, int>, std::pair<size_t, size_t> > &counts);
   void drop_links(); // collective when links exist
   int find_link(int ft, int rank) const;

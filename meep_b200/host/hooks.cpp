@@ -63,6 +63,28 @@ void mb200_hook_fields_D2(fields *self) {
   next(self);
 }
 
+// A DFT monitor removed mid-run (dft_flux::remove() etc. -> delete of its dft_chunks, reference
+// src/dft.cpp:131-144) frees the host `dft` array: its device mirror must go with it, or a later
+// download would write into freed memory and a new monitor whose array lands on the same address
+// would inherit the old accumulations.
+extern "C" {
+void mb200_hook_dft_chunk_D1(dft_chunk *self) __asm__("_ZN4meep9dft_chunkD1Ev");
+void mb200_hook_dft_chunk_D2(dft_chunk *self) __asm__("_ZN4meep9dft_chunkD2Ev");
+}
+static void forget_dft_mirror(dft_chunk *self) {
+  if (Engine *E = Engine::owner_of(self->dft)) E->forget(self->dft);
+}
+void mb200_hook_dft_chunk_D1(dft_chunk *self) {
+  static void (*next)(dft_chunk *) = (void (*)(dft_chunk *))next_definition_of_caller();
+  forget_dft_mirror(self);
+  next(self);
+}
+void mb200_hook_dft_chunk_D2(dft_chunk *self) {
+  static void (*next)(dft_chunk *) = (void (*)(dft_chunk *))next_definition_of_caller();
+  forget_dft_mirror(self);
+  next(self);
+}
+
 // ---- point probes: every fields::get_field variant funnels into this one (reference
 //      src/monitor.cpp:128-133).  Reads the one or two values from HBM when the device copy is
 //      the current one, so monitoring a point every step does not download whole arrays.
@@ -89,6 +111,18 @@ void fields::loop_in_chunks(field_chunkloop chunkloop, void *chunkloop_data, con
   static fn next = (fn)next_definition_of_caller();
   if (Engine *E = Engine::find(this)) E->sync_host();
   next(this, chunkloop, chunkloop_data, where, cgrid, use_symmetry, snap_unit_dims);
+}
+
+// ---- sources added mid-run -------------------------------------------------------------------------
+// fields_chunk::add_source (src/sources.cpp) may MERGE a new source into an existing src_vol
+// (add_amplitudes_from: same component, src_time and indices) — the amplitudes change in place and
+// nothing else does.  A global generation counter, part of every Engine's fingerprint, makes the
+// cached source plans (which hold uploaded amplitude copies) be re-recorded.
+void fields_chunk::add_source(field_type ft, src_vol &&src) {
+  typedef void (*fn)(fields_chunk *, field_type, src_vol &&);
+  static fn next = (fn)next_definition_of_caller();
+  Engine::source_generation++;
+  next(this, ft, std::move(src));
 }
 
 // ---- host-side writers of field arrays -----------------------------------------------------------

@@ -79,6 +79,22 @@ void fields::step() {
 
     phase_material();
 
+    // The reference refreshes the conductivity inverses AFTER phase_material (src/step.cpp:58-62):
+    // mix_with() changes the conductivities (and may allocate them) and marks condinv stale.  The
+    // loop above served the mirror set-up of the ordinary case; this one catches a phase-in step.
+    {
+      bool refreshed = false;
+      for (int i = 0; i < num_chunks; i++) {
+        if (chunks[i]->is_mine() && chunks[i]->s->condinv_stale) refreshed = true;
+        chunks[i]->s->update_condinv();
+      }
+      if (refreshed) {
+        E.scan(this); // condinv arrays may be new
+        E.upload_materials();
+        E.invalidate_plans();
+      }
+    }
+
     for (int h = 0; h < 2; ++h) {
       const HalfStep &H = kHalves[h];
       const double t_half = time() + 0.5 * dt * h;
@@ -188,9 +204,18 @@ void fields::step_boundaries(field_type ft) {
   Engine &E = Engine::get(this);
   Scope scope(E, this);
 
-  const bool was_valid = chunk_connections_valid;
-  connect_chunks(); // re-connect if !chunk_connections_valid (host tables, reference code)
-  if (!was_valid) E.invalidate_plans();
+  // connect_chunks() re-connects if !chunk_connections_valid — and the flag it tests is first
+  // and-ed over all processes when materials changed (sync_chunk_connections), so another rank's
+  // lazy allocation can force a re-connection here that the local flag did not announce: detect
+  // the re-connection itself (connect_the_chunks in connect.cpp bumps connect_epoch).
+  // Comparing against the epoch of the last invalidation also covers a re-connection made
+  // outside this function (user code calling connect_chunks()).
+  connect_chunks();
+  const bool was_valid = E.connect_epoch == E.plans_epoch;
+  if (!was_valid) {
+    E.invalidate_plans();
+    E.plans_epoch = E.connect_epoch;
+  }
 
   // Peer-memory links follow the chunk connections (connect.cpp bumps connect_epoch); all
   // processes reach the first in-step exchange after a (collective) re-connection together.

@@ -250,19 +250,26 @@ int main(int argc, char **argv) {
     probes(f, gv);
     dump_fields(f);
   }
-  else if (cs == "3d_phase_in" || cs == "3d_bloch_change") {
+  else if (cs == "3d_phase_in" || cs == "3d_phase_in_cond" || cs == "3d_bloch_change") {
     // fields::phase_in_material (material arrays rewritten on the host every step while phasing,
     // src/step.cpp:141-166) / use_bloch changed mid-run (boundary phases and connections rebuilt)
     g_L = 1.6;
     grid_volume gv = vol3d(1.6, 1.6, 1.2, a);
-    structure s(gv, one, cs == "3d_phase_in" ? pml(0.3) : no_pml(), identity(), num_chunks);
-    structure s2(gv, eps_box, cs == "3d_phase_in" ? pml(0.3) : no_pml(), identity(), num_chunks);
+    const bool phase_in = cs != "3d_bloch_change";
+    structure s(gv, one, phase_in ? pml(0.3) : no_pml(), identity(), num_chunks);
+    structure s2(gv, eps_box, phase_in ? pml(0.3) : no_pml(), identity(), num_chunks);
+    if (cs == "3d_phase_in_cond") { // the phased-in structure INTRODUCES conductivity (condinv appears mid-run)
+      s2.set_conductivity(Dx, cond_slab);
+      s2.set_conductivity(Dy, cond_slab);
+      s2.set_conductivity(Dz, cond_slab);
+      s2.set_conductivity(By, cond_slab);
+    }
     fields f(&s);
     gaussian_src_time src(0.5, 0.4);
     f.add_point_source(Ez, src, vec(0.8, 0.8, 0.6));
     if (cs == "3d_bloch_change") f.use_bloch(vec(0.1, 0.2, 0.0));
     for (int i = 0; i < nsteps / 3; ++i) f.step();
-    if (cs == "3d_phase_in") f.phase_in_material(&s2, 0.5 * (nsteps / 3) * f.dt);
+    if (phase_in) f.phase_in_material(&s2, 0.5 * (nsteps / 3) * f.dt);
     else f.use_bloch(vec(0.3, -0.1, 0.25));
     for (int i = 0; i < 2 * (nsteps / 3); ++i) f.step();
     probes(f, gv);
@@ -288,6 +295,11 @@ int main(int argc, char **argv) {
     dft_flux fl = f.add_dft_flux_box(box, 0.3, 0.7, 5);
     for (int i = 0; i < q; ++i) f.step();
     dump_flux("flux.before_reset", fl);
+    // a monitor removed mid-run and a new one of the same shape added (its arrays are likely to
+    // land on the addresses just freed): the new one must start from zero, and the host readers
+    // below must not be handed the freed arrays
+    fl.remove();
+    dft_flux fl2 = f.add_dft_flux_box(box, 0.3, 0.7, 5);
     f.remove_sources();
     for (int i = 0; i < 3; ++i) f.step();
     std::vector<double> e0 = {f.field_energy()};
@@ -296,6 +308,7 @@ int main(int argc, char **argv) {
     for (int i = 0; i < q; ++i) f.step();
     e0.push_back(f.field_energy());
     dump("energy", e0.data(), sizeof(double), e0.size());
+    dump_flux("flux.second_monitor", fl2);
     probes(f, gv);
     dump_fields(f);
   }
@@ -501,19 +514,20 @@ int main(int argc, char **argv) {
     dump_fields(f);
   }
   else if (cs == "c3_au_sphere") {
-    // BASELINE config 3 (scaled twin): Drude + 5 Lorentz "Au" sphere (constants from the
-    // reference's python/materials.py:340-364), PML, flux box with many frequencies
+    // BASELINE config 3 (scaled twin): Drude + 5 Lorentz "Au" sphere, all six poles with the
+    // constants of the reference's python/materials.py:340-364, PML, flux box with 100 frequencies.
+    // Unit length 0.1 um (materials.py's um_scale = 0.1), i.e. 10 nm pixels at resolution 10: with
+    // 1 um units the Drude term has omega_p dt = 2.0 and the run diverges in the reference itself.
+    // Here omega_p dt = 0.2 and max|field| stays O(1) (checked by tests/parity_util.compare).
     g_L = 2.4;
     grid_volume gv = vol3d(g_L, g_L, g_L, a);
     structure s(gv, one, pml(0.6), identity(), num_chunks);
-    const double eV = 1 / 1.23984193;
-    // (the 13.32 eV pole is moved to 4.5 eV: at the twin's resolution 10 it would have
-    //  omega_0*dt > 2 and be numerically unstable in the reference as well)
-    const double frq[6] = {1e-3 /* Drude: value only scales sigma */, 0.415 * eV, 0.830 * eV, 2.969 * eV, 4.304 * eV, 4.5 * eV};
+    const double um = getenv("MB200_C3_UM") ? atof(getenv("MB200_C3_UM")) : 0.1;
+    const double eV = um / 1.23984193;
+    const double frq[6] = {1e-3 /* Drude: value only scales sigma */, 0.415 * eV, 0.830 * eV, 2.969 * eV, 4.304 * eV, 13.32 * eV};
     const double gam[6] = {0.053 * eV, 0.241 * eV, 0.345 * eV, 0.870 * eV, 2.494 * eV, 2.214 * eV};
     const double wp = 9.03 * eV;
     const double fstr[6] = {0.760, 0.024, 0.010, 0.071, 0.601, 4.384};
-    static double sig_scale = 1;
     struct sig : public material_function {
       double scale;
       virtual double chi1p1(field_type, const vec &r) { return scale * sphere(r); }
@@ -524,17 +538,18 @@ int main(int argc, char **argv) {
     };
     for (int k = 0; k < 6; ++k) {
       sig sg;
-      sg.scale = k == 0 ? fstr[k] * wp * wp / (frq[k] * frq[k]) : fstr[k] * wp * wp / (frq[k] * frq[k]);
+      sg.scale = fstr[k] * wp * wp / (frq[k] * frq[k]);
       s.add_susceptibility(sg, E_stuff, lorentzian_susceptibility(frq[k], gam[k], k == 0));
     }
-    (void)sig_scale;
     fields f(&s);
     f.use_real_fields();
-    gaussian_src_time src(1.5, 1.0);
+    const double fc = getenv("MB200_C3_FC") ? atof(getenv("MB200_C3_FC")) : 0.4;
+    gaussian_src_time src(fc, 0.75 * fc); // 250 nm centre wavelength (a longer one makes the 240 nm cell quasi-static:
+                                          // B is then pure cancellation noise of curl E, an ill-conditioned parity case)
     src.is_integrated = false;
     f.add_point_source(Ez, src, vec(0.15 * g_L + 0.6, 0.5 * g_L, 0.5 * g_L));
     volume box(vec(0.25 * g_L, 0.25 * g_L, 0.25 * g_L), vec(0.75 * g_L, 0.75 * g_L, 0.75 * g_L));
-    dft_flux fl = f.add_dft_flux_box(box, 1.0, 2.0, 20);
+    dft_flux fl = f.add_dft_flux_box(box, 0.6 * fc, 1.4 * fc, 100);
     for (int i = 0; i < nsteps; ++i) f.step();
     probes(f, gv);
     dump_flux("flux.box", fl);

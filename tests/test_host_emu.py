@@ -20,7 +20,7 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_bend_flux", 150, 0),
     ("2d_te_pml", 60, 2),
     ("1d_polariton", 100, 3),
-    ("c3_au_sphere", 20, 0),
+    ("c3_au_sphere", 60, 0),
     ("lorentz_3d", 30, 2),
     ("c4_aniso_ring", 15, 0),
     ("offdiag_2d", 60, 0),
@@ -36,6 +36,7 @@ CASES = [  # (case, steps, num_chunks)
     ("gyro_saturated_3d", 30, 0),
     ("lorentz_aniso_sigma", 30, 4),
     ("3d_phase_in", 45, 2),
+    ("3d_phase_in_cond", 24, 0),
     ("3d_bloch_change", 45, 3),
     ("3d_midrun_changes", 48, 2),
     ("3d_tiled", 30, 0),

@@ -25,7 +25,8 @@ CASES = [  # (case, steps, num_chunks)
     ("2d_bend_flux", 200, 4),
     ("2d_te_pml", 100, 2),
     ("1d_polariton", 200, 3),
-    ("c3_au_sphere", 100, 0),          # BASELINE config 3 twin
+    ("c3_au_sphere", 300, 0),          # BASELINE config 3 twin (stable: 10 nm pixels), 100-frequency flux box
+    ("c3_au_sphere", 200, 8),
     ("lorentz_3d", 60, 3),
     ("c4_aniso_ring", 60, 0),          # BASELINE config 4 twin
     ("c4_aniso_ring", 30, 8),
@@ -43,6 +44,7 @@ CASES = [  # (case, steps, num_chunks)
     ("gyro_saturated_3d", 60, 0),
     ("lorentz_aniso_sigma", 60, 0),
     ("3d_phase_in", 60, 0),
+    ("3d_phase_in_cond", 60, 2),
     ("3d_bloch_change", 60, 2),
     ("3d_midrun_changes", 80, 0),
     ("3d_tiled", 40, 0),
@@ -73,7 +75,8 @@ def test_b200_matches_reference_f64(case, steps, chunks):
                                                ("c4_aniso_ring", 40, 0), ("dft_fields_3d", 40, 0),
                                                ("cyl_m1_flux", 100, 0), ("gyro_lorentz_3d", 40, 0),
                                                ("3d_bfast", 40, 0), ("lorentz_aniso_sigma", 40, 0),
-                                               ("cond_chi3_3d", 40, 0)])
+                                               ("cond_chi3_3d", 40, 0), ("c3_au_sphere", 200, 0),
+                                               ("c3_au_sphere", 200, 8)])
 def test_b200_matches_reference_f32(case, steps, chunks):
     ref = run_case("ref", "f32", case, steps, chunks)
     got = run_case("b200", "f32", case, steps, chunks)
