@@ -123,12 +123,17 @@ void *mb200_bench_create3d(const char *workload, int nx, int ny, int nz, int num
       g_cz = 0.5 * nz / a;
       b->gv = vol3d(nx / a, ny / a, nz / a, a);
       cube_material mat;
+      const bool trace = getenv("MEEP_B200_VERBOSE") && atoi(getenv("MEEP_B200_VERBOSE"));
+      double t0 = wall_time();
       b->s = new structure(b->gv, mat, pml(1.0), identity(), num_chunks, 0.5, false);
+      if (trace) fprintf(stderr, "bench: structure %.3f s\n", wall_time() - t0);
+      t0 = wall_time();
       b->f = new fields(b->s);
       b->f->use_real_fields();
       gaussian_src_time src(0.15, 0.1);
       src.is_integrated = false; // a current source, the Python front end's default
       b->f->add_point_source(Ez, src, b->gv.center() + vec(0.05, 0.05, 0.05));
+      if (trace) fprintf(stderr, "bench: fields + source %.3f s\n", wall_time() - t0);
       b->probe_pt = b->gv.center() + vec(0.35, 0.25, 0.15);
       b->cells = (double)nx * ny * nz;
     }
@@ -196,8 +201,12 @@ void *mb200_bench_create3d(const char *workload, int nx, int ny, int nz, int num
 int mb200_bench_step(void *h, int nsteps) {
   Bench *b = (Bench *)h;
   try {
-    for (int i = 0; i < nsteps; ++i)
+    const bool trace = getenv("MEEP_B200_VERBOSE") && atoi(getenv("MEEP_B200_VERBOSE"));
+    for (int i = 0; i < nsteps; ++i) {
+      const double t0 = trace ? wall_time() : 0;
       b->f->step();
+      if (trace && b->f->t <= 4) fprintf(stderr, "bench: step %d took %.3f s (host)\n", b->f->t, wall_time() - t0);
+    }
     return 0;
   } catch (std::exception &e) {
     fprintf(stderr, "mb200_bench_step: %s\n", e.what());

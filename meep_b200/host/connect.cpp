@@ -6,10 +6,12 @@
 // O(not-owned points x chunks) with several hash-map lookups per point and a full-volume scan for
 // metal points: 14 s at 256^3 / 27 chunks, ~1 min at 512^3, and they grow with the SQUARE of the
 // chunk count in a multi-GPU run.  Here the same tables (same contents, same order) are produced
-// with: the owner chunk of a point found by testing the previous owner first; table vectors
-// resolved once per (chunk pair, field type, phase class) instead of per point; a single pass
-// (sizes are read off the finished vectors); metal points found by walking only the boundary
-// planes of the owned volume.  Host code only — nothing here touches field values.
+// with: the not-owned slabs walked in runs (rows) whose table entries are arithmetic progressions —
+// the per-point work of the reference (locate_component_point, on_metal_boundary, owner search,
+// polarisation matching) is done once per run, i.e. the walk is analytic in the box intersections
+// of slabs, owned volumes and the cell; table vectors resolved once per (chunk pair, field type,
+// phase class); a single pass (sizes are read off the finished vectors); metal points found by
+// walking only the boundary planes of the owned volume.  Host code only — nothing here touches field values.
 #include <algorithm>
 #include <atomic>
 #include <deque>
@@ -195,98 +197,202 @@ void fields::connect_the_chunks() {
     };
     int last_j = i;
 
+    // The not-owned slabs of chunk i are walked in the reference's order (LOOP_OVER_VOL_NOTOWNED,
+    // src/meep/vec.hpp:180-186: slab by slab, loops 1,2,3 nested) but in RUNS along the innermost
+    // loop direction of extent > 1: the first point of a run goes through the reference's
+    // per-point logic (locate_component_point, on_metal_boundary, owner search); how far the same
+    // answer holds — same periodic image, same owner chunk, no metal plane — follows from the
+    // chunk and cell bounds along that direction, and the last point of the run is re-checked.
+    // All table entries of a run are arithmetic progressions.  With symmetries or cylindrical
+    // coordinates runs have length 1 (the per-point walk).
+    const bool runs_ok = S.multiplicity() == 1 && gv.dim != Dcyl;
+    const int ncmp = 2 - is_real;
+    struct PolPair { // a matching pair of polarisations of chunks i and j (src/boundaries.cpp:556-591)
+      polarization_state *pi, *pj, *po;
+      size_t ni, cni;
+    };
+    std::vector<PolPair> pol_pairs;
+
+    auto head_of_run = [&](component corig, const ivec &here, component &c, ivec &there,
+                           std::complex<double> &thephase, int &j) -> bool {
+      c = corig;
+      there = here;
+      if (!locate_component_point(&c, &there, &thephase) || on_metal_boundary(there)) return false;
+      // the chunk that owns `there` (ownership is exclusive): try the previous owner first
+      j = -1;
+      if (chunks[last_j]->gv.owns(there)) j = last_j;
+      else
+        for (int jj = 0; jj < num_chunks; jj++)
+          if (chunks[jj]->gv.owns(there)) {
+            j = jj;
+            break;
+          }
+      if (j < 0) return false;
+      last_j = j;
+      return true;
+    };
+
     FOR_COMPONENTS(corig) {
-      if (have_component(corig)) LOOP_OVER_VOL_NOTOWNED(vi, corig, n) {
-          IVEC_LOOP_ILOC(vi, here);
-          component c = corig;
-          // We're looking at a border element...
-          std::complex<double> thephase;
-          if (!locate_component_point(&c, &here, &thephase) || on_metal_boundary(here)) continue;
-          // the chunk that owns `here` (ownership is exclusive): try the previous owner first
-          int j = -1;
-          if (chunks[last_j]->gv.owns(here)) j = last_j;
-          else
-            for (int jj = 0; jj < num_chunks; jj++)
-              if (chunks[jj]->gv.owns(here)) {
-                j = jj;
-                break;
+      if (!have_component(corig)) continue;
+      ivec sis(vi.dim, 0), sie(vi.dim, 0);
+      for (int ib = 0; vi.get_boundary_icorners(corig, ib, &sis, &sie); ib++) {
+        // geometry of LOOP_OVER_IVECS(vi, sis, sie, n)
+        const ptrdiff_t is_[3] = {sis.yucky_val(0), sis.yucky_val(1), sis.yucky_val(2)};
+        const ptrdiff_t nn[3] = {(sie.yucky_val(0) - is_[0]) / 2 + 1, (sie.yucky_val(1) - is_[1]) / 2 + 1,
+                                 (sie.yucky_val(2) - is_[2]) / 2 + 1};
+        if (nn[0] <= 0 || nn[1] <= 0 || nn[2] <= 0) continue;
+        const direction dd[3] = {vi.yucky_direction(0), vi.yucky_direction(1), vi.yucky_direction(2)};
+        const ptrdiff_t ss[3] = {vi.stride(dd[0]), vi.stride(dd[1]), vi.stride(dd[2])};
+        const ivec rel = sis - vi.little_corner();
+        const ptrdiff_t idx0 =
+            rel.yucky_val(0) / 2 * ss[0] + rel.yucky_val(1) / 2 * ss[1] + rel.yucky_val(2) / 2 * ss[2];
+        const int rdim = nn[2] > 1 ? 2 : (nn[1] > 1 ? 1 : 0); // loops after rdim have one iteration
+        const direction rd = dd[rdim];
+        const ptrdiff_t lim0 = rdim > 0 ? nn[0] : 1, lim1 = rdim > 1 ? nn[1] : 1;
+        for (ptrdiff_t o0 = 0; o0 < lim0; o0++)
+          for (ptrdiff_t o1 = 0; o1 < lim1; o1++)
+            for (ptrdiff_t k = 0; k < nn[rdim];) {
+              ptrdiff_t ii[3] = {o0, o1, 0};
+              ii[rdim] = k;
+              ivec here(vi.dim);
+              here.set_direction(dd[0], is_[0] + 2 * ii[0]);
+              here.set_direction(dd[1], is_[1] + 2 * ii[1]);
+              here.set_direction(dd[2], is_[2] + 2 * ii[2]);
+              const ptrdiff_t n = idx0 + ii[0] * ss[0] + ii[1] * ss[1] + ii[2] * ss[2];
+              component c;
+              ivec there(vi.dim);
+              std::complex<double> thephase;
+              int j;
+              if (!head_of_run(corig, here, c, there, thephase, j)) {
+                ++k;
+                continue;
               }
-          if (j < 0) continue;
-          last_j = j;
-          const bool j_is_mine = chunks[j]->is_mine();
-          if (!i_is_mine && !j_is_mine) continue;
-          if (is_B(corig) && is_B(c) && B_redundant[5 * i + corig - Bx] && B_redundant[5 * j + c - Bx])
-            continue;
+              // ---- length of the run
+              ptrdiff_t len = 1;
+              if (runs_ok && nn[rdim] - k > 1 && ss[rdim] != 0) {
+                const int tr = there.in_direction(rd);
+                int hi = chunks[j]->gv.big_corner().in_direction(rd); // owned: coordinate <= io + 2n
+                hi = std::min(hi, user_volume.big_corner().in_direction(rd));
+                len = std::min<ptrdiff_t>(nn[rdim] - k, (hi - tr) / 2 + 1);
+                if (user_volume.has_boundary(High, rd) && boundaries[High][rd] == Metallic) {
+                  const int m = user_volume.big_corner().in_direction(rd);
+                  if (m > tr && (m - tr) % 2 == 0) len = std::min<ptrdiff_t>(len, (m - tr) / 2);
+                }
+                if (len < 1) len = 1;
+                if (len > 1) { // re-check the far end with the per-point logic
+                  ivec here2 = here, there2(vi.dim);
+                  here2.set_direction(rd, here.in_direction(rd) + 2 * (int)(len - 1));
+                  component c2;
+                  std::complex<double> ph2;
+                  int j2;
+                  const int keep_last = last_j;
+                  ivec expect = there;
+                  expect.set_direction(rd, tr + 2 * (int)(len - 1));
+                  if (!head_of_run(corig, here2, c2, there2, ph2, j2) || j2 != j || c2 != c || ph2 != thephase ||
+                      there2 != expect)
+                    len = 1;
+                  last_j = keep_last;
+                }
+              }
+              const bool j_is_mine = chunks[j]->is_mine();
+              if ((!i_is_mine && !j_is_mine) ||
+                  (is_B(corig) && is_B(c) && B_redundant[5 * i + corig - Bx] && B_redundant[5 * j + c - Bx])) {
+                k += len;
+                continue;
+              }
 
-          const connect_phase ip = connect_phase_from_phase(thephase);
-          const ptrdiff_t m = chunks[j]->gv.index(c, here);
-          const std::complex<realnum> ph(thephase.real(), thephase.imag());
-          const int ncmp = 2 - is_real;
+              const connect_phase ip = connect_phase_from_phase(thephase);
+              const ptrdiff_t m = chunks[j]->gv.index(c, there);
+              const ptrdiff_t dn = ss[rdim], dm = chunks[j]->gv.stride(rd);
+              const std::complex<realnum> ph(thephase.real(), thephase.imag());
 
-          {
-            Slot &s = slot(type(c), ip, j);
-            if (i_is_mine) {
-              if (ip == CONNECT_PHASE) s.phases->push_back(ph);
-              for (int cmp = 0; cmp < ncmp; cmp++)
-                s.in->push_back(chunks[i]->f[corig][cmp] + n);
-            }
-            if (j_is_mine)
-              for (int cmp = 0; cmp < ncmp; cmp++)
-                s.out->push_back(chunks[j]->f[c][cmp] + m);
-          }
+              {
+                Slot &s = slot(type(c), ip, j);
+                if (i_is_mine) {
+                  if (ip == CONNECT_PHASE) s.phases->insert(s.phases->end(), (size_t)len, ph);
+                  realnum *base[2] = {chunks[i]->f[corig][0] + n, ncmp > 1 ? chunks[i]->f[corig][1] + n : nullptr};
+                  for (ptrdiff_t q = 0; q < len; ++q)
+                    for (int cmp = 0; cmp < ncmp; cmp++)
+                      s.in->push_back(base[cmp] + q * dn);
+                }
+                if (j_is_mine) {
+                  realnum *base[2] = {chunks[j]->f[c][0] + m, ncmp > 1 ? chunks[j]->f[c][1] + m : nullptr};
+                  for (ptrdiff_t q = 0; q < len; ++q)
+                    for (int cmp = 0; cmp < ncmp; cmp++)
+                      s.out->push_back(base[cmp] + q * dm);
+                }
+              }
 
-          if (needs_W_notowned[corig]) {
-            Slot &s = slot(is_electric(corig) ? WE_stuff : WH_stuff, ip, j);
-            if (i_is_mine) {
-              if (ip == CONNECT_PHASE) s.phases->push_back(ph);
-              for (int cmp = 0; cmp < ncmp; cmp++)
-                s.in->push_back((chunks[i]->f_w[corig][cmp] ? chunks[i]->f_w[corig][cmp]
-                                                            : chunks[i]->f[corig][cmp]) +
-                                n);
-            }
-            if (j_is_mine)
-              for (int cmp = 0; cmp < ncmp; cmp++)
-                s.out->push_back(
-                    (chunks[j]->f_w[c][cmp] ? chunks[j]->f_w[c][cmp] : chunks[j]->f[c][cmp]) + m);
-          }
+              if (needs_W_notowned[corig]) {
+                Slot &s = slot(is_electric(corig) ? WE_stuff : WH_stuff, ip, j);
+                if (i_is_mine) {
+                  if (ip == CONNECT_PHASE) s.phases->insert(s.phases->end(), (size_t)len, ph);
+                  realnum *base[2];
+                  for (int cmp = 0; cmp < ncmp; cmp++)
+                    base[cmp] = (chunks[i]->f_w[corig][cmp] ? chunks[i]->f_w[corig][cmp] : chunks[i]->f[corig][cmp]) + n;
+                  for (ptrdiff_t q = 0; q < len; ++q)
+                    for (int cmp = 0; cmp < ncmp; cmp++)
+                      s.in->push_back(base[cmp] + q * dn);
+                }
+                if (j_is_mine) {
+                  realnum *base[2];
+                  for (int cmp = 0; cmp < ncmp; cmp++)
+                    base[cmp] = (chunks[j]->f_w[c][cmp] ? chunks[j]->f_w[c][cmp] : chunks[j]->f[c][cmp]) + m;
+                  for (ptrdiff_t q = 0; q < len; ++q)
+                    for (int cmp = 0; cmp < ncmp; cmp++)
+                      s.out->push_back(base[cmp] + q * dm);
+                }
+              }
 
-          if (is_electric(corig) || is_magnetic(corig)) {
-            const field_type f = is_electric(corig) ? PE_stuff : PH_stuff;
-            for (polarization_state *pi = chunks[i]->pol[type(corig)]; pi; pi = pi->next)
-              for (polarization_state *pj = chunks[j]->pol[type(c)]; pj; pj = pj->next)
-                if (*pi->s == *pj->s) {
-                  polarization_state *po = NULL;
-                  if (pi->data && i_is_mine)
-                    po = pi;
-                  else if (pj->data && j_is_mine)
-                    po = pj;
-                  if (po) {
-                    const size_t ni = po->s->num_internal_notowned_needed(corig, po->data);
-                    if (ni) {
-                      Slot &s = slot(f, CONNECT_COPY, j);
-                      for (size_t k = 0; k < ni; ++k) {
-                        if (i_is_mine) s.in->push_back(po->s->internal_notowned_ptr(k, corig, n, pi->data));
-                        if (j_is_mine) s.out->push_back(po->s->internal_notowned_ptr(k, c, m, pj->data));
+              if (is_electric(corig) || is_magnetic(corig)) {
+                const field_type f = is_electric(corig) ? PE_stuff : PH_stuff;
+                // which polarisation pairs exchange internal values here: the same for every point
+                // of the run (depends on the components and the data blocks only)
+                pol_pairs.clear();
+                for (polarization_state *pi = chunks[i]->pol[type(corig)]; pi; pi = pi->next)
+                  for (polarization_state *pj = chunks[j]->pol[type(c)]; pj; pj = pj->next)
+                    if (*pi->s == *pj->s) {
+                      polarization_state *po = NULL;
+                      if (pi->data && i_is_mine)
+                        po = pi;
+                      else if (pj->data && j_is_mine)
+                        po = pj;
+                      if (po) {
+                        const size_t ni = po->s->num_internal_notowned_needed(corig, po->data);
+                        const size_t cni = po->s->num_cinternal_notowned_needed(corig, po->data);
+                        if (ni || cni) pol_pairs.push_back(PolPair{pi, pj, po, ni, cni});
                       }
                     }
-                    const size_t cni = po->s->num_cinternal_notowned_needed(corig, po->data);
-                    if (cni) {
-                      Slot &s = slot(f, ip, j);
-                      for (size_t k = 0; k < cni; ++k) {
-                        if (i_is_mine) {
-                          if (ip == CONNECT_PHASE) s.phases->push_back(ph);
-                          for (int cmp = 0; cmp < ncmp; cmp++)
-                            s.in->push_back(po->s->cinternal_notowned_ptr(k, corig, cmp, n, pi->data));
+                if (!pol_pairs.empty())
+                  for (ptrdiff_t q = 0; q < len; ++q) { // point-major, as the reference pushes them
+                    const ptrdiff_t nq = n + q * dn, mq = m + q * dm;
+                    for (const PolPair &pp : pol_pairs) {
+                      if (pp.ni) {
+                        Slot &s = slot(f, CONNECT_COPY, j);
+                        for (size_t kk = 0; kk < pp.ni; ++kk) {
+                          if (i_is_mine) s.in->push_back(pp.po->s->internal_notowned_ptr(kk, corig, nq, pp.pi->data));
+                          if (j_is_mine) s.out->push_back(pp.po->s->internal_notowned_ptr(kk, c, mq, pp.pj->data));
                         }
-                        if (j_is_mine)
-                          for (int cmp = 0; cmp < ncmp; cmp++)
-                            s.out->push_back(po->s->cinternal_notowned_ptr(k, c, cmp, m, pj->data));
+                      }
+                      if (pp.cni) {
+                        Slot &s = slot(f, ip, j);
+                        for (size_t kk = 0; kk < pp.cni; ++kk) {
+                          if (i_is_mine) {
+                            if (ip == CONNECT_PHASE) s.phases->push_back(ph);
+                            for (int cmp = 0; cmp < ncmp; cmp++)
+                              s.in->push_back(pp.po->s->cinternal_notowned_ptr(kk, corig, cmp, nq, pp.pi->data));
+                          }
+                          if (j_is_mine)
+                            for (int cmp = 0; cmp < ncmp; cmp++)
+                              s.out->push_back(pp.po->s->cinternal_notowned_ptr(kk, c, cmp, mq, pp.pj->data));
+                        }
                       }
                     }
                   }
-                }
-          }
-        }
+              }
+              k += len;
+            }
+      }
     }
 
     // sizes of the comm blocks of every pair (j -> i) that was touched (src/boundaries.cpp:406-451)

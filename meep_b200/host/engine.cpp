@@ -2,6 +2,7 @@
 #include "engine.hpp"
 #include "meep_internals.hpp"
 #include "comm.hpp"
+#include "hostmem.hpp"
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -87,6 +88,8 @@ Engine::Engine(fields *) {
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   fuse = env_int("MEEP_B200_FUSE", 1) != 0;
   eager = env_int("MEEP_B200_EAGER", 0) != 0;
+  lazy_host = env_int("MEEP_B200_LAZY_HOST", 1) != 0;
+  release_host = env_int("MEEP_B200_RELEASE_HOST", 1);
   verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
   merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
@@ -124,11 +127,17 @@ Engine::~Engine() {
 void *Engine::dev(const void *host) const {
   if (!host) return nullptr;
   const uintptr_t a = (uintptr_t)host;
+  // table translation asks for millions of consecutive elements of the same array
+  if (a >= hit_lo_ && a < hit_hi_) return hit_dev_ + (a - hit_lo_);
   auto it = arrs_.upper_bound(a);
   if (it != arrs_.begin()) {
     --it;
-    if (a >= it->first && a < it->first + it->second.bytes)
-      return (char *)it->second.dev + (a - it->first);
+    if (a >= it->first && a < it->first + it->second.bytes) {
+      hit_lo_ = it->first;
+      hit_hi_ = it->first + it->second.bytes;
+      hit_dev_ = (char *)it->second.dev;
+      return hit_dev_ + (a - hit_lo_);
+    }
   }
   meep::abort("meep_b200: host pointer %p is not part of any mirrored array", host);
   return nullptr;
@@ -145,6 +154,7 @@ void *Engine::ensure(const void *host, size_t bytes, bool is_field, int init) {
     }
     mb200_free(ctx, it->second.dev); // same address, different size: the host re-allocated
     arrs_.erase(it);
+    hit_lo_ = hit_hi_ = 0;
     if (backups.count(host)) {
       mb200_free(ctx, backups[host]);
       backups.erase(host);
@@ -157,12 +167,29 @@ void *Engine::ensure(const void *host, size_t bytes, bool is_field, int init) {
   arr.seen = true;
   check(mb200_malloc(ctx, bytes, &arr.dev), "mb200_malloc");
   if (init == 0) {
-    check(mb200_h2d(ctx, arr.dev, host, bytes), "mb200_h2d");
-    stats.h2d_bytes += bytes;
+    upload_array(host, arr.dev, bytes);
+    arr.fresh = true; // just uploaded: the bulk uploads of this enter() skip it
   }
   arrs_[a] = arr;
   invalidate_plans();
   return arr.dev;
+}
+
+// Host array -> device twin.  An array whose interior pages were never touched still holds the
+// zeros it was allocated with (hostmem.hpp): its twin is a device memset plus the two partial
+// pages at its ends, and the host pages stay unborn.
+void Engine::upload_array(const void *host, void *dev, size_t bytes) {
+  char *lo, *hi;
+  if (lazy_host && interior_untouched(host, bytes) && page_interior(host, bytes, &lo, &hi)) {
+    const size_t head = (size_t)(lo - (const char *)host), tail = (size_t)((const char *)host + bytes - hi);
+    check(mb200_memset(ctx, dev, 0, bytes), "mb200_memset");
+    if (head) check(mb200_h2d(ctx, dev, host, head), "mb200_h2d");
+    if (tail) check(mb200_h2d(ctx, (char *)dev + (bytes - tail), hi, tail), "mb200_h2d");
+    stats.h2d_bytes += head + tail;
+    return;
+  }
+  check(mb200_h2d(ctx, dev, host, bytes), "mb200_h2d");
+  stats.h2d_bytes += bytes;
 }
 
 void Engine::ensure_from(const void *host, size_t bytes, const void *src_host) {
@@ -177,6 +204,7 @@ void Engine::forget(const void *host) {
   invalidate_plans();
   mb200_free(ctx, it->second.dev);
   arrs_.erase(it);
+  hit_lo_ = hit_hi_ = 0;
   if (backups.count(host)) {
     mb200_free(ctx, backups[host]);
     backups.erase(host);
@@ -482,6 +510,7 @@ void Engine::scan(fields *f) {
     if (!it->second.seen) {
       mb200_free(ctx, it->second.dev);
       it = arrs_.erase(it);
+      hit_lo_ = hit_hi_ = 0;
       invalidate_plans();
     }
     else
@@ -563,10 +592,11 @@ void Engine::upload_fields() {
     check(mb200_memset(ctx, kv.second.dev, 0, kv.second.nblocks), "memset(pzero)");
   for (auto &kv : arrs_)
     if (kv.second.is_field) {
-      check(mb200_h2d(ctx, kv.second.dev, (const void *)kv.first, kv.second.bytes), "h2d");
-      stats.h2d_bytes += kv.second.bytes;
+      if (!kv.second.fresh) upload_array((const void *)kv.first, kv.second.dev, kv.second.bytes);
+      kv.second.fresh = false;
     }
   stats.uploads++;
+  host_resident = true;
 }
 
 void Engine::download_fields() {
@@ -576,6 +606,24 @@ void Engine::download_fields() {
       stats.d2h_bytes += kv.second.bytes;
     }
   stats.downloads++;
+  host_resident = true;
+}
+
+// The device copy is the authoritative one: the host pages of the field arrays only hold stale
+// values.  MEEP_B200_RELEASE_HOST: 0 = keep them, 1 (default) = drop them once after an upload
+// (a run that never downloads then never holds field pages on the host: 1024^3 on one GPU needs
+// ~30 GB of host RAM instead of ~125 GB), 2 = also after every download.
+void Engine::release_host_fields() {
+  if (!host_resident || release_host == 0 || state != DEVICE_NEWER) return;
+  if (release_host == 1 && stats.downloads > released_at_download) {
+    host_resident = false; // a reader pulled the arrays: assume it will again, keep the pages
+    released_at_download = stats.downloads;
+    return;
+  }
+  for (auto &kv : arrs_)
+    if (kv.second.is_field) release_interior((void *)kv.first, kv.second.bytes);
+  host_resident = false;
+  released_at_download = stats.downloads;
 }
 
 void Engine::upload_materials() {
@@ -583,8 +631,11 @@ void Engine::upload_materials() {
     kv.second.fresh = false; // recomputed on next use
   for (auto &kv : arrs_)
     if (!kv.second.is_field) {
-      check(mb200_h2d(ctx, kv.second.dev, (const void *)kv.first, kv.second.bytes), "h2d");
-      stats.h2d_bytes += kv.second.bytes;
+      if (!kv.second.fresh) {
+        check(mb200_h2d(ctx, kv.second.dev, (const void *)kv.first, kv.second.bytes), "h2d");
+        stats.h2d_bytes += kv.second.bytes;
+      }
+      kv.second.fresh = false;
     }
   materials_dirty = false;
 }
@@ -609,26 +660,40 @@ void Engine::enter(fields *f) {
   if (depth++ > 0) return;
   current_ = this;
   const uint64_t fp = fingerprint(f);
+  const double t0 = verbose ? meep::wall_time() : 0;
   if (fp != last_fingerprint || arrs_.empty()) {
-    const size_t before = arrs_.size();
     // arrays that are new to us are uploaded from the host by ensure(); existing mirrors keep
     // their (possibly newer) device contents
     scan(f);
-    (void)before;
     last_fingerprint = fp;
     invalidate_plans();
     materials_dirty = true;
+    if (verbose) {
+      mb200_sync(ctx);
+      fprintf(stderr, "meep_b200: mirror scan (%zu arrays, %.2f GB on device): %.3f s\n", arrs_.size(),
+              mb200_bytes_allocated(ctx) / 1e9, meep::wall_time() - t0);
+    }
   }
+  const double t1 = verbose ? meep::wall_time() : 0;
+  const bool up_mat = materials_dirty, up_fld = state == HOST_NEWER;
   if (materials_dirty) upload_materials();
   if (state == HOST_NEWER) {
     upload_fields();
     state = COHERENT;
+  }
+  for (auto &kv : arrs_)
+    kv.second.fresh = false;
+  if (verbose && (up_mat || up_fld)) {
+    mb200_sync(ctx);
+    fprintf(stderr, "meep_b200: upload (materials %d, fields %d): %.3f s\n", (int)up_mat, (int)up_fld,
+            meep::wall_time() - t1);
   }
 }
 
 void Engine::leave(fields *f, bool modified) {
   if (--depth > 0) return;
   if (modified) state = DEVICE_NEWER;
+  if (in_step && !cw_mode && !eager) release_host_fields();
   // lazily allocated arrays changed the pointer set: remember the new fingerprint so the next
   // step does not rescan
   last_fingerprint = fingerprint(f);

@@ -181,6 +181,7 @@ public:
     size_t bytes = 0;
     bool is_field = false; // true: device-authoritative between steps; false: material (host)
     bool seen = false;
+    bool fresh = false; // uploaded by ensure() during the current enter()
   };
   // device address of a host element pointer (NULL -> NULL); aborts if the array is unknown
   void *dev(const void *host) const;
@@ -200,6 +201,12 @@ public:
   uint64_t pzero_flag_addr(const void *host_elem) const;
   const uint8_t *szero_flags(const void *host_sigma, size_t ntot);
   bool zero_skip = true; // MEEP_B200_ZERO_SKIP=0 disables
+  void upload_array(const void *host, void *dev, size_t bytes);
+  void release_host_fields();
+  bool lazy_host = true;    // MEEP_B200_LAZY_HOST=0: always copy host arrays, never probe their pages
+  int release_host = 1;     // MEEP_B200_RELEASE_HOST (see release_host_fields)
+  bool host_resident = false; // field pages may be resident on the host (set by up/downloads)
+  int64_t released_at_download = 0;
   void upload_fields();
   void download_fields();
   void upload_materials();
@@ -265,6 +272,8 @@ public:
 
 private:
   std::map<uintptr_t, Arr> arrs_; // keyed by host base address
+  mutable uintptr_t hit_lo_ = 0, hit_hi_ = 0; // last array dev() resolved
+  mutable char *hit_dev_ = nullptr;
   struct Flags {
     uint8_t *dev = nullptr;
     size_t ntot = 0, nblocks = 0;

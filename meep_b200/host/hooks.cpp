@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include "engine.hpp"
+#include "hostmem.hpp"
 #include "meep_internals.hpp"
 
 using namespace std;
@@ -111,6 +112,27 @@ void fields::loop_in_chunks(field_chunkloop chunkloop, void *chunkloop_data, con
   static fn next = (fn)next_definition_of_caller();
   if (Engine *E = Engine::find(this)) E->sync_host();
   next(this, chunkloop, chunkloop_data, where, cgrid, use_symmetry, snap_unit_dims);
+}
+
+// ---- field arrays are born without host pages -------------------------------------------------------
+// fields_chunk::alloc_f (src/fields.cpp:480-504) restated: same arrays, same aliasing of H to B,
+// but the zero contents are zero-fill-on-demand pages (hostmem.hpp) instead of a store loop, so a
+// simulation that is set up and then stepped on the device never materialises them on the host.
+bool fields_chunk::alloc_f(component c) {
+  bool changed = false;
+  if (is_mine()) DOCMP {
+      if (!f[c][cmp]) {
+        changed = true;
+        if (is_magnetic(c)) {
+          const component bc = direction_component(Bx, component_direction(c));
+          if (!f[bc][cmp]) f[bc][cmp] = new_zeroed_lazily(gv.ntot());
+          f[c][cmp] = f[bc][cmp];
+        }
+        else
+          f[c][cmp] = new_zeroed_lazily(gv.ntot());
+      }
+    }
+  return changed;
 }
 
 // ---- sources added mid-run -------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "engine.hpp"
+#include "hostmem.hpp"
 #include "loop_desc.hpp"
 #include "meep_internals.hpp"
 #include <stdio.h>
@@ -214,19 +215,18 @@ bool fields_chunk::step_db(field_type ft) {
           // lazy allocation, mirrored on the device (src/step_db.cpp:67-75): the host arrays
           // must exist because the reference's connection tables and accessors use them
           if (dsig != NO_DIRECTION && s->conductivity[cc][d_c] && !f_cond[cc][cmp]) {
-            f_cond[cc][cmp] = new realnum[gv.ntot()];
-            memset(f_cond[cc][cmp], 0, nbytes);
+            f_cond[cc][cmp] = new_zeroed_lazily(gv.ntot());
             E->ensure_from(f_cond[cc][cmp], nbytes, NULL);
           }
           if (dsigu != NO_DIRECTION && !f_u[cc][cmp]) {
-            f_u[cc][cmp] = new realnum[gv.ntot()];
-            memcpy(f_u[cc][cmp], the_f, nbytes); // (host copy is refreshed on the next download)
+            // (the device twin is initialised from the device copy of the_f; the host array is
+            //  only an address until the next download fills it)
+            f_u[cc][cmp] = new_zeroed_lazily(gv.ntot());
             E->ensure_from(f_u[cc][cmp], nbytes, the_f);
             allocated_u = true;
           }
           if (use_bfast && !f_bfast[cc][cmp]) {
-            f_bfast[cc][cmp] = new realnum[gv.ntot()];
-            memset(f_bfast[cc][cmp], 0, nbytes);
+            f_bfast[cc][cmp] = new_zeroed_lazily(gv.ntot());
             E->ensure_from(f_bfast[cc][cmp], nbytes, NULL);
           }
 

@@ -12,6 +12,7 @@
 #include <typeinfo>
 
 #include "engine.hpp"
+#include "hostmem.hpp"
 #include "loop_desc.hpp"
 #include "meep_internals.hpp"
 
@@ -107,8 +108,7 @@ bool fields_chunk::update_eh(field_type ft, bool skip_w_components) {
       }
       realnum *&scratch = f_minus_p[dc][cmp];
       if (wanted && !scratch) {
-        scratch = new realnum[npts];
-        memset(scratch, 0, nbytes);
+        scratch = new_zeroed_lazily(npts);
         E->ensure(scratch, nbytes, true, 1);
       }
       else if (!wanted && scratch) { // no longer needed: release host and device copies
@@ -214,15 +214,14 @@ bool fields_chunk::update_eh(field_type ft, bool skip_w_components) {
       if (first_tile) {
         // E/H start out aliased to D/B; split them when the update is not the identity
         if (f[ec][cmp] == f[dc][cmp] && (s->chi1inv[ec][dir[0]] || any_fmp || dsigw != NO_DIRECTION)) {
-          f[ec][cmp] = new realnum[npts];
-          memcpy(f[ec][cmp], f[dc][cmp], nbytes);
+          // (device twin copied from the device copy of D/B; the host array is filled by the next download)
+          f[ec][cmp] = new_zeroed_lazily(npts);
           E->ensure_from(f[ec][cmp], nbytes, f[dc][cmp]);
           allocated_eh = true;
         }
         // the W auxiliary field of the PML ODE
         if (dsigw != NO_DIRECTION && !f_w[ec][cmp]) {
-          f_w[ec][cmp] = new realnum[npts];
-          memcpy(f_w[ec][cmp], f[ec][cmp], nbytes);
+          f_w[ec][cmp] = new_zeroed_lazily(npts);
           E->ensure_from(f_w[ec][cmp], nbytes, f[ec][cmp]);
           if (needs_W_notowned(ec)) allocated_eh = true; // its halo must be communicated
         }

@@ -11,6 +11,7 @@
 #include <typeinfo>
 
 #include "engine.hpp"
+#include "hostmem.hpp"
 #include "loop_desc.hpp"
 #include "meep_internals.hpp"
 
@@ -54,7 +55,12 @@ bool fields_chunk::update_pols(field_type ft) {
       if (p->data) {
         p->s->init_internal_data(f, dt, gv, p->data);
         const std::pair<realnum *, size_t> blk = polarisation_block(p->s, p->data);
-        if (blk.second) E->ensure_from(blk.first, blk.second, NULL);
+        if (blk.second) {
+          E->ensure_from(blk.first, blk.second, NULL);
+          // init_internal_data just memset the block: hand the zero pages back (they read as zero
+          // again on demand) — six Au poles are three times the field arrays' footprint
+          if (E->lazy_host) release_interior(blk.first, blk.second);
+        }
         allocated_fields = true;
       }
     }

@@ -186,3 +186,41 @@ def test_ld_preload_over_a_program_linked_against_the_reference_only(tmp_path):
     assert "meep_b200: recorded" in r.stdout  # the engine, not the CPU loops, did the stepping
     ref = run_case("ref", "f64", "3d_metal", 12, 2)
     compare(read_dump(out), ref, TOL["f64"])
+
+
+CONNECT_LAYOUTS = ["pml27", "pml64", "pml72", "pml27_complex", "metal5", "bloch4", "periodic_k0", "xperiodic_ypml",
+                   "mirror2d", "rotate3d", "cyl3", "gyro3", "aniso_sigma4", "bend2d", "1d3"]
+
+
+@pytest.mark.parametrize("layout", CONNECT_LAYOUTS)
+def test_connection_tables_identical_to_the_reference(layout, tmp_path):
+    """the analytic (run-based) connect_the_chunks / find_metals of meep_b200/host/connect.cpp build
+    the SAME tables as the reference's per-point versions (src/boundaries.cpp:315-638): every entry
+    of connections_in/out (as array id + offset, in order), connection_phases, comm_sizes and
+    zeroes, on the SURVEY 8e layouts (27 / 64 / 72 chunks) and on periodic, Bloch, symmetric,
+    cylindrical, metallic, 1-D/2-D and polarisation-carrying cells"""
+    import numpy as np
+    from parity_util import driver, read_dump
+    outs = {}
+    for arm in ("ref", "emu"):
+        out = str(tmp_path / ("tables_%s.bin" % arm))
+        r = subprocess.run([driver("connect_driver", arm, "f64"), layout, out], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=600,
+                           env=dict(os.environ, OMP_NUM_THREADS="2"))
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs[arm] = read_dump(out)
+    ref, got = outs["ref"], outs["emu"]
+    # the reference's `comm_sizes[key] += 0` leaves zero-size entries behind (src/boundaries.cpp:445-446);
+    # get_comm_size() reads a missing key as 0, so they carry no information
+    for d in (ref, got):
+        rows = d["comm_sizes"].reshape(-1, 5)
+        d["comm_sizes"] = rows[rows[:, 4] > 0].ravel()
+    # a key the reference left behind with an empty vector carries no information
+    ref = {k: v for k, v in ref.items() if v.size or k == "comm_sizes"}
+    got = {k: v for k, v in got.items() if v.size or k == "comm_sizes"}
+    assert set(ref) == set(got), (sorted(set(ref) - set(got))[:5], sorted(set(got) - set(ref))[:5])
+    assert sum(v.size for k, v in ref.items() if ".in." in k) > 0
+    for k in ref:
+        assert ref[k].shape == got[k].shape, k
+        assert not (ref[k] < 0).any() or "phases" in k, "unresolved pointer in %s" % k
+        assert np.array_equal(ref[k], got[k]), k
