@@ -16,12 +16,16 @@ fields::step().  A "step" is one FDTD time step (one pass of the hot path over t
   roofline: dominant kernel (fused D/B update) algorithmic bytes / CUDA-event time / measured HBM peak
   cpu_baseline: the unmodified reference (oracle/_ref) on this box's host cores, bounded sample
 
-N>1 (torchrun, one process per GPU): the cell is sharded with the reference's own split_by_cost —
-every rank owns one leaf of the binary partition (plus its PML sub-chunks) — and chunk boundaries
-that cross ranks are exchanged device-to-device (pack kernel -> grouped ncclSend/ncclRecv ->
-unpack kernel) once per sub-phase.  Weak scaling (default): n^3 cells per GPU, stacked along x
-(n*N x n x n); --scaling strong keeps n^3 in total.  rank/size and the few host-side reductions
-come from the MPI-free runtime in meep_b200/host/mympi_b200.cpp (MPI is not installed).
+N>1 (torchrun, one process per GPU): BASELINE.json configs[4], the north-star case — the 1024^3
+dielectric+PML cell, STRONG scaling: the cell is sharded with the reference's own split_by_cost
+(8 ranks: 2x2x2 leaves of 512^3, three cross-GPU faces each), every rank owns one leaf of the binary
+partition plus its PML sub-chunks, and chunk boundaries that cross ranks are exchanged
+device-to-device through peer memory once per sub-phase.  --scaling weak stacks n^3 cells per GPU
+along x instead; --size overrides the edge.  rank/size and the few host-side reductions come from
+the MPI-free runtime in meep_b200/host/mympi_b200.cpp (MPI is not installed).
+Every line carries `probe`: field values at fixed points of the cell after the same number of steps,
+read through fields::get_field — identical numbers for every N on the same cell (sharding changes
+nothing in the arithmetic), so the lines of a scaling run check each other's VALUES, not only speed.
 """
 import argparse
 import ctypes as C
@@ -123,6 +127,27 @@ def workload_text(workload, nx, ny, nz, world):
               "(BASELINE.json configs[3], scaled)" % (nx, ny, nz)}[workload]
 
 
+def scaling_label(args, n_dev):
+    """strong: one fixed cell over all GPUs (a 1-GPU line is part of the strong series when it runs the
+    series' 1024^3 cell); weak otherwise"""
+    if n_dev > 1 and not args.replicas:
+        return args.scaling
+    return "strong" if (args.workload == "c2" and args.n == 1024 and args.scaling == "strong") else "weak"
+
+
+def csrc_stamp():
+    """identifies the kernel sources a committed ncu capture was taken on"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "meep_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
+    with open(os.path.join(ROOT, "include", "meep_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
 def cpu_baseline_obj(r):
     return {"value": r["cells_per_s"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference",
             "sample": "same workload at %d^3 (%d chunks), %d timed steps after %d warm-up, OpenMP on all host "
@@ -144,8 +169,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", "--n", dest="n", type=int, default=512,
-                    help="cells per edge of the workload (use --size under torchrun: --n is ambiguous there)")
+    ap.add_argument("--size", "--n", dest="n", type=int, default=0,
+                    help="cells per edge of the workload (use --size under torchrun: --n is ambiguous there); "
+                         "default: 512 on one GPU (BASELINE.json configs[1]), 1024 on several (configs[4])")
     ap.add_argument("--cpu-n", type=int, default=192, help="edge of the bounded CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--prec", default="f64", choices=["f64", "f32"])
@@ -153,11 +179,20 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"],
                     help="c2: dielectric+PML (headline); c3: Au Drude-Lorentz sphere + 100-frequency flux "
                          "box; c4: anisotropic Si ring (n x n x n/4)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N>1: strong = one --size^3 cell over all GPUs (default, the north-star case); "
+                         "weak = --size^3 per GPU stacked along x")
     ap.add_argument("--replicas", action="store_true",
                     help="N>1: independent replicas instead of one sharded problem")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.n <= 0:
+        if args.workload != "c2":
+            args.n = {"c3": 320, "c4": 512}[args.workload]
+        elif max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) > 1 and not args.replicas:
+            args.n = 1024 if args.scaling == "strong" else 512
+        else:
+            args.n = int(os.environ.get("MEEP_B200_BENCH_N1", "512"))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,7 +209,7 @@ def main():
         line = {"impl": "reference", "metric": "Yee cell-updates/s", "value": r["cells_per_s"],
                 "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": r["warmup"],
                 "ms_per_step": 1e3 * r["seconds"] / r["steps"], "higher_is_better": True,
-                "scaling": args.scaling if n_dev > 1 and not args.replicas else "weak",
+                "scaling": scaling_label(args, n_dev),
                 "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
                 "config": {"workload": workload_text(args.workload, nx, args.n, nz, n_dev), "n": args.n,
                            "cell": [nx, args.n, nz], "sample_n": r["n"], "sample_num_chunks": r["num_chunks"],
@@ -195,6 +230,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     os.environ["MEEP_B200_DEVICE"] = str(local_rank)
+    # host-side set-up (material fill, connection tables) uses the host cores this rank may claim;
+    # the reference's initialize() falls back to ONE OpenMP thread when the variable is unset
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(local_world, 1))))
     if args.replicas:
         os.environ["MEEP_B200_WORLD_SIZE"] = "1"  # the C++ runtime sees a single process
         os.environ["MEEP_B200_RANK"] = "0"
@@ -288,11 +327,23 @@ def main():
     e2e_s = max_over_ranks(e2e_s)
     if acc != acc:
         raise RuntimeError("NaN in the probed field")
+    # copies are made by the rank that owns the source / the probed point: report the busiest rank
+    e2e_h2d = max_over_ranks((e1[1] - e0[1]) / args.steps)
+    e2e_d2h = max_over_ranks((e1[2] - e0[2]) / args.steps)
+    # value check across GPU counts: the same points of the same cell after the same number of steps
+    nprobe = 8
+    pv = (C.c_double * nprobe)()
+    drv.mb200_bench_probes.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    drv.mb200_bench_probes(h, pv, nprobe)
+    drv.mb200_bench_time_step.argtypes = [C.c_void_p]
+    probe = {"after_steps": int(drv.mb200_bench_time_step(h)), "component": "Ez",
+             "points": "cell centre + (0.35,0.25,0.15) + k*(L/16)*(1,-1,1), k=0..7 (alternating sign), via fields::get_field",
+             "values": [float(x) for x in pv]}
 
     # ---- timed region 3 (context for e2e): a COLD run of K steps — every field array starts on the
     # host (upload inside the timed region) and ends on the host (download inside it)
     cold = None
-    if world == 1:
+    if world == 1 and drv.mb200_bench_field_bytes(h) < 20e9:
         host.meep_b200_mark_host_dirty.argtypes = [C.c_void_p]
         host.meep_b200_mark_host_dirty(fptr)  # arrays are downloaded; the next step re-uploads them
         c0 = stats()
@@ -324,6 +375,12 @@ def main():
     peaks, peak_src = measured_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_step = drv.mb200_bench_algorithmic_bytes_per_step(h)
+    # kernels that skip known-zero polarisation blocks move less than the dense model: never credit
+    # bytes that were not moved (the per-kernel figures count the blocks actually processed)
+    kernel_sum = sum(v["alg_bytes_per_step"] for v in prof.values())
+    kernel_sum_smaller = bool(prof) and kernel_sum < alg_step
+    if kernel_sum_smaller:
+        alg_step = kernel_sum
     dom = max(prof.items(), key=lambda kv: kv[1]["ms_per_step"]) if prof else (None, None)
     roofline = None
     if dom[0]:
@@ -338,19 +395,31 @@ def main():
                     "whole_step": {"alg_bytes_per_step": alg_step,
                                    "achieved": alg_step / (dev_ms / args.steps * 1e-3) / 1e9,
                                    "frac": alg_step / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
-                                   "bytes_per_cell": alg_step / (cells / ranks_per_problem)},
+                                   "bytes_per_cell": alg_step / (cells / ranks_per_problem),
+                                   "model": "SURVEY 8d accounting on the actual chunk layout (every array element "
+                                            "a half-step must read / write counted once; halo copies not counted)"
+                                            + ("; polarisation arrays counted only over the blocks the kernels "
+                                               "do not skip (zero-block flags, measured)" if kernel_sum_smaller else "")},
                     "kernels": prof}
 
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of
-    # this very configuration (null for any other size / workload / precision)
-    if roofline and dom[0] == "step3" and args.workload == "c2" and args.n == 512 and args.prec == "f64" \
-            and world == 1:
+    # DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture of this
+    # very configuration (profiles/traffic_<workload>_<n>_<prec>.json).  The capture names the kernel
+    # sources it was taken on: a capture of another build is reported as such, not as this build's.
+    if roofline and world == 1:
+        tf = os.path.join(ROOT, "profiles", "traffic_%s_%d_%s.json" % (args.workload, args.n, args.prec))
         try:
-            with open(os.path.join(ROOT, "profiles", "r1n_ncu_traffic_c2_512.json")) as fh:
-                roofline["traffic"] = json.load(fh)["step3_plain_traffic_bytes_per_launch"]
-                roofline["traffic_source"] = "profiles/r1n_ncu_traffic_c2_512.json (ncu --set full, dram__bytes_read+write)"
+            with open(tf) as fh:
+                t = json.load(fh)
+            if t.get("kernel") == dom[0]:
+                roofline["traffic"] = t["dram_bytes_per_launch"]
+                roofline["traffic_source"] = "%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, " \
+                                             "mean over the launches of the kernel)" % os.path.relpath(tf, ROOT)
+                roofline["traffic_build"] = t.get("csrc_stamp")
+                roofline["traffic_build_is_this_build"] = t.get("csrc_stamp") == csrc_stamp()
         except (OSError, KeyError, ValueError):
             pass
+    if roofline:
+        roofline["csrc_stamp"] = csrc_stamp()
 
     nproblems = world // ranks_per_problem
     if roofline and world > 1:
@@ -358,7 +427,7 @@ def main():
     value = cells * args.steps * nproblems / (dev_ms * 1e-3)
     line = {"metric": "Yee cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": args.scaling if sharded else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": scaling_label(args, world), "vs_baseline": None,
             "dtype": args.prec, "data": "synthetic",
             "config": {"workload": workload_text(args.workload, nx, args.n, nz, world),
                        "n": args.n, "cell": [nx, args.n, nz], "num_chunks": drv.mb200_bench_num_chunks(h),
@@ -366,13 +435,17 @@ def main():
                        if sharded else ("replicas only" if world > 1 else "single GPU"),
                        "l2_policy": "inputs larger than L2: %.1f GB of field arrays streamed per step vs 126 MB L2"
                                     % (drv.mb200_bench_field_bytes(h) / 1e9) + " (per rank)",
-                       "setup_s": t_setup, "warmup_s": t_warm},
+                       "setup_s": t_setup, "warmup_s": t_warm,
+                       "host_max_rss_gb": __import__("resource").getrusage(
+                           __import__("resource").RUSAGE_SELF).ru_maxrss / 1048576.0,
+                       "host_threads": int(os.environ.get("OMP_NUM_THREADS", "1"))},
             "e2e": {"value": cells * args.steps * nproblems / e2e_s, "unit": "cell-updates/s",
-                    "h2d_bytes_per_step": (e1[1] - e0[1]) / args.steps,
-                    "d2h_bytes_per_step": (e1[2] - e0[2]) / args.steps,
+                    "h2d_bytes_per_step": e2e_h2d,
+                    "d2h_bytes_per_step": e2e_d2h,
                     "what": "K x (fields::step() + fields::get_field probe) through the meep C++ API; field "
                             "arrays stay resident in HBM between steps (state, like model weights)",
                     "cold_start": cold},
+            "probe": probe,
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roofline}

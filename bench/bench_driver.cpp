@@ -220,6 +220,19 @@ double mb200_bench_probe(void *h) {
   return real(b->f->get_field(Ez, b->probe_pt));
 }
 
+// Ez at n fixed points of the cell (the same physical points whatever the sharding); every rank
+// gets every value (fields::get_field reduces over the processes)
+void mb200_bench_probes(void *h, double *out, int n) {
+  Bench *b = (Bench *)h;
+  const vec c = b->gv.center();
+  const double step = b->gv.nx() / b->gv.a / 16.0;
+  for (int k = 0; k < n; ++k) {
+    const double s = (k % 2 ? -1.0 : 1.0) * k * step * 0.5;
+    const vec p = c + vec(0.35 + s, 0.25 - s, 0.15 + s);
+    out[k] = real(b->f->get_field(Ez, p));
+  }
+}
+
 double mb200_bench_cells(void *h) { return ((Bench *)h)->cells; }
 int mb200_bench_num_chunks(void *h) { return ((Bench *)h)->f->num_chunks; }
 int mb200_bench_time_step(void *h) { return ((Bench *)h)->f->t; }

@@ -490,6 +490,14 @@ int mb200_profile_enable(mb200_ctx *ctx, int on);
 int mb200_profile_reset(mb200_ctx *ctx);
 /* sums since the last reset (synchronises): launches, device ms, algorithmic bytes */
 int mb200_profile_get(mb200_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes);
+/* Phase marks: mb200_mark records a CUDA event on the context's stream, labelled `tag`;
+ * mb200_marks_collect waits for the last mark and returns, for every pair of consecutive marks,
+ * the EARLIER mark's tag and the device time between the two (ms), then forgets all marks.
+ * Replaces the host wall clocks that the reference's timing_scope puts around each phase of
+ * fields::step (src/time.cpp:92-110, src/step.cpp:64-121): launches are asynchronous here, so a
+ * host clock would measure launch latency.  Returns the number of intervals written (<= cap). */
+int mb200_mark(mb200_ctx *ctx, int tag);
+int mb200_marks_collect(mb200_ctx *ctx, int *tags, double *ms, int cap, int *n);
 /* total kernels launched by this context since creation */
 int64_t mb200_launch_count(mb200_ctx *ctx);
 

@@ -218,6 +218,8 @@ def declare(lib):
         "mb200_profile_enable": (i, [vp, i]),
         "mb200_profile_reset": (i, [vp]),
         "mb200_profile_get": (i, [vp, i, P(i64), P(d), P(d)]),
+        "mb200_mark": (i, [vp, i]),
+        "mb200_marks_collect": (i, [vp, P(i), P(d), i, P(i)]),
         "mb200_launch_count": (i64, [vp]),
     }
     for name, (res, args) in sig.items():

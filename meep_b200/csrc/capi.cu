@@ -36,7 +36,11 @@ struct ProfRec {
   int kind;
   cudaEvent_t a, b;
   double bytes;
+  // kernels that skip known-zero blocks: bytes = base + per_block * (blocks counted by the launch)
+  int slot = -1;
+  double per_block = 0;
 };
+constexpr int kWorkSlots = 4096; // pinned host ring the per-launch work counters are copied to
 
 struct mb200_ctx {
   int device;
@@ -51,6 +55,11 @@ struct mb200_ctx {
   void *run_buf;
   size_t run_cap;
   int *d_err; // latched device-side error word (flag-wait time-out)
+  std::vector<std::pair<int, cudaEvent_t> > marks; // phase marks (mb200_mark)
+  std::vector<cudaEvent_t> event_pool;
+  unsigned long long *d_work;  // [0] Lorentz blocks updated, [1] polarisation blocks read by f_minus_p
+  unsigned long long *h_work;  // pinned: 2 words per slot
+  int next_slot;
 };
 
 struct mb200_plan {
@@ -75,6 +84,10 @@ static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("M
 // 6 -> 1.36 ms per step (16 planes per CTA).
 static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 4;
 
+// MEEP_B200_PLAIN_PER_JOB=0: run the fast-path jobs through the table-driven kernel (descriptor in
+// shared memory) instead of one launch per job with the descriptor in constant space
+static const bool g_plain_per_job = !(getenv("MEEP_B200_PLAIN_PER_JOB") && atoi(getenv("MEEP_B200_PLAIN_PER_JOB")) == 0);
+
 template <typename T>
 static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
   const dim3 grid((unsigned)p->tiles), block(kThreads);
@@ -91,7 +104,7 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
     case MB200_K_LORENTZ:
       if (p->all_plain) { // (for this kind: every job uses the zero-block variant)
         lorentz_blocked_kernel<T><<<grid, block, 0, s>>>((const mb200_lorentz_job_t *)p->d_jobs,
-                                                         p->d_prefix, p->njobs);
+                                                         p->d_prefix, p->njobs, c->d_work);
         break;
       }
       lorentz_kernel<T><<<grid, block, 0, s>>>((const mb200_lorentz_job_t *)p->d_jobs, p->d_prefix,
@@ -99,7 +112,7 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       break;
     case MB200_K_FMP:
       fmp_kernel<T><<<grid, block, 0, s>>>((const mb200_fmp_job_t *)p->d_jobs, p->d_prefix,
-                                           p->njobs);
+                                           p->njobs, c->d_work);
       break;
     case MB200_K_SOURCE:
       source_kernel<T><<<grid, block, 0, s>>>((const mb200_src_job_t *)p->d_jobs, p->d_prefix,
@@ -155,7 +168,8 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
         break;
       }
       launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
-                      p->all_plain, g_split_general, s);
+                      p->all_plain, g_split_general, s, (const mb200_step3_job_t *)p->h_jobs.data(),
+                      p->h_prefix.data(), g_plain_per_job);
       break;
   }
   return cudaGetLastError();
@@ -198,6 +212,10 @@ int mb200_init(int device, mb200_ctx **out) {
   CUDA_TRY(cudaEventCreate(&c->t1));
   CUDA_TRY(cudaMalloc((void **)&c->d_err, sizeof(int)));
   CUDA_TRY(cudaMemset(c->d_err, 0, sizeof(int)));
+  CUDA_TRY(cudaMalloc((void **)&c->d_work, 2 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(c->d_work, 0, 2 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMallocHost((void **)&c->h_work, 2 * sizeof(unsigned long long) * kWorkSlots));
+  c->next_slot = 0;
   *out = c;
   return 0;
 }
@@ -212,6 +230,10 @@ void mb200_destroy(mb200_ctx *c) {
   }
   if (c->run_buf) cudaFree(c->run_buf);
   if (c->d_err) cudaFree(c->d_err);
+  for (auto &m : c->marks) cudaEventDestroy(m.second);
+  for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+  if (c->d_work) cudaFree(c->d_work);
+  if (c->h_work) cudaFreeHost(c->h_work);
   cudaEventDestroy(c->t0);
   cudaEventDestroy(c->t1);
   cudaStreamDestroy(c->stream);
@@ -325,7 +347,7 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
     p->points += pts;
   }
   p->tiles = prefix[njobs];
-  if (kind == MB200_K_STEP3) {
+  if (kind == MB200_K_STEP3 || kind == MB200_K_LORENTZ) {
     p->h_jobs.assign((const char *)jobs, (const char *)jobs + js * njobs);
     p->h_prefix = prefix;
   }
@@ -377,6 +399,24 @@ int mb200_plan_run(mb200_ctx *c, mb200_plan *p, const void *run_data, size_t run
   if (c->profiling) {
     rec.kind = (p->kind == MB200_K_STEP3 && !p->all_plain) ? MB200_K_STEP3_GENERAL : p->kind;
     rec.bytes = p->bytes;
+    const double R = p->dtype == MB200_F64 ? 8.0 : 4.0;
+    const bool blocked_lorentz = p->kind == MB200_K_LORENTZ && p->all_plain;
+    if ((blocked_lorentz || p->kind == MB200_K_FMP) && c->next_slot < kWorkSlots) {
+      // bytes actually moved: only the blocks the kernel did not skip (plan_metrics.h counts the
+      // dense volume, which is what a kernel without zero-block skipping would move)
+      rec.slot = c->next_slot++;
+      if (blocked_lorentz) { // P, P_prev r/w + sigma, W r per updated element; 2 flag bytes per block
+        rec.per_block = 6.0 * R * MB200_ZBLOCK;
+        rec.bytes = 0;
+        for (int j = 0; j < p->njobs; ++j)
+          rec.bytes += 2.0 * (double)ceil_div(((const mb200_lorentz_job_t *)p->h_jobs.data())[j].ntot, MB200_ZBLOCK);
+      }
+      else { // D r + f_minus_p w for every element; P r only for the blocks not known to be zero
+        rec.per_block = R * MB200_ZBLOCK;
+        rec.bytes = 2.0 * R * p->points;
+      }
+      CUDA_TRY(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(unsigned long long), c->stream));
+    }
     CUDA_TRY(cudaEventCreate(&rec.a));
     CUDA_TRY(cudaEventCreate(&rec.b));
     CUDA_TRY(cudaEventRecord(rec.a, c->stream));
@@ -389,6 +429,9 @@ int mb200_plan_run(mb200_ctx *c, mb200_plan *p, const void *run_data, size_t run
   c->launches += 1;
   if (c->profiling) {
     CUDA_TRY(cudaEventRecord(rec.b, c->stream));
+    if (rec.slot >= 0)
+      CUDA_TRY(cudaMemcpyAsync(c->h_work + 2 * rec.slot, c->d_work, 2 * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, c->stream));
     c->recs.push_back(rec);
   }
   return 0;
@@ -694,11 +737,14 @@ static int prof_collect(mb200_ctx *c) {
     CUDA_TRY(cudaEventElapsedTime(&f, r.a, r.b));
     c->prof_launches[r.kind] += 1;
     c->prof_ms[r.kind] += f;
+    if (r.slot >= 0) // (the stream was synchronised above: the counters have landed)
+      r.bytes += r.per_block * (double)c->h_work[2 * r.slot + (r.kind == MB200_K_FMP ? 1 : 0)];
     c->prof_bytes[r.kind] += r.bytes;
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
   c->recs.clear();
+  c->next_slot = 0;
   return 0;
 }
 
@@ -722,6 +768,35 @@ int mb200_profile_get(mb200_ctx *c, int kind, int64_t *launches, double *ms, dou
   if (launches) *launches = c->prof_launches[kind];
   if (ms) *ms = c->prof_ms[kind];
   if (bytes) *bytes = c->prof_bytes[kind];
+  return 0;
+}
+int mb200_mark(mb200_ctx *c, int tag) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaEvent_t e;
+  if (!c->event_pool.empty()) {
+    e = c->event_pool.back();
+    c->event_pool.pop_back();
+  }
+  else
+    CUDA_TRY(cudaEventCreate(&e));
+  CUDA_TRY(cudaEventRecord(e, c->stream));
+  c->marks.push_back(std::make_pair(tag, e));
+  return 0;
+}
+int mb200_marks_collect(mb200_ctx *c, int *tags, double *ms, int cap, int *n) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  *n = 0;
+  if (!c->marks.empty()) CUDA_TRY(cudaEventSynchronize(c->marks.back().second));
+  for (size_t k = 0; k + 1 < c->marks.size() && *n < cap; ++k) {
+    float f = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, c->marks[k].second, c->marks[k + 1].second));
+    tags[*n] = c->marks[k].first;
+    ms[*n] = f;
+    *n += 1;
+  }
+  for (auto &m : c->marks)
+    c->event_pool.push_back(m.second);
+  c->marks.clear();
   return 0;
 }
 int64_t mb200_launch_count(mb200_ctx *c) { return c->launches; }

@@ -112,6 +112,70 @@ MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int t
     metal_yz[c] = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
                   iz == C.metal_hi[2];
   }
+  // Interior CTAs (nearly all of them): every component is updated on every marched plane, no
+  // metal x-plane is crossed, and the curl operands are the three arrays of the other field type in
+  // cyclic order (g1 of component c = G[(c+2)%3], g2 = G[(c+1)%3]: src/fields.cpp:428-456), so the
+  // centre value of each is loaded once for the two components that use it.  Same arithmetic, in
+  // the same order, as the general loop below: 15 loads and 6 stores per point instead of 18 and
+  // 6, no per-plane predicates, cursors instead of index arithmetic.
+  bool full = J.c[0].g1 == J.c[1].g2 && J.c[1].g1 == J.c[2].g2 && J.c[2].g1 == J.c[0].g2 &&
+              (int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const mb200_step3_comp_t &C = J.c[c];
+    full = full && myz[c] && ix0 >= C.lo[0] && ix_end - 1 <= C.hi[0] &&
+           !(C.metal_lo[0] >= ix0 && C.metal_lo[0] < ix_end) && !(C.metal_hi[0] >= ix0 && C.metal_hi[0] < ix_end) &&
+           (C.e != nullptr) == (J.c[0].e != nullptr) && (C.u != nullptr) == (J.c[0].u != nullptr);
+  }
+  if (full) {
+    const bool epi = J.c[0].e != nullptr, hasu = epi && J.c[0].u != nullptr;
+    // All arrays of a chunk share one index space of fewer than 2^32 elements (checked above), so a
+    // single 32-bit cursor addresses every operand: one IMAD.WIDE.U32 per access against a base
+    // that is a constant-bank operand (per-job launch) instead of 64-bit pointer arithmetic.
+    const T *G0 = (const T *)J.c[1].g1, *G1 = (const T *)J.c[2].g1, *G2 = (const T *)J.c[0].g1;
+    const unsigned s10 = (unsigned)J.c[0].s1, s20 = (unsigned)J.c[0].s2, s11 = (unsigned)J.c[1].s1,
+                   s21 = (unsigned)J.c[1].s2, s12 = (unsigned)J.c[2].s1, s22 = (unsigned)J.c[2].s2;
+    T *f0 = (T *)J.c[0].f, *f1 = (T *)J.c[1].f, *f2 = (T *)J.c[2].f;
+    const T *u0 = (const T *)J.c[0].u, *u1 = (const T *)J.c[1].u, *u2 = (const T *)J.c[2].u;
+    T *e0 = (T *)J.c[0].e, *e1 = (T *)J.c[1].e, *e2 = (T *)J.c[2].e;
+    const T k0 = (T)J.c[0].dtdx, k1 = (T)J.c[1].dtdx, k2 = (T)J.c[2].dtdx;
+    const unsigned sxu = (unsigned)sx;
+    unsigned q = (unsigned)i;
+    for (int ix = ix0; ix < ix_end; ++ix, q += sxu) {
+      // ---- all loads first
+      const T g0 = ldro(G0 + q), g1 = ldro(G1 + q), g2 = ldro(G2 + q);
+      const T a10 = ldro(G2 + (q + s10)), a20 = ldro(G1 + (q + s20)); // component 0: g1 = G2, g2 = G1
+      const T a11 = ldro(G0 + (q + s11)), a21 = ldro(G2 + (q + s21)); // component 1: g1 = G0, g2 = G2
+      const T a12 = ldro(G1 + (q + s12)), a22 = ldro(G0 + (q + s22)); // component 2: g1 = G1, g2 = G0
+      const T v0 = f0[q], v1 = f1[q], v2 = f2[q];
+      T w0 = T(1), w1 = T(1), w2 = T(1);
+      if (hasu) {
+        w0 = ldro(u0 + q);
+        w1 = ldro(u1 + q);
+        w2 = ldro(u2 + q);
+      }
+      // ---- then arithmetic + stores
+      T dg = a10 - g2;
+      dg = dg + g1 - a20;
+      const T d0 = v0 - k0 * dg;
+      dg = a11 - g0;
+      dg = dg + g2 - a21;
+      const T d1 = v1 - k1 * dg;
+      dg = a12 - g1;
+      dg = dg + g0 - a22;
+      const T d2 = v2 - k2 * dg;
+      f0[q] = d0;
+      f1[q] = d1;
+      f2[q] = d2;
+      if (epi) {
+        const T dd0 = metal_yz[0] ? T(0) : d0, dd1 = metal_yz[1] ? T(0) : d1, dd2 = metal_yz[2] ? T(0) : d2;
+        e0[q] = hasu ? dd0 * w0 : dd0;
+        e1[q] = hasu ? dd1 * w1 : dd1;
+        e2[q] = hasu ? dd2 * w2 : dd2;
+      }
+    }
+    return;
+  }
   for (int ix = ix0; ix < ix_end; ++ix, i += sx) {
     T fv[3], a1[3], c1[3], c2[3], a2[3], uv[3];
     bool m[3];
@@ -507,6 +571,19 @@ __global__ void __launch_bounds__(kThreads)
   step3_plain_thread<T>(J, tile, threadIdx.x);
 }
 
+// ---- one job per launch, descriptor in kernel-parameter (constant) space ---------------------------
+// The fast path normally has ONE job per GPU (the interior chunk; up to three when source planes
+// split it).  Staged in shared memory the descriptor costs ~40 LDS per marched plane — pointers,
+// bounds and strides do not fit in registers next to the 18 values in flight.  Passed by value as
+// a __grid_constant__ parameter every field is a constant-bank operand of the instruction that
+// uses it: no load, no register.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    step3_plain_job_kernel(const __grid_constant__ mb200_step3_job_t J) {
+  step3_plain_thread<T>(J, (int64_t)blockIdx.x, threadIdx.x);
+}
+constexpr int kMaxJobLaunches = 8; // more plain jobs than this: one table-driven launch
+
 // ---- job table in kernel-parameter (constant) space ---------------------------------------------
 // The job descriptor is CTA-uniform.  Staging it in shared memory costs an LDS (and a short-
 // scoreboard stall) for every pointer/flag use inside the marching loop; passed by value as a
@@ -556,8 +633,15 @@ static void launch_step3_params(const mb200_step3_job_t *h_jobs, const int64_t *
 
 template <typename T>
 static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
-                         int64_t tiles, bool all_plain, int split, cudaStream_t s) {
-  if (all_plain)
+                         int64_t tiles, bool all_plain, int split, cudaStream_t s,
+                         const mb200_step3_job_t *h_jobs, const int64_t *h_prefix, bool per_job) {
+  if (all_plain && per_job && njobs <= kMaxJobLaunches) {
+    for (int j = 0; j < njobs; ++j) {
+      const int64_t t = h_prefix[j + 1] - h_prefix[j];
+      if (t > 0) step3_plain_job_kernel<T><<<dim3((unsigned)t), dim3(kThreads), 0, s>>>(h_jobs[j]);
+    }
+  }
+  else if (all_plain)
     step3_plain_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
   else if (split == 4) // MEEP_B200_SPLIT_PML=4|5|6: CTAs per SM (64 / 51 / 42 registers)
     step3c_kernel<T, 4><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);

@@ -472,15 +472,18 @@ __global__ void __launch_bounds__(kThreads)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     lorentz_blocked_kernel(const mb200_lorentz_job_t *__restrict__ jobs,
-                           const int64_t *__restrict__ tile_prefix, int njobs) {
+                           const int64_t *__restrict__ tile_prefix, int njobs,
+                           unsigned long long *__restrict__ work) {
   __shared__ mb200_lorentz_job_t J;
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   // a CTA walks kZBlocksPerCta consecutive blocks, so that skipped blocks cost a flag test and
   // not a CTA launch
   const int64_t nblocks = (J.ntot + MB200_ZBLOCK - 1) / MB200_ZBLOCK;
+  int done = 0; // blocks actually updated (the measured-bytes accounting: work[0])
   for (int64_t b = tile * kZBlocksPerCta; b < (tile + 1) * kZBlocksPerCta && b < nblocks; ++b) {
     if (J.szero[b] && J.pzero[b]) continue; // sigma = P = P_prev = 0 here: nothing changes
+    ++done;
     const int64_t base = b * MB200_ZBLOCK + threadIdx.x;
     bool zero = true;
 #pragma unroll
@@ -491,6 +494,7 @@ __global__ void __launch_bounds__(kThreads)
     const int allzero = __syncthreads_and(zero ? 1 : 0);
     if (threadIdx.x == 0) J.pzero[b] = allzero ? 1 : 0;
   }
+  if (threadIdx.x == 0 && done) atomicAdd(work, (unsigned long long)done);
 }
 
 template <typename T>
@@ -510,10 +514,17 @@ __global__ void block_zero_flags_kernel(const T *__restrict__ arr, int64_t n, ui
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     fmp_kernel(const mb200_fmp_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
-               int njobs) {
+               int njobs, unsigned long long *__restrict__ work) {
   __shared__ mb200_fmp_job_t J;
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
+  static_assert(kThreads * kItems1D == MB200_ZBLOCK, "one zero-flag block per CTA");
+  if (threadIdx.x == 0) { // polarisation blocks this CTA reads (the others are known to be zero): work[1]
+    int nread = 0;
+    for (int k = 0; k < J.np; ++k)
+      if (!(J.pzero[k] && J.pzero[k][tile])) ++nread;
+    if (nread) atomicAdd(work + 1, (unsigned long long)nread);
+  }
   const int64_t base = tile * (kThreads * kItems1D) + threadIdx.x;
 #pragma unroll
   for (int r = 0; r < kItems1D; ++r) {

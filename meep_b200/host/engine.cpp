@@ -84,13 +84,17 @@ Engine::Engine(fields *) {
                 "time-stepping path (fields::step requires a B200)");
   int device = env_int("MEEP_B200_DEVICE", env_int("LOCAL_RANK", 0));
   if (device >= mb200_device_count()) device = device % mb200_device_count();
+  const double t_init = meep::wall_time();
   check(mb200_init(device, &ctx), "mb200_init");
+  if (env_int("MEEP_B200_VERBOSE", 0))
+    fprintf(stderr, "meep_b200: device context on GPU %d ready in %.3f s\n", device, meep::wall_time() - t_init);
   emulated = dlsym(RTLD_DEFAULT, "mb200_is_emulator") != nullptr;
   fuse = env_int("MEEP_B200_FUSE", 1) != 0;
   eager = env_int("MEEP_B200_EAGER", 0) != 0;
   lazy_host = env_int("MEEP_B200_LAZY_HOST", 1) != 0;
   release_host = env_int("MEEP_B200_RELEASE_HOST", 1);
   verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
+  device_timers = env_int("MEEP_B200_TIMERS", 0) != 0;
   merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   p2p = env_int("MEEP_B200_P2P", 1) != 0;

@@ -255,6 +255,7 @@ public:
   Stats stats;
   bool fuse = true;        // MEEP_B200_FUSE=0 disables the fused step3 path
   bool verbose = false;    // MEEP_B200_VERBOSE=1: print the recorded plans
+  bool device_timers = false; // MEEP_B200_TIMERS=1 (or verbosity > 1): CUDA-event phase timers in fields::step
   bool eager = false;      // MEEP_B200_EAGER=1: download after every step (debug/safety)
   int nan_check_every = 16;
   // finiteness probe

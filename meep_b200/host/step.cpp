@@ -95,37 +95,59 @@ void fields::step() {
       }
     }
 
+    // Phase timers.  The reference brackets each phase with a host wall clock (timing_scope,
+    // src/step.cpp:64-121); launches are asynchronous here, so with verbosity > 1 (or
+    // MEEP_B200_TIMERS=1) each phase boundary is a CUDA event on the engine's stream instead and
+    // the device times are credited to the same time_sinks when the step ends (see below).
+    const bool dev_timers = E.device_timers || verbosity > 1;
+    auto mark = [&](time_sink s) {
+      if (dev_timers) check(mb200_mark(E.ctx, (int)s), "mb200_mark");
+    };
+    time_sink_to_duration_map discard; // host launch time of a phase is not phase time
+    auto phase_clock = [&](time_sink s) {
+      if (dev_timers) return timing_scope(&discard, s);
+      return with_timing_scope(s);
+    };
     for (int h = 0; h < 2; ++h) {
       const HalfStep &H = kHalves[h];
       const double t_half = time() + 0.5 * dt * h;
       calc_sources(t_half); // currents driving this family
+      mark(H.t_update_db);
       {
-        auto timer = with_timing_scope(H.t_update_db);
+        auto timer = phase_clock(H.t_update_db);
         step_db(H.db);
       }
+      mark(Stepping);
       step_source(H.db);
+      mark(H.t_bnd_db);
       {
-        auto timer = with_timing_scope(H.t_bnd_db);
+        auto timer = phase_clock(H.t_bnd_db);
         step_boundaries(H.db);
       }
       calc_sources(t_half + 0.5 * dt); // integrated sources enter the E/H update
+      mark(H.t_update_eh);
       {
-        auto timer = with_timing_scope(H.t_update_eh);
+        auto timer = phase_clock(H.t_update_eh);
         update_eh(H.eh);
       }
+      mark(H.t_bnd_w);
       {
-        auto timer = with_timing_scope(H.t_bnd_w);
+        auto timer = phase_clock(H.t_bnd_w);
         step_boundaries(H.w);
       }
+      mark(Stepping);
       update_pols(H.eh);
+      mark(H.t_bnd_p);
       {
-        auto timer = with_timing_scope(H.t_bnd_p);
+        auto timer = phase_clock(H.t_bnd_p);
         step_boundaries(H.p);
       }
+      mark(H.t_bnd_eh);
       {
-        auto timer = with_timing_scope(H.t_bnd_eh);
+        auto timer = phase_clock(H.t_bnd_eh);
         step_boundaries(H.eh);
       }
+      mark(Stepping);
       if (fluxes) { // legacy flux planes integrate the host arrays
         E.download_fields();
         if (h == 0) fluxes->update_half();
@@ -134,7 +156,35 @@ void fields::step() {
     }
 
     t += 1;
+    mark(FourierTransforming);
     update_dfts();
+    mark(Stepping);
+    if (dev_timers) {
+      // One synchronisation per step.  The per-phase sinks (FieldUpdateB ... BoundarySteppingE)
+      // receive their device time; the time the host spent waiting for the device is what the
+      // reference's exclusive sinks measure, so it is moved from Stepping (where the wait above
+      // is clocked) to Boundaries / FourierTransforming for the phases that belong there.
+      int tags[64], n = 0;
+      double ms[64];
+      const double w0 = wall_time();
+      check(mb200_marks_collect(E.ctx, tags, ms, 64, &n), "mb200_marks_collect");
+      (void)w0;
+      for (int k = 0; k < n; ++k) {
+        const time_sink sink = (time_sink)tags[k];
+        const double sec = ms[k] * 1e-3;
+        if (sink == Stepping) continue; // already clocked by the enclosing am_now_working_on(Stepping)
+        if (sink == FourierTransforming) {
+          times_spent[FourierTransforming] += sec;
+          times_spent[Stepping] -= sec;
+          continue;
+        }
+        times_spent[sink] += sec;
+        if (sink >= BoundarySteppingB && sink <= BoundarySteppingE) {
+          times_spent[Boundaries] += sec;
+          times_spent[Stepping] -= sec;
+        }
+      }
+    }
     finished_working();
 
     changed_materials = false; // any material changes were handled in connect_chunks()

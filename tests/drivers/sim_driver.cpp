@@ -207,9 +207,18 @@ int main(int argc, char **argv) {
     gaussian_src_time src(0.15, 0.1);
     src.is_integrated = (cs == "c2_3d_pml_integrated");
     f.add_point_source(Ez, src, gv.center() + vec(0.05, 0.05, 0.05));
+    const double w0 = wall_time();
     for (int i = 0; i < nsteps; ++i) f.step();
     probes(f, gv);
     dump_fields(f);
+    if (getenv("MB200_DUMP_TIMES")) { // phase timers as fields::time_spent_on reports them (not a parity quantity)
+      const time_sink sinks[] = {Stepping, Boundaries, FourierTransforming, FieldUpdateB, FieldUpdateH, FieldUpdateD,
+                                 FieldUpdateE, BoundarySteppingB, BoundarySteppingH, BoundarySteppingD, BoundarySteppingE};
+      std::vector<double> tv;
+      for (time_sink sk : sinks) tv.push_back(f.time_spent_on(sk)[0]);
+      tv.push_back(wall_time() - w0);
+      dump("times", tv.data(), sizeof(double), tv.size());
+    }
   }
   else if (cs == "3d_metal") { // no PML: metallic walls (zero_metal path)
     g_L = 1.6;

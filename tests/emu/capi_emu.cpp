@@ -39,6 +39,7 @@ struct mb200_ctx {
   std::chrono::steady_clock::time_point t0;
   int64_t prof_launches[MB200_NUM_KINDS];
   double prof_bytes[MB200_NUM_KINDS];
+  std::vector<std::pair<int, std::chrono::steady_clock::time_point> > marks;
 };
 
 struct mb200_plan {
@@ -509,6 +510,20 @@ int mb200_profile_get(mb200_ctx *c, int kind, int64_t *launches, double *ms, dou
   if (launches) *launches = c->prof_launches[kind];
   if (ms) *ms = 0;
   if (bytes) *bytes = c->prof_bytes[kind];
+  return 0;
+}
+int mb200_mark(mb200_ctx *c, int tag) {
+  c->marks.push_back(std::make_pair(tag, std::chrono::steady_clock::now()));
+  return 0;
+}
+int mb200_marks_collect(mb200_ctx *c, int *tags, double *ms, int cap, int *n) {
+  *n = 0;
+  for (size_t k = 0; k + 1 < c->marks.size() && *n < cap; ++k) {
+    tags[*n] = c->marks[k].first;
+    ms[*n] = std::chrono::duration<double, std::milli>(c->marks[k + 1].second - c->marks[k].second).count();
+    *n += 1;
+  }
+  c->marks.clear();
   return 0;
 }
 int64_t mb200_launch_count(mb200_ctx *c) { return c->launches; }

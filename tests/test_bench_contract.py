@@ -46,7 +46,8 @@ def test_reference_arm_under_a_two_rank_launch_only_rank_zero_reports():
         outs.append(_run(["--gpus", "2"], env=env).strip())
     assert outs[1] == ""
     d = json.loads(outs[0])
-    assert d["n_gpus"] == 2 and "1024x512x512" in d["config"]["workload"]
+    # N > 1: the north-star case (BASELINE.json configs[4]): 1024^3, strong scaling
+    assert d["n_gpus"] == 2 and "1024x1024x1024" in d["config"]["workload"] and d["scaling"] == "strong"
 
 
 def test_max_over_ranks_reduction_with_gloo_world_size_2(tmp_path):

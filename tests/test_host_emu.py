@@ -224,3 +224,18 @@ def test_connection_tables_identical_to_the_reference(layout, tmp_path):
         assert ref[k].shape == got[k].shape, k
         assert not (ref[k] < 0).any() or "phases" in k, "unresolved pointer in %s" % k
         assert np.array_equal(ref[k], got[k]), k
+
+
+def test_phase_timers_are_credited_from_device_marks():
+    """MEEP_B200_TIMERS=1 (or verbosity > 1): fields::time_spent_on reports per-phase DEVICE time taken
+    from marks on the engine's stream (include/meep_b200.h: mb200_mark), not host launch latency"""
+    d = run_case("emu", "f64", "c2_3d_pml", 12, env={"MEEP_B200_TIMERS": "1", "MB200_DUMP_TIMES": "1"})
+    t = d["times"]
+    stepping, bnd, ft, ub, uh, ud, ue = t[:7]
+    wall = t[-1]
+    assert ub > 0 and ud > 0 and bnd > 0
+    # the per-phase sinks hold device time only: they add up to no more than the wall time of the loop
+    # (Boundaries also holds the host time of connect_the_chunks, as in the reference)
+    assert ub + uh + ud + ue <= wall * 1.05
+    d0 = run_case("emu", "f64", "c2_3d_pml", 12, env={"MB200_DUMP_TIMES": "1"})
+    assert d0["times"].shape == t.shape
