@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MB200_ABI_VERSION 1
+#define MB200_ABI_VERSION 2
 
 enum { MB200_F64 = 0, MB200_F32 = 1 };
 
@@ -349,6 +349,11 @@ typedef struct {
   int64_t stride[3];
   double dt;
   int32_t ix_lo, ix_hi;
+  /* the noepi_n planes from noepi_lo on (array index along direction 0; n = 0: none) are updated WITHOUT the
+   * fused E/H epilogue: they hold source points, so fields::step_source must run between the D and
+   * the E update there (src/step.cpp:98-109) and update_eh covers them with its own pass.  One job
+   * (one launch) per chunk instead of three. */
+  int32_t noepi_lo, noepi_n;
   mb200_step3_comp_t c[3];
 } mb200_step3_job_t;
 
@@ -473,6 +478,11 @@ int mb200_ipc_import(mb200_ctx *ctx, const void *handle64, void **out);
 int mb200_ipc_close(mb200_ctx *ctx, void *imported);
 int mb200_flag_signal(mb200_ctx *ctx, uint64_t *flag, uint64_t value);
 int mb200_flag_wait(mb200_ctx *ctx, const uint64_t *flag, uint64_t value);
+/* the same for up to MB200_MAX_FLAGS words in ONE launch (a GPU has up to 7 neighbours in a 2x2x2
+ * partition; one launch per word would put ~30 one-thread kernels into every time step) */
+#define MB200_MAX_FLAGS 32
+int mb200_flag_signal_many(mb200_ctx *ctx, uint64_t *const *flags, const uint64_t *values, int n);
+int mb200_flag_wait_many(mb200_ctx *ctx, const uint64_t *const *flags, const uint64_t *values, int n);
 
 /* ---- flags[b] = 1 if arr[b*MB200_ZBLOCK .. ) is identically zero, else 0 (n elements) */
 int mb200_block_zero_flags(mb200_ctx *ctx, int dtype, const void *arr, int64_t n, uint8_t *flags);

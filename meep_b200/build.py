@@ -6,7 +6,9 @@ Products (all git-ignored, all travel to the GPU box with gpurun):
   meep_b200/lib/libmeep_b200_<p>.so     host replacement TUs (meep_b200/host/*.cpp) compiled
                                         against the reference's unmodified meep.hpp; interposes
                                         the hot-path symbols of libmeep.  p = f64 | f32
-  oracle/_ref/libmeep_ref_<p>.so        the unmodified reference (oracle / CPU baseline / host API)
+  oracle/_ref/libmeep_ref_<p>.so        the unmodified reference as ORACLE / CPU baseline (tests, smoke, bench --impl reference)
+  third_party/libmeep_host/libmeep_host_<p>.so   the same objects linked as the "installed Meep" the product sits on:
+                                        the reference's non-hot-path host code (structure, fields set-up, readers)
   oracle/_build/liboracle.so            plain-C restatement of the inner loops (oracle/fdtd_oracle.c)
   tests/_build/*                        test-only emulator, parity drivers, golden generator
 
@@ -29,6 +31,7 @@ LIB = os.path.join(ROOT, "meep_b200", "lib")
 CSRC = os.path.join(ROOT, "meep_b200", "csrc")
 HOST = os.path.join(ROOT, "meep_b200", "host")
 OREF = os.path.join(ROOT, "oracle", "_ref")
+HOSTLIB = os.path.join(ROOT, "third_party", "libmeep_host")  # the "installed Meep" under the drop-in
 OBUILD = os.path.join(ROOT, "oracle", "_build")
 TBUILD = os.path.join(ROOT, "tests", "_build")
 
@@ -80,7 +83,8 @@ def build_cuda(force=False):
 
 def build_reference(precs=PRECS):
     """The unmodified reference stepping core -> oracle/_ref (recipe: oracle/ref_build/Makefile)."""
-    outs = [os.path.join(OREF, "libmeep_ref_%s.so" % p) for p in precs]
+    outs = [os.path.join(OREF, "libmeep_ref_%s.so" % p) for p in precs] + \
+        [os.path.join(HOSTLIB, "libmeep_host_%s.so" % p) for p in precs]
     if have_reference():
         _run(["make", "-C", os.path.join(ROOT, "oracle", "ref_build"), "-j8",
               "PRECS=" + " ".join(precs), "REF=" + REF])
@@ -99,10 +103,10 @@ def build_host(prec, backend="cuda"):
     """Host replacement TUs -> libmeep_b200_<prec>.so (backend 'emu' = test-only emulator)."""
     if backend == "cuda":
         out = os.path.join(LIB, "libmeep_b200_%s.so" % prec)
-        link = ["-L" + LIB, "-lmeepb200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../oracle/_ref"]
+        link = ["-L" + LIB, "-lmeepb200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../third_party/libmeep_host"]
     else:
         out = os.path.join(TBUILD, "libmeep_b200_emu_%s.so" % prec)
-        link = ["-L" + TBUILD, "-lmeepb200_emu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../oracle/_ref"]
+        link = ["-L" + TBUILD, "-lmeepb200_emu", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../third_party/libmeep_host"]
     if not have_reference():
         if not os.path.exists(out):
             raise RuntimeError("%s missing and the reference headers are not available" % out)
@@ -119,9 +123,15 @@ def build_host(prec, backend="cuda"):
             _run([GXX, "-std=c++14", "-O2", "-fPIC", "-Wall", "-Wno-unused-variable"] + _ref_includes(prec) +
                  ["-I" + HOST, "-c", src, "-o", obj])
         objs.append(obj)
-    if _stale(out, objs):
+    if _stale(out, objs + [os.path.join(HOSTLIB, "libmeep_host_%s.so" % prec)]):
         _run([GXX, "-shared", "-fPIC", "-o", out] + objs + link +
-             ["-L" + OREF, "-lmeep_ref_" + prec, "-ldl"])
+             ["-L" + HOSTLIB, "-lmeep_host_" + prec, "-ldl"])
+    # the same objects WITHOUT a dependency on any libmeep: the form to LD_PRELOAD over a program that
+    # already links its own installed libmeep (INTEGRATION.md route A) — every non-hot-path symbol
+    # then binds to that installation, and no second copy of the library enters the process
+    pre = out.replace("libmeep_b200_", "libmeep_b200_preload_")
+    if _stale(pre, objs):
+        _run([GXX, "-shared", "-fPIC", "-o", pre] + objs + link + ["-ldl"])
     return out
 
 
@@ -148,6 +158,14 @@ def build_oracle_c():
     return out
 
 
+def _meep_link(arm, prec):
+    """which build of the reference a test program runs on: the ORACLE (arm 'ref': the unmodified
+    reference does the time stepping) or the installed-Meep host library under the drop-in"""
+    if arm == "ref":
+        return ["-L" + OREF, "-lmeep_ref_" + prec, "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-ldl"]
+    return ["-L" + HOSTLIB, "-lmeep_host_" + prec, "-Wl,-rpath,$ORIGIN/../../third_party/libmeep_host", "-ldl"]
+
+
 def build_drivers(prec, arms=("ref", "b200", "emu")):
     """tests/drivers/*.cpp linked against the reference alone / the drop-in / the emulated drop-in."""
     os.makedirs(TBUILD, exist_ok=True)
@@ -164,7 +182,7 @@ def build_drivers(prec, arms=("ref", "b200", "emu")):
                 if not os.path.exists(out):
                     raise RuntimeError("%s missing and the reference headers are not available" % out)
                 continue
-            deps = [src, os.path.join(OREF, "libmeep_ref_%s.so" % prec)]
+            deps = [src, os.path.join(OREF, "libmeep_ref_%s.so" % prec), os.path.join(HOSTLIB, "libmeep_host_%s.so" % prec)]
             link = []
             if arm == "b200":
                 deps.append(os.path.join(LIB, "libmeep_b200_%s.so" % prec))
@@ -175,7 +193,7 @@ def build_drivers(prec, arms=("ref", "b200", "emu")):
             if _stale(out, deps):
                 _run([GXX, "-std=c++14", "-O2", "-w", "-fopenmp"] + _ref_includes(prec) +
                      ["-I" + os.path.join(ROOT, "include"), "-I" + HOST, src, "-o", out, "-Wl,--no-as-needed"] + link +
-                     ["-L" + OREF, "-lmeep_ref_" + prec, "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-ldl"])
+                     _meep_link(arm, prec))
     return outs
 
 
@@ -196,7 +214,7 @@ def build_reference_tests(prec, arms=("ref", "b200", "emu"), names=None):
             outs[(name, arm)] = out
             if not have_reference():
                 continue  # prebuilt (or absent: the test then skips)
-            deps = [src, os.path.join(OREF, "libmeep_ref_%s.so" % prec)]
+            deps = [src, os.path.join(OREF, "libmeep_ref_%s.so" % prec), os.path.join(HOSTLIB, "libmeep_host_%s.so" % prec)]
             link = []
             if arm == "b200":
                 deps.append(os.path.join(LIB, "libmeep_b200_%s.so" % prec))
@@ -206,8 +224,7 @@ def build_reference_tests(prec, arms=("ref", "b200", "emu"), names=None):
                 link = ["-L" + TBUILD, "-lmeep_b200_emu_" + prec, "-lmeepb200_emu", "-Wl,-rpath,$ORIGIN"]
             if _stale(out, deps):
                 _run([GXX, "-std=c++11", "-O2", "-w", "-fopenmp"] + _ref_includes(prec) +
-                     [src, "-o", out, "-Wl,--no-as-needed"] + link +
-                     ["-L" + OREF, "-lmeep_ref_" + prec, "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-ldl"])
+                     [src, "-o", out, "-Wl,--no-as-needed"] + link + _meep_link(arm, prec))
     return outs
 
 
@@ -222,10 +239,10 @@ def build_bench(prec):
                 raise RuntimeError("%s missing and the reference headers are not available" % o)
         return so, exe
     common = [GXX, "-std=c++14", "-O2", "-w", "-fopenmp"] + _ref_includes(prec)
-    if _stale(so, [src, os.path.join(LIB, "libmeep_b200_%s.so" % prec)]):
+    if _stale(so, [src, os.path.join(LIB, "libmeep_b200_%s.so" % prec), os.path.join(HOSTLIB, "libmeep_host_%s.so" % prec)]):
         _run(common + ["-fPIC", "-shared", src, "-o", so, "-Wl,--no-as-needed", "-L" + LIB,
-                       "-lmeep_b200_" + prec, "-lmeepb200", "-L" + OREF, "-lmeep_ref_" + prec,
-                       "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-ldl"])
+                       "-lmeep_b200_" + prec, "-lmeepb200", "-L" + HOSTLIB, "-lmeep_host_" + prec,
+                       "-Wl,-rpath,$ORIGIN", "-Wl,-rpath,$ORIGIN/../../third_party/libmeep_host", "-ldl"])
     if _stale(exe, [src, os.path.join(OREF, "libmeep_ref_%s.so" % prec)]):
         _run(common + ["-DMB200_BENCH_MAIN", src, "-o", exe, "-L" + OREF, "-lmeep_ref_" + prec,
                        "-Wl,-rpath,$ORIGIN/../../oracle/_ref", "-ldl"])

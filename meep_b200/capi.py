@@ -108,7 +108,8 @@ class Step3Comp(C.Structure):
 
 class Step3Job(C.Structure):
     _fields_ = [("n", C.c_int32 * 3), ("reserved", C.c_int32), ("stride", C.c_int64 * 3),
-                ("dt", C.c_double), ("ix_lo", C.c_int32), ("ix_hi", C.c_int32), ("c", Step3Comp * 3)]
+                ("dt", C.c_double), ("ix_lo", C.c_int32), ("ix_hi", C.c_int32),
+                ("noepi_lo", C.c_int32), ("noepi_n", C.c_int32), ("c", Step3Comp * 3)]
 
 
 class BetaJob(C.Structure):
@@ -211,6 +212,8 @@ def declare(lib):
         "mb200_ipc_close": (i, [vp, vp]),
         "mb200_flag_signal": (i, [vp, vp, C.c_uint64]),
         "mb200_flag_wait": (i, [vp, vp, C.c_uint64]),
+        "mb200_flag_signal_many": (i, [vp, vp, vp, i]),
+        "mb200_flag_wait_many": (i, [vp, vp, vp, i]),
         "mb200_block_zero_flags": (i, [vp, i, vp, i64, vp]),
         "mb200_check_finite": (i, [vp, i, vp, i64, vp]),
         "mb200_timer_start": (i, [vp]),
@@ -242,7 +245,7 @@ def load(path=None):
         raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
     lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
     declare(lib)
-    if lib.mb200_abi_version() != 1:
+    if lib.mb200_abi_version() != 2:
         raise RuntimeError("libmeepb200 ABI version mismatch")
     if path is None:
         _lib = lib

@@ -84,9 +84,14 @@ static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("M
 // 6 -> 1.36 ms per step (16 planes per CTA).
 static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 4;
 
-// MEEP_B200_PLAIN_PER_JOB=0: run the fast-path jobs through the table-driven kernel (descriptor in
-// shared memory) instead of one launch per job with the descriptor in constant space
-static const bool g_plain_per_job = !(getenv("MEEP_B200_PLAIN_PER_JOB") && atoi(getenv("MEEP_B200_PLAIN_PER_JOB")) == 0);
+// Fast-path kernel form.  Measured at 512^3 double (profiles/README.md, r2d-r2g; per-launch ncu times,
+// B half / D-E half): table-driven kernel with the masked march — 1597 / 2350 us (the default);
+// one launch per job with the descriptor in constant space — 1592 / 2490 us (MEEP_B200_PLAIN_PER_JOB=1);
+// interior march with deduplicated operands and a 32-bit cursor, half the instructions per point —
+// 1639 / 2790 us (MEEP_B200_PLAIN_FAST=1).  Fewer instructions did not help: the kernel is not
+// issue-bound.  Neither did more CTAs per SM (5: 1894 us, 6: 2120 us for the B half) nor staging
+// the operands through shared memory with 8-byte cp.async (2518 / 2896 us).
+static const bool g_plain_per_job = getenv("MEEP_B200_PLAIN_PER_JOB") && atoi(getenv("MEEP_B200_PLAIN_PER_JOB")) != 0;
 
 template <typename T>
 static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
@@ -130,10 +135,15 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       dft_kernel<T><<<grid, block, 0, s>>>((const mb200_dft_job_t *)p->d_jobs, p->d_prefix,
                                            p->njobs, (const T *)d_run);
       break;
-    case MB200_K_FLUX:
-      flux_kernel<T><<<grid, block, 0, s>>>((const mb200_flux_job_t *)p->d_jobs, p->d_prefix,
-                                            p->njobs);
+    case MB200_K_FLUX: {
+      // (plan_create checked that the jobs share nomega and out; plan_run sized c->run_buf)
+      const mb200_flux_job_t &J0 = *(const mb200_flux_job_t *)p->h_jobs.data();
+      flux_partial_kernel<T><<<grid, block, 0, s>>>((const mb200_flux_job_t *)p->d_jobs, p->d_prefix,
+                                                    p->njobs, (double *)d_run, J0.nomega);
+      flux_final_kernel<<<dim3((unsigned)ceil_div(J0.nomega, kThreads / 32)), block, 0, s>>>(
+          (const double *)d_run, p->tiles, J0.nomega, J0.nomega, J0.out);
       break;
+    }
     case MB200_K_BETA:
       beta_kernel<T><<<grid, block, 0, s>>>((const mb200_beta_job_t *)p->d_jobs, p->d_prefix,
                                             p->njobs);
@@ -208,6 +218,14 @@ int mb200_init(int device, mb200_ctx **out) {
   memset(c->prof_ms, 0, sizeof(c->prof_ms));
   memset(c->prof_bytes, 0, sizeof(c->prof_bytes));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    const int v = getenv("MEEP_B200_PLAIN_FAST") ? atoi(getenv("MEEP_B200_PLAIN_FAST")) : 0;
+    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_plain_fast, &v, sizeof(int)));
+  }
+  if (const char *e = getenv("MEEP_B200_PAIR_PLANES")) {
+    const int v = atoi(e);
+    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pair_planes, &v, sizeof(int)));
+  }
   CUDA_TRY(cudaEventCreate(&c->t0));
   CUDA_TRY(cudaEventCreate(&c->t1));
   CUDA_TRY(cudaMalloc((void **)&c->d_err, sizeof(int)));
@@ -347,7 +365,15 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
     p->points += pts;
   }
   p->tiles = prefix[njobs];
-  if (kind == MB200_K_STEP3 || kind == MB200_K_LORENTZ) {
+  if (kind == MB200_K_FLUX)
+    for (int j = 1; j < njobs; ++j) {
+      const mb200_flux_job_t *F = (const mb200_flux_job_t *)jobs;
+      if (F[j].nomega != F[0].nomega || F[j].out != F[0].out) {
+        delete p;
+        return fail("mb200_plan_create: the jobs of a flux plan must share nomega and out");
+      }
+    }
+  if (kind == MB200_K_STEP3 || kind == MB200_K_LORENTZ || kind == MB200_K_FLUX) {
     p->h_jobs.assign((const char *)jobs, (const char *)jobs + js * njobs);
     p->h_prefix = prefix;
   }
@@ -384,6 +410,16 @@ int mb200_plan_run(mb200_ctx *c, mb200_plan *p, const void *run_data, size_t run
   if (p->tiles == 0) return 0;
   CUDA_TRY(cudaSetDevice(c->device));
   const bool needs_run = p->kind == MB200_K_SOURCE || p->kind == MB200_K_DFT || p->kind == MB200_K_NOISE;
+  if (p->kind == MB200_K_FLUX) { // scratch for the per-tile partial sums (first stage of the tree)
+    const size_t need = sizeof(double) * (size_t)p->tiles *
+                        (size_t)((const mb200_flux_job_t *)p->h_jobs.data())->nomega;
+    if (need > c->run_cap) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (c->run_buf) CUDA_TRY(cudaFree(c->run_buf));
+      c->run_cap = need * 2 + 4096;
+      CUDA_TRY(cudaMalloc(&c->run_buf, c->run_cap));
+    }
+  }
   if (needs_run) {
     if (!run_data || !run_bytes) return fail("mb200_plan_run: kind %d needs run_data", p->kind);
     if (run_bytes > c->run_cap) {
@@ -657,6 +693,28 @@ __global__ void flag_wait_kernel(const volatile uint64_t *flag, uint64_t value, 
   *err = 1;
 }
 
+struct FlagSet {
+  uint64_t *flag[MB200_MAX_FLAGS];
+  uint64_t value[MB200_MAX_FLAGS];
+  int n;
+};
+__global__ void flag_signal_many_kernel(const __grid_constant__ FlagSet S) {
+  __threadfence_system();
+  if ((int)threadIdx.x < S.n) *(volatile uint64_t *)S.flag[threadIdx.x] = S.value[threadIdx.x];
+}
+__global__ void flag_wait_many_kernel(const __grid_constant__ FlagSet S, int *err, long long max_iters) {
+  if ((int)threadIdx.x >= S.n) return;
+  const volatile uint64_t *f = S.flag[threadIdx.x];
+  for (long long it = 0; it < max_iters; ++it) {
+    if (*f >= S.value[threadIdx.x]) {
+      __threadfence_system();
+      return;
+    }
+    __nanosleep(100);
+  }
+  *err = 1;
+}
+
 int mb200_ipc_export(mb200_ctx *c, void *devptr, void *handle64) {
   CUDA_TRY(cudaSetDevice(c->device));
   cudaIpcMemHandle_t h;
@@ -704,6 +762,59 @@ int mb200_flag_wait(mb200_ctx *c, const uint64_t *flag, uint64_t value) {
     CUDA_TRY(cudaEventRecord(rec.a, c->stream));
   }
   flag_wait_kernel<<<1, 1, 0, c->stream>>>(flag, value, c->d_err, max_iters);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 1;
+  if (c->profiling) {
+    CUDA_TRY(cudaEventRecord(rec.b, c->stream));
+    c->recs.push_back(rec);
+  }
+  return 0;
+}
+
+static long long peer_timeout_iters() {
+  static long long max_iters = 0;
+  if (!max_iters) {
+    const char *e = getenv("MEEP_B200_PEER_TIMEOUT_S");
+    double secs = e ? atof(e) : 60.0;
+    if (!(secs > 0)) secs = 60.0;
+    max_iters = (long long)(secs * 5e6);
+  }
+  return max_iters;
+}
+int mb200_flag_signal_many(mb200_ctx *c, uint64_t *const *flags, const uint64_t *values, int n) {
+  if (n <= 0) return 0;
+  if (n > MB200_MAX_FLAGS) return fail("mb200_flag_signal_many: more than %d flags", MB200_MAX_FLAGS);
+  CUDA_TRY(cudaSetDevice(c->device));
+  FlagSet S;
+  S.n = n;
+  for (int k = 0; k < n; ++k) {
+    S.flag[k] = flags[k];
+    S.value[k] = values[k];
+  }
+  flag_signal_many_kernel<<<1, 32, 0, c->stream>>>(S);
+  CUDA_TRY(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+int mb200_flag_wait_many(mb200_ctx *c, const uint64_t *const *flags, const uint64_t *values, int n) {
+  if (n <= 0) return 0;
+  if (n > MB200_MAX_FLAGS) return fail("mb200_flag_wait_many: more than %d flags", MB200_MAX_FLAGS);
+  CUDA_TRY(cudaSetDevice(c->device));
+  FlagSet S;
+  S.n = n;
+  for (int k = 0; k < n; ++k) {
+    S.flag[k] = (uint64_t *)flags[k];
+    S.value[k] = values[k];
+  }
+  ProfRec rec;
+  if (c->profiling) {
+    rec.kind = MB200_K_EXCHANGE;
+    rec.bytes = 0;
+    CUDA_TRY(cudaEventCreate(&rec.a));
+    CUDA_TRY(cudaEventCreate(&rec.b));
+    CUDA_TRY(cudaEventRecord(rec.a, c->stream));
+  }
+  flag_wait_many_kernel<<<1, 32, 0, c->stream>>>(S, c->d_err, peer_timeout_iters());
   CUDA_TRY(cudaGetLastError());
   c->launches += 1;
   if (c->profiling) {

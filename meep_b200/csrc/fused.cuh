@@ -33,6 +33,10 @@ MB200_HD mb200_box_t step3_box(const mb200_step3_job_t &J) {
 }
 // planes of direction 0 marched per CTA: J.reserved (0 = default)
 MB200_HD int step3_t1(const mb200_step3_job_t &J) { return J.reserved > 0 ? J.reserved : kT1; }
+// does plane ix get the fused E/H epilogue? (not the planes that hold source points)
+MB200_HD bool step3_epi_plane(const mb200_step3_job_t &J, int ix) {
+  return ix < J.noepi_lo || ix >= J.noepi_lo + J.noepi_n;
+}
 MB200_HD int64_t step3_tiles(const mb200_step3_job_t &J) {
   return box_tiles(step3_box(J), step3_t1(J));
 }
@@ -65,7 +69,8 @@ inline double step3_bytes(const mb200_step3_job_t &J, double R) {
     if (!C.f) continue;
     const double q = step3_comp_points(J, C);
     int arrays = 2 + (C.pmlu.sig ? 2 : 0) + (C.cnd ? 2 + (C.pml.sig ? 2 : 0) : 0);
-    if (C.e) arrays += 1 + (C.u ? 1 : 0) + (C.pmlw.sig ? 3 : 0);
+    int epi_arrays = 0;
+    if (C.e) epi_arrays = 1 + (C.u ? 1 : 0) + (C.pmlw.sig ? 3 : 0);
     const void *gs[2] = {C.g1, C.g2};
     for (int k = 0; k < 2; ++k) {
       bool seen = gs[k] == nullptr;
@@ -77,6 +82,16 @@ inline double step3_bytes(const mb200_step3_job_t &J, double R) {
       }
     }
     bytes += R * arrays * q;
+    if (epi_arrays) { // the epilogue skips the source planes
+      double frac = 1.0;
+      int lo = C.lo[0] > J.ix_lo ? C.lo[0] : J.ix_lo, hi = C.hi[0] < J.ix_hi ? C.hi[0] : J.ix_hi;
+      if (hi >= lo && J.noepi_n > 0) {
+        const int last = J.noepi_lo + J.noepi_n - 1;
+        const int nlo = J.noepi_lo > lo ? J.noepi_lo : lo, nhi = last < hi ? last : hi;
+        if (nhi >= nlo) frac = 1.0 - (double)(nhi - nlo + 1) / (double)(hi - lo + 1);
+      }
+      bytes += R * epi_arrays * q * frac;
+    }
   }
   return bytes;
 }
@@ -86,6 +101,13 @@ inline double step3_bytes(const mb200_step3_job_t &J, double R) {
 // chunk of a PML-padded cell: ~89 % of the cells of BASELINE config 2), fused E/H update
 // without f_w.  All loads of a grid point (3 f + 12 g + 3 chi1inv) are issued before the first
 // store, so each warp keeps ~4.6 KB in flight instead of ~1.3 KB.
+// MEEP_B200_PAIR_PLANES=0 (read once by capi.cu into this device flag) switches the two-planes-in-flight
+// form of the B half-step off
+#ifdef __CUDACC__
+__device__ int g_pair_planes = 1;
+__device__ int g_plain_fast = 0; // MEEP_B200_PLAIN_FAST=1: interior threads take the lean march (measured slower)
+__device__ __forceinline__ bool step3_pair_planes() { return g_pair_planes != 0; }
+#endif
 MB200_HD bool step3_is_plain(const mb200_step3_job_t &J) {
   for (int c = 0; c < 3; ++c) {
     const mb200_step3_comp_t &C = J.c[c];
@@ -95,7 +117,164 @@ MB200_HD bool step3_is_plain(const mb200_step3_job_t &J) {
   return true;
 }
 
+// "Use" a loaded value without emitting an instruction: everything the compiler must have issued
+// to produce the value stays above this point, so loads cannot be sunk below the first store of
+// a marching step (they were, for the chi1inv operands: two memory latencies per plane instead of one).
+MB200_HD void keep_above(double v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" ::"d"(v));
+#else
+  (void)v;
+#endif
+}
+MB200_HD void keep_above(float v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" ::"f"(v));
+#else
+  (void)v;
+#endif
+}
+
+// The march of an interior thread of the fast path (see step3_plain_thread): all three components
+// updated on every plane, cyclic curl operands G0..G2 with each centre value loaded once, one
+// 32-bit cursor for every array (all arrays of a chunk share an index space of < 2^32 elements) so
+// that an access is one IMAD.WIDE.U32 against a base held in the constant bank.  EPI: the diagonal
+// E = chi1inv D (or H = B / mu) epilogue is fused; HASU: chi1inv is not identically 1.
+template <typename T, bool EPI, bool HASU>
+MB200_HD void step3_plain_fast(const mb200_step3_job_t &J, int64_t i, int64_t sx, int ix0, int ix_end,
+                               const bool (&metal_yz)[3]) {
+  const T *G0 = (const T *)J.c[1].g1, *G1 = (const T *)J.c[2].g1, *G2 = (const T *)J.c[0].g1;
+  const unsigned s10 = (unsigned)J.c[0].s1, s20 = (unsigned)J.c[0].s2, s11 = (unsigned)J.c[1].s1,
+                 s21 = (unsigned)J.c[1].s2, s12 = (unsigned)J.c[2].s1, s22 = (unsigned)J.c[2].s2;
+  T *f0 = (T *)J.c[0].f, *f1 = (T *)J.c[1].f, *f2 = (T *)J.c[2].f;
+  const T *u0 = (const T *)J.c[0].u, *u1 = (const T *)J.c[1].u, *u2 = (const T *)J.c[2].u;
+  T *e0 = (T *)J.c[0].e, *e1 = (T *)J.c[1].e, *e2 = (T *)J.c[2].e;
+  const T k0 = (T)J.c[0].dtdx, k1 = (T)J.c[1].dtdx, k2 = (T)J.c[2].dtdx;
+  const unsigned sxu = (unsigned)sx;
+  unsigned q = (unsigned)i;
+  int ix = ix0;
+#ifdef __CUDA_ARCH__
+  // Without the epilogue (the B half-step of a chunk whose H aliases B) a point has only 12
+  // operands; the kernel is bound by bytes in flight per SM, so two planes are loaded before the
+  // first store (MEEP_B200_PAIR_PLANES=0 switches this off for A/B runs).
+  if (!EPI && step3_pair_planes())
+    for (; ix + 1 < ix_end; ix += 2, q += 2 * sxu) {
+      const unsigned r = q + sxu;
+      const T g0 = ldro(G0 + q), g1 = ldro(G1 + q), g2 = ldro(G2 + q);
+      const T h0 = ldro(G0 + r), h1 = ldro(G1 + r), h2 = ldro(G2 + r);
+      const T a10 = ldro(G2 + (q + s10)), a20 = ldro(G1 + (q + s20));
+      const T a11 = ldro(G0 + (q + s11)), a21 = ldro(G2 + (q + s21));
+      const T a12 = ldro(G1 + (q + s12)), a22 = ldro(G0 + (q + s22));
+      const T b10 = ldro(G2 + (r + s10)), b20 = ldro(G1 + (r + s20));
+      const T b11 = ldro(G0 + (r + s11)), b21 = ldro(G2 + (r + s21));
+      const T b12 = ldro(G1 + (r + s12)), b22 = ldro(G0 + (r + s22));
+      const T v0 = f0[q], v1 = f1[q], v2 = f2[q], x0 = f0[r], x1 = f1[r], x2 = f2[r];
+      keep_above(b12);
+      keep_above(b22);
+      keep_above(x2);
+      T dg = a10 - g2;
+      dg = dg + g1 - a20;
+      f0[q] = v0 - k0 * dg;
+      dg = a11 - g0;
+      dg = dg + g2 - a21;
+      f1[q] = v1 - k1 * dg;
+      dg = a12 - g1;
+      dg = dg + g0 - a22;
+      f2[q] = v2 - k2 * dg;
+      dg = b10 - h2;
+      dg = dg + h1 - b20;
+      f0[r] = x0 - k0 * dg;
+      dg = b11 - h0;
+      dg = dg + h2 - b21;
+      f1[r] = x1 - k1 * dg;
+      dg = b12 - h1;
+      dg = dg + h0 - b22;
+      f2[r] = x2 - k2 * dg;
+    }
+#endif
+  for (; ix < ix_end; ++ix, q += sxu) {
+    // ---- all loads first
+    const T g0 = ldro(G0 + q), g1 = ldro(G1 + q), g2 = ldro(G2 + q);
+    const T a10 = ldro(G2 + (q + s10)), a20 = ldro(G1 + (q + s20)); // component 0: g1 = G2, g2 = G1
+    const T a11 = ldro(G0 + (q + s11)), a21 = ldro(G2 + (q + s21)); // component 1: g1 = G0, g2 = G2
+    const T a12 = ldro(G1 + (q + s12)), a22 = ldro(G0 + (q + s22)); // component 2: g1 = G1, g2 = G0
+    const T v0 = f0[q], v1 = f1[q], v2 = f2[q];
+    T w0 = T(1), w1 = T(1), w2 = T(1);
+    if (HASU) {
+      w0 = ldro(u0 + q);
+      w1 = ldro(u1 + q);
+      w2 = ldro(u2 + q);
+      keep_above(w0);
+      keep_above(w1);
+      keep_above(w2);
+    }
+    keep_above(a12);
+    keep_above(a22);
+    // ---- then arithmetic + stores
+    T dg = a10 - g2;
+    dg = dg + g1 - a20;
+    const T d0 = v0 - k0 * dg;
+    dg = a11 - g0;
+    dg = dg + g2 - a21;
+    const T d1 = v1 - k1 * dg;
+    dg = a12 - g1;
+    dg = dg + g0 - a22;
+    const T d2 = v2 - k2 * dg;
+    f0[q] = d0;
+    f1[q] = d1;
+    f2[q] = d2;
+    if (EPI && step3_epi_plane(J, ix)) {
+      const T dd0 = metal_yz[0] ? T(0) : d0, dd1 = metal_yz[1] ? T(0) : d1, dd2 = metal_yz[2] ? T(0) : d2;
+      e0[q] = HASU ? dd0 * w0 : dd0;
+      e1[q] = HASU ? dd1 * w1 : dd1;
+      e2[q] = HASU ? dd2 * w2 : dd2;
+    }
+  }
+}
+
+// The general march of the fast path: per-plane masks (edge CTAs, planes outside a component's
+// owned range, metal planes), all loads of a grid point before its first store.
 template <typename T>
+MB200_HD void step3_plain_general(const mb200_step3_job_t &J, int64_t i, int64_t sx, int ix0, int ix_end,
+                                  const bool (&myz)[3], const bool (&metal_yz)[3]) {
+  for (int ix = ix0; ix < ix_end; ++ix, i += sx) {
+    T fv[3], a1[3], c1[3], c2[3], a2[3], uv[3];
+    bool m[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { // ---- all loads first
+      const mb200_step3_comp_t &C = J.c[c];
+      m[c] = myz[c] && ix >= C.lo[0] && ix <= C.hi[0];
+      if (m[c]) {
+        const T *g1 = (const T *)C.g1, *g2 = (const T *)C.g2;
+        fv[c] = ((const T *)C.f)[i];
+        a1[c] = ldro(g1 + i + C.s1);
+        c1[c] = ldro(g1 + i);
+        c2[c] = ldro(g2 + i);
+        a2[c] = ldro(g2 + i + C.s2);
+        uv[c] = (C.e && C.u) ? ldro((const T *)C.u + i) : T(1);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { // ---- then arithmetic + stores
+      const mb200_step3_comp_t &C = J.c[c];
+      if (m[c]) {
+        T dg = a1[c] - c1[c];
+        dg = dg + c2[c] - a2[c];
+        const T d = fv[c] - (T)C.dtdx * dg;
+        ((T *)C.f)[i] = d;
+        if (C.e && step3_epi_plane(J, ix)) {
+          const bool metal = metal_yz[c] || ix == C.metal_lo[0] || ix == C.metal_hi[0];
+          const T dd = metal ? T(0) : d;
+          ((T *)C.e)[i] = C.u ? dd * uv[c] : dd;
+        }
+      }
+    }
+  }
+}
+
+// FAST: interior threads take step3_plain_fast (opt-in per-job kernel only; measured slower than the
+// masked march, see capi.cu) — a template parameter so that the default kernel carries none of it
+template <typename T, bool FAST = false>
 MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
   const mb200_box_t box = step3_box(J);
   int ix0, ix_end, iy, iz;
@@ -127,88 +306,19 @@ MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int t
            !(C.metal_lo[0] >= ix0 && C.metal_lo[0] < ix_end) && !(C.metal_hi[0] >= ix0 && C.metal_hi[0] < ix_end) &&
            (C.e != nullptr) == (J.c[0].e != nullptr) && (C.u != nullptr) == (J.c[0].u != nullptr);
   }
+#ifdef __CUDA_ARCH__
+  full = full && FAST && g_plain_fast != 0;
+#else
+  full = full && FAST;
+#endif
   if (full) {
     const bool epi = J.c[0].e != nullptr, hasu = epi && J.c[0].u != nullptr;
-    // All arrays of a chunk share one index space of fewer than 2^32 elements (checked above), so a
-    // single 32-bit cursor addresses every operand: one IMAD.WIDE.U32 per access against a base
-    // that is a constant-bank operand (per-job launch) instead of 64-bit pointer arithmetic.
-    const T *G0 = (const T *)J.c[1].g1, *G1 = (const T *)J.c[2].g1, *G2 = (const T *)J.c[0].g1;
-    const unsigned s10 = (unsigned)J.c[0].s1, s20 = (unsigned)J.c[0].s2, s11 = (unsigned)J.c[1].s1,
-                   s21 = (unsigned)J.c[1].s2, s12 = (unsigned)J.c[2].s1, s22 = (unsigned)J.c[2].s2;
-    T *f0 = (T *)J.c[0].f, *f1 = (T *)J.c[1].f, *f2 = (T *)J.c[2].f;
-    const T *u0 = (const T *)J.c[0].u, *u1 = (const T *)J.c[1].u, *u2 = (const T *)J.c[2].u;
-    T *e0 = (T *)J.c[0].e, *e1 = (T *)J.c[1].e, *e2 = (T *)J.c[2].e;
-    const T k0 = (T)J.c[0].dtdx, k1 = (T)J.c[1].dtdx, k2 = (T)J.c[2].dtdx;
-    const unsigned sxu = (unsigned)sx;
-    unsigned q = (unsigned)i;
-    for (int ix = ix0; ix < ix_end; ++ix, q += sxu) {
-      // ---- all loads first
-      const T g0 = ldro(G0 + q), g1 = ldro(G1 + q), g2 = ldro(G2 + q);
-      const T a10 = ldro(G2 + (q + s10)), a20 = ldro(G1 + (q + s20)); // component 0: g1 = G2, g2 = G1
-      const T a11 = ldro(G0 + (q + s11)), a21 = ldro(G2 + (q + s21)); // component 1: g1 = G0, g2 = G2
-      const T a12 = ldro(G1 + (q + s12)), a22 = ldro(G0 + (q + s22)); // component 2: g1 = G1, g2 = G0
-      const T v0 = f0[q], v1 = f1[q], v2 = f2[q];
-      T w0 = T(1), w1 = T(1), w2 = T(1);
-      if (hasu) {
-        w0 = ldro(u0 + q);
-        w1 = ldro(u1 + q);
-        w2 = ldro(u2 + q);
-      }
-      // ---- then arithmetic + stores
-      T dg = a10 - g2;
-      dg = dg + g1 - a20;
-      const T d0 = v0 - k0 * dg;
-      dg = a11 - g0;
-      dg = dg + g2 - a21;
-      const T d1 = v1 - k1 * dg;
-      dg = a12 - g1;
-      dg = dg + g0 - a22;
-      const T d2 = v2 - k2 * dg;
-      f0[q] = d0;
-      f1[q] = d1;
-      f2[q] = d2;
-      if (epi) {
-        const T dd0 = metal_yz[0] ? T(0) : d0, dd1 = metal_yz[1] ? T(0) : d1, dd2 = metal_yz[2] ? T(0) : d2;
-        e0[q] = hasu ? dd0 * w0 : dd0;
-        e1[q] = hasu ? dd1 * w1 : dd1;
-        e2[q] = hasu ? dd2 * w2 : dd2;
-      }
-    }
+    if (hasu) step3_plain_fast<T, true, true>(J, i, sx, ix0, ix_end, metal_yz);
+    else if (epi) step3_plain_fast<T, true, false>(J, i, sx, ix0, ix_end, metal_yz);
+    else step3_plain_fast<T, false, false>(J, i, sx, ix0, ix_end, metal_yz);
     return;
   }
-  for (int ix = ix0; ix < ix_end; ++ix, i += sx) {
-    T fv[3], a1[3], c1[3], c2[3], a2[3], uv[3];
-    bool m[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { // ---- all loads first
-      const mb200_step3_comp_t &C = J.c[c];
-      m[c] = myz[c] && ix >= C.lo[0] && ix <= C.hi[0];
-      if (m[c]) {
-        const T *g1 = (const T *)C.g1, *g2 = (const T *)C.g2;
-        fv[c] = ((const T *)C.f)[i];
-        a1[c] = ldro(g1 + i + C.s1);
-        c1[c] = ldro(g1 + i);
-        c2[c] = ldro(g2 + i);
-        a2[c] = ldro(g2 + i + C.s2);
-        uv[c] = (C.e && C.u) ? ldro((const T *)C.u + i) : T(1);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { // ---- then arithmetic + stores
-      const mb200_step3_comp_t &C = J.c[c];
-      if (m[c]) {
-        T dg = a1[c] - c1[c];
-        dg = dg + c2[c] - a2[c];
-        const T d = fv[c] - (T)C.dtdx * dg;
-        ((T *)C.f)[i] = d;
-        if (C.e) {
-          const bool metal = metal_yz[c] || ix == C.metal_lo[0] || ix == C.metal_hi[0];
-          const T dd = metal ? T(0) : d;
-          ((T *)C.e)[i] = C.u ? dd * uv[c] : dd;
-        }
-      }
-    }
-  }
+  step3_plain_general<T>(J, i, sx, ix0, ix_end, myz, metal_yz);
 }
 
 // ---- general path --------------------------------------------------------------------------------
@@ -271,7 +381,7 @@ MB200_HD void step3_load(const mb200_step3_comp_t &C, int64_t i, int ix, int iy,
 
 template <typename T>
 MB200_HD void step3_compute_store(const mb200_step3_comp_t &C, int64_t i, bool metal, T dt2,
-                                  const Step3Vals<T> &v) {
+                                  const Step3Vals<T> &v, bool epi_plane = true) {
   T dg = v.a1 - v.c1;
   dg = dg + v.c2 - v.a2;
   const T curl = (T)C.dtdx * dg;
@@ -297,7 +407,7 @@ MB200_HD void step3_compute_store(const mb200_step3_comp_t &C, int64_t i, bool m
   else
     fn = xn;
   stout((T *)C.f + i, fn);
-  if (C.e) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
+  if (C.e && epi_plane) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
     const T d = metal ? T(0) : fn;
     const T val = C.u ? d * v.u : d;
     if (C.pmlw.sig) {
@@ -340,7 +450,7 @@ MB200_HD void step3_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
       if (m[c])
         step3_compute_store<T>(J.c[c], i,
                                metal_yz[c] || ix == J.c[c].metal_lo[0] || ix == J.c[c].metal_hi[0],
-                               dt2, v[c]);
+                               dt2, v[c], step3_epi_plane(J, ix));
   }
 }
 
@@ -463,7 +573,7 @@ MB200_HD void step3c_march(const mb200_step3_job_t &J, const mb200_step3_comp_t 
     else
       fn = xn;
     stout(pf, fn);
-    if (EPI) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
+    if (EPI && step3_epi_plane(J, ix)) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
       const bool metal = metal_yz || ix == mlo || ix == mhi;
       const T d = metal ? T(0) : fn;
       const T val = HASU ? d * u : d;
@@ -578,9 +688,9 @@ __global__ void __launch_bounds__(kThreads)
 // a __grid_constant__ parameter every field is a constant-bank operand of the instruction that
 // uses it: no load, no register.
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
     step3_plain_job_kernel(const __grid_constant__ mb200_step3_job_t J) {
-  step3_plain_thread<T>(J, (int64_t)blockIdx.x, threadIdx.x);
+  step3_plain_thread<T, true>(J, (int64_t)blockIdx.x, threadIdx.x);
 }
 constexpr int kMaxJobLaunches = 8; // more plain jobs than this: one table-driven launch
 

@@ -607,26 +607,62 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---- dft_flux::flux inner sum ------------------------------------------------------------------
+// Deterministic two-stage tree, no atomics.  Stage 1: a CTA takes kFluxPts consecutive monitor
+// points of one job; warp v walks points v, v+8, ... with its lanes on 32 consecutive frequencies
+// (the dft arrays are point-major/frequency-minor, so every access is a contiguous 32 x 2R line),
+// accumulating Re(E conj(H)) in double; the eight warps' sums are combined through shared memory
+// in a fixed order and written to partial[tile][frequency].  Stage 2: one warp per frequency
+// strides over the tiles and folds its lanes with __shfl_down_sync.  The order of every addition
+// is a function of the problem size only: two calls give bit-identical spectra.
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    flux_kernel(const mb200_flux_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
-                int njobs) {
+    flux_partial_kernel(const mb200_flux_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
+                        int njobs, double *__restrict__ partial, int nomega_stride) {
   __shared__ mb200_flux_job_t J;
+  __shared__ double s_acc[kThreads / 32][32];
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
   const int64_t p0 = tile * kFluxPts;
   const int np = (int)min((int64_t)kFluxPts, J.npts - p0);
   const T *e = (const T *)J.e + 2 * p0 * J.nomega, *h = (const T *)J.h + 2 * p0 * J.nomega;
-  for (int w = threadIdx.x; w < J.nomega; w += kThreads) {
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  double *out = partial + (int64_t)blockIdx.x * nomega_stride;
+  for (int w0 = 0; w0 < J.nomega; w0 += 32) {
+    const int w = w0 + lane;
     double acc = 0;
-    for (int p = 0; p < np; ++p) {
-      const int64_t o = 2 * ((int64_t)p * J.nomega + w);
-      // Re(E conj(H)) = Er*Hr + Ei*Hi, formed in realnum then widened (src/dft.cpp:547-550)
-      acc += (double)(e[o] * h[o] + e[o + 1] * h[o + 1]);
+    if (w < J.nomega)
+      for (int p = warp; p < np; p += kThreads / 32) {
+        const int64_t o = 2 * ((int64_t)p * J.nomega + w);
+        // Re(E conj(H)) = Er*Hr + Ei*Hi, formed in realnum then widened (src/dft.cpp:547-550)
+        acc += (double)(e[o] * h[o] + e[o + 1] * h[o + 1]);
+      }
+    s_acc[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && w < J.nomega) {
+      double sum = s_acc[0][lane];
+#pragma unroll
+      for (int v = 1; v < kThreads / 32; ++v)
+        sum += s_acc[v][lane];
+      out[w] = sum;
     }
-    atomicAdd(J.out + w, acc);
+    __syncthreads();
   }
+}
+
+// out[w] += sum over tiles of partial[tile][w]; one warp per frequency
+__global__ void __launch_bounds__(kThreads)
+    flux_final_kernel(const double *__restrict__ partial, int64_t ntiles, int nomega, int nomega_stride,
+                      double *__restrict__ out) {
+  const int w = blockIdx.x * (kThreads / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (w >= nomega) return; // (whole warps leave together)
+  double acc = 0;
+  for (int64_t t = lane; t < ntiles; t += 32)
+    acc += partial[t * nomega_stride + w];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1)
+    acc += __shfl_down_sync(0xffffffffu, acc, d);
+  if (lane == 0) out[w] += acc;
 }
 
 // ---- finiteness probe --------------------------------------------------------------------------

@@ -40,43 +40,22 @@ connect_phase connect_phase_from_phase(std::complex<double> thephase) {
 
 } // namespace
 
-// Walks LOOP_OVER_VOL_OWNED(vi, c, n) in the reference's order but visits only the points for
-// which IVEC_LOOP_AT_BOUNDARY (src/meep/vec.hpp:336-339) holds.
-template <typename F>
-static void for_each_owned_boundary_point(const grid_volume &vi, component c, F visit) {
-  const ivec is = vi.little_owned_corner(c), ie = vi.big_corner();
-  const ptrdiff_t is1 = is.yucky_val(0), is2 = is.yucky_val(1), is3 = is.yucky_val(2);
-  const ptrdiff_t n1 = (ie.yucky_val(0) - is1) / 2 + 1, n2 = (ie.yucky_val(1) - is2) / 2 + 1,
-                  n3 = (ie.yucky_val(2) - is3) / 2 + 1;
-  const direction d1 = vi.yucky_direction(0), d2 = vi.yucky_direction(1), d3 = vi.yucky_direction(2);
-  const ptrdiff_t s1 = vi.stride(d1), s2 = vi.stride(d2), s3 = vi.stride(d3);
-  const ivec rel = is - vi.little_corner();
-  const ptrdiff_t idx0 = rel.yucky_val(0) / 2 * s1 + rel.yucky_val(1) / 2 * s2 + rel.yucky_val(2) / 2 * s3;
-  if (n1 <= 0 || n2 <= 0 || n3 <= 0) return;
-  for (ptrdiff_t i1 = 0; i1 < n1; i1++) {
-    const bool b1 = s1 != 0 && (i1 == 0 || i1 == n1 - 1);
-    for (ptrdiff_t i2 = 0; i2 < n2; i2++) {
-      const bool b2 = s2 != 0 && (i2 == 0 || i2 == n2 - 1);
-      auto emit = [&](ptrdiff_t i3) {
-        ivec here(vi.dim);
-        here.set_direction(d1, is1 + 2 * i1);
-        here.set_direction(d2, is2 + 2 * i2);
-        here.set_direction(d3, is3 + 2 * i3);
-        visit(idx0 + i1 * s1 + i2 * s2 + i3 * s3, here);
-      };
-      if (b1 || b2) {
-        for (ptrdiff_t i3 = 0; i3 < n3; i3++)
-          emit(i3);
-      }
-      else if (s3 != 0) {
-        emit(0);
-        if (n3 > 1) emit(n3 - 1);
-      }
-    }
-  }
-}
-
+// fields::find_metals (src/boundaries.cpp:315-345) lists, in LOOP_OVER_VOL_OWNED order, the owned
+// points for which on_metal_boundary() holds.  That predicate only compares one coordinate at a
+// time with at most three values per direction (src/boundaries.cpp:191-205), so the metal points
+// of a chunk are whole coordinate planes: flag the loop indices that sit on such a plane once per
+// direction, then walk rows — a row on a flagged plane is taken whole, any other row contributes
+// its (at most three) flagged points.  Same list, same order, no per-point work.
 void fields::find_metals() {
+  const double t_start = wall_time();
+  // metal coordinates per direction
+  std::vector<int> metal_coord[5];
+  LOOP_OVER_DIRECTIONS(gv.dim, d) {
+    if (user_volume.has_boundary(High, d) && boundaries[High][d] == Metallic)
+      metal_coord[d].push_back(user_volume.big_corner().in_direction(d));
+    if (boundaries[Low][d] == Magnetic) metal_coord[d].push_back(user_volume.little_corner().in_direction(d) + 1);
+    if (boundaries[Low][d] == Metallic) metal_coord[d].push_back(user_volume.little_corner().in_direction(d));
+  }
   for (int i = 0; i < num_chunks; i++)
     if (chunks[i]->is_mine()) {
       const grid_volume vi = chunks[i]->gv;
@@ -84,10 +63,41 @@ void fields::find_metals() {
         delete[] chunks[i]->zeroes[ft];
         std::vector<realnum *> found;
         DOCMP FOR_COMPONENTS(c) {
-          if (type(c) == ft && chunks[i]->f[c][cmp])
-            for_each_owned_boundary_point(vi, c, [&](ptrdiff_t n, const ivec &here) {
-              if (on_metal_boundary(here)) found.push_back(chunks[i]->f[c][cmp] + n);
-            });
+          if (type(c) != ft || !chunks[i]->f[c][cmp]) continue;
+          realnum *base = chunks[i]->f[c][cmp];
+          // geometry of LOOP_OVER_VOL_OWNED(vi, c, n)
+          const ivec is = vi.little_owned_corner(c), ie = vi.big_corner();
+          const ptrdiff_t is_[3] = {is.yucky_val(0), is.yucky_val(1), is.yucky_val(2)};
+          const ptrdiff_t nn[3] = {(ie.yucky_val(0) - is_[0]) / 2 + 1, (ie.yucky_val(1) - is_[1]) / 2 + 1,
+                                   (ie.yucky_val(2) - is_[2]) / 2 + 1};
+          if (nn[0] <= 0 || nn[1] <= 0 || nn[2] <= 0) continue;
+          const direction dd[3] = {vi.yucky_direction(0), vi.yucky_direction(1), vi.yucky_direction(2)};
+          const ptrdiff_t ss[3] = {vi.stride(dd[0]), vi.stride(dd[1]), vi.stride(dd[2])};
+          const ivec rel = is - vi.little_corner();
+          const ptrdiff_t idx0 =
+              rel.yucky_val(0) / 2 * ss[0] + rel.yucky_val(1) / 2 * ss[1] + rel.yucky_val(2) / 2 * ss[2];
+          std::vector<char> flag[3];
+          std::vector<ptrdiff_t> flagged3;
+          for (int k = 0; k < 3; ++k) {
+            flag[k].assign((size_t)nn[k], 0);
+            if (!has_direction(gv.dim, dd[k])) continue; // (a loop of one iteration over a direction the grid lacks)
+            for (int mc : metal_coord[dd[k]]) {
+              const ptrdiff_t off = mc - is_[k];
+              if (off >= 0 && off % 2 == 0 && off / 2 < nn[k]) flag[k][(size_t)(off / 2)] = 1;
+            }
+          }
+          for (ptrdiff_t i3 = 0; i3 < nn[2]; ++i3)
+            if (flag[2][(size_t)i3]) flagged3.push_back(i3);
+          for (ptrdiff_t i1 = 0; i1 < nn[0]; ++i1)
+            for (ptrdiff_t i2 = 0; i2 < nn[1]; ++i2) {
+              realnum *row = base + idx0 + i1 * ss[0] + i2 * ss[1];
+              if (flag[0][(size_t)i1] || flag[1][(size_t)i2])
+                for (ptrdiff_t i3 = 0; i3 < nn[2]; ++i3)
+                  found.push_back(row + i3 * ss[2]);
+              else
+                for (ptrdiff_t i3 : flagged3)
+                  found.push_back(row + i3 * ss[2]);
+            }
         }
         typedef realnum *realnum_ptr;
         chunks[i]->num_zeroes[ft] = found.size();
@@ -95,6 +105,8 @@ void fields::find_metals() {
         std::copy(found.begin(), found.end(), chunks[i]->zeroes[ft]);
       }
     }
+  if (getenv("MEEP_B200_VERBOSE") && atoi(getenv("MEEP_B200_VERBOSE")))
+    master_printf("meep_b200: find_metals: %.3f s\n", wall_time() - t_start);
 }
 
 void fields::connect_the_chunks() {

@@ -76,7 +76,7 @@ void Engine::for_each(const std::function<void(Engine &)> &fn) {
     fn(*kv.second);
 }
 
-Engine::Engine(fields *) {
+Engine::Engine(fields *f) : self(f) {
   if (mb200_abi_version() != MB200_ABI_VERSION)
     meep::abort("meep_b200: libmeepb200 ABI version mismatch");
   if (mb200_device_count() < 1)
@@ -96,6 +96,7 @@ Engine::Engine(fields *) {
   verbose = env_int("MEEP_B200_VERBOSE", 0) != 0;
   device_timers = env_int("MEEP_B200_TIMERS", 0) != 0;
   merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
+  defer_local = env_int("MEEP_B200_DEFER_LOCAL", 1) != 0;
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   p2p = env_int("MEEP_B200_P2P", 1) != 0;
   halo_runs = env_int("MEEP_B200_HALO_RUNS", 1) != 0;
@@ -644,8 +645,28 @@ void Engine::upload_materials() {
   materials_dirty = false;
 }
 
+// The same-device D/B halo copies that fields::step_boundaries postponed: made now, from the
+// current owner values, through the ordinary exchange code restricted to same-process pairs (no
+// other process is needed, so any single rank may do this at any time).
+void Engine::refresh_deferred_halos() {
+  if (refresh_local || (!halos_stale[D_stuff] && !halos_stale[B_stuff])) return;
+  const bool was_in_step = in_step;
+  refresh_local = true;
+  in_step = false;
+  keep_on_device++;
+  for (field_type ft : {B_stuff, D_stuff})
+    if (halos_stale[ft]) {
+      halos_stale[ft] = false;
+      self->step_boundaries(ft);
+    }
+  keep_on_device--;
+  in_step = was_in_step;
+  refresh_local = false;
+}
+
 void Engine::sync_host() {
   if (state == DEVICE_NEWER) {
+    refresh_deferred_halos();
     download_fields();
     state = COHERENT;
     // whoever reads the arrays on the host now must not be handed NaNs (or stale halos after a
@@ -663,6 +684,9 @@ void Engine::sync_host() {
 void Engine::enter(fields *f) {
   if (depth++ > 0) return;
   current_ = this;
+  // a stand-alone entry point (reference/user code running a piece of the schedule by itself) may
+  // read or propagate not-owned D/B values: bring them up to date first
+  if (!in_step && state == DEVICE_NEWER) refresh_deferred_halos();
   const uint64_t fp = fingerprint(f);
   const double t0 = verbose ? meep::wall_time() : 0;
   if (fp != last_fingerprint || arrs_.empty()) {
@@ -696,6 +720,7 @@ void Engine::enter(fields *f) {
 
 void Engine::leave(fields *f, bool modified) {
   if (--depth > 0) return;
+  const double t_leave = verbose ? meep::wall_time() : 0;
   if (modified) state = DEVICE_NEWER;
   if (in_step && !cw_mode && !eager) release_host_fields();
   // lazily allocated arrays changed the pointer set: remember the new fingerprint so the next
@@ -712,6 +737,8 @@ void Engine::leave(fields *f, bool modified) {
     sync_host();
     state = HOST_NEWER;
   }
+  if (verbose && meep::wall_time() - t_leave > 0.05)
+    fprintf(stderr, "meep_b200: leaving an entry point took %.3f s on the host\n", meep::wall_time() - t_leave);
 }
 
 // ---- finiteness probe (stands in for the host read of src/step.cpp:137-138) ----------------------
@@ -796,6 +823,8 @@ static bool fuse_group(const Recorder &R, const Recorder::Group &g,
   out.dt = R.curl[g.first].dt;
   out.ix_lo = 0;
   out.ix_hi = out.n[0];
+  out.noepi_lo = 0;
+  out.noepi_n = 0;
   for (int c = 0; c < 3; ++c) {
     const mb200_curl_job_t &J = R.curl[g.first + c];
     if (!J.g1 || !J.g2) return false;
@@ -844,26 +873,11 @@ static bool fuse_group(const Recorder &R, const Recorder::Group &g,
       fused.c[c].metal_hi[d] = g.epi[c].metal_hi[d];
     }
   }
-  if (g.slab_lo > g.slab_hi) { // no source planes: the whole chunk is fused
-    out_jobs.push_back(fused);
-    return true;
-  }
-  if (g.slab_lo > 0) {
-    mb200_step3_job_t j = fused;
-    j.ix_hi = g.slab_lo - 1;
-    out_jobs.push_back(j);
-  }
-  {
-    mb200_step3_job_t j = out; // source planes: D only; E follows in update_eh after step_source
-    j.ix_lo = g.slab_lo;
-    j.ix_hi = g.slab_hi;
-    out_jobs.push_back(j);
-  }
-  if (g.slab_hi < out.n[0]) {
-    mb200_step3_job_t j = fused;
-    j.ix_lo = g.slab_hi + 1;
-    out_jobs.push_back(j);
-  }
+  // planes that hold source points are updated without the epilogue (step_source runs between the
+  // D and the E update there: src/step.cpp:98-109; update_eh covers them afterwards): same job
+  fused.noepi_lo = g.slab_lo;
+  fused.noepi_n = g.slab_hi - g.slab_lo + 1;
+  out_jobs.push_back(fused);
   return true;
 }
 
@@ -932,18 +946,25 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
     case PH_BND:
       push(ph, MB200_K_ZERO, make_plan(*this, MB200_K_ZERO, R.zero.data(), R.zero.size()));
       if (!R.links.empty()) { // peer-memory mode: the pack jobs store straight into the neighbours' HBM
+        // What the neighbours wait for goes first: pack (a few MB over NVLink), signal, and only
+        // then the same-device copies — the neighbours' blocks arrive while those run, so the wait
+        // before the unpack has the NVLink latency and most of the skew between GPUs behind it.
         ph.links = R.links;
-        Launch pre, mid, post;
+        Launch pre, sig, wait, post;
         pre.kind = KIND_P2P_PRE;
-        mid.kind = KIND_P2P_MID;
+        sig.kind = KIND_P2P_SIGNAL;
+        wait.kind = KIND_P2P_WAIT;
         post.kind = KIND_P2P_POST;
         ph.launches.push_back(pre);
+        push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.pack.data(), R.pack.size()));
+        ph.launches.push_back(sig);
         push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.halo.data(), R.halo.size()));
-        ph.launches.push_back(mid);
+        ph.launches.push_back(wait);
         push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.unpack.data(), R.unpack.size()));
         ph.launches.push_back(post);
         break;
       }
+      push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.pack.data(), R.pack.size()));
       push(ph, MB200_K_HALO, make_plan(*this, MB200_K_HALO, R.halo.data(), R.halo.size()));
       if (!R.sends.empty() || !R.recvs.empty()) {
         Launch l;
@@ -1005,7 +1026,8 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
     fprintf(stderr, "meep_b200: recorded %s:", names[id]);
     for (const Launch &l : ph.launches)
       if (l.kind >= KIND_P2P_PRE)
-        fprintf(stderr, " [p2p sync %d]", l.kind - KIND_P2P_PRE);
+        fprintf(stderr, " [p2p %s]", l.kind == KIND_P2P_PRE ? "wait consumed" : l.kind == KIND_P2P_SIGNAL ? "signal packed"
+                                     : l.kind == KIND_P2P_WAIT ? "wait packed" : "signal consumed");
       else if (l.kind == KIND_EXCHANGE)
         fprintf(stderr, " [exchange: %zu sends, %zu recvs]", l.sends.size(), l.recvs.size());
       else
@@ -1034,30 +1056,46 @@ void Engine::end_record(Phase &ph, PhaseId id, fields *f) {
 
 void Engine::run(Phase &ph, fields *f) {
   for (Launch &l : ph.launches) {
-    if (l.kind == KIND_P2P_PRE) {
-      // what I stored into the neighbour's arena last time must have been consumed
+    if (l.kind == KIND_P2P_PRE || l.kind == KIND_P2P_SIGNAL || l.kind == KIND_P2P_WAIT || l.kind == KIND_P2P_POST) {
+      // all sequence words of this phase in one launch (a 2x2x2 leaf has up to 7 neighbours)
+      std::vector<uint64_t *> flags;
+      std::vector<uint64_t> values;
       for (int k : ph.links) {
         P2PLink &p = links[k];
-        p.seq += 1;
-        if (p.send_count)
-          check(mb200_flag_wait(ctx, (const uint64_t *)((char *)p.mine + 8), p.seq - 1), "flag_wait");
+        if (l.kind == KIND_P2P_PRE) {
+          // what I stored into the neighbour's arena last time must have been consumed
+          p.seq += 1;
+          if (p.send_count) {
+            flags.push_back((uint64_t *)((char *)p.mine + 8));
+            values.push_back(p.seq - 1);
+          }
+        }
+        else if (l.kind == KIND_P2P_SIGNAL) {
+          if (p.send_count) {
+            flags.push_back((uint64_t *)p.theirs);
+            values.push_back(p.seq);
+          }
+        }
+        else if (l.kind == KIND_P2P_WAIT) {
+          if (p.recv_count) {
+            flags.push_back((uint64_t *)p.mine);
+            values.push_back(p.seq);
+          }
+        }
+        else if (p.recv_count) {
+          flags.push_back((uint64_t *)((char *)p.theirs + 8));
+          values.push_back(p.seq);
+        }
       }
-      continue;
-    }
-    if (l.kind == KIND_P2P_MID) {
-      for (int k : ph.links)
-        if (links[k].send_count)
-          check(mb200_flag_signal(ctx, (uint64_t *)links[k].theirs, links[k].seq), "flag_signal");
-      for (int k : ph.links)
-        if (links[k].recv_count)
-          check(mb200_flag_wait(ctx, (const uint64_t *)links[k].mine, links[k].seq), "flag_wait");
-      continue;
-    }
-    if (l.kind == KIND_P2P_POST) {
-      for (int k : ph.links)
-        if (links[k].recv_count)
-          check(mb200_flag_signal(ctx, (uint64_t *)((char *)links[k].theirs + 8), links[k].seq),
-                "flag_signal");
+      const bool waiting = l.kind == KIND_P2P_PRE || l.kind == KIND_P2P_WAIT;
+      for (size_t k0 = 0; k0 < flags.size(); k0 += MB200_MAX_FLAGS) {
+        const int n = (int)std::min<size_t>(MB200_MAX_FLAGS, flags.size() - k0);
+        if (waiting)
+          check(mb200_flag_wait_many(ctx, (const uint64_t *const *)(flags.data() + k0), values.data() + k0, n),
+                "flag_wait");
+        else
+          check(mb200_flag_signal_many(ctx, flags.data() + k0, values.data() + k0, n), "flag_signal");
+      }
       continue;
     }
     if (l.kind == KIND_EXCHANGE) {

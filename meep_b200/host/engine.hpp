@@ -64,7 +64,7 @@ struct Launch {
   // EXCHANGE (kind == KIND_EXCHANGE): comm blocks sent to / received from other processes
   std::vector<mb200_xfer_t> sends, recvs;
 };
-enum { KIND_EXCHANGE = 100, KIND_P2P_PRE = 101, KIND_P2P_MID = 102, KIND_P2P_POST = 103 };
+enum { KIND_EXCHANGE = 100, KIND_P2P_PRE = 101, KIND_P2P_SIGNAL = 102, KIND_P2P_POST = 103, KIND_P2P_WAIT = 104 };
 
 // Peer-memory exchange: one link per (field type, neighbour process).  `mine` lives in MY HBM and
 // is written by the neighbour's pack kernel over NVLink; `theirs` is the neighbour's arena for me
@@ -108,7 +108,8 @@ struct Recorder {
   std::vector<const meep::src_time *> src_times;
   std::vector<mb200_src_job_t> dip;       // mode 1 (integrated dipoles)
   std::vector<const meep::src_time *> dip_times;
-  std::vector<mb200_halo_job_t> halo;   // same-process pairs + packing of outgoing comm blocks
+  std::vector<mb200_halo_job_t> halo;   // same-process pairs
+  std::vector<mb200_halo_job_t> pack;   // packing of outgoing comm blocks (into the neighbour's HBM / a send buffer)
   std::vector<mb200_halo_job_t> unpack; // scatter of received comm blocks
   std::vector<mb200_xfer_t> sends, recvs;
   std::vector<int> links;
@@ -166,6 +167,13 @@ public:
   bool defer_ok[meep::NUM_FIELD_TYPES] = {}; // global decision: D/B connections may be merged
   bool deferred_exchange[meep::NUM_FIELD_TYPES] = {}; // D/B connections ride with the E/H ones
   bool connections_valid = false; // fields::chunk_connections_valid at the last step_db
+  // same-device D/B halo copies postponed until somebody can look (see fields::step_boundaries)
+  bool defer_local = true;        // MEEP_B200_DEFER_LOCAL=0: carry them out every step
+  bool local_deferred[meep::NUM_FIELD_TYPES] = {}; // the cached E/H exchange plan leaves them out
+  bool halos_stale[meep::NUM_FIELD_TYPES] = {};    // steps were taken since the last refresh
+  bool refresh_local = false;     // inside refresh_deferred_halos
+  meep::fields *self = nullptr;
+  void refresh_deferred_halos();
 
   // Brackets every interposed entry point.  On the outermost entry it validates the mirror
   // (array set, materials) and uploads field arrays if the host copy is (or may be) newer.

@@ -103,6 +103,14 @@ void fields::step() {
     auto mark = [&](time_sink s) {
       if (dev_timers) check(mb200_mark(E.ctx, (int)s), "mb200_mark");
     };
+    double t_trace = wall_time();
+    auto trace = [&](const char *what) { // MEEP_B200_VERBOSE=1: where the host time of a (first) step goes
+      if (!E.verbose) return;
+      const double now = wall_time();
+      if (now - t_trace > 0.05) fprintf(stderr, "meep_b200: step %d: %s took %.3f s on the host\n", t, what, now - t_trace);
+      t_trace = now;
+    };
+    trace("phase_material / condinv");
     time_sink_to_duration_map discard; // host launch time of a phase is not phase time
     auto phase_clock = [&](time_sink s) {
       if (dev_timers) return timing_scope(&discard, s);
@@ -117,6 +125,7 @@ void fields::step() {
         auto timer = phase_clock(H.t_update_db);
         step_db(H.db);
       }
+      trace("step_db");
       mark(Stepping);
       step_source(H.db);
       mark(H.t_bnd_db);
@@ -124,12 +133,14 @@ void fields::step() {
         auto timer = phase_clock(H.t_bnd_db);
         step_boundaries(H.db);
       }
+      trace("step_boundaries(D/B)");
       calc_sources(t_half + 0.5 * dt); // integrated sources enter the E/H update
       mark(H.t_update_eh);
       {
         auto timer = phase_clock(H.t_update_eh);
         update_eh(H.eh);
       }
+      trace("update_eh");
       mark(H.t_bnd_w);
       {
         auto timer = phase_clock(H.t_bnd_w);
@@ -147,6 +158,7 @@ void fields::step() {
         auto timer = phase_clock(H.t_bnd_eh);
         step_boundaries(H.eh);
       }
+      trace("step_boundaries(W, P, E/H) + update_pols");
       mark(Stepping);
       if (fluxes) { // legacy flux planes integrate the host arrays
         E.download_fields();
@@ -260,6 +272,7 @@ void fields::step_boundaries(field_type ft) {
   // the re-connection itself (connect_the_chunks in connect.cpp bumps connect_epoch).
   // Comparing against the epoch of the last invalidation also covers a re-connection made
   // outside this function (user code calling connect_chunks()).
+  const bool refresh = E.refresh_local; // Engine::refresh_deferred_halos: same-process pairs only
   connect_chunks();
   const bool was_valid = E.connect_epoch == E.plans_epoch;
   if (!was_valid) {
@@ -293,7 +306,7 @@ void fields::step_boundaries(field_type ft) {
   // (B) connections are carried out together with the E (H) ones: half as many launches and —
   // across GPUs — half as many (latency-bound) transfers per time step, same final arrays.
   const field_type partner = ft == D_stuff ? E_stuff : (ft == B_stuff ? H_stuff : ft);
-  if (!was_valid || changed_materials || !E.defer_known) {
+  if (!refresh && (!was_valid || changed_materials || !E.defer_known)) {
     // (re)decide, together with all other processes — these three conditions are the same on
     // every rank, as the reference itself requires for sync_chunk_connections()
     for (field_type fdb : {D_stuff, B_stuff}) {
@@ -319,6 +332,24 @@ void fields::step_boundaries(field_type ft) {
   const bool take_partner = E.in_step && (ft == E_stuff || ft == H_stuff) &&
                             E.deferred_exchange[ft == E_stuff ? D_stuff : B_stuff];
 
+  // Deferred local copies.  The D (B) connections that ride with the E (H) exchange only keep the
+  // not-owned D (B) values identical to the reference's arrays — nothing on the device reads them
+  // (that is what defer_ok established) unless a DFT monitor accumulates a D or B component.  For
+  // pairs of chunks on the SAME device they are therefore not carried out every step at all: the
+  // copies are made once, from the then-current owner values, before anybody can look — before a
+  // download and before any stand-alone entry point (Engine::refresh_deferred_halos).  At 512^3
+  // that is 41 % of all halo transfers.  Pairs that cross devices keep riding with E (H): a
+  // refresh must not need the other process.
+  const field_type ftdb = ft == E_stuff ? D_stuff : B_stuff;
+  bool defer_local = false;
+  if (take_partner && E.defer_local) {
+    defer_local = true;
+    for (int i = 0; i < num_chunks && defer_local; i++)
+      if (chunks[i]->is_mine())
+        for (dft_chunk *d = chunks[i]->dft_chunks; d; d = d->next_in_chunk)
+          if (is_D(d->c) || is_B(d->c)) defer_local = false;
+  }
+
   am_now_working_on(Boundaries);
   run_phase(E, this, PH_BND, ft, E.in_step, [&]() {
     Recorder &R = E.rec();
@@ -327,8 +358,9 @@ void fields::step_boundaries(field_type ft) {
       E.deferred_exchange[ft] = defer;
       E.free_phase(E.phase(PH_BND, partner));
     }
+    if (take_partner) E.local_deferred[ftdb] = defer_local;
     for (int i = 0; i < num_chunks; i++) {
-      if (!chunks[i]->is_mine()) continue;
+      if (!chunks[i]->is_mine() || refresh) continue; // (a refresh only copies)
       // Do the metals first!  (fields_chunk::zero_metal, src/boundaries.cpp:310-313)
       const size_t nz = chunks[i]->num_zeroes[ft];
       if (nz) {
@@ -356,14 +388,18 @@ void fields::step_boundaries(field_type ft) {
     std::vector<field_type> fts;
     if (take_partner) fts.push_back(ft == E_stuff ? D_stuff : B_stuff);
     if (!(E.in_step && partner != ft && defer)) fts.push_back(ft);
-    for (field_type ft : fts)
+    for (field_type ftl : fts)
     for (int j = 0; j < num_chunks; j++)
       for (int i = 0; i < num_chunks; i++) {
+        const field_type ft_outer = ft;
+        const field_type ft = ftl; // (the body below is written for "the field type being connected")
         const chunk_pair pair{j, i};
         const size_t tot = comm_size_tot(ft, pair);
         if (!tot) continue;
         const bool j_mine = chunks[j]->is_mine(), i_mine = chunks[i]->is_mine();
         if (!j_mine && !i_mine) continue;
+        if (refresh && !(j_mine && i_mine)) continue;
+        if (defer_local && ft != ft_outer && j_mine && i_mine) continue; // copied by the next refresh instead
         uint64_t block = 0; // device comm block for a cross-process pair
         if (j_mine != i_mine && use_links) {
           // the block is a slice of the arena in the RECEIVER's memory: packed straight into the
@@ -483,11 +519,12 @@ void fields::step_boundaries(field_type ft) {
               hj.dst_flag = (const uint64_t *)E.aux_upload(fl.data(), fl.size() * 8);
             }
           }
-          ((j_mine || i_mine) && j_mine == i_mine ? R.halo : (j_mine ? R.halo : R.unpack)).push_back(hj);
+          (j_mine == i_mine ? R.halo : (j_mine ? R.pack : R.unpack)).push_back(hj);
           off += n;
         }
       }
   });
+  if (E.in_step && take_partner && E.local_deferred[ftdb]) E.halos_stale[ftdb] = true;
   finished_working();
 }
 

@@ -464,6 +464,18 @@ int mb200_ipc_close(mb200_ctx *, void *imported) {
   g_imports.erase(it);
   return 0;
 }
+int mb200_flag_signal(mb200_ctx *, uint64_t *flag, uint64_t value);
+int mb200_flag_wait(mb200_ctx *, const uint64_t *flag, uint64_t value);
+int mb200_flag_signal_many(mb200_ctx *c, uint64_t *const *flags, const uint64_t *values, int n) {
+  for (int k = 0; k < n; ++k)
+    if (mb200_flag_signal(c, flags[k], values[k])) return 1;
+  return 0;
+}
+int mb200_flag_wait_many(mb200_ctx *c, const uint64_t *const *flags, const uint64_t *values, int n) {
+  for (int k = 0; k < n; ++k)
+    if (mb200_flag_wait(c, flags[k], values[k])) return 1;
+  return 0;
+}
 int mb200_flag_signal(mb200_ctx *, uint64_t *flag, uint64_t value) {
   __atomic_store_n(flag, value, __ATOMIC_RELEASE);
   return 0;

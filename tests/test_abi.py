@@ -51,7 +51,7 @@ def test_struct_layouts_match_the_header():
 
 
 def test_abi_version():
-    assert capi.load().mb200_abi_version() == 1
+    assert capi.load().mb200_abi_version() == 2
 
 
 @pytest.mark.skipif(have_gpu(), reason="this check is for machines without a GPU")

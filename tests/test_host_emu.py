@@ -177,7 +177,7 @@ def test_ld_preload_over_a_program_linked_against_the_reference_only(tmp_path):
     preloaded, and produces the reference's arrays"""
     from parity_util import TBUILD, driver, read_dump
     exe = driver("sim_driver", "ref", "f64")
-    pre = ":".join([os.path.join(TBUILD, "libmeep_b200_emu_f64.so"), os.path.join(TBUILD, "libmeepb200_emu.so")])
+    pre = ":".join([os.path.join(TBUILD, "libmeep_b200_preload_emu_f64.so"), os.path.join(TBUILD, "libmeepb200_emu.so")])
     out = str(tmp_path / "pre.bin")
     env = dict(os.environ, LD_PRELOAD=pre, MEEP_B200_VERBOSE="1", OMP_NUM_THREADS="2")
     r = subprocess.run([exe, "3d_metal", "12", out, "2"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,

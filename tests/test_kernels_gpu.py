@@ -336,6 +336,30 @@ def test_halo_zero_source_fmp_flux(prec):
 
     assert rel_err(flux(DevMem(prec)), flux(HostMem(prec))) <= (1e-12 if prec == "f64" else 1e-5)
 
+    # the device sum is a fixed two-stage tree (no atomics): bit-identical from run to run, also for
+    # several jobs (dft_chunk pairs) accumulating into one spectrum and for more frequencies than a warp
+    npt2, nom2 = 5000, 100
+    e2 = rng.uniform(-1, 1, 2 * npt2 * nom2).astype(T)
+    h2 = rng.uniform(-1, 1, 2 * npt2 * nom2).astype(T)
+
+    def flux2(mem):
+        out0 = np.zeros(nom2)
+        po = mem.put(out0)
+        jobs = []
+        for lo, hi in ((0, 1234), (1234, 5000)):
+            j = capi.FluxJob()
+            j.e, j.h = mem.put(e2[2 * lo * nom2:2 * hi * nom2]), mem.put(h2[2 * lo * nom2:2 * hi * nom2])
+            j.npts, j.nomega, j.out = hi - lo, nom2, po
+            jobs.append(j)
+        mem.run(capi.K_FLUX, jobs)
+        out = mem.get(po, out0)
+        mem.close()
+        return out
+
+    a, b = flux2(DevMem(prec)), flux2(DevMem(prec))
+    assert np.array_equal(a, b)
+    assert rel_err(a, flux2(HostMem(prec))) <= (1e-12 if prec == "f64" else 1e-5)
+
 
 def test_size_independent_properties_at_scale():
     """at a size the oracle would take long for: linearity of the curl update and exactness of

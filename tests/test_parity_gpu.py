@@ -125,7 +125,7 @@ def test_ld_preload_over_a_program_linked_against_the_reference_only(tmp_path):
     lib = os.path.join(ROOT, "meep_b200", "lib")
     exe = driver("sim_driver", "ref", "f64")
     out = str(tmp_path / "pre.bin")
-    env = dict(os.environ, LD_PRELOAD=":".join([os.path.join(lib, "libmeep_b200_f64.so"),
+    env = dict(os.environ, LD_PRELOAD=":".join([os.path.join(lib, "libmeep_b200_preload_f64.so"),
                                                 os.path.join(lib, "libmeepb200.so")]),
                MEEP_B200_VERBOSE="1", OMP_NUM_THREADS="2")
     r = subprocess.run([exe, "c2_3d_pml", "40", out, "0"], env=env, stdout=subprocess.PIPE,
