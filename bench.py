@@ -119,8 +119,10 @@ def workload_text(workload, nx, ny, nz, world):
     """config.workload: the same text for the device arm and the reference arm"""
     return {
         "c2": "c2: 3D dielectric box %dx%dx%d, PML(1.0) on all faces, non-dispersive, Gaussian Ez dipole, "
-              "res 10, Courant 0.5, real fields (BASELINE.json configs[1]%s)"
-              % (nx, ny, nz, "" if world == 1 else "; configs[4] scaling form"),
+              "res 10, Courant 0.5, real fields (BASELINE.json %s)"
+              % (nx, ny, nz, "configs[1]" if (nx, ny, nz) == (512, 512, 512) and world == 1 else
+                 ("configs[4]: 1024^3 strong-scaling series" if (nx, ny, nz) == (1024, 1024, 1024) else
+                  "configs[1] geometry; configs[4] scaling form")),
         "c3": "c3: Drude + 5 Lorentz Au sphere %dx%dx%d, PML(1.0), 100-frequency DFT flux box "
               "(BASELINE.json configs[2], scaled to fit one GPU in double)" % (nx, ny, nz),
         "c4": "c4: anisotropic subpixel-smoothed Si ring %dx%dx%d, off-diagonal chi1inv, PML(1.0) "
@@ -186,13 +188,17 @@ def main():
                     help="N>1: independent replicas instead of one sharded problem")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.auto_n = args.n <= 0
     if args.n <= 0:
         if args.workload != "c2":
             args.n = {"c3": 320, "c4": 512}[args.workload]
         elif max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) > 1 and not args.replicas:
             args.n = 1024 if args.scaling == "strong" else 512
         else:
-            args.n = int(os.environ.get("MEEP_B200_BENCH_N1", "512"))
+            # one GPU: the same 1024^3 cell as the multi-GPU lines (the north-star case; it fits one B200:
+            # 102 GB of HBM), so that the 1/2/4/8-GPU lines form ONE strong-scaling series; configs[1]
+            # (512^3) is measured in the same run and reported under "configs1_512"
+            args.n = int(os.environ.get("MEEP_B200_BENCH_N1", "1024"))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -232,8 +238,11 @@ def main():
     os.environ["MEEP_B200_DEVICE"] = str(local_rank)
     # host-side set-up (material fill, connection tables) uses the host cores this rank may claim;
     # the reference's initialize() falls back to ONE OpenMP thread when the variable is unset
+    # (torchrun exports OMP_NUM_THREADS=1 to every rank unless the user set it: MEEP_B200_HOST_THREADS
+    # is the explicit override here)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(local_world, 1))))
+    os.environ["OMP_NUM_THREADS"] = os.environ.get(
+        "MEEP_B200_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(local_world, 1))))
     if args.replicas:
         os.environ["MEEP_B200_WORLD_SIZE"] = "1"  # the C++ runtime sees a single process
         os.environ["MEEP_B200_RANK"] = "0"
@@ -261,195 +270,227 @@ def main():
     host.meep_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     host.meep_b200_sync_host.argtypes = [C.c_void_p]
 
-    t0 = time.time()
-    nx = args.n * world if (sharded and args.scaling == "weak") else args.n
-    nz = args.n // 4 if args.workload == "c4" else args.n
-    h = drv.mb200_bench_create3d(args.workload.encode(), nx, args.n, nz, 0)
-    if not h:
-        raise RuntimeError("bench driver failed to build the workload")
-    t_setup = time.time() - t0
-    cells = drv.mb200_bench_cells(h)  # the whole (possibly sharded) cell
-    fptr = drv.mb200_bench_fields(h)
-    ranks_per_problem = world if sharded else 1
+    live = []  # simulations not yet destroyed (a failed measurement must not keep 100 GB of HBM)
 
-    def stats():
-        a = (C.c_double * 8)()
-        host.meep_b200_get_stats(fptr, a)
-        return list(a)
+    def measure(n, light=False):
+        """one complete measurement of workload size n (light: skip the cold-start context run)"""
+        t0 = time.time()
+        nx = n * world if (sharded and args.scaling == "weak") else n
+        nz = n // 4 if args.workload == "c4" else n
+        h = drv.mb200_bench_create3d(args.workload.encode(), nx, n, nz, 0)
+        if not h:
+            raise RuntimeError("bench driver failed to build the workload")
+        live.append(h)
+        t_setup = time.time() - t0
+        cells = drv.mb200_bench_cells(h)  # the whole (possibly sharded) cell
+        fptr = drv.mb200_bench_fields(h)
+        ranks_per_problem = world if sharded else 1
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+        def stats():
+            a = (C.c_double * 8)()
+            host.meep_b200_get_stats(fptr, a)
+            return list(a)
 
-    def max_over_ranks(x):
-        return dist_max(x, world, "cuda")
+        def barrier():
+            if world > 1:
+                dist.barrier()
 
-    # warm-up: first step uploads all arrays, allocates PML aux fields, builds connection
-    # tables (reference host code) and all launch plans
-    t0 = time.time()
-    if drv.mb200_bench_step(h, args.warmup):
-        raise RuntimeError("warm-up failed")
-    ctx = host.meep_b200_ctx(fptr)
-    lib.mb200_sync(ctx)
-    t_warm = time.time() - t0
+        def max_over_ranks(x):
+            return dist_max(x, world, "cuda")
 
-    # ---- timed region 1: device-resident throughput (CUDA events on the engine's stream) --------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    s0 = stats()
-    barrier()
-    lib.mb200_sync(ctx)
-    lib.mb200_timer_start(ctx)
-    if drv.mb200_bench_step(h, args.steps):
-        raise RuntimeError("timed steps failed")
-    ms = C.c_double()
-    lib.mb200_timer_stop(ctx, C.byref(ms))  # synchronises
-    barrier()
-    s1 = stats()
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-    dev_ms = max_over_ranks(ms.value)
-    launches = int(s1[3] - s0[3])
+        # warm-up: first step uploads all arrays, allocates PML aux fields, builds connection
+        # tables (reference host code) and all launch plans
+        t0 = time.time()
+        if drv.mb200_bench_step(h, args.warmup):
+            raise RuntimeError("warm-up failed")
+        ctx = host.meep_b200_ctx(fptr)
+        lib.mb200_sync(ctx)
+        t_warm = time.time() - t0
 
-    # ---- timed region 2: end to end through the public API, host-visible result every step -------
-    barrier()
-    lib.mb200_sync(ctx)
-    e0 = stats()
-    t0 = time.perf_counter()
-    acc = 0.0
-    for _ in range(args.steps):
-        drv.mb200_bench_step(h, 1)
-        acc += drv.mb200_bench_probe(h)  # fields::get_field -> D2H of the probed values
-    lib.mb200_sync(ctx)
-    e2e_s = time.perf_counter() - t0
-    barrier()
-    e1 = stats()
-    e2e_s = max_over_ranks(e2e_s)
-    if acc != acc:
-        raise RuntimeError("NaN in the probed field")
-    # copies are made by the rank that owns the source / the probed point: report the busiest rank
-    e2e_h2d = max_over_ranks((e1[1] - e0[1]) / args.steps)
-    e2e_d2h = max_over_ranks((e1[2] - e0[2]) / args.steps)
-    # value check across GPU counts: the same points of the same cell after the same number of steps
-    nprobe = 8
-    pv = (C.c_double * nprobe)()
-    drv.mb200_bench_probes.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
-    drv.mb200_bench_probes(h, pv, nprobe)
-    drv.mb200_bench_time_step.argtypes = [C.c_void_p]
-    probe = {"after_steps": int(drv.mb200_bench_time_step(h)), "component": "Ez",
-             "points": "cell centre + (0.35,0.25,0.15) + k*(L/16)*(1,-1,1), k=0..7 (alternating sign), via fields::get_field",
-             "values": [float(x) for x in pv]}
+        # ---- timed region 1: device-resident throughput (CUDA events on the engine's stream) --------
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        s0 = stats()
+        barrier()
+        lib.mb200_sync(ctx)
+        lib.mb200_timer_start(ctx)
+        if drv.mb200_bench_step(h, args.steps):
+            raise RuntimeError("timed steps failed")
+        ms = C.c_double()
+        lib.mb200_timer_stop(ctx, C.byref(ms))  # synchronises
+        barrier()
+        s1 = stats()
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+        dev_ms = max_over_ranks(ms.value)
+        launches = int(s1[3] - s0[3])
 
-    # ---- timed region 3 (context for e2e): a COLD run of K steps — every field array starts on the
-    # host (upload inside the timed region) and ends on the host (download inside it)
-    cold = None
-    if world == 1 and drv.mb200_bench_field_bytes(h) < 20e9:
-        host.meep_b200_mark_host_dirty.argtypes = [C.c_void_p]
-        host.meep_b200_mark_host_dirty(fptr)  # arrays are downloaded; the next step re-uploads them
-        c0 = stats()
+        # ---- timed region 2: end to end through the public API, host-visible result every step -------
+        barrier()
+        lib.mb200_sync(ctx)
+        e0 = stats()
         t0 = time.perf_counter()
-        drv.mb200_bench_step(h, args.steps)
-        host.meep_b200_sync_host(fptr)
-        cold_s = time.perf_counter() - t0
-        c1 = stats()
-        cold = {"value": cells * args.steps / cold_s, "unit": "cell-updates/s", "seconds": cold_s,
-                "h2d_bytes": c1[1] - c0[1], "d2h_bytes": c1[2] - c0[2],
-                "what": "K steps starting and ending with all field arrays in (pageable) host memory"}
+        acc = 0.0
+        for _ in range(args.steps):
+            drv.mb200_bench_step(h, 1)
+            acc += drv.mb200_bench_probe(h)  # fields::get_field -> D2H of the probed values
+        lib.mb200_sync(ctx)
+        e2e_s = time.perf_counter() - t0
+        barrier()
+        e1 = stats()
+        e2e_s = max_over_ranks(e2e_s)
+        if acc != acc:
+            raise RuntimeError("NaN in the probed field")
+        # copies are made by the rank that owns the source / the probed point: report the busiest rank
+        e2e_h2d = max_over_ranks((e1[1] - e0[1]) / args.steps)
+        e2e_d2h = max_over_ranks((e1[2] - e0[2]) / args.steps)
+        # value check across GPU counts: the same points of the same cell after the same number of steps
+        nprobe = 8
+        pv = (C.c_double * nprobe)()
+        drv.mb200_bench_probes.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        drv.mb200_bench_probes(h, pv, nprobe)
+        drv.mb200_bench_time_step.argtypes = [C.c_void_p]
+        probe = {"after_steps": int(drv.mb200_bench_time_step(h)), "component": "Ez",
+                 "points": "cell centre + (0.35,0.25,0.15) + s_k*(1,-1,1), s_k = +-0.1 k, k=0..7, via fields::get_field",
+                 "values": [float(x) for x in pv]}
 
-    # ---- profiling pass (separate, not part of any reported throughput): per-kind CUDA events ---
-    lib.mb200_profile_reset(ctx)
-    lib.mb200_profile_enable(ctx, 1)
-    nprof = min(args.steps, 10)
-    drv.mb200_bench_step(h, nprof)
-    lib.mb200_profile_enable(ctx, 0)
-    prof = {}
-    kinds = ["curl", "edhb", "lorentz", "fmp", "source", "halo", "zero", "dft", "flux", "step3", "beta", "exchange",
-             "cylint", "cylr0", "step3_pml", "bfast", "average", "gyro", "noise"]
-    for k, name in enumerate(kinds):
-        n_, ms_, by_ = C.c_int64(), C.c_double(), C.c_double()
-        lib.mb200_profile_get(ctx, k, C.byref(n_), C.byref(ms_), C.byref(by_))
-        if n_.value:
-            prof[name] = {"launches_per_step": n_.value / nprof, "ms_per_step": ms_.value / nprof,
-                          "alg_bytes_per_step": by_.value / nprof}
+        # ---- timed region 3 (context for e2e): a COLD run of K steps — every field array starts on the
+        # host (upload inside the timed region) and ends on the host (download inside it)
+        cold = None
+        if world == 1 and not light and drv.mb200_bench_field_bytes(h) < 20e9:
+            host.meep_b200_mark_host_dirty.argtypes = [C.c_void_p]
+            host.meep_b200_mark_host_dirty(fptr)  # arrays are downloaded; the next step re-uploads them
+            c0 = stats()
+            t0 = time.perf_counter()
+            drv.mb200_bench_step(h, args.steps)
+            host.meep_b200_sync_host(fptr)
+            cold_s = time.perf_counter() - t0
+            c1 = stats()
+            cold = {"value": cells * args.steps / cold_s, "unit": "cell-updates/s", "seconds": cold_s,
+                    "h2d_bytes": c1[1] - c0[1], "d2h_bytes": c1[2] - c0[2],
+                    "what": "K steps starting and ending with all field arrays in (pageable) host memory"}
 
-    peaks, peak_src = measured_peaks()
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_step = drv.mb200_bench_algorithmic_bytes_per_step(h)
-    # kernels that skip known-zero polarisation blocks move less than the dense model: never credit
-    # bytes that were not moved (the per-kernel figures count the blocks actually processed)
-    kernel_sum = sum(v["alg_bytes_per_step"] for v in prof.values())
-    kernel_sum_smaller = bool(prof) and kernel_sum < alg_step
-    if kernel_sum_smaller:
-        alg_step = kernel_sum
-    dom = max(prof.items(), key=lambda kv: kv[1]["ms_per_step"]) if prof else (None, None)
-    roofline = None
-    if dom[0]:
-        d = dom[1]
-        per_launch_bytes = d["alg_bytes_per_step"] / d["launches_per_step"]
-        per_launch_ms = d["ms_per_step"] / d["launches_per_step"]
-        achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
-                    "share_of_step": d["ms_per_step"] / sum(v["ms_per_step"] for v in prof.values()),
-                    "whole_step": {"alg_bytes_per_step": alg_step,
-                                   "achieved": alg_step / (dev_ms / args.steps * 1e-3) / 1e9,
-                                   "frac": alg_step / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
-                                   "bytes_per_cell": alg_step / (cells / ranks_per_problem),
-                                   "model": "SURVEY 8d accounting on the actual chunk layout (every array element "
-                                            "a half-step must read / write counted once; halo copies not counted)"
-                                            + ("; polarisation arrays counted only over the blocks the kernels "
-                                               "do not skip (zero-block flags, measured)" if kernel_sum_smaller else "")},
-                    "kernels": prof}
+        # ---- profiling pass (separate, not part of any reported throughput): per-kind CUDA events ---
+        lib.mb200_profile_reset(ctx)
+        lib.mb200_profile_enable(ctx, 1)
+        nprof = min(args.steps, 10)
+        drv.mb200_bench_step(h, nprof)
+        lib.mb200_profile_enable(ctx, 0)
+        prof = {}
+        kinds = ["curl", "edhb", "lorentz", "fmp", "source", "halo", "zero", "dft", "flux", "step3", "beta", "exchange",
+                 "cylint", "cylr0", "step3_pml", "bfast", "average", "gyro", "noise"]
+        for k, name in enumerate(kinds):
+            n_, ms_, by_ = C.c_int64(), C.c_double(), C.c_double()
+            lib.mb200_profile_get(ctx, k, C.byref(n_), C.byref(ms_), C.byref(by_))
+            if n_.value:
+                prof[name] = {"launches_per_step": n_.value / nprof, "ms_per_step": ms_.value / nprof,
+                              "alg_bytes_per_step": by_.value / nprof}
 
-    # DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture of this
-    # very configuration (profiles/traffic_<workload>_<n>_<prec>.json).  The capture names the kernel
-    # sources it was taken on: a capture of another build is reported as such, not as this build's.
-    if roofline and world == 1:
-        tf = os.path.join(ROOT, "profiles", "traffic_%s_%d_%s.json" % (args.workload, args.n, args.prec))
+        peaks, peak_src = measured_peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_step = drv.mb200_bench_algorithmic_bytes_per_step(h)
+        # kernels that skip known-zero polarisation blocks move less than the dense model: never credit
+        # bytes that were not moved (the per-kernel figures count the blocks actually processed)
+        kernel_sum = sum(v["alg_bytes_per_step"] for v in prof.values())
+        kernel_sum_smaller = bool(prof) and kernel_sum < alg_step
+        if kernel_sum_smaller:
+            alg_step = kernel_sum
+        dom = max(prof.items(), key=lambda kv: kv[1]["ms_per_step"]) if prof else (None, None)
+        roofline = None
+        if dom[0]:
+            d = dom[1]
+            per_launch_bytes = d["alg_bytes_per_step"] / d["launches_per_step"]
+            per_launch_ms = d["ms_per_step"] / d["launches_per_step"]
+            achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "alg_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
+                        "share_of_step": d["ms_per_step"] / sum(v["ms_per_step"] for v in prof.values()),
+                        "whole_step": {"alg_bytes_per_step": alg_step,
+                                       "achieved": alg_step / (dev_ms / args.steps * 1e-3) / 1e9,
+                                       "frac": alg_step / (dev_ms / args.steps * 1e-3) / 1e9 / peak,
+                                       "bytes_per_cell": alg_step / (cells / ranks_per_problem),
+                                       "model": "SURVEY 8d accounting on the actual chunk layout (every array element "
+                                                "a half-step must read / write counted once; halo copies not counted)"
+                                                + ("; polarisation arrays counted only over the blocks the kernels "
+                                                   "do not skip (zero-block flags, measured)" if kernel_sum_smaller else "")},
+                        "kernels": prof}
+
+        # DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture of this
+        # very configuration (profiles/traffic_<workload>_<n>_<prec>.json).  The capture names the kernel
+        # sources it was taken on: a capture of another build is reported as such, not as this build's.
+        if roofline and world == 1:
+            tf = os.path.join(ROOT, "profiles", "traffic_%s_%d_%s.json" % (args.workload, n, args.prec))
+            try:
+                with open(tf) as fh:
+                    t = json.load(fh)
+                if t.get("kernel") == dom[0]:
+                    roofline["traffic"] = t["dram_bytes_per_launch"]
+                    roofline["traffic_source"] = "%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, " \
+                                                 "mean over the launches of the kernel)" % os.path.relpath(tf, ROOT)
+                    roofline["traffic_build"] = t.get("csrc_stamp")
+                    roofline["traffic_build_is_this_build"] = t.get("csrc_stamp") == csrc_stamp()
+            except (OSError, KeyError, ValueError):
+                pass
+        if roofline:
+            roofline["csrc_stamp"] = csrc_stamp()
+
+        nproblems = world // ranks_per_problem
+        if roofline and world > 1:
+            roofline["note"] = "rank 0's share of the cell; kernels are identical on every rank"
+        value = cells * args.steps * nproblems / (dev_ms * 1e-3)
+        line = {"metric": "Yee cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": scaling_label(args, world), "vs_baseline": None,
+                "dtype": args.prec, "data": "synthetic",
+                "config": {"workload": workload_text(args.workload, nx, n, nz, world),
+                           "n": n, "cell": [nx, n, nz], "num_chunks": drv.mb200_bench_num_chunks(h),
+                           "parallelism": ("sharded: split_by_cost over %d ranks, device-to-device halo exchange" % world)
+                           if sharded else ("replicas only" if world > 1 else "single GPU"),
+                           "l2_policy": "inputs larger than L2: %.1f GB of field arrays streamed per step vs 126 MB L2"
+                                        % (drv.mb200_bench_field_bytes(h) / 1e9) + " (per rank)",
+                           "setup_s": t_setup, "warmup_s": t_warm,
+                           "host_max_rss_gb": __import__("resource").getrusage(
+                               __import__("resource").RUSAGE_SELF).ru_maxrss / 1048576.0,
+                           "host_threads": int(os.environ.get("OMP_NUM_THREADS", "1"))},
+                "e2e": {"value": cells * args.steps * nproblems / e2e_s, "unit": "cell-updates/s",
+                        "h2d_bytes_per_step": e2e_h2d,
+                        "d2h_bytes_per_step": e2e_d2h,
+                        "what": "K x (fields::step() + fields::get_field probe) through the meep C++ API; field "
+                                "arrays stay resident in HBM between steps (state, like model weights)",
+                        "cold_start": cold},
+                "probe": probe,
+                "gpu_launches": launches,
+                "clocks": sampler.summary(),
+                "roofline": roofline}
+        drv.mb200_bench_destroy(h)
+        live.remove(h)
+        return line
+
+    north_star_n1 = world == 1 and args.workload == "c2" and args.n == 1024 and args.auto_n
+    try:
+        line = measure(args.n)
+    except Exception as e:  # the 1024^3 cell needs ~105 GB of HBM and ~40 GB of host RAM: if this box
+        if not north_star_n1:  # cannot hold it, the 1-GPU line falls back to BASELINE.json configs[1]
+            raise
+        sys.stderr.write("bench.py: 1024^3 on one GPU failed (%s); falling back to 512^3\n" % e)
+        for hh in list(live):
+            drv.mb200_bench_destroy(hh)
+            live.remove(hh)
+        args.n = 512
+        north_star_n1 = False
+        line = measure(512)
+    if north_star_n1:
+        # BASELINE.json configs[1] (512^3, the reference's 1-GPU case) measured in the same run
         try:
-            with open(tf) as fh:
-                t = json.load(fh)
-            if t.get("kernel") == dom[0]:
-                roofline["traffic"] = t["dram_bytes_per_launch"]
-                roofline["traffic_source"] = "%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, " \
-                                             "mean over the launches of the kernel)" % os.path.relpath(tf, ROOT)
-                roofline["traffic_build"] = t.get("csrc_stamp")
-                roofline["traffic_build_is_this_build"] = t.get("csrc_stamp") == csrc_stamp()
-        except (OSError, KeyError, ValueError):
-            pass
-    if roofline:
-        roofline["csrc_stamp"] = csrc_stamp()
-
-    nproblems = world // ranks_per_problem
-    if roofline and world > 1:
-        roofline["note"] = "rank 0's share of the cell; kernels are identical on every rank"
-    value = cells * args.steps * nproblems / (dev_ms * 1e-3)
-    line = {"metric": "Yee cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": scaling_label(args, world), "vs_baseline": None,
-            "dtype": args.prec, "data": "synthetic",
-            "config": {"workload": workload_text(args.workload, nx, args.n, nz, world),
-                       "n": args.n, "cell": [nx, args.n, nz], "num_chunks": drv.mb200_bench_num_chunks(h),
-                       "parallelism": ("sharded: split_by_cost over %d ranks, device-to-device halo exchange" % world)
-                       if sharded else ("replicas only" if world > 1 else "single GPU"),
-                       "l2_policy": "inputs larger than L2: %.1f GB of field arrays streamed per step vs 126 MB L2"
-                                    % (drv.mb200_bench_field_bytes(h) / 1e9) + " (per rank)",
-                       "setup_s": t_setup, "warmup_s": t_warm,
-                       "host_max_rss_gb": __import__("resource").getrusage(
-                           __import__("resource").RUSAGE_SELF).ru_maxrss / 1048576.0,
-                       "host_threads": int(os.environ.get("OMP_NUM_THREADS", "1"))},
-            "e2e": {"value": cells * args.steps * nproblems / e2e_s, "unit": "cell-updates/s",
-                    "h2d_bytes_per_step": e2e_h2d,
-                    "d2h_bytes_per_step": e2e_d2h,
-                    "what": "K x (fields::step() + fields::get_field probe) through the meep C++ API; field "
-                            "arrays stay resident in HBM between steps (state, like model weights)",
-                    "cold_start": cold},
-            "probe": probe,
-            "gpu_launches": launches,
-            "clocks": sampler.summary(),
-            "roofline": roofline}
-
+            c1 = measure(512, light=True)
+            line["configs1_512"] = {k: c1[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
+            line["configs1_512"]["workload"] = c1["config"]["workload"]
+            line["configs1_512"]["roofline"] = {k: c1["roofline"][k] for k in
+                                                ("kernel", "achieved", "peak", "frac", "whole_step", "traffic")
+                                                if k in c1["roofline"]}
+        except Exception as e:
+            line["configs1_512"] = {"failed": str(e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         a2 = argparse.Namespace(**vars(args))
         a2.steps, a2.warmup = args.cpu_steps, 3
@@ -458,7 +499,6 @@ def main():
         except Exception as e:  # the baseline is reported, never required for the device number
             line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": os.cpu_count(),
                                     "kind": "reference", "sample": "failed: %s" % e}
-    drv.mb200_bench_destroy(h)
     if rank == 0:
         emit(line)
     if world > 1:

@@ -36,7 +36,7 @@ OBUILD = os.path.join(ROOT, "oracle", "_build")
 TBUILD = os.path.join(ROOT, "tests", "_build")
 
 HOST_TUS = ["engine", "step", "step_db", "update_eh", "update_pols", "dft_hot", "hooks", "guards",
-            "mympi_b200", "connect", "sync_magnetic", "hostmem"]
+            "mympi_b200", "connect", "sync_magnetic", "hostmem", "materials_fill"]
 
 
 def have_reference():

@@ -98,3 +98,98 @@ def test_dropin_interposes_the_hot_path_symbols():
                  "meep::step_curl(", "meep::step_update_EDHB(", "meep::step_curl_stride1(",
                  "meep::fields_chunk::needs_W_prev("]:
         assert want in syms, want
+
+
+# ---- the link-level seam: every hot-path symbol must bind to the drop-in -----------------
+HOT_PATH_PATTERNS = [
+    r"^meep::fields::step\(\)$", r"^meep::fields::step_boundaries\(", r"^meep::fields::process_incoming_chunk_data\(",
+    r"^meep::fields::step_source\(", r"^meep::fields::calc_sources\(", r"^meep::fields::phase_material\(\)$",
+    r"^meep::fields_chunk::step_source\(", r"^meep::fields_chunk::calc_sources\(", r"^meep::fields_chunk::phase_material\(",
+    r"^meep::fields::step_db\(", r"^meep::fields_chunk::step_db\(",
+    r"^meep::step_curl(_stride1)?\(", r"^meep::step_update_EDHB(_stride1)?\(", r"^meep::step_beta(_stride1)?\(",
+    r"^meep::step_bfast(_stride1)?\(",
+    r"^meep::fields::update_eh\(", r"^meep::fields_chunk::update_eh\(", r"^meep::fields_chunk::needs_W_prev\(",
+    r"^meep::fields::update_pols\(", r"^meep::fields_chunk::update_pols\(",
+    r"^meep::lorentzian_susceptibility::update_P\(", r"^meep::lorentzian_susceptibility::subtract_P\(",
+    r"^meep::dft_chunk::update_dft\(", r"^meep::fields_chunk::update_dfts\(", r"^meep::fields::update_dfts\(\)$",
+    r"^meep::dft_flux::flux\(\)$",
+    r"^meep::fields::connect_the_chunks\(\)$", r"^meep::fields::find_metals\(\)$",
+]
+
+
+def _defined_text_symbols(lib):
+    """{demangled: mangled} of the functions a shared library defines"""
+    import subprocess
+    raw = subprocess.run(["nm", "-D", "--defined-only", lib], stdout=subprocess.PIPE, text=True, check=True).stdout
+    dem = subprocess.run(["nm", "-D", "-C", "--defined-only", lib], stdout=subprocess.PIPE, text=True, check=True).stdout
+    out = {}
+    for a, b in zip(raw.splitlines(), dem.splitlines()):
+        pa, pb = a.split(None, 2), b.split(None, 2)
+        if len(pa) == 3 and pa[1] in "TW":
+            out[pb[2]] = pa[2]
+    return out
+
+
+def _hot_path_symbols(dropin, hostlib):
+    import re
+    d, h = _defined_text_symbols(dropin), _defined_text_symbols(hostlib)
+    hot = {}
+    for pat in HOT_PATH_PATTERNS:
+        names = [n for n in h if re.search(pat, n)]
+        assert names, "the host library defines nothing matching %s" % pat
+        for n in names:
+            assert n in d, "hot-path symbol %s is NOT defined by the drop-in" % n
+            hot[n] = d[n]
+    return hot
+
+
+@pytest.mark.parametrize("route", ["link_order", "ld_preload"])
+def test_hot_path_symbols_bind_to_the_dropin(route):
+    """dladdr of what the process actually resolves, for every symbol of the link-level seam"""
+    import subprocess
+    tb = os.path.join(ROOT, "tests", "_build")
+    hostlib = os.path.join(ROOT, "third_party", "libmeep_host", "libmeep_host_f64.so")
+    dropin = os.path.join(tb, "libmeep_b200_emu_f64.so")
+    hot = _hot_path_symbols(dropin, hostlib)
+    assert len(hot) >= 30
+    env = dict(os.environ)
+    if route == "link_order":
+        exe = os.path.join(tb, "binding_driver_emu_f64")
+    else:  # a program that only knows the reference library, drop-in preloaded
+        exe = os.path.join(tb, "binding_driver_ref_f64")
+        env["LD_PRELOAD"] = ":".join([os.path.join(tb, "libmeep_b200_preload_emu_f64.so"),
+                                      os.path.join(tb, "libmeepb200_emu.so")])
+    r = subprocess.run([exe], input="\n".join(hot.values()) + "\n", env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    got = dict(line.split() for line in r.stdout.splitlines() if line.startswith("_Z"))
+    assert set(got) == set(hot.values())
+    wrong = {s: lib for s, lib in got.items() if not lib.startswith("libmeep_b200")}
+    assert not wrong, "hot-path symbols bound outside the drop-in: %s" % wrong
+
+
+def test_ld_debug_shows_no_hot_path_binding_into_the_reference(tmp_path):
+    """LD_DEBUG=bindings of a real (emulated-device) simulation: whenever any object binds one of the
+    hot-path symbols, the target is the drop-in, never the host/reference library"""
+    import re
+    import subprocess
+    tb = os.path.join(ROOT, "tests", "_build")
+    hostlib = os.path.join(ROOT, "third_party", "libmeep_host", "libmeep_host_f64.so")
+    hot = set(_hot_path_symbols(os.path.join(tb, "libmeep_b200_emu_f64.so"), hostlib).values())
+    log = str(tmp_path / "ld")
+    env = dict(os.environ, LD_DEBUG="bindings", LD_DEBUG_OUTPUT=log, OMP_NUM_THREADS="1")
+    r = subprocess.run([os.path.join(tb, "sim_driver_emu_f64"), "3d_metal", "3", str(tmp_path / "o.bin"), "2"], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:]
+    seen, bad = 0, []
+    for f in os.listdir(tmp_path):
+        if not f.startswith("ld."):
+            continue
+        for line in open(os.path.join(tmp_path, f), errors="replace"):
+            m = re.search(r"binding file (\S+) \[\d+\] to (\S+) \[\d+\]: normal symbol `([^']+)'", line)
+            if m and m.group(3) in hot:
+                seen += 1
+                if "libmeep_b200" not in os.path.basename(m.group(2)):
+                    bad.append((m.group(1), m.group(2), m.group(3)))
+    assert seen > 0, "no hot-path binding was logged at all"
+    assert not bad, bad[:5]

@@ -34,7 +34,8 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # same workload text as the device arm prints for the default configuration
-    assert "512x512x512" in d["config"]["workload"] and "BASELINE.json configs[1]" in d["config"]["workload"]
+    # (one GPU runs the 1024^3 cell of the scaling series; configs[1] = 512^3 rides along in the device arm)
+    assert "1024x1024x1024" in d["config"]["workload"] and d["scaling"] == "strong"
 
 
 @pytest.mark.skipif(not os.path.exists(REF_EXE), reason="reference bench driver not built")

@@ -19,7 +19,8 @@ def _ngpu():
 
 @pytest.mark.parametrize("case,steps,chunks,world", [("c2_3d_pml", 40, 2, 2), ("3d_bloch", 40, 4, 2),
                                                      ("lorentz_3d", 30, 2, 2), ("c4_aniso_ring", 20, 4, 2),
-                                                     ("cyl_m1", 60, 4, 2)])
+                                                     ("cyl_m1", 60, 4, 2), ("c3_au_sphere", 120, 8, 2),
+                                                     ("3d_sync_magnetic", 40, 4, 2), ("dft_fields_3d", 40, 2, 2)])
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 def test_two_gpu_sharded_run_matches_reference(case, steps, chunks, world, transport):
     if _ngpu() < world:
