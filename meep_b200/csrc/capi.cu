@@ -222,6 +222,10 @@ int mb200_init(int device, mb200_ctx **out) {
     const int v = getenv("MEEP_B200_PLAIN_FAST") ? atoi(getenv("MEEP_B200_PLAIN_FAST")) : 0;
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_plain_fast, &v, sizeof(int)));
   }
+  if (const char *e = getenv("MEEP_B200_PML_PAIR")) {
+    const int v = atoi(e);
+    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pml_pair, &v, sizeof(int)));
+  }
   if (const char *e = getenv("MEEP_B200_PAIR_PLANES")) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pair_planes, &v, sizeof(int)));

@@ -614,6 +614,136 @@ MB200_HD void step3c_march(const mb200_step3_job_t &J, const mb200_step3_comp_t 
   }
 }
 
+template <typename T, bool PML, bool FU, bool CND, int EPI>
+MB200_HD void step3c_dispatch(const mb200_step3_job_t &J, const mb200_step3_comp_t &C, int64_t i, int64_t sx,
+                              int ix0, int ix_end, int iy, int iz);
+#ifdef __CUDACC__
+__device__ int g_pml_pair = 1; // MEEP_B200_PML_PAIR=0: one plane per iteration for every variant
+// The same march with TWO x-planes loaded before the first store, for the variants with few
+// operands (a face PML chunk gives each component at most one auxiliary level: 6-9 loads per
+// point).  The PML kernel is latency-bound (ncu, 512^3: issue slots 25 % busy, DRAM 52 %, DRAM bytes
+// = 1.03 x algorithmic): with one component per thread a plane keeps only 6-9 loads in flight per
+// thread against 15-18 in the fast path.  All arrays of a chunk share one index space, so a single
+// 32-bit cursor addresses every operand and the descriptor fields stay in shared memory.
+template <typename T, bool PML, bool FU, bool CND, int EPI> struct Step3cVals {
+  T f, a1, c1, c2, a2, fu, fcnd, cnd, cndinv, u, fw, e, kms, sinv, kmsu, sinvu, kapw, sigw;
+};
+template <typename T, bool PML, bool FU, bool CND, int EPI>
+__device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, const mb200_step3_comp_t &C,
+                                                  int64_t i, int64_t sx, int ix0, int ix_end, int iy, int iz) {
+  constexpr bool FW = EPI == 2;
+  const bool HASU = EPI != 0 && C.u != nullptr;
+  const T dtdx = (T)C.dtdx, dt2 = (T)J.dt * T(0.5);
+  const unsigned sxu = (unsigned)sx, s1 = (unsigned)C.s1, s2 = (unsigned)C.s2;
+  const int dk = PML ? C.pml.ks[0] : 0, dku = FU ? C.pmlu.ks[0] : 0, dkw = FW ? C.pmlw.ks[0] : 0;
+  int k = PML ? pml_k(C.pml, ix0, iy, iz) : 0, ku = FU ? pml_k(C.pmlu, ix0, iy, iz) : 0,
+      kw = FW ? pml_k(C.pmlw, ix0, iy, iz) : 0;
+  bool metal_yz = false;
+  int mlo = -1, mhi = -1;
+  if (EPI) {
+    metal_yz = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] || iz == C.metal_hi[2];
+    mlo = C.metal_lo[0];
+    mhi = C.metal_hi[0];
+  }
+  typedef Step3cVals<T, PML, FU, CND, EPI> V;
+  auto load = [&](unsigned q, int k, int ku, int kw, V &v) {
+    v.f = ldmut((const T *)C.f + q);
+    v.a1 = ldro((const T *)C.g1 + (q + s1));
+    v.c1 = ldro((const T *)C.g1 + q);
+    v.c2 = ldro((const T *)C.g2 + q);
+    v.a2 = ldro((const T *)C.g2 + (q + s2));
+    if (FU) {
+      v.fu = ldmut((const T *)C.fu + q);
+      v.kmsu = ldro((const T *)C.pmlu.kap + ku) - ldro((const T *)C.pmlu.sig + ku);
+      v.sinvu = ldro((const T *)C.pmlu.siginv + ku);
+    }
+    if (CND) {
+      v.cnd = ldro((const T *)C.cnd + q);
+      v.cndinv = ldro((const T *)C.cndinv + q);
+      if (PML) v.fcnd = ldmut((const T *)C.fcnd + q);
+    }
+    if (PML) {
+      v.kms = ldro((const T *)C.pml.kap + k) - ldro((const T *)C.pml.sig + k);
+      v.sinv = ldro((const T *)C.pml.siginv + k);
+    }
+    v.u = HASU ? ldro((const T *)C.u + q) : T(1);
+    if (FW) {
+      v.fw = ldmut((const T *)C.fw + q);
+      v.e = ldmut((const T *)C.e + q);
+      v.kapw = ldro((const T *)C.pmlw.kap + kw);
+      v.sigw = ldro((const T *)C.pmlw.sig + kw);
+    }
+  };
+  auto finish = [&](unsigned q, int ix, const V &v) { // arithmetic and stores: as step3c_march
+    T dg = v.a1 - v.c1;
+    dg = dg + v.c2 - v.a2;
+    const T curl = dtdx * dg;
+    const T x = FU ? v.fu : v.f;
+    T xn;
+    if (!PML) {
+      if (CND) xn = ((1 - dt2 * v.cnd) * x - curl) * v.cndinv;
+      else xn = x - curl;
+    }
+    else if (CND) {
+      const T fcn = ((1 - dt2 * v.cnd) * v.fcnd - curl) * v.cndinv;
+      stout((T *)C.fcnd + q, fcn);
+      xn = (v.kms * x + (fcn - v.fcnd)) * v.sinv;
+    }
+    else
+      xn = (v.kms * x - curl) * v.sinv;
+    T fn;
+    if (FU) {
+      stout((T *)C.fu + q, xn);
+      fn = v.sinvu * (v.kmsu * v.f + xn - v.fu);
+    }
+    else
+      fn = xn;
+    stout((T *)C.f + q, fn);
+    if (EPI && step3_epi_plane(J, ix)) {
+      const bool metal = metal_yz || ix == mlo || ix == mhi;
+      const T d = metal ? T(0) : fn;
+      const T val = HASU ? d * v.u : d;
+      if (FW) {
+        stout((T *)C.fw + q, val);
+        stout((T *)C.e + q, v.e + ((v.kapw + v.sigw) * val - (v.kapw - v.sigw) * v.fw));
+      }
+      else
+        stout((T *)C.e + q, val);
+    }
+  };
+  unsigned q = (unsigned)i;
+  int ix = ix0;
+  for (; ix + 1 < ix_end; ix += 2, q += 2 * sxu, k += 2 * dk, ku += 2 * dku, kw += 2 * dkw) {
+    V a, b;
+    load(q, k, ku, kw, a);
+    load(q + sxu, k + dk, ku + dku, kw + dkw, b);
+    finish(q, ix, a);
+    finish(q + sxu, ix + 1, b);
+  }
+  if (ix < ix_end) {
+    V a;
+    load(q, k, ku, kw, a);
+    finish(q, ix, a);
+  }
+}
+#endif
+
+template <typename T, bool PML, bool FU, bool CND, int EPI>
+MB200_HD void step3c_dispatch(const mb200_step3_job_t &J, const mb200_step3_comp_t &C, int64_t i, int64_t sx,
+                              int ix0, int ix_end, int iy, int iz) {
+#ifdef __CUDA_ARCH__
+  // operands per point: pair the planes only while two planes fit the 64-register budget of 4 CTAs/SM
+  constexpr int kOperands = 5 + (FU ? 3 : 0) + (CND ? (PML ? 3 : 2) : 0) + (PML ? 2 : 0) + (EPI ? 1 : 0) +
+                            (EPI == 2 ? 4 : 0);
+  if (kOperands <= 10 && g_pml_pair != 0 &&
+      (int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32)) {
+    step3c_pair_march<T, PML, FU, CND, EPI>(J, C, i, sx, ix0, ix_end, iy, iz);
+    return;
+  }
+#endif
+  step3c_march<T, PML, FU, CND, EPI>(J, C, i, sx, ix0, ix_end, iy, iz);
+}
+
 template <typename T>
 MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int tid) {
   const mb200_box_t box = step3_box(J);
@@ -636,7 +766,7 @@ MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int
   switch (variant) { // CTA-uniform
 #define MB200_S3C(v)                                                                               \
   case v:                                                                                          \
-    step3c_march<T, ((v) / 12) != 0, (((v) / 6) % 2) != 0, (((v) / 3) % 2) != 0, (v) % 3>(         \
+    step3c_dispatch<T, ((v) / 12) != 0, (((v) / 6) % 2) != 0, (((v) / 3) % 2) != 0, (v) % 3>(      \
         J, C, i, sx, ix0, ix_end, iy, iz);                                                         \
     break;
     MB200_S3C(0) MB200_S3C(1) MB200_S3C(2) MB200_S3C(3) MB200_S3C(4) MB200_S3C(5)

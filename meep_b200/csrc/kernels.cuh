@@ -208,7 +208,10 @@ template <typename T> MB200_HD void beta_thread(const mb200_beta_job_t &J, int64
 
 // list form: one thread per transfer.  Run-length form: the tiles after the PHASE tiles hold
 // kHaloRunsPerTile runs each, one warp per run, lanes striding through its elements.
-constexpr int kHaloRunsPerWarp = 4; // amortises the per-CTA job staging over more values
+// one run per warp: the kernel is latency-bound (ncu: 92 % of cycles without an eligible warp, achieved
+// occupancy 35 % of a theoretical 75 % with four runs per warp — a few long-running CTAs at the
+// tail), so the work is spread over four times as many warps, each with eight loads in flight
+constexpr int kHaloRunsPerWarp = 1;
 constexpr int kHaloRunsPerTile = (kThreads / 32) * kHaloRunsPerWarp;
 MB200_HD int64_t halo_list_tiles(const mb200_halo_job_t &J) {
   const int64_t n = J.nrun > 0 ? J.n_phase : J.n_phase + J.n_negate + J.n_copy;
@@ -224,15 +227,15 @@ template <typename T> MB200_HD void halo_thread(const mb200_halo_job_t &J, int64
   const int64_t r0 = (tile - lt) * kHaloRunsPerTile + (tid / 32) * kHaloRunsPerWarp;
   for (int64_t r = r0; r < r0 + kHaloRunsPerWarp && r < J.nrun; ++r) {
     const mb200_halo_run_t run = J.runs[r];
-    // four loads in flight per lane before the first store
-    for (int e = tid % 32; e < run.n; e += 128) {
-      T v[4];
+    // eight loads in flight per lane before the first store
+    for (int e = tid % 32; e < run.n; e += 256) {
+      T v[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 8; ++q)
         if (e + 32 * q < run.n)
           v[q] = ldmut((const T *)(uintptr_t)(run.src0 + (int64_t)(e + 32 * q) * run.dsrc));
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 8; ++q)
         if (e + 32 * q < run.n)
           stout((T *)(uintptr_t)(run.dst0 + (int64_t)(e + 32 * q) * run.ddst), run.negate ? -v[q] : v[q]);
     }
