@@ -237,6 +237,7 @@ MB200_HD void step3_plain_fast(const mb200_step3_job_t &J, int64_t i, int64_t sx
 template <typename T>
 MB200_HD void step3_plain_general(const mb200_step3_job_t &J, int64_t i, int64_t sx, int ix0, int ix_end,
                                   const bool (&myz)[3], const bool (&metal_yz)[3]) {
+  const int nlo = J.noepi_lo, nhi = J.noepi_lo + J.noepi_n;
   for (int ix = ix0; ix < ix_end; ++ix, i += sx) {
     T fv[3], a1[3], c1[3], c2[3], a2[3], uv[3];
     bool m[3];
@@ -262,7 +263,7 @@ MB200_HD void step3_plain_general(const mb200_step3_job_t &J, int64_t i, int64_t
         dg = dg + c2[c] - a2[c];
         const T d = fv[c] - (T)C.dtdx * dg;
         ((T *)C.f)[i] = d;
-        if (C.e && step3_epi_plane(J, ix)) {
+        if (C.e && (ix < nlo || ix >= nhi)) {
           const bool metal = metal_yz[c] || ix == C.metal_lo[0] || ix == C.metal_hi[0];
           const T dd = metal ? T(0) : d;
           ((T *)C.e)[i] = C.u ? dd * uv[c] : dd;
@@ -519,6 +520,7 @@ MB200_HD void step3c_march(const mb200_step3_job_t &J, const mb200_step3_comp_t 
     mlo = C.metal_lo[0];
     mhi = C.metal_hi[0];
   }
+  const int nlo = J.noepi_lo, nhi = J.noepi_lo + J.noepi_n; // planes without the epilogue (registers, not LDS per plane)
 
   for (int ix = ix0; ix < ix_end; ++ix) {
     // ---- all loads of this point (as step3_load) ----
@@ -573,7 +575,7 @@ MB200_HD void step3c_march(const mb200_step3_job_t &J, const mb200_step3_comp_t 
     else
       fn = xn;
     stout(pf, fn);
-    if (EPI && step3_epi_plane(J, ix)) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
+    if (EPI && (ix < nlo || ix >= nhi)) { // fused diagonal update_eh (src/step_generic.cpp:682-699, 774-782)
       const bool metal = metal_yz || ix == mlo || ix == mhi;
       const T d = metal ? T(0) : fn;
       const T val = HASU ? d * u : d;
@@ -645,6 +647,7 @@ __device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, co
     mlo = C.metal_lo[0];
     mhi = C.metal_hi[0];
   }
+  const int nlo = J.noepi_lo, nhi = J.noepi_lo + J.noepi_n;
   typedef Step3cVals<T, PML, FU, CND, EPI> V;
   auto load = [&](unsigned q, int k, int ku, int kw, V &v) {
     v.f = ldmut((const T *)C.f + q);
@@ -699,7 +702,7 @@ __device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, co
     else
       fn = xn;
     stout((T *)C.f + q, fn);
-    if (EPI && step3_epi_plane(J, ix)) {
+    if (EPI && (ix < nlo || ix >= nhi)) {
       const bool metal = metal_yz || ix == mlo || ix == mhi;
       const T d = metal ? T(0) : fn;
       const T val = HASU ? d * v.u : d;
