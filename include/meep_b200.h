@@ -397,6 +397,13 @@ int mb200_free(mb200_ctx *ctx, void *p);
 int mb200_memset(mb200_ctx *ctx, void *p, int value, size_t bytes);
 int mb200_h2d(mb200_ctx *ctx, void *dst, const void *src, size_t bytes); /* async if src pinned */
 int mb200_d2h(mb200_ctx *ctx, void *dst, const void *src, size_t bytes); /* synchronises */
+/* Sub-box of a 3-D array in the reference layout (planes of `rows` rows of `row_elems` elements;
+ * last index fastest): copies elements [lo0, lo0+cnt0) x [lo1, lo1+cnt1) x [lo2, lo2+cnt2) of the
+ * device array to the same positions of the host array (one 3-D copy; does NOT synchronise — call
+ * mb200_sync when all boxes are queued).  What the host readers of a sub-volume need
+ * (fields::loop_in_chunks consumers: flux planes, slices, integrals over a box) instead of every array. */
+int mb200_d2h_box(mb200_ctx *ctx, void *host, const void *dev, size_t elem_size, int64_t rows, int64_t row_elems,
+                  int64_t lo0, int64_t lo1, int64_t lo2, int64_t cnt0, int64_t cnt1, int64_t cnt2);
 int mb200_d2d(mb200_ctx *ctx, void *dst, const void *src, size_t bytes);
 int mb200_host_alloc(size_t bytes, void **out); /* pinned host memory */
 int mb200_host_free(void *p);

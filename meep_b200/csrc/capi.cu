@@ -307,6 +307,24 @@ int mb200_d2h(mb200_ctx *c, void *dst, const void *src, size_t bytes) {
   return 0;
 }
 
+int mb200_d2h_box(mb200_ctx *c, void *host, const void *dev, size_t elem_size, int64_t rows, int64_t row_elems,
+                  int64_t lo0, int64_t lo1, int64_t lo2, int64_t cnt0, int64_t cnt1, int64_t cnt2) {
+  if (cnt0 <= 0 || cnt1 <= 0 || cnt2 <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  // (cudaMemcpy3D: x = fastest index in BYTES, y = rows, z = planes)
+  p.srcPtr = make_cudaPitchedPtr(const_cast<void *>(dev), (size_t)row_elems * elem_size, (size_t)row_elems * elem_size,
+                                 (size_t)rows);
+  p.dstPtr = make_cudaPitchedPtr(host, (size_t)row_elems * elem_size, (size_t)row_elems * elem_size, (size_t)rows);
+  p.srcPos = make_cudaPos((size_t)lo2 * elem_size, (size_t)lo1, (size_t)lo0);
+  p.dstPos = p.srcPos;
+  p.extent = make_cudaExtent((size_t)cnt2 * elem_size, (size_t)cnt1, (size_t)cnt0);
+  p.kind = cudaMemcpyDeviceToHost;
+  CUDA_TRY(cudaMemcpy3DAsync(&p, c->stream));
+  return 0;
+}
+
 int mb200_d2d(mb200_ctx *c, void *dst, const void *src, size_t bytes) {
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));

@@ -97,6 +97,7 @@ Engine::Engine(fields *f) : self(f) {
   device_timers = env_int("MEEP_B200_TIMERS", 0) != 0;
   merge_exchanges = env_int("MEEP_B200_MERGE_EXCHANGES", 1) != 0;
   defer_local = env_int("MEEP_B200_DEFER_LOCAL", 1) != 0;
+  if (getenv("MEEP_B200_REGION_SYNC")) region_fraction_limit = atof(getenv("MEEP_B200_REGION_SYNC"));
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   p2p = env_int("MEEP_B200_P2P", 1) != 0;
   halo_runs = env_int("MEEP_B200_HALO_RUNS", 1) != 0;
@@ -679,6 +680,78 @@ void Engine::sync_host() {
       if (flag) meep::abort("simulation fields are NaN or Inf");
     }
   }
+}
+
+void Engine::sync_host_region(const volume &where) {
+  // (force_reader_sync: a reader called from INSIDE fields::step, where the device copy is newer
+  // although `state` only says so when the step ends — the legacy flux_vol planes)
+  const bool forced = force_reader_sync;
+  if (state != DEVICE_NEWER && !forced) return;
+  fields *f = self;
+  bool ok = region_fraction_limit > 0 && f->S.multiplicity() == 1 && f->gv.dim == D3 && where.dim == D3;
+  LOOP_OVER_DIRECTIONS(f->gv.dim, d) {
+    if (f->boundaries[High][d] == Periodic || f->boundaries[Low][d] == Periodic) ok = false;
+  }
+  if (!ok) {
+    if (forced) download_fields();
+    else sync_host();
+    return;
+  }
+  struct Box {
+    realnum *host;
+    int64_t rows, row_elems, lo[3], cnt[3];
+  };
+  std::vector<Box> boxes;
+  double part = 0, total = 0;
+  const ivec lo_i = f->gv.round_vec(where.get_min_corner()), hi_i = f->gv.round_vec(where.get_max_corner());
+  for (int i = 0; i < f->num_chunks; ++i) {
+    fields_chunk *fc = f->chunks[i];
+    if (!fc->is_mine()) continue;
+    const grid_volume &gv = fc->gv;
+    const direction ds[3] = {X, Y, Z};
+    int64_t lo[3], cnt[3];
+    bool empty = false;
+    for (int k = 0; k < 3; ++k) {
+      // array index range along direction k touched by a reader of `where`: 2 pixels of margin for
+      // interpolation weights and centred-grid averages
+      const int io = gv.little_corner().in_direction(ds[k]);
+      int a = (lo_i.in_direction(ds[k]) - io) / 2 - 3, b = (hi_i.in_direction(ds[k]) - io) / 2 + 3;
+      if (a < 0) a = 0;
+      if (b > gv.num_direction(ds[k])) b = gv.num_direction(ds[k]);
+      if (b < a) empty = true;
+      lo[k] = a;
+      cnt[k] = b - a + 1;
+    }
+    const double ntot = (double)gv.ntot();
+    FOR_COMPONENTS(c) for (int cmp = 0; cmp < 2; ++cmp) {
+      realnum *p = fc->f[c][cmp];
+      if (!p) continue;
+      if (is_magnetic(c) && p == fc->f[direction_component(Bx, component_direction(c))][cmp]) continue; // H aliases B
+      total += ntot;
+      if (empty) continue;
+      part += (double)cnt[0] * cnt[1] * cnt[2];
+      boxes.push_back(Box{p, gv.ny() + 1, gv.nz() + 1, {lo[0], lo[1], lo[2]}, {cnt[0], cnt[1], cnt[2]}});
+    }
+  }
+  if (total == 0 || part > region_fraction_limit * total) {
+    if (forced) download_fields();
+    else sync_host();
+    return;
+  }
+  refresh_deferred_halos();
+  for (const Box &b : boxes) {
+    check(mb200_d2h_box(ctx, b.host, dev(b.host), sizeof(realnum), b.rows, b.row_elems, b.lo[0], b.lo[1], b.lo[2],
+                        b.cnt[0], b.cnt[1], b.cnt[2]),
+          "mb200_d2h_box");
+    stats.d2h_bytes += (double)b.cnt[0] * b.cnt[1] * b.cnt[2] * sizeof(realnum);
+  }
+  check(mb200_sync(ctx), "device synchronisation");
+  host_resident = true;
+  stats.region_downloads++;
+  if (verbose && stats.region_downloads <= 8)
+    fprintf(stderr, "meep_b200: sub-volume download: %zu boxes, %.3f MB (%.2f %% of the field arrays)\n",
+            boxes.size(), part * sizeof(realnum) / 1e6, 100.0 * part / total);
+  // (state stays DEVICE_NEWER: only the box is current on the host)
 }
 
 void Engine::enter(fields *f) {

@@ -140,6 +140,7 @@ struct Stats {
   int64_t uploads = 0, downloads = 0;
   double h2d_bytes = 0, d2h_bytes = 0;
   int64_t plan_builds = 0;
+  int64_t region_downloads = 0;
 };
 
 class Engine {
@@ -181,6 +182,13 @@ public:
   void leave(meep::fields *f, bool modified_fields);
   // make the host arrays current (called by the interposed readers in hooks.cpp)
   void sync_host();
+  // make current only what a reader of the sub-volume `where` can touch (the field arrays of the
+  // chunks it overlaps, restricted to the index box of `where` + 2 pixels); falls back to
+  // sync_host() when images of the volume could be read (symmetries, periodic boundaries) or the
+  // box is most of the cell.  The device copy stays the authoritative one.
+  void sync_host_region(const meep::volume &where);
+  bool force_reader_sync = false;
+  double region_fraction_limit = 0.3; // MEEP_B200_REGION_SYNC (0 disables sub-volume downloads)
   void mark_host_dirty() { if (state != DEVICE_NEWER) state = HOST_NEWER; }
 
   // ---- mirror ---------------------------------------------------------------------------------

@@ -110,7 +110,9 @@ void fields::loop_in_chunks(field_chunkloop chunkloop, void *chunkloop_data, con
                             component cgrid, bool use_symmetry, bool snap_unit_dims) {
   typedef void (*fn)(fields *, field_chunkloop, void *, const volume &, component, bool, bool);
   static fn next = (fn)next_definition_of_caller();
-  if (Engine *E = Engine::find(this)) E->sync_host();
+  // only what a reader of `where` can touch is brought to the host (a flux plane, a slice, a box to
+  // integrate over): Engine::sync_host_region
+  if (Engine *E = Engine::find(this)) E->sync_host_region(where);
   next(this, chunkloop, chunkloop_data, where, cgrid, use_symmetry, snap_unit_dims);
 }
 

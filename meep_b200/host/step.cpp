@@ -160,10 +160,13 @@ void fields::step() {
       }
       trace("step_boundaries(W, P, E/H) + update_pols");
       mark(Stepping);
-      if (fluxes) { // legacy flux planes integrate the host arrays
-        E.download_fields();
+      if (fluxes) {
+        // legacy flux planes (flux_vol, src/meep.hpp:2322-2351) integrate host arrays through
+        // loop_in_chunks: the interposed loop_in_chunks downloads just the planes they read
+        E.force_reader_sync = true;
         if (h == 0) fluxes->update_half();
         else fluxes->update();
+        E.force_reader_sync = false;
       }
     }
 

@@ -363,6 +363,38 @@ int main(int argc, char **argv) {
     f.restore_magnetic_fields();
     f.restore_magnetic_fields();
   }
+  else if (cs == "3d_flux_planes") {
+    // host readers of SUB-VOLUMES while the arrays live on the device: legacy flux planes (flux_vol,
+    // updated twice per step inside fields::step), flux / energy in a box, a field integral over a
+    // thin slab — each brings only the index box it reads to the host (Engine::sync_host_region)
+    g_L = 3.0;
+    grid_volume gv = vol3d(3.0, 2.6, 2.2, a);
+    structure s(gv, eps_box, pml(0.5), identity(), num_chunks);
+    fields f(&s);
+    f.use_real_fields();
+    gaussian_src_time src(0.4, 0.3);
+    f.add_point_source(Ez, src, vec(1.1, 1.3, 1.0));
+    flux_vol *fx = f.add_flux_plane(vec(1.9, 0.7, 0.6), vec(1.9, 1.9, 1.6));
+    flux_vol *fy = f.add_flux_plane(vec(0.8, 1.9, 0.6), vec(2.0, 1.9, 1.6));
+    flux_vol *fz = f.add_flux_plane(vec(0.8, 0.7, 1.6), vec(2.0, 1.9, 1.6));
+    std::vector<double> rec;
+    const volume box(vec(0.9, 0.9, 0.8), vec(1.5, 1.6, 1.3));
+    const volume slab(vec(0.7, 0.7, 1.2), vec(2.1, 1.9, 1.3));
+    for (int i = 0; i < nsteps; ++i) {
+      f.step();
+      rec.push_back(fx->flux());
+      rec.push_back(fy->flux());
+      rec.push_back(fz->flux());
+      if (i % 5 == 4) {
+        rec.push_back(f.electric_energy_in_box(box));
+        rec.push_back(f.flux_in_box(X, volume(vec(1.6, 0.8, 0.7), vec(1.6, 1.8, 1.5))));
+        rec.push_back(f.field_energy_in_box(slab));
+      }
+    }
+    dump("monitors", rec.data(), sizeof(double), rec.size());
+    probes(f, gv);
+    dump_fields(f);
+  }
   else if (cs == "3d_xperiodic_ypml") {
     g_L = 1.0;
     grid_volume gv = vol3d(1.0, 3.0, 1.0, a);
@@ -528,7 +560,7 @@ int main(int argc, char **argv) {
     // Unit length 0.1 um (materials.py's um_scale = 0.1), i.e. 10 nm pixels at resolution 10: with
     // 1 um units the Drude term has omega_p dt = 2.0 and the run diverges in the reference itself.
     // Here omega_p dt = 0.2 and max|field| stays O(1) (checked by tests/parity_util.compare).
-    g_L = 2.4;
+    g_L = getenv("MB200_TEST_L") ? atof(getenv("MB200_TEST_L")) : 2.4;
     grid_volume gv = vol3d(g_L, g_L, g_L, a);
     structure s(gv, one, pml(0.6), identity(), num_chunks);
     const double um = getenv("MB200_C3_UM") ? atof(getenv("MB200_C3_UM")) : 0.1;

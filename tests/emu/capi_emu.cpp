@@ -263,6 +263,15 @@ int mb200_h2d(mb200_ctx *, void *dst, const void *src, size_t bytes) {
   memcpy(dst, src, bytes);
   return 0;
 }
+int mb200_d2h_box(mb200_ctx *, void *host, const void *dev, size_t elem_size, int64_t rows, int64_t row_elems,
+                  int64_t lo0, int64_t lo1, int64_t lo2, int64_t cnt0, int64_t cnt1, int64_t cnt2) {
+  for (int64_t a = lo0; a < lo0 + cnt0; ++a)
+    for (int64_t b = lo1; b < lo1 + cnt1; ++b) {
+      const size_t off = (size_t)((a * rows + b) * row_elems + lo2) * elem_size;
+      memcpy((char *)host + off, (const char *)dev + off, (size_t)cnt2 * elem_size);
+    }
+  return 0;
+}
 int mb200_d2h(mb200_ctx *, void *dst, const void *src, size_t bytes) {
   memcpy(dst, src, bytes);
   return 0;

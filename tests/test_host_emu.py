@@ -41,6 +41,7 @@ CASES = [  # (case, steps, num_chunks)
     ("3d_midrun_changes", 48, 2),
     ("3d_tiled", 30, 0),
     ("3d_sync_magnetic", 30, 0),
+    ("3d_flux_planes", 40, 2),
     ("3d_bfast", 40, 0),
     ("2d_bfast", 80, 3),
     ("cyl_m0", 60, 0),

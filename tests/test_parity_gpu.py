@@ -49,6 +49,7 @@ CASES = [  # (case, steps, num_chunks)
     ("3d_midrun_changes", 80, 0),
     ("3d_tiled", 40, 0),
     ("3d_sync_magnetic", 60, 2),
+    ("3d_flux_planes", 60, 3),
     ("3d_bfast", 80, 0),
     ("2d_bfast", 150, 3),
     ("cyl_m0", 150, 0),
