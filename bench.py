@@ -4,10 +4,15 @@
   python bench.py --gpus N --steps K --warmup W            # device arm (one process per GPU)
   python bench.py --impl reference --steps K --warmup W    # the reference's CPU path, host cores
 
-Workload (N=1): BASELINE.json configs[1] — 3-D dielectric box 512^3, PML on all faces,
-non-dispersive, Gaussian dipole source, double precision, built through the reference's public
-C++ API (meep::structure / meep::fields) by bench/bench_driver.cpp and stepped with
-fields::step().  A "step" is one FDTD time step (one pass of the hot path over the grid).
+Workload: BASELINE.json's metric is quoted "at 1/2/4/8 B200" on the 1024^3 dielectric+PML cell
+(configs[4], the north-star case), which fits ONE B200 (102 GB of HBM, 25 GB of host RAM), so every
+N — including N=1 — runs that cell: the lines of a scaling run form one strong-scaling series.
+BASELINE.json configs[1] (the same geometry at 512^3, the reference's 1-GPU case) is measured in the
+same N=1 run and reported under "configs1_512"; `--size 512` makes it the headline instead.  If the
+box cannot hold 1024^3 the N=1 line falls back to 512^3 (and says so in config.workload).
+3-D dielectric box, PML on all faces, non-dispersive, Gaussian dipole source, double precision, built
+through the reference's public C++ API (meep::structure / meep::fields) by bench/bench_driver.cpp and
+stepped with fields::step().  A "step" is one FDTD time step (one pass of the hot path over the grid).
 
   value   : cells * K / device time (CUDA events on the engine's stream), fields resident in HBM
   e2e     : the same K steps through the public API as a user's monitoring loop runs them:

@@ -650,12 +650,15 @@ void Engine::upload_materials() {
 // current owner values, through the ordinary exchange code restricted to same-process pairs (no
 // other process is needed, so any single rank may do this at any time).
 void Engine::refresh_deferred_halos() {
-  if (refresh_local || (!halos_stale[D_stuff] && !halos_stale[B_stuff])) return;
+  bool any = false;
+  for (field_type ft : {B_stuff, D_stuff, PH_stuff, PE_stuff})
+    any = any || halos_stale[ft];
+  if (refresh_local || !any) return;
   const bool was_in_step = in_step;
   refresh_local = true;
   in_step = false;
   keep_on_device++;
-  for (field_type ft : {B_stuff, D_stuff})
+  for (field_type ft : {B_stuff, D_stuff, PH_stuff, PE_stuff})
     if (halos_stale[ft]) {
       halos_stale[ft] = false;
       self->step_boundaries(ft);

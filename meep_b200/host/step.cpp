@@ -353,6 +353,14 @@ void fields::step_boundaries(field_type ft) {
           if (is_D(d->c) || is_B(d->c)) defer_local = false;
   }
 
+  // The same for the polarisation halos (PE/PH: one value per Lorentzian pole and boundary point,
+  // src/susceptibility.cpp:283-295): not-owned P values only feed the not-owned points of
+  // f_minus_p, which a diagonal update_eh never reads — for the six-pole Au sphere they are six
+  // times the E halo, in list form because the zero-block flags travel with them.
+  const bool pol_ft = ft == PE_stuff || ft == PH_stuff;
+  const bool defer_pol = pol_ft && E.in_step && !refresh && E.defer_local && E.defer_known &&
+                         E.defer_ok[ft == PE_stuff ? D_stuff : B_stuff];
+
   am_now_working_on(Boundaries);
   run_phase(E, this, PH_BND, ft, E.in_step, [&]() {
     Recorder &R = E.rec();
@@ -403,6 +411,7 @@ void fields::step_boundaries(field_type ft) {
         if (!j_mine && !i_mine) continue;
         if (refresh && !(j_mine && i_mine)) continue;
         if (defer_local && ft != ft_outer && j_mine && i_mine) continue; // copied by the next refresh instead
+        if (defer_pol && j_mine && i_mine) continue;
         uint64_t block = 0; // device comm block for a cross-process pair
         if (j_mine != i_mine && use_links) {
           // the block is a slice of the arena in the RECEIVER's memory: packed straight into the
@@ -528,6 +537,7 @@ void fields::step_boundaries(field_type ft) {
       }
   });
   if (E.in_step && take_partner && E.local_deferred[ftdb]) E.halos_stale[ftdb] = true;
+  if (defer_pol) E.halos_stale[ft] = true;
   finished_working();
 }
 
