@@ -738,7 +738,7 @@ MB200_HD void step3c_dispatch(const mb200_step3_job_t &J, const mb200_step3_comp
   // operands per point: pair the planes only while two planes fit the 64-register budget of 4 CTAs/SM
   constexpr int kOperands = 5 + (FU ? 3 : 0) + (CND ? (PML ? 3 : 2) : 0) + (PML ? 2 : 0) + (EPI ? 1 : 0) +
                             (EPI == 2 ? 4 : 0);
-  if (kOperands <= (sizeof(T) == 4 ? 13 : 10) && g_pml_pair != 0 && // (single precision: half the registers per value)
+  if (kOperands <= 10 && g_pml_pair != 0 &&
       (int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32)) {
     step3c_pair_march<T, PML, FU, CND, EPI>(J, C, i, sx, ix0, ix_end, iy, iz);
     return;

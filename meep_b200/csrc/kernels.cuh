@@ -489,10 +489,36 @@ __global__ void __launch_bounds__(kThreads)
     ++done;
     const int64_t base = b * MB200_ZBLOCK + threadIdx.x;
     bool zero = true;
+    // the four elements of a thread: all loads before the first store (the stores to P / P_prev
+    // would otherwise fence the loads of the next element: one memory latency per element)
+    constexpr int kPer = MB200_ZBLOCK / kThreads;
+    T pc[kPer], ppv[kPer], sv[kPer], wv[kPer];
+    bool own[kPer], in[kPer];
+    T *p = (T *)J.p, *pp = (T *)J.pp;
 #pragma unroll
-    for (int r = 0; r < MB200_ZBLOCK / kThreads; ++r) {
+    for (int r = 0; r < kPer; ++r) {
       const int64_t idx = base + (int64_t)r * kThreads;
-      if (idx < J.ntot) zero = lorentz_blocked_point<T>(J, idx) && zero;
+      in[r] = idx < J.ntot;
+      own[r] = in[r] && lorentz_owned(J, idx);
+      pc[r] = in[r] ? p[idx] : T(0);
+      ppv[r] = in[r] ? pp[idx] : T(0);
+      sv[r] = own[r] ? ldro((const T *)J.s + idx) : T(0);
+      wv[r] = own[r] ? ldro((const T *)J.w + idx) : T(0);
+    }
+#pragma unroll
+    for (int r = 0; r < kPer; ++r) {
+      const int64_t idx = base + (int64_t)r * kThreads;
+      if (!in[r]) continue;
+      if (!own[r]) { // not-owned points are not updated; they still count for the zero flag
+        zero = zero && pc[r] == T(0) && ppv[r] == T(0);
+        continue;
+      }
+      // same expression as lorentz_blocked_point / src/susceptibility.cpp:251-257
+      const T pn = (T)J.gamma1inv * (pc[r] * (2 - (T)J.omega0dtsqr_denom) - (T)J.gamma1 * ppv[r] +
+                                     (T)J.omega0dtsqr * (sv[r] * wv[r]));
+      p[idx] = pn;
+      pp[idx] = pc[r];
+      zero = zero && pn == T(0) && pc[r] == T(0);
     }
     const int allzero = __syncthreads_and(zero ? 1 : 0);
     if (threadIdx.x == 0) J.pzero[b] = allzero ? 1 : 0;
@@ -529,10 +555,31 @@ __global__ void __launch_bounds__(kThreads)
     if (nread) atomicAdd(work + 1, (unsigned long long)nread);
   }
   const int64_t base = tile * (kThreads * kItems1D) + threadIdx.x;
+  // two elements at a time, all their loads before the first store (the store to f_minus_p would
+  // otherwise fence the loads of the next element)
+  T *fmp = (T *)J.fmp;
+  const int64_t zb = tile; // one zero-flag block per CTA (static_assert above)
 #pragma unroll
-  for (int r = 0; r < kItems1D; ++r) {
-    const int64_t i = base + (int64_t)r * kThreads;
-    if (i < J.ntot) fmp_point<T>(J, i);
+  for (int r = 0; r < kItems1D; r += 2) {
+    const int64_t i0 = base + (int64_t)r * kThreads, i1 = i0 + kThreads;
+    const bool in0 = i0 < J.ntot, in1 = i1 < J.ntot;
+    T v0 = T(0), v1 = T(0), p0[MB200_MAX_P], p1[MB200_MAX_P];
+    if (in0) v0 = J.d ? ldro((const T *)J.d + i0) : fmp[i0];
+    if (in1) v1 = J.d ? ldro((const T *)J.d + i1) : fmp[i1];
+#pragma unroll
+    for (int k = 0; k < MB200_MAX_P; ++k) {
+      const bool live = k < J.np && !(J.pzero[k] && J.pzero[k][zb]);
+      p0[k] = (live && in0) ? ldro((const T *)J.p[k] + i0) : T(0);
+      p1[k] = (live && in1) ? ldro((const T *)J.p[k] + i1) : T(0);
+    }
+#pragma unroll
+    for (int k = 0; k < MB200_MAX_P; ++k)
+      if (k < J.np) { // (same order of subtractions as fmp_point / src/susceptibility.cpp:264-281)
+        v0 -= p0[k];
+        v1 -= p1[k];
+      }
+    if (in0) fmp[i0] = v0;
+    if (in1) fmp[i1] = v1;
   }
 }
 
