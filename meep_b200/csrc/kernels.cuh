@@ -555,31 +555,10 @@ __global__ void __launch_bounds__(kThreads)
     if (nread) atomicAdd(work + 1, (unsigned long long)nread);
   }
   const int64_t base = tile * (kThreads * kItems1D) + threadIdx.x;
-  // two elements at a time, all their loads before the first store (the store to f_minus_p would
-  // otherwise fence the loads of the next element)
-  T *fmp = (T *)J.fmp;
-  const int64_t zb = tile; // one zero-flag block per CTA (static_assert above)
 #pragma unroll
-  for (int r = 0; r < kItems1D; r += 2) {
-    const int64_t i0 = base + (int64_t)r * kThreads, i1 = i0 + kThreads;
-    const bool in0 = i0 < J.ntot, in1 = i1 < J.ntot;
-    T v0 = T(0), v1 = T(0), p0[MB200_MAX_P], p1[MB200_MAX_P];
-    if (in0) v0 = J.d ? ldro((const T *)J.d + i0) : fmp[i0];
-    if (in1) v1 = J.d ? ldro((const T *)J.d + i1) : fmp[i1];
-#pragma unroll
-    for (int k = 0; k < MB200_MAX_P; ++k) {
-      const bool live = k < J.np && !(J.pzero[k] && J.pzero[k][zb]);
-      p0[k] = (live && in0) ? ldro((const T *)J.p[k] + i0) : T(0);
-      p1[k] = (live && in1) ? ldro((const T *)J.p[k] + i1) : T(0);
-    }
-#pragma unroll
-    for (int k = 0; k < MB200_MAX_P; ++k)
-      if (k < J.np) { // (same order of subtractions as fmp_point / src/susceptibility.cpp:264-281)
-        v0 -= p0[k];
-        v1 -= p1[k];
-      }
-    if (in0) fmp[i0] = v0;
-    if (in1) fmp[i1] = v1;
+  for (int r = 0; r < kItems1D; ++r) {
+    const int64_t i = base + (int64_t)r * kThreads;
+    if (i < J.ntot) fmp_point<T>(J, i);
   }
 }
 
