@@ -397,6 +397,9 @@ int mb200_free(mb200_ctx *ctx, void *p);
 int mb200_memset(mb200_ctx *ctx, void *p, int value, size_t bytes);
 int mb200_h2d(mb200_ctx *ctx, void *dst, const void *src, size_t bytes); /* async if src pinned */
 int mb200_d2h(mb200_ctx *ctx, void *dst, const void *src, size_t bytes); /* synchronises */
+/* the same copy queued on the context's stream WITHOUT synchronising: a download of many arrays is
+ * one mb200_sync after the last of them instead of one stream synchronisation per array */
+int mb200_d2h_async(mb200_ctx *ctx, void *dst, const void *src, size_t bytes);
 /* Sub-box of a 3-D array in the reference layout (planes of `rows` rows of `row_elems` elements;
  * last index fastest): copies elements [lo0, lo0+cnt0) x [lo1, lo1+cnt1) x [lo2, lo2+cnt2) of the
  * device array to the same positions of the host array (one 3-D copy; does NOT synchronise — call

@@ -177,6 +177,7 @@ def declare(lib):
         "mb200_memset": (i, [vp, vp, i, sz]),
         "mb200_h2d": (i, [vp, vp, vp, sz]),
         "mb200_d2h": (i, [vp, vp, vp, sz]),
+        "mb200_d2h_async": (i, [vp, vp, vp, sz]),
         "mb200_d2h_box": (i, [vp, vp, vp, sz, i64, i64, i64, i64, i64, i64, i64, i64]),
         "mb200_d2d": (i, [vp, vp, vp, sz]),
         "mb200_host_alloc": (i, [sz, P(vp)]),

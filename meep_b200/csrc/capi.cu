@@ -226,6 +226,10 @@ int mb200_init(int device, mb200_ctx **out) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pml_pair, &v, sizeof(int)));
   }
+  if (const char *e = getenv("MEEP_B200_PML_LEAN")) {
+    const int v = atoi(e);
+    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pml_lean, &v, sizeof(int)));
+  }
   if (const char *e = getenv("MEEP_B200_PAIR_PLANES")) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pair_planes, &v, sizeof(int)));
@@ -304,6 +308,12 @@ int mb200_d2h(mb200_ctx *c, void *dst, const void *src, size_t bytes) {
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int mb200_d2h_async(mb200_ctx *c, void *dst, const void *src, size_t bytes) {
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
   return 0;
 }
 

@@ -620,7 +620,8 @@ template <typename T, bool PML, bool FU, bool CND, int EPI>
 MB200_HD void step3c_dispatch(const mb200_step3_job_t &J, const mb200_step3_comp_t &C, int64_t i, int64_t sx,
                               int ix0, int ix_end, int iy, int iz);
 #ifdef __CUDACC__
-__device__ int g_pml_pair = 1; // MEEP_B200_PML_PAIR=0: one plane per iteration for every variant
+__device__ int g_pml_pair = 10; // MEEP_B200_PML_PAIR=n: variants with up to n operands per point march two planes at a time (0: none)
+__device__ int g_pml_lean = 1;  // MEEP_B200_PML_LEAN=0: one-plane marches keep a 64-bit cursor per array (the round-1 form)
 // The same march with TWO x-planes loaded before the first store, for the variants with few
 // operands (a face PML chunk gives each component at most one auxiliary level: 6-9 loads per
 // point).  The PML kernel is latency-bound (ncu, 512^3: issue slots 25 % busy, DRAM 52 %, DRAM bytes
@@ -630,7 +631,7 @@ __device__ int g_pml_pair = 1; // MEEP_B200_PML_PAIR=0: one plane per iteration 
 template <typename T, bool PML, bool FU, bool CND, int EPI> struct Step3cVals {
   T f, a1, c1, c2, a2, fu, fcnd, cnd, cndinv, u, fw, e, kms, sinv, kmsu, sinvu, kapw, sigw;
 };
-template <typename T, bool PML, bool FU, bool CND, int EPI>
+template <typename T, bool PML, bool FU, bool CND, int EPI, bool PAIR = true>
 __device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, const mb200_step3_comp_t &C,
                                                   int64_t i, int64_t sx, int ix0, int ix_end, int iy, int iz) {
   constexpr bool FW = EPI == 2;
@@ -716,14 +717,15 @@ __device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, co
   };
   unsigned q = (unsigned)i;
   int ix = ix0;
-  for (; ix + 1 < ix_end; ix += 2, q += 2 * sxu, k += 2 * dk, ku += 2 * dku, kw += 2 * dkw) {
-    V a, b;
-    load(q, k, ku, kw, a);
-    load(q + sxu, k + dk, ku + dku, kw + dkw, b);
-    finish(q, ix, a);
-    finish(q + sxu, ix + 1, b);
-  }
-  if (ix < ix_end) {
+  if (PAIR)
+    for (; ix + 1 < ix_end; ix += 2, q += 2 * sxu, k += 2 * dk, ku += 2 * dku, kw += 2 * dkw) {
+      V a, b;
+      load(q, k, ku, kw, a);
+      load(q + sxu, k + dk, ku + dku, kw + dkw, b);
+      finish(q, ix, a);
+      finish(q + sxu, ix + 1, b);
+    }
+  for (; ix < ix_end; ++ix, q += sxu, k += dk, ku += dku, kw += dkw) {
     V a;
     load(q, k, ku, kw, a);
     finish(q, ix, a);
@@ -738,13 +740,20 @@ MB200_HD void step3c_dispatch(const mb200_step3_job_t &J, const mb200_step3_comp
   // operands per point: pair the planes only while two planes fit the 64-register budget of 4 CTAs/SM
   constexpr int kOperands = 5 + (FU ? 3 : 0) + (CND ? (PML ? 3 : 2) : 0) + (PML ? 2 : 0) + (EPI ? 1 : 0) +
                             (EPI == 2 ? 4 : 0);
-  if (kOperands <= 10 && g_pml_pair != 0 &&
-      (int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32)) {
-    step3c_pair_march<T, PML, FU, CND, EPI>(J, C, i, sx, ix0, ix_end, iy, iz);
-    return;
+  if ((int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32)) {
+    if (kOperands <= 10 && kOperands <= g_pml_pair) {
+      step3c_pair_march<T, PML, FU, CND, EPI, true>(J, C, i, sx, ix0, ix_end, iy, iz);
+      return;
+    }
+    if (g_pml_lean != 0) {
+      step3c_pair_march<T, PML, FU, CND, EPI, false>(J, C, i, sx, ix0, ix_end, iy, iz);
+      return;
+    }
   }
 #endif
+#if !defined(__CUDA_ARCH__) || !defined(MB200_PML_LEAN_ONLY)
   step3c_march<T, PML, FU, CND, EPI>(J, C, i, sx, ix0, ix_end, iy, iz);
+#endif
 }
 
 template <typename T>

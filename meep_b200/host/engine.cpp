@@ -112,6 +112,11 @@ Engine::Engine(fields *f) : self(f) {
 
 Engine::~Engine() {
   if (current_ == this) current_ = nullptr;
+  if (verbose)
+    fprintf(stderr, "meep_b200: engine summary: %lld steps, %lld uploads, %lld downloads, %lld region downloads, "
+            "%.3f MB h2d, %.3f MB d2h, %lld plan builds\n", (long long)stats.steps, (long long)stats.uploads,
+            (long long)stats.downloads, (long long)stats.region_downloads, stats.h2d_bytes / 1e6, stats.d2h_bytes / 1e6,
+            (long long)stats.plan_builds);
   recording_ = false;
   invalidate_plans();
   drop_links();
@@ -606,11 +611,14 @@ void Engine::upload_fields() {
 }
 
 void Engine::download_fields() {
+  // all copies queued, then ONE synchronisation (a small run has tens of arrays: a stream
+  // synchronisation per array made a download cost more than the step it follows)
   for (auto &kv : arrs_)
     if (kv.second.is_field) {
-      check(mb200_d2h(ctx, (void *)kv.first, kv.second.dev, kv.second.bytes), "d2h");
+      check(mb200_d2h_async(ctx, (void *)kv.first, kv.second.dev, kv.second.bytes), "d2h");
       stats.d2h_bytes += kv.second.bytes;
     }
+  check(mb200_sync(ctx), "device synchronisation");
   stats.downloads++;
   host_resident = true;
 }
@@ -696,7 +704,11 @@ void Engine::sync_host_region(const volume &where) {
     if (f->boundaries[High][d] == Periodic || f->boundaries[Low][d] == Periodic) ok = false;
   }
   if (!ok) {
-    if (forced) download_fields();
+    if (forced) {
+      // (several loop_in_chunks calls of one flux update: nothing runs on the device in between)
+      if (!forced_download_done) download_fields();
+      forced_download_done = true;
+    }
     else sync_host();
     return;
   }
@@ -737,7 +749,11 @@ void Engine::sync_host_region(const volume &where) {
     }
   }
   if (total == 0 || part > region_fraction_limit * total) {
-    if (forced) download_fields();
+    if (forced) {
+      // (several loop_in_chunks calls of one flux update: nothing runs on the device in between)
+      if (!forced_download_done) download_fields();
+      forced_download_done = true;
+    }
     else sync_host();
     return;
   }

@@ -188,6 +188,7 @@ public:
   // box is most of the cell.  The device copy stays the authoritative one.
   void sync_host_region(const meep::volume &where);
   bool force_reader_sync = false;
+  bool forced_download_done = false; // the arrays were all downloaded since force_reader_sync was raised
   double region_fraction_limit = 0.3; // MEEP_B200_REGION_SYNC (0 disables sub-volume downloads)
   void mark_host_dirty() { if (state != DEVICE_NEWER) state = HOST_NEWER; }
 

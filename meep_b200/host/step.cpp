@@ -164,6 +164,7 @@ void fields::step() {
         // legacy flux planes (flux_vol, src/meep.hpp:2322-2351) integrate host arrays through
         // loop_in_chunks: the interposed loop_in_chunks downloads just the planes they read
         E.force_reader_sync = true;
+        E.forced_download_done = false;
         if (h == 0) fluxes->update_half();
         else fluxes->update();
         E.force_reader_sync = false;

@@ -276,6 +276,10 @@ int mb200_d2h(mb200_ctx *, void *dst, const void *src, size_t bytes) {
   memcpy(dst, src, bytes);
   return 0;
 }
+int mb200_d2h_async(mb200_ctx *, void *dst, const void *src, size_t bytes) {
+  memcpy(dst, src, bytes);
+  return 0;
+}
 int mb200_d2d(mb200_ctx *, void *dst, const void *src, size_t bytes) {
   memmove(dst, src, bytes);
   return 0;

@@ -32,3 +32,20 @@ def test_two_gpu_sharded_run_matches_reference(case, steps, chunks, world, trans
                       env={"MEEP_B200_P2P": "1" if transport == "peer" else "0"})
     rep = compare(got, ref, TOL["f64"])
     print(case, "worst group rel-L2 %.2e" % max(rep.values()))
+
+
+@pytest.mark.parametrize("case,steps,chunks", [("c2_3d_pml", 40, 2), ("3d_bloch", 40, 4), ("c3_au_sphere", 60, 8)])
+def test_two_ranks_sharing_one_gpu_match_reference(case, steps, chunks):
+    """The cross-process exchange on a ONE-GPU box (the driver's test box): two ranks, both on device 0,
+    each packing its comm blocks into the other PROCESS's device memory (CUDA IPC works between
+    processes on the same device exactly as between devices) and signalling through the same flag
+    words.  Slower than two GPUs — the two contexts time-slice the device while one of them spins
+    on a flag — but the code path, the tables and the values are those of the multi-GPU run."""
+    if _ngpu() < 1:
+        pytest.skip("needs a GPU")
+    ref = run_case("ref", "f64", case, steps, chunks)
+    got = run_case_mp("b200", "f64", case, steps, chunks, 2,
+                      env={"MEEP_B200_P2P": "1", "MEEP_B200_DEVICE": "0", "MEEP_B200_PEER_TIMEOUT_S": "60"},
+                      timeout=600)
+    rep = compare(got, ref, TOL["f64"])
+    print(case, "worst group rel-L2 %.2e" % max(rep.values()))
