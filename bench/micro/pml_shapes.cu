@@ -21,6 +21,37 @@
 
 using namespace mb200;
 
+namespace mb200 {
+// ---- fast-path chunks and PML chunks in ONE launch ------------------------------------------------
+// EXPERIMENT (negative result, kept here and not in the product): launched one after the other, the
+// fast-path kernel runs at the HBM rate and the PML kernel, which is latency-bound on its thin slabs,
+// leaves a third of it unused.  In one grid with the two kinds of CTA interleaved (of every U = P + Q consecutive CTAs, Q take PML units
+// and P fast-path tiles, spread evenly) every SM holds both kinds at any time: the PML CTAs wait on
+// their loads while the fast-path CTAs keep the memory system busy.  Measured (B200, 512^3 and 1024^3
+// cells): 2.89 / 23.1 ms mixed against 2.85 / 22.4 ms for the two launches — the joint register
+// allocation (64 registers, 1.6 KB of spill code) costs the fast path more than the mixing gains.  jobs[0 .. n_plain) are the
+// fast-path jobs, jobs[n_plain .. n_plain + n_pml) the others; a PML unit is (tile, component).
+template <typename T, int MINB, int BUDGET = step3c_budget<T>(MINB)>
+__global__ void __launch_bounds__(kThreads, MINB)
+    step3_mixed_kernel(const mb200_step3_job_t *__restrict__ jobs, const int64_t *__restrict__ prefix_plain,
+                       int n_plain, const int64_t *__restrict__ prefix_pml, int n_pml, int64_t units_plain,
+                       int64_t units_pml) {
+  __shared__ mb200_step3_job_t J;
+  const int64_t U = units_plain + units_pml, b = (int64_t)blockIdx.x;
+  const int64_t q0 = b * units_pml / U, q1 = (b + 1) * units_pml / U;
+  int64_t tile;
+  if (q1 > q0) {
+    stage_job_at(&J, jobs + n_plain, prefix_pml, n_pml, q0 / 3, &tile);
+    step3c_thread<T, BUDGET, false>(J, (int)(q0 % 3), tile, threadIdx.x);
+  }
+  else {
+    stage_job_at(&J, jobs, prefix_plain, n_plain, b - q0, &tile);
+    step3_plain_thread<T>(J, tile, threadIdx.x);
+  }
+}
+
+} // namespace mb200
+
 #define CK(x)                                                                                      \
   do {                                                                                             \
     cudaError_t e_ = (x);                                                                          \
@@ -169,11 +200,6 @@ template <typename F> static float time_best(F launch) {
   return best;
 }
 
-static void set_flags(int pair, int lean) {
-  CK(cudaMemcpyToSymbol(g_pml_pair, &pair, sizeof(int)));
-  CK(cudaMemcpyToSymbol(g_pml_lean, &lean, sizeof(int)));
-}
-
 static void report(const char *shape, const char *form, int t1, const Chunk &K, float ms) {
   printf("{\"shape\": \"%s\", \"form\": \"%s\", \"t1\": %d, \"cells\": %.0f, \"alg_MB\": %.1f, \"ms\": %.4f, \"GBps\": %.0f}\n",
          shape, form, t1, K.cells, K.alg_bytes / 1e6, ms, K.alg_bytes / ms / 1e6);
@@ -181,7 +207,11 @@ static void report(const char *shape, const char *form, int t1, const Chunk &K, 
 }
 
 int main(int argc, char **argv) {
+  // pml_shapes [interior cells per edge] [PML thickness in cells] [shape filter] [form filter] [planes per CTA]
   const int n_int = argc > 1 ? atoi(argv[1]) : 492, thick = argc > 2 ? atoi(argv[2]) : 10;
+  const char *shape_filter = argc > 3 && strcmp(argv[3], "all") ? argv[3] : nullptr;
+  const char *form_filter = argc > 4 && strcmp(argv[4], "all") ? argv[4] : nullptr;
+  const int only_t1 = argc > 5 ? atoi(argv[5]) : 0;
   struct Shape {
     const char *name;
     int n[3];
@@ -195,7 +225,9 @@ int main(int argc, char **argv) {
       {"all26", {0, 0, 0}, 0},                          // the 26 PML chunks of the cell in one launch, as bench.py runs them
   };
   for (const Shape &S : shapes) {
+    if (shape_filter && !strstr(S.name, shape_filter)) continue;
     for (int t1 : {8, 16, 32}) {
+      if (only_t1 && t1 != only_t1) continue;
       Chunk K;
       std::vector<mb200_step3_job_t> jobs;
       if (strcmp(S.name, "all26")) {
@@ -221,19 +253,22 @@ int main(int argc, char **argv) {
       CK(cudaDeviceSynchronize());
       struct Form {
         const char *name;
-        int pair, lean, minb;
+        int minb, budget;
       };
-      const Form forms[] = {{"c4_pair10_lean", 10, 1, 4}, {"c4_pair9_lean", 9, 1, 4}, {"c4_single_lean", 0, 1, 4},
-                            {"c4_single_wide", 0, 0, 4},  {"c3_pair10_lean", 10, 1, 3}, {"c5_single_lean", 0, 1, 5}};
+      // budget = values in flight per thread; planes per iteration = budget / operands of the variant (1..4)
+      const Form forms[] = {{"c4_b10", 4, 10}, {"c4_b20", 4, 20}, {"c3_b20", 3, 20}, {"c3_b28", 3, 28},
+                            {"c2_b30", 2, 30}, {"c2_b40", 2, 40}, {"c2_b52", 2, 52}};
       for (const Form &F : forms) {
-        set_flags(F.pair, F.lean);
-        float ms;
-        if (F.minb == 4) ms = time_best([&] { step3c_kernel<double, 4><<<g3, kThreads>>>(T.d_jobs, T.d_prefix, T.njobs); });
-        else if (F.minb == 3) ms = time_best([&] { step3c_kernel<double, 3><<<g3, kThreads>>>(T.d_jobs, T.d_prefix, T.njobs); });
-        else ms = time_best([&] { step3c_kernel<double, 5><<<g3, kThreads>>>(T.d_jobs, T.d_prefix, T.njobs); });
+        if (form_filter && !strstr(F.name, form_filter)) continue;
+        float ms = 0;
+#define RUN(MB, BU)                                                                                            \
+  if (F.minb == MB && F.budget == BU)                                                                        \
+    ms = time_best([&] { step3c_kernel<double, MB, false, BU><<<g3, kThreads>>>(T.d_jobs, T.d_prefix, T.njobs); });
+        RUN(4, 10) RUN(4, 20) RUN(3, 20) RUN(3, 28) RUN(2, 30) RUN(2, 40) RUN(2, 52)
+#undef RUN
         report(S.name, F.name, t1, K, ms);
       }
-      if (t1 == 16) {
+      if (t1 == 16 && !form_filter) {
         float ms = time_best([&] { step3_kernel<double><<<g1, kThreads>>>(T.d_jobs, T.d_prefix, T.njobs); });
         report(S.name, "three_components_per_thread", t1, K, ms);
       }
@@ -241,7 +276,7 @@ int main(int argc, char **argv) {
       cudaFree(T.d_prefix);
       free_all();
       // the same shape without PML through the fast-path kernel: what the shape alone costs
-      if (t1 == 16) {
+      if (t1 == 16 && !form_filter) {
         Chunk P = make_chunk(S.n, 0, true, t1);
         if (!strcmp(S.name, "all26")) continue;
         Table TP = upload(std::vector<mb200_step3_job_t>(1, P.J));
@@ -252,6 +287,53 @@ int main(int argc, char **argv) {
         free_all();
       }
     }
+  }
+  // ---- the interior chunk (fast path) and the 26 PML chunks: one after the other vs one mixed grid
+  if (!shape_filter || !strcmp(shape_filter, "mixed")) {
+    const int t1 = 16;
+    std::vector<mb200_step3_job_t> jobs;
+    const int ni[3] = {n_int, n_int, n_int};
+    Chunk P = make_chunk(ni, 0, true, t1), K;
+    memset(&K, 0, sizeof(K));
+    jobs.push_back(P.J);
+    for (int m = 1; m < 27; ++m) {
+      int pos[3] = {m % 3, (m / 3) % 3, m / 9}, n[3], mask = 0;
+      for (int d = 0; d < 3; ++d) {
+        n[d] = pos[d] == 0 ? n_int : thick;
+        if (pos[d] != 0) mask |= 1 << d;
+      }
+      Chunk Q = make_chunk(n, mask, false, t1);
+      jobs.push_back(Q.J);
+      K.cells += Q.cells;
+      K.alg_bytes += Q.alg_bytes;
+    }
+    Table TP = upload(std::vector<mb200_step3_job_t>(1, jobs[0]));
+    Table TQ = upload(std::vector<mb200_step3_job_t>(jobs.begin() + 1, jobs.end()));
+    Table TA = upload(jobs); // (only the job array of this one is used)
+    const float ms_p = time_best([&] { step3_plain_kernel<double><<<(unsigned)TP.tiles, kThreads>>>(TP.d_jobs, TP.d_prefix, 1); });
+    report("interior", "plain_alone", t1, P, ms_p);
+    const float ms_q4 = time_best([&] { step3c_kernel<double, 4><<<(unsigned)(3 * TQ.tiles), kThreads>>>(TQ.d_jobs, TQ.d_prefix, TQ.njobs); });
+    report("all26", "pml_alone_c4", t1, K, ms_q4);
+    const float ms_q3 = time_best([&] { step3c_kernel<double, 3><<<(unsigned)(3 * TQ.tiles), kThreads>>>(TQ.d_jobs, TQ.d_prefix, TQ.njobs); });
+    report("all26", "pml_alone_c3", t1, K, ms_q3);
+    Chunk S = P;
+    S.cells += K.cells;
+    S.alg_bytes += K.alg_bytes;
+    const float ms_seq = time_best([&] {
+      step3_plain_kernel<double><<<(unsigned)TP.tiles, kThreads>>>(TP.d_jobs, TP.d_prefix, 1);
+      step3c_kernel<double, 4><<<(unsigned)(3 * TQ.tiles), kThreads>>>(TQ.d_jobs, TQ.d_prefix, TQ.njobs);
+    });
+    report("interior+all26", "two_launches_c4", t1, S, ms_seq);
+    const unsigned gm = (unsigned)(TP.tiles + 3 * TQ.tiles);
+    const float ms_m4 = time_best([&] {
+      step3_mixed_kernel<double, 4><<<gm, kThreads>>>(TA.d_jobs, TP.d_prefix, 1, TQ.d_prefix, TQ.njobs, TP.tiles, 3 * TQ.tiles);
+    });
+    report("interior+all26", "mixed_c4", t1, S, ms_m4);
+    const float ms_m3 = time_best([&] {
+      step3_mixed_kernel<double, 3><<<gm, kThreads>>>(TA.d_jobs, TP.d_prefix, 1, TQ.d_prefix, TQ.njobs, TP.tiles, 3 * TQ.tiles);
+    });
+    report("interior+all26", "mixed_c3", t1, S, ms_m3);
+    free_all();
   }
   return 0;
 }

@@ -226,10 +226,6 @@ int mb200_init(int device, mb200_ctx **out) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pml_pair, &v, sizeof(int)));
   }
-  if (const char *e = getenv("MEEP_B200_PML_LEAN")) {
-    const int v = atoi(e);
-    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pml_lean, &v, sizeof(int)));
-  }
   if (const char *e = getenv("MEEP_B200_PAIR_PLANES")) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pair_planes, &v, sizeof(int)));

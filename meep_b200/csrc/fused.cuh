@@ -616,24 +616,21 @@ MB200_HD void step3c_march(const mb200_step3_job_t &J, const mb200_step3_comp_t 
   }
 }
 
-template <typename T, bool PML, bool FU, bool CND, int EPI>
-MB200_HD void step3c_dispatch(const mb200_step3_job_t &J, const mb200_step3_comp_t &C, int64_t i, int64_t sx,
-                              int ix0, int ix_end, int iy, int iz);
 #ifdef __CUDACC__
-__device__ int g_pml_pair = 10; // MEEP_B200_PML_PAIR=n: variants with up to n operands per point march two planes at a time (0: none)
-__device__ int g_pml_lean = 1;  // MEEP_B200_PML_LEAN=0: one-plane marches keep a 64-bit cursor per array (the round-1 form)
-// The same march with TWO x-planes loaded before the first store, for the variants with few
-// operands (a face PML chunk gives each component at most one auxiliary level: 6-9 loads per
-// point).  The PML kernel is latency-bound (ncu, 512^3: issue slots 25 % busy, DRAM 52 %, DRAM bytes
-// = 1.03 x algorithmic): with one component per thread a plane keeps only 6-9 loads in flight per
-// thread against 15-18 in the fast path.  All arrays of a chunk share one index space, so a single
-// 32-bit cursor addresses every operand and the descriptor fields stay in shared memory.
-template <typename T, bool PML, bool FU, bool CND, int EPI> struct Step3cVals {
+__device__ int g_pml_pair = 4; // MEEP_B200_PML_PAIR=n: at most n x-planes in flight per thread (1: one plane per iteration)
+// The same march with NP x-planes loaded before the first store.  The PML kernel is latency-bound
+// (ncu, 512^3: issue slots 25 % busy, DRAM 52 %, DRAM bytes = 1.03 x algorithmic): with one component
+// per thread a plane keeps only 6-13 loads in flight per thread against 15-18 in the fast path, so the
+// register budget of the launch configuration is spent on planes: NP = budget / operands per point.
+// All arrays of a chunk share one index space, so a single 32-bit cursor addresses every operand and
+// the descriptor fields stay in shared memory (a 64-bit cursor per array, as in step3c_march, costs
+// 2 registers per array: measured 4 % slower at one plane, bench/micro/pml_shapes.cu).
+template <typename T> struct Step3cVals {
   T f, a1, c1, c2, a2, fu, fcnd, cnd, cndinv, u, fw, e, kms, sinv, kmsu, sinvu, kapw, sigw;
 };
-template <typename T, bool PML, bool FU, bool CND, int EPI, bool PAIR = true>
-__device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, const mb200_step3_comp_t &C,
-                                                  int64_t i, int64_t sx, int ix0, int ix_end, int iy, int iz) {
+template <typename T, bool PML, bool FU, bool CND, int EPI, int NP>
+__device__ __forceinline__ void step3c_multi_march(const mb200_step3_job_t &J, const mb200_step3_comp_t &C,
+                                                   int64_t i, int64_t sx, int ix0, int ix_end, int iy, int iz) {
   constexpr bool FW = EPI == 2;
   const bool HASU = EPI != 0 && C.u != nullptr;
   const T dtdx = (T)C.dtdx, dt2 = (T)J.dt * T(0.5);
@@ -649,7 +646,7 @@ __device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, co
     mhi = C.metal_hi[0];
   }
   const int nlo = J.noepi_lo, nhi = J.noepi_lo + J.noepi_n;
-  typedef Step3cVals<T, PML, FU, CND, EPI> V;
+  typedef Step3cVals<T> V;
   auto load = [&](unsigned q, int k, int ku, int kw, V &v) {
     v.f = ldmut((const T *)C.f + q);
     v.a1 = ldro((const T *)C.g1 + (q + s1));
@@ -717,13 +714,15 @@ __device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, co
   };
   unsigned q = (unsigned)i;
   int ix = ix0;
-  if (PAIR)
-    for (; ix + 1 < ix_end; ix += 2, q += 2 * sxu, k += 2 * dk, ku += 2 * dku, kw += 2 * dkw) {
-      V a, b;
-      load(q, k, ku, kw, a);
-      load(q + sxu, k + dk, ku + dku, kw + dkw, b);
-      finish(q, ix, a);
-      finish(q + sxu, ix + 1, b);
+  if (NP > 1 && g_pml_pair > 1)
+    for (; ix + NP <= ix_end; ix += NP, q += NP * sxu, k += NP * dk, ku += NP * dku, kw += NP * dkw) {
+      V v[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+        load(q + p * sxu, k + p * dk, ku + p * dku, kw + p * dkw, v[p]);
+#pragma unroll
+      for (int p = 0; p < NP; ++p)
+        finish(q + p * sxu, ix + p, v[p]);
     }
   for (; ix < ix_end; ++ix, q += sxu, k += dk, ku += dku, kw += dkw) {
     V a;
@@ -733,30 +732,24 @@ __device__ __forceinline__ void step3c_pair_march(const mb200_step3_job_t &J, co
 }
 #endif
 
-template <typename T, bool PML, bool FU, bool CND, int EPI>
+// BUDGET: values a thread may hold in flight (what the registers of the launch configuration leave
+// after addressing: see step3c_kernel); WIDE: a chunk with 2^32 or more elements per array (64-bit cursors)
+template <typename T, bool PML, bool FU, bool CND, int EPI, int BUDGET, bool WIDE>
 MB200_HD void step3c_dispatch(const mb200_step3_job_t &J, const mb200_step3_comp_t &C, int64_t i, int64_t sx,
                               int ix0, int ix_end, int iy, int iz) {
 #ifdef __CUDA_ARCH__
-  // operands per point: pair the planes only while two planes fit the 64-register budget of 4 CTAs/SM
-  constexpr int kOperands = 5 + (FU ? 3 : 0) + (CND ? (PML ? 3 : 2) : 0) + (PML ? 2 : 0) + (EPI ? 1 : 0) +
-                            (EPI == 2 ? 4 : 0);
-  if ((int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32)) {
-    if (kOperands <= 10 && kOperands <= g_pml_pair) {
-      step3c_pair_march<T, PML, FU, CND, EPI, true>(J, C, i, sx, ix0, ix_end, iy, iz);
-      return;
-    }
-    if (g_pml_lean != 0) {
-      step3c_pair_march<T, PML, FU, CND, EPI, false>(J, C, i, sx, ix0, ix_end, iy, iz);
-      return;
-    }
+  if (!WIDE) {
+    constexpr int kOperands = 5 + (FU ? 3 : 0) + (CND ? (PML ? 3 : 2) : 0) + (PML ? 2 : 0) + (EPI ? 1 : 0) +
+                              (EPI == 2 ? 4 : 0);
+    constexpr int kPlanes = BUDGET / kOperands < 1 ? 1 : (BUDGET / kOperands > 4 ? 4 : BUDGET / kOperands);
+    step3c_multi_march<T, PML, FU, CND, EPI, kPlanes>(J, C, i, sx, ix0, ix_end, iy, iz);
+    return;
   }
 #endif
-#if !defined(__CUDA_ARCH__) || !defined(MB200_PML_LEAN_ONLY)
   step3c_march<T, PML, FU, CND, EPI>(J, C, i, sx, ix0, ix_end, iy, iz);
-#endif
 }
 
-template <typename T>
+template <typename T, int BUDGET = 0, bool WIDE = true>
 MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int tid) {
   const mb200_box_t box = step3_box(J);
   int ix0, ix_end, iy, iz;
@@ -778,7 +771,7 @@ MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int
   switch (variant) { // CTA-uniform
 #define MB200_S3C(v)                                                                               \
   case v:                                                                                          \
-    step3c_dispatch<T, ((v) / 12) != 0, (((v) / 6) % 2) != 0, (((v) / 3) % 2) != 0, (v) % 3>(      \
+    step3c_dispatch<T, ((v) / 12) != 0, (((v) / 6) % 2) != 0, (((v) / 3) % 2) != 0, (v) % 3, BUDGET, WIDE>( \
         J, C, i, sx, ix0, ix_end, iy, iz);                                                         \
     break;
     MB200_S3C(0) MB200_S3C(1) MB200_S3C(2) MB200_S3C(3) MB200_S3C(4) MB200_S3C(5)
@@ -789,9 +782,19 @@ MB200_HD void step3c_thread(const mb200_step3_job_t &J, int c, int64_t tile, int
   }
 }
 
+// does any array of the job have 2^32 or more elements (the 32-bit cursors of the multi-plane march)?
+inline bool step3_wide(const mb200_step3_job_t &J) {
+  return (int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) >= ((int64_t)1 << 32);
+}
+
 #ifdef __CUDACC__
 
-template <typename T, int MINB>
+// values in flight per thread that MINB CTAs of 256 threads per SM leave room for: 65536 / (256 MINB)
+// registers, ~24 of them for addressing, bounds and constants; a double takes two
+template <typename T> constexpr int step3c_budget(int minb) {
+  return (65536 / (kThreads * minb) - (minb == 3 ? 29 : 24)) / (int)(sizeof(T) / 4);
+}
+template <typename T, int MINB, bool WIDE = false, int BUDGET = step3c_budget<T>(MINB)>
 __global__ void __launch_bounds__(kThreads, MINB)
     step3c_kernel(const mb200_step3_job_t *__restrict__ jobs,
                   const int64_t *__restrict__ tile_prefix, int njobs) {
@@ -800,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
   // consecutive CTAs take the three components of the same tile: the curl operands they share
   // are fetched from DRAM once and found in L2 by the other two
   stage_job_at(&J, jobs, tile_prefix, njobs, (int64_t)(blockIdx.x / 3), &tile);
-  step3c_thread<T>(J, (int)(blockIdx.x % 3), tile, threadIdx.x);
+  step3c_thread<T, BUDGET, WIDE>(J, (int)(blockIdx.x % 3), tile, threadIdx.x);
 }
 
 template <typename T>
@@ -895,14 +898,18 @@ static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, i
   }
   else if (all_plain)
     step3_plain_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
-  else if (split == 4) // MEEP_B200_SPLIT_PML=4|5|6: CTAs per SM (64 / 51 / 42 registers)
-    step3c_kernel<T, 4><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
-  else if (split == 5)
-    step3c_kernel<T, 5><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
-  else if (split == 6)
-    step3c_kernel<T, 6><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
-  else if (split)
-    step3c_kernel<T, 3><<<dim3((unsigned)(3 * tiles)), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
+  else if (split) { // MEEP_B200_SPLIT_PML=2..6: CTAs per SM (128 / 85 / 64 / 51 / 42 registers per thread)
+    bool wide = false;
+    for (int j = 0; j < njobs; ++j)
+      wide = wide || step3_wide(h_jobs[j]);
+    const dim3 grid((unsigned)(3 * tiles)), block(kThreads);
+    if (wide) step3c_kernel<T, 4, true><<<grid, block, 0, s>>>(jobs, prefix, njobs);
+    else if (split == 2) step3c_kernel<T, 2><<<grid, block, 0, s>>>(jobs, prefix, njobs);
+    else if (split == 3) step3c_kernel<T, 3><<<grid, block, 0, s>>>(jobs, prefix, njobs);
+    else if (split == 5) step3c_kernel<T, 5><<<grid, block, 0, s>>>(jobs, prefix, njobs);
+    else if (split == 6) step3c_kernel<T, 6><<<grid, block, 0, s>>>(jobs, prefix, njobs);
+    else step3c_kernel<T, 4><<<grid, block, 0, s>>>(jobs, prefix, njobs);
+  }
   else
     step3_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
 }
