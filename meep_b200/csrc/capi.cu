@@ -226,6 +226,10 @@ int mb200_init(int device, mb200_ctx **out) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pml_pair, &v, sizeof(int)));
   }
+  if (const char *e = getenv("MEEP_B200_FMP_SIMPLE")) {
+    const int v = atoi(e);
+    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_fmp_simple, &v, sizeof(int)));
+  }
   if (const char *e = getenv("MEEP_B200_PAIR_PLANES")) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pair_planes, &v, sizeof(int)));

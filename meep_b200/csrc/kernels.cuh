@@ -23,6 +23,7 @@ constexpr int kT1 = 8; // loop-1 planes marched per CTA
 constexpr int kItems1D = 4;  // elements per thread for streaming 1-D jobs
 constexpr int kDftPts = 64;  // monitor points per CTA in dft_kernel
 constexpr int kFluxPts = 256; // points per CTA in flux_kernel
+constexpr int kFmpBlocks = 4; // zero-flag blocks per CTA in fmp_kernel
 
 // host+device: tile decomposition of a box
 struct BoxTiling {
@@ -106,6 +107,8 @@ template <typename T> MB200_HD void curl_thread(const mb200_curl_job_t &J, int64
 }
 
 constexpr int kBatch = 4; // loop-1 planes whose loads are issued together
+constexpr int kEdhbT1 = 16;   // loop-1 planes marched per CTA in edhb_kernel
+constexpr int kEdhbBatch = 8; // planes in flight per thread for the plain E = chi1inv D update
 constexpr int kZBlocksPerCta = 16; // zero-block Lorentz kernel: blocks walked by one CTA
 
 // step_update_EDHB.  Diagonal, linear jobs (the common case when the update could not be fused
@@ -113,7 +116,7 @@ constexpr int kZBlocksPerCta = 16; // zero-block Lorentz kernel: blocks walked b
 // issues the loads of kBatch planes before the first store; everything else goes point by point.
 template <typename T> MB200_HD void edhb_thread(const mb200_edhb_job_t &J, int64_t tile, int tid) {
   int i1_0, i1_end, i2, i3;
-  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3)) return;
+  if (!box_thread_point(J.box, tile, tid, i1_0, i1_end, i2, i3, kEdhbT1)) return;
   int64_t i = box_index(J.box, i1_0, i2, i3);
   int kw = pml_k(J.pmlw, i1_0, i2, i3);
   const int64_t s1 = J.box.s[0];
@@ -122,6 +125,23 @@ template <typename T> MB200_HD void edhb_thread(const mb200_edhb_job_t &J, int64
     T *f = (T *)J.f, *fw = (T *)J.fw;
     const T *g = (const T *)J.g, *u = (const T *)J.u;
     const T *sigw = (const T *)J.pmlw.sig, *kapw = (const T *)J.pmlw.kap;
+    if (!sigw) {
+      // E = chi1inv D (two loads and a store per point): kEdhbBatch planes in flight per thread
+      for (int i1 = i1_0; i1 < i1_end; i1 += kEdhbBatch, i += kEdhbBatch * s1) {
+        T gv[kEdhbBatch], uv[kEdhbBatch];
+#pragma unroll
+        for (int k = 0; k < kEdhbBatch; ++k)
+          if (i1 + k < i1_end) {
+            const int64_t idx = i + k * s1;
+            gv[k] = ldro(g + idx);
+            uv[k] = u ? ldro(u + idx) : T(1);
+          }
+#pragma unroll
+        for (int k = 0; k < kEdhbBatch; ++k)
+          if (i1 + k < i1_end) f[i + k * s1] = u ? gv[k] * uv[k] : gv[k];
+      }
+      return;
+    }
     for (int i1 = i1_0; i1 < i1_end; i1 += kBatch, i += kBatch * s1, kw += kBatch * dk) {
       T gv[kBatch], uv[kBatch], fv[kBatch], fwv[kBatch], kv[kBatch], sv[kBatch];
 #pragma unroll
@@ -130,26 +150,39 @@ template <typename T> MB200_HD void edhb_thread(const mb200_edhb_job_t &J, int64
           const int64_t idx = i + k * s1;
           gv[k] = ldro(g + idx);
           uv[k] = u ? ldro(u + idx) : T(1);
-          if (sigw) {
-            fv[k] = f[idx];
-            fwv[k] = fw[idx];
-            kv[k] = ldro(kapw + kw + k * dk);
-            sv[k] = ldro(sigw + kw + k * dk);
-          }
+          fv[k] = f[idx];
+          fwv[k] = fw[idx];
+          kv[k] = ldro(kapw + kw + k * dk);
+          sv[k] = ldro(sigw + kw + k * dk);
         }
 #pragma unroll
       for (int k = 0; k < kBatch; ++k)
         if (i1 + k < i1_end) {
           const int64_t idx = i + k * s1;
           const T val = u ? gv[k] * uv[k] : gv[k];
-          if (sigw) { // src/step_generic.cpp:596-602
-            fw[idx] = val;
-            f[idx] = fv[k] + ((kv[k] + sv[k]) * val - (kv[k] - sv[k]) * fwv[k]);
-          }
-          else
-            f[idx] = val;
+          fw[idx] = val; // src/step_generic.cpp:596-602
+          f[idx] = fv[k] + ((kv[k] + sv[k]) * val - (kv[k] - sv[k]) * fwv[k]);
         }
     }
+    return;
+  }
+  if (J.u1 && J.u2 && !J.chi3 && !J.pmlw.sig) {
+    // full 3x3 chi1inv outside PML (anisotropic media; src/step_generic.cpp:588-615): 14 loads and one
+    // store per point, two planes in flight (same expression as edhb_point)
+    T *f = (T *)J.f;
+    const T *g = (const T *)J.g, *g1 = (const T *)J.g1, *g2 = (const T *)J.g2;
+    const T *u = (const T *)J.u, *u1 = (const T *)J.u1, *u2 = (const T *)J.u2;
+    const int64_t s = J.s, sa = J.s1, sb = J.s2;
+    auto value = [&](int64_t q) {
+      return ldro(g + q) * ldro(u + q) + offdiag(u1, g1, q, s, sa) + offdiag(u2, g2, q, s, sb);
+    };
+    int i1 = i1_0;
+    for (; i1 + 1 < i1_end; i1 += 2, i += 2 * s1) {
+      const T v0 = value(i), v1 = value(i + s1);
+      f[i] = v0;
+      f[i + s1] = v1;
+    }
+    if (i1 < i1_end) f[i] = value(i);
     return;
   }
   for (int i1 = i1_0; i1 < i1_end; ++i1, i += s1, kw += dk)
@@ -484,8 +517,32 @@ __global__ void __launch_bounds__(kThreads)
   // not a CTA launch
   const int64_t nblocks = (J.ntot + MB200_ZBLOCK - 1) / MB200_ZBLOCK;
   int done = 0; // blocks actually updated (the measured-bytes accounting: work[0])
+  // Everything the march needs from the descriptor, read once (the compiler cannot keep shared-memory
+  // fields in registers across the barrier and the flag store of each block).  The owned-box test of
+  // lorentz_owned in 32-bit arithmetic when the array has fewer than 2^31 elements: its 64-bit
+  // divisions (two per element, three more per block for the box corner) were most of the kernel's
+  // instructions — ~400 per element against 6 memory accesses.
+  const int64_t ntot = J.ntot, s0 = J.box.s[0], s1 = J.box.s[1], idx0 = J.box.idx0;
+  const bool small = ntot < ((int64_t)1 << 31);
+  const int64_t c1 = idx0 / s0, cr = idx0 - c1 * s0, c2 = cr / s1, c3 = cr - c2 * s1;
+  const unsigned us0 = (unsigned)s0, us1 = (unsigned)s1, l1 = (unsigned)c1, l2 = (unsigned)c2, l3 = (unsigned)c3;
+  const unsigned n1 = (unsigned)J.box.n[0], n2 = (unsigned)J.box.n[1], n3 = (unsigned)J.box.n[2];
+  auto owned = [&](int64_t idx) -> bool {
+    if (small) {
+      const unsigned u = (unsigned)idx, a1 = u / us0, r = u - a1 * us0, a2 = r / us1, a3 = r - a2 * us1;
+      return a1 - l1 < n1 && a2 - l2 < n2 && a3 - l3 < n3; // (unsigned: below the corner wraps to huge)
+    }
+    const int64_t a1 = idx / s0, r = idx - a1 * s0, a2 = r / s1, a3 = r - a2 * s1;
+    return a1 >= c1 && a1 < c1 + n1 && a2 >= c2 && a2 < c2 + n2 && a3 >= c3 && a3 < c3 + n3;
+  };
+  T *const p = (T *)J.p, *const pp = (T *)J.pp;
+  const T *const sg = (const T *)J.s, *const wg = (const T *)J.w;
+  const uint8_t *const szero = J.szero;
+  uint8_t *const pzero = J.pzero;
+  const T gamma1inv = (T)J.gamma1inv, gamma1 = (T)J.gamma1, omega0dtsqr = (T)J.omega0dtsqr,
+          two_minus_denom = 2 - (T)J.omega0dtsqr_denom;
   for (int64_t b = tile * kZBlocksPerCta; b < (tile + 1) * kZBlocksPerCta && b < nblocks; ++b) {
-    if (J.szero[b] && J.pzero[b]) continue; // sigma = P = P_prev = 0 here: nothing changes
+    if (szero[b] && pzero[b]) continue; // sigma = P = P_prev = 0 here: nothing changes
     ++done;
     const int64_t base = b * MB200_ZBLOCK + threadIdx.x;
     bool zero = true;
@@ -494,16 +551,15 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int kPer = MB200_ZBLOCK / kThreads;
     T pc[kPer], ppv[kPer], sv[kPer], wv[kPer];
     bool own[kPer], in[kPer];
-    T *p = (T *)J.p, *pp = (T *)J.pp;
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
       const int64_t idx = base + (int64_t)r * kThreads;
-      in[r] = idx < J.ntot;
-      own[r] = in[r] && lorentz_owned(J, idx);
+      in[r] = idx < ntot;
+      own[r] = in[r] && owned(idx);
       pc[r] = in[r] ? p[idx] : T(0);
       ppv[r] = in[r] ? pp[idx] : T(0);
-      sv[r] = own[r] ? ldro((const T *)J.s + idx) : T(0);
-      wv[r] = own[r] ? ldro((const T *)J.w + idx) : T(0);
+      sv[r] = own[r] ? ldro(sg + idx) : T(0);
+      wv[r] = own[r] ? ldro(wg + idx) : T(0);
     }
 #pragma unroll
     for (int r = 0; r < kPer; ++r) {
@@ -514,14 +570,13 @@ __global__ void __launch_bounds__(kThreads)
         continue;
       }
       // same expression as lorentz_blocked_point / src/susceptibility.cpp:251-257
-      const T pn = (T)J.gamma1inv * (pc[r] * (2 - (T)J.omega0dtsqr_denom) - (T)J.gamma1 * ppv[r] +
-                                     (T)J.omega0dtsqr * (sv[r] * wv[r]));
+      const T pn = gamma1inv * (pc[r] * two_minus_denom - gamma1 * ppv[r] + omega0dtsqr * (sv[r] * wv[r]));
       p[idx] = pn;
       pp[idx] = pc[r];
       zero = zero && pn == T(0) && pc[r] == T(0);
     }
     const int allzero = __syncthreads_and(zero ? 1 : 0);
-    if (threadIdx.x == 0) J.pzero[b] = allzero ? 1 : 0;
+    if (threadIdx.x == 0) pzero[b] = allzero ? 1 : 0;
   }
   if (threadIdx.x == 0 && done) atomicAdd(work, (unsigned long long)done);
 }
@@ -540,25 +595,74 @@ __global__ void block_zero_flags_kernel(const T *__restrict__ arr, int64_t n, ui
 
 // ---- 1-D jobs ----------------------------------------------------------------------------------
 
+__device__ int g_fmp_simple = 0;
+// A CTA takes kFmpBlocks consecutive zero-flag blocks (MB200_ZBLOCK elements each).  The flags of
+// its blocks are read once, by the first threads, into shared memory: read per element they put a
+// dependent byte load in front of every polarisation load (two memory latencies per element instead
+// of one), and with one block per CTA the job look-up cost as much as the block itself.
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
     fmp_kernel(const mb200_fmp_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
                int njobs, unsigned long long *__restrict__ work) {
   __shared__ mb200_fmp_job_t J;
+  __shared__ uint8_t s_zero[kFmpBlocks][MB200_MAX_P];
   int64_t tile;
   stage_job(&J, jobs, tile_prefix, njobs, &tile);
-  static_assert(kThreads * kItems1D == MB200_ZBLOCK, "one zero-flag block per CTA");
+  static_assert(kThreads * kItems1D == MB200_ZBLOCK, "kItems1D elements per thread and block");
+  static_assert(kFmpBlocks * MB200_MAX_P <= kThreads, "one thread per (block, pole) flag");
+  const int64_t ntot = J.ntot, nblocks = (ntot + MB200_ZBLOCK - 1) / MB200_ZBLOCK, b0 = tile * kFmpBlocks;
+  const int np = J.np;
+  if (threadIdx.x < kFmpBlocks * MB200_MAX_P) {
+    const int blk = threadIdx.x / MB200_MAX_P, k = threadIdx.x % MB200_MAX_P;
+    const int64_t b = b0 + blk;
+    s_zero[blk][k] = (k < np && b < nblocks && J.pzero[k] && J.pzero[k][b]) ? 1 : 0;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) { // polarisation blocks this CTA reads (the others are known to be zero): work[1]
     int nread = 0;
-    for (int k = 0; k < J.np; ++k)
-      if (!(J.pzero[k] && J.pzero[k][tile])) ++nread;
+    for (int blk = 0; blk < kFmpBlocks && b0 + blk < nblocks; ++blk)
+      for (int k = 0; k < np; ++k)
+        if (!s_zero[blk][k]) ++nread;
     if (nread) atomicAdd(work + 1, (unsigned long long)nread);
   }
-  const int64_t base = tile * (kThreads * kItems1D) + threadIdx.x;
+  T *const fmp = (T *)J.fmp;
+  const T *const d = (const T *)J.d;
+  if (g_fmp_simple) { // MEEP_B200_FMP_SIMPLE=1: element by element as in round 1 (A/B switch)
+    for (int blk = 0; blk < kFmpBlocks; ++blk)
 #pragma unroll
-  for (int r = 0; r < kItems1D; ++r) {
-    const int64_t i = base + (int64_t)r * kThreads;
-    if (i < J.ntot) fmp_point<T>(J, i);
+      for (int r = 0; r < kItems1D; ++r) {
+        const int64_t i = (b0 + blk) * MB200_ZBLOCK + threadIdx.x + (int64_t)r * kThreads;
+        if (i < ntot) fmp_point<T>(J, i);
+      }
+    return;
+  }
+  for (int blk = 0; blk < kFmpBlocks; ++blk) {
+    const int64_t base = (b0 + blk) * MB200_ZBLOCK + threadIdx.x;
+    if (base - threadIdx.x >= ntot) break;
+    // two elements at a time, all their loads first: 2 (1 + n_pol) values in flight per thread at four
+    // CTAs per SM (four elements at once need 98 registers: two CTAs per SM, measured 30 % slower)
+#pragma unroll
+    for (int h = 0; h < kItems1D; h += 2) {
+      T v[2], pv[2][MB200_MAX_P];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t i = base + (int64_t)(h + r) * kThreads;
+        const bool in = i < ntot;
+        v[r] = in ? (d ? ldro(d + i) : fmp[i]) : T(0);
+#pragma unroll
+        for (int k = 0; k < MB200_MAX_P; ++k)
+          pv[r][k] = (in && k < np && !s_zero[blk][k]) ? ldro((const T *)J.p[k] + i) : T(0);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t i = base + (int64_t)(h + r) * kThreads;
+        T x = v[r];
+#pragma unroll
+        for (int k = 0; k < MB200_MAX_P; ++k)
+          if (k < np) x -= pv[r][k];
+        if (i < ntot) fmp[i] = x;
+      }
+    }
   }
 }
 

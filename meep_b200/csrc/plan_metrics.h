@@ -51,7 +51,7 @@ inline void job_metrics(int kind, int dtype, const void *jobs, int j, int64_t *t
     }
     case MB200_K_EDHB: {
       const mb200_edhb_job_t &J = ((const mb200_edhb_job_t *)jobs)[j];
-      *tiles = box_tiles(J.box);
+      *tiles = box_tiles(J.box, kEdhbT1);
       *points = box_points(J.box);
       int arrays = 1 + 1 + (J.u ? 1 : 0) + (J.u1 ? 2 : 0) + (J.u2 ? 2 : 0) + (J.chi3 ? 2 : 0) +
                    (J.pmlw.sig ? 3 : 0);
@@ -69,7 +69,7 @@ inline void job_metrics(int kind, int dtype, const void *jobs, int j, int64_t *t
     }
     case MB200_K_FMP: {
       const mb200_fmp_job_t &J = ((const mb200_fmp_job_t *)jobs)[j];
-      *tiles = ceil_div(J.ntot, kThreads * kItems1D);
+      *tiles = ceil_div(ceil_div(J.ntot, (int64_t)MB200_ZBLOCK), (int64_t)kFmpBlocks);
       *points = (double)J.ntot;
       *bytes = R * (2 + J.np) * *points;
       break;
