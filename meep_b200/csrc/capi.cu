@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 
 #include "kernels.cuh"
@@ -70,6 +71,7 @@ struct mb200_plan {
   double bytes, points;
   size_t job_size;
   bool all_plain; // STEP3: every job qualifies for the fast-path kernel
+  int *d_group;   // EDHB: first job of the component triple a job belongs to (or the job itself), see plan_create
   std::vector<char> h_jobs;       // STEP3: host copy (jobs are passed by value in param space)
   std::vector<int64_t> h_prefix;
 };
@@ -91,6 +93,8 @@ static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("
 // 1639 / 2790 us (MEEP_B200_PLAIN_FAST=1).  Fewer instructions did not help: the kernel is not
 // issue-bound.  Neither did more CTAs per SM (5: 1894 us, 6: 2120 us for the B half) nor staging
 // the operands through shared memory with 8-byte cp.async (2518 / 2896 us).
+// MEEP_B200_EDHB_INTERLEAVE=0: the three component jobs of an off-diagonal E update one after the other
+static const bool g_edhb_interleave = !getenv("MEEP_B200_EDHB_INTERLEAVE") || atoi(getenv("MEEP_B200_EDHB_INTERLEAVE")) != 0;
 static const bool g_plain_per_job = getenv("MEEP_B200_PLAIN_PER_JOB") && atoi(getenv("MEEP_B200_PLAIN_PER_JOB")) != 0;
 
 template <typename T>
@@ -104,7 +108,7 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       break;
     case MB200_K_EDHB:
       edhb_kernel<T><<<grid, block, 0, s>>>((const mb200_edhb_job_t *)p->d_jobs, p->d_prefix,
-                                            p->njobs);
+                                            p->njobs, p->d_group);
       break;
     case MB200_K_LORENTZ:
       if (p->all_plain) { // (for this kind: every job uses the zero-block variant)
@@ -372,6 +376,7 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
   p->job_size = js;
   p->d_jobs = nullptr;
   p->d_prefix = nullptr;
+  p->d_group = nullptr;
   p->bytes = p->points = 0;
   p->all_plain = kind == MB200_K_STEP3 && njobs > 0;
   if (kind == MB200_K_STEP3)
@@ -396,6 +401,48 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
     p->bytes += b;
     p->points += pts;
   }
+  // E = chi1inv D with off-diagonal chi1inv: the job of one component also reads the D arrays of the
+  // other two (4-point averages).  Emitted per component, each job sweeps the chunk long after the
+  // previous one and every D array comes from DRAM three times.  Three consecutive jobs over the
+  // same chunk (same strides, boxes within one point of each other) are therefore INTERLEAVED tile
+  // by tile — CTA b of the triple takes tile b / 3 of job b % 3, as step3c_kernel does for its three
+  // components — so that the shared operands are found in L2.  Each job of a triple is given the
+  // tile count of the largest (surplus CTAs find an empty march).
+  std::vector<int> group(njobs);
+  bool any_group = false;
+  if (kind == MB200_K_EDHB && g_edhb_interleave) {
+    const mb200_edhb_job_t *E = (const mb200_edhb_job_t *)jobs;
+    for (int j = 0; j < njobs; ++j)
+      group[j] = j;
+    for (int j = 0; j + 2 < njobs;) {
+      bool ok = true;
+      for (int k = 0; k < 3 && ok; ++k) {
+        ok = (E[j + k].u1 || E[j + k].u2) && !E[j + k].pmlw.sig;
+        for (int d = 0; d < 3 && ok; ++d)
+          ok = E[j + k].box.s[d] == E[j].box.s[d] && abs(E[j + k].box.n[d] - E[j].box.n[d]) <= 1;
+      }
+      if (!ok) {
+        ++j;
+        continue;
+      }
+      for (int k = 0; k < 3; ++k) // (prefix is rebuilt below)
+        group[j + k] = j;
+      any_group = true;
+      j += 3;
+    }
+    if (any_group) {
+      std::vector<int64_t> tiles_of(njobs);
+      for (int j = 0; j < njobs; ++j)
+        tiles_of[j] = prefix[j + 1] - prefix[j];
+      for (int j = 0; j < njobs; ++j)
+        if (group[j] == j && j + 2 < njobs && group[j + 1] == j && group[j + 2] == j) {
+          const int64_t t = std::max(tiles_of[j], std::max(tiles_of[j + 1], tiles_of[j + 2]));
+          tiles_of[j] = tiles_of[j + 1] = tiles_of[j + 2] = t;
+        }
+      for (int j = 0; j < njobs; ++j)
+        prefix[j + 1] = prefix[j] + tiles_of[j];
+    }
+  }
   p->tiles = prefix[njobs];
   if (kind == MB200_K_FLUX)
     for (int j = 1; j < njobs; ++j) {
@@ -419,6 +466,10 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
     CUDA_TRY(cudaMemcpyAsync(p->d_jobs, jobs, js * njobs, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(p->d_prefix, prefix.data(), sizeof(int64_t) * (njobs + 1),
                              cudaMemcpyHostToDevice, c->stream));
+    if (any_group) {
+      CUDA_TRY(cudaMalloc((void **)&p->d_group, sizeof(int) * njobs));
+      CUDA_TRY(cudaMemcpyAsync(p->d_group, group.data(), sizeof(int) * njobs, cudaMemcpyHostToDevice, c->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream)); // prefix is a stack-owned vector
   }
   *out = p;
@@ -431,6 +482,7 @@ void mb200_plan_destroy(mb200_ctx *c, mb200_plan *p) {
   cudaStreamSynchronize(c->stream);
   if (p->d_jobs) cudaFree(p->d_jobs);
   if (p->d_prefix) cudaFree(p->d_prefix);
+  if (p->d_group) cudaFree(p->d_group);
   delete p;
 }
 

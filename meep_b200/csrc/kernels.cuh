@@ -409,14 +409,36 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---- step_update_EDHB --------------------------------------------------------------------------
+// group != NULL: group[j] is the first job of the component triple job j belongs to (group[j] == j and
+// group[j + 1] != j for a single job); the CTAs of a triple are dealt out tile by tile (see plan_create)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
     edhb_kernel(const mb200_edhb_job_t *__restrict__ jobs, const int64_t *__restrict__ tile_prefix,
-                int njobs) {
+                int njobs, const int *__restrict__ group) {
   __shared__ mb200_edhb_job_t J;
-  int64_t tile;
-  stage_job(&J, jobs, tile_prefix, njobs, &tile);
-  edhb_thread<T>(J, tile, threadIdx.x);
+  __shared__ int s_job;
+  __shared__ int64_t s_tile;
+  if (threadIdx.x == 0) {
+    int j = find_job(tile_prefix, njobs, (int64_t)blockIdx.x);
+    int64_t t = (int64_t)blockIdx.x - __ldg(tile_prefix + j);
+    if (group) {
+      const int j0 = __ldg(group + j);
+      if (j0 != j || (j + 1 < njobs && __ldg(group + j + 1) == j)) { // member of a triple
+        const int64_t local = (int64_t)blockIdx.x - __ldg(tile_prefix + j0);
+        j = j0 + (int)(local % 3);
+        t = local / 3;
+      }
+    }
+    s_job = j;
+    s_tile = t;
+  }
+  __syncthreads();
+  const int *src = reinterpret_cast<const int *>(jobs + s_job);
+  int *dst = reinterpret_cast<int *>(&J);
+  for (int k = threadIdx.x; k < (int)(sizeof(J) / sizeof(int)); k += blockDim.x)
+    dst[k] = __ldg(src + k);
+  __syncthreads();
+  edhb_thread<T>(J, s_tile, threadIdx.x);
 }
 
 // ---- lorentzian update_P -----------------------------------------------------------------------
