@@ -52,6 +52,21 @@ __global__ void __launch_bounds__(kThreads, MINB)
 
 } // namespace mb200
 
+// EXPERIMENT: the interior march alone (no masks, no table look-ups, descriptor in constant space) over every
+// tile of a job whose components own the whole box — what a launch restricted to interior tiles would run at
+template <typename T, int MINB, bool EPI, int NP>
+__global__ void __launch_bounds__(mb200::kThreads, MINB) lean_kernel(const __grid_constant__ mb200_step3_job_t J) {
+  using namespace mb200;
+  const mb200_box_t box = step3_box(J);
+  int ix0, ix_end, iy, iz;
+  if (!box_thread_point(box, (int64_t)blockIdx.x, threadIdx.x, ix0, ix_end, iy, iz, step3_t1(J))) return;
+  if (iy < 1 || iz < 1) return;
+  if (ix0 < 1) ix0 = 1;
+  const int64_t i = box_index(box, ix0, iy, iz);
+  const bool metal_yz[3] = {false, false, false};
+  step3_plain_fast<T, EPI, EPI, NP>(J, i, box.s[0], ix0, ix_end, metal_yz);
+}
+
 #define CK(x)                                                                                      \
   do {                                                                                             \
     cudaError_t e_ = (x);                                                                          \
@@ -287,6 +302,68 @@ int main(int argc, char **argv) {
         free_all();
       }
     }
+  }
+  // ---- fast path: table-driven masked march (the product's default) vs the interior march alone
+  if (shape_filter && !strcmp(shape_filter, "lean")) {
+    const int t1 = 16;
+    const int ni[3] = {n_int, n_int, n_int};
+    for (int half = 0; half < 2; ++half) {
+      Chunk P = make_chunk(ni, 0, true, t1);
+      if (half == 0) { // B half: H aliases B, no epilogue
+        for (int c = 0; c < 3; ++c)
+          P.J.c[c].e = nullptr, P.J.c[c].u = nullptr;
+        P.alg_bytes = 9 * 8.0 * P.cells;
+      }
+      Table TP = upload(std::vector<mb200_step3_job_t>(1, P.J));
+      const unsigned g = (unsigned)TP.tiles;
+      const char *hn = half ? "DE" : "B";
+      char name[64];
+#define REP(T, label, launch)                                                                                  \
+  {                                                                                                            \
+    Chunk Q = P;                                                                                               \
+    Q.alg_bytes = P.alg_bytes * sizeof(T) / 8;                                                                 \
+    const float ms = time_best([&] { launch; });                                                               \
+    snprintf(name, sizeof(name), "%s_%s_%s", hn, #T, label);                                                   \
+    report("interior", name, t1, Q, ms);                                                                       \
+  }
+      REP(double, "masked", (step3_plain_kernel<double><<<g, kThreads>>>(TP.d_jobs, TP.d_prefix, 1)))
+      REP(float, "masked", (step3_plain_kernel<float><<<g, kThreads>>>(TP.d_jobs, TP.d_prefix, 1)))
+      if (half == 0) {
+        REP(double, "lean_c4_np1", (lean_kernel<double, 4, false, 1><<<g, kThreads>>>(P.J)))
+        REP(double, "lean_c4_np2", (lean_kernel<double, 4, false, 2><<<g, kThreads>>>(P.J)))
+        REP(double, "lean_c3_np3", (lean_kernel<double, 3, false, 3><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c4_np2", (lean_kernel<float, 4, false, 2><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c4_np3", (lean_kernel<float, 4, false, 3><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c4_np4", (lean_kernel<float, 4, false, 4><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c5_np2", (lean_kernel<float, 5, false, 2><<<g, kThreads>>>(P.J)))
+      }
+      else {
+        REP(double, "lean_c4_np1", (lean_kernel<double, 4, true, 1><<<g, kThreads>>>(P.J)))
+        REP(double, "lean_c3_np2", (lean_kernel<double, 3, true, 2><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c4_np1", (lean_kernel<float, 4, true, 1><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c4_np2", (lean_kernel<float, 4, true, 2><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c5_np1", (lean_kernel<float, 5, true, 1><<<g, kThreads>>>(P.J)))
+        REP(float, "lean_c3_np3", (lean_kernel<float, 3, true, 3><<<g, kThreads>>>(P.J)))
+      }
+      // the product's pair of launches (full threads + boundary shell)
+      {
+        std::vector<int> rest;
+        step3_rest_tiles(P.J, rest);
+        int *d_rest;
+        CK(cudaMalloc((void **)&d_rest, sizeof(int) * (rest.size() + 1)));
+        CK(cudaMemcpy(d_rest, rest.data(), sizeof(int) * rest.size(), cudaMemcpyHostToDevice));
+        const unsigned gr = (unsigned)rest.size();
+        REP(double, "lean_plus_rest", (step3_lean_kernel<double><<<g, kThreads>>>(P.J), step3_rest_kernel<double><<<gr, kThreads>>>(TP.d_jobs, d_rest)))
+        REP(float, "lean_plus_rest", (step3_lean_kernel<float><<<g, kThreads>>>(P.J), step3_rest_kernel<float><<<gr, kThreads>>>(TP.d_jobs, d_rest)))
+        fprintf(stderr, "rest tiles: %zu of %lld\n", rest.size(), (long long)TP.tiles);
+        cudaFree(d_rest);
+      }
+#undef REP
+      cudaFree(TP.d_jobs);
+      cudaFree(TP.d_prefix);
+      free_all();
+    }
+    return 0;
   }
   // ---- the interior chunk (fast path) and the 26 PML chunks: one after the other vs one mixed grid
   if (!shape_filter || !strcmp(shape_filter, "mixed")) {

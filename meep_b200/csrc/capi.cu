@@ -71,6 +71,8 @@ struct mb200_plan {
   double bytes, points;
   size_t job_size;
   bool all_plain; // STEP3: every job qualifies for the fast-path kernel
+  int *d_rest;    // STEP3, all_plain: tiles that hold threads the lean kernel does not march (per job, see h_rest_prefix)
+  std::vector<int64_t> h_rest_prefix;
   int *d_group;   // EDHB: first job of the component triple a job belongs to (or the job itself), see plan_create
   std::vector<char> h_jobs;       // STEP3: host copy (jobs are passed by value in param space)
   std::vector<int64_t> h_prefix;
@@ -86,16 +88,18 @@ static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("M
 // 6 -> 1.36 ms per step (16 planes per CTA).
 static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 4;
 
-// Fast-path kernel form.  Measured at 512^3 double (profiles/README.md, r2d-r2g; per-launch ncu times,
-// B half / D-E half): table-driven kernel with the masked march — 1597 / 2350 us (the default);
-// one launch per job with the descriptor in constant space — 1592 / 2490 us (MEEP_B200_PLAIN_PER_JOB=1);
-// interior march with deduplicated operands and a 32-bit cursor, half the instructions per point —
-// 1639 / 2790 us (MEEP_B200_PLAIN_FAST=1).  Fewer instructions did not help: the kernel is not
-// issue-bound.  Neither did more CTAs per SM (5: 1894 us, 6: 2120 us for the B half) nor staging
-// the operands through shared memory with 8-byte cp.async (2518 / 2896 us).
-// MEEP_B200_EDHB_INTERLEAVE=0: the three component jobs of an off-diagonal E update one after the other
-static const bool g_edhb_interleave = !getenv("MEEP_B200_EDHB_INTERLEAVE") || atoi(getenv("MEEP_B200_EDHB_INTERLEAVE")) != 0;
-static const bool g_plain_per_job = getenv("MEEP_B200_PLAIN_PER_JOB") && atoi(getenv("MEEP_B200_PLAIN_PER_JOB")) != 0;
+// Fast-path kernel form.  Default: one table-driven launch with the masked march for every thread (the
+// round-1 form).  MEEP_B200_PLAIN_LEAN=1: two launches per job, the lean march (fused.cuh:
+// step3_lean_kernel) for full threads and the masked march for the boundary shell (step3_rest_kernel).
+// Measured (B200, 512^3; bench/micro/pml_shapes.cu "lean", profiles/r2ab_*): over the SAME tiles the
+// separately compiled lean march beats the masked one by 4 % (double, B half, two planes in flight),
+// 1 % (double, D-E half), 19 % and 10 % (single) — but 16 % of the tiles hold a boundary thread (the
+// iz = 0 column sits in every first z-tile) and re-walking them costs more than the lean march gains:
+// whole fast path 3.85 -> 4.15 ms double, 2.52 -> 2.52 ms single.  Earlier forms, per-launch ncu times
+// B half / D-E half at 512^3 double (profiles/README.md, r2d-r2g): masked march 1597 / 2350 us; ONE
+// kernel holding both marches 1639 / 2790 us; more CTAs per SM (5: 1894 us, 6: 2120 us for the B half);
+// operands staged through shared memory with 8-byte cp.async 2518 / 2896 us.
+static const bool g_plain_lean = getenv("MEEP_B200_PLAIN_LEAN") && atoi(getenv("MEEP_B200_PLAIN_LEAN")) != 0;
 
 template <typename T>
 static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
@@ -183,7 +187,7 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
       }
       launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
                       p->all_plain, g_split_general, s, (const mb200_step3_job_t *)p->h_jobs.data(),
-                      p->h_prefix.data(), g_plain_per_job);
+                      p->h_prefix.data(), p->d_rest, p->h_rest_prefix.data());
       break;
   }
   return cudaGetLastError();
@@ -222,10 +226,6 @@ int mb200_init(int device, mb200_ctx **out) {
   memset(c->prof_ms, 0, sizeof(c->prof_ms));
   memset(c->prof_bytes, 0, sizeof(c->prof_bytes));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  {
-    const int v = getenv("MEEP_B200_PLAIN_FAST") ? atoi(getenv("MEEP_B200_PLAIN_FAST")) : 0;
-    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_plain_fast, &v, sizeof(int)));
-  }
   if (const char *e = getenv("MEEP_B200_PML_PAIR")) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pml_pair, &v, sizeof(int)));
@@ -233,10 +233,6 @@ int mb200_init(int device, mb200_ctx **out) {
   if (const char *e = getenv("MEEP_B200_FMP_SIMPLE")) {
     const int v = atoi(e);
     CUDA_TRY(cudaMemcpyToSymbol(mb200::g_fmp_simple, &v, sizeof(int)));
-  }
-  if (const char *e = getenv("MEEP_B200_PAIR_PLANES")) {
-    const int v = atoi(e);
-    CUDA_TRY(cudaMemcpyToSymbol(mb200::g_pair_planes, &v, sizeof(int)));
   }
   CUDA_TRY(cudaEventCreate(&c->t0));
   CUDA_TRY(cudaEventCreate(&c->t1));
@@ -377,6 +373,7 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
   p->d_jobs = nullptr;
   p->d_prefix = nullptr;
   p->d_group = nullptr;
+  p->d_rest = nullptr;
   p->bytes = p->points = 0;
   p->all_plain = kind == MB200_K_STEP3 && njobs > 0;
   if (kind == MB200_K_STEP3)
@@ -466,6 +463,16 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
     CUDA_TRY(cudaMemcpyAsync(p->d_jobs, jobs, js * njobs, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(p->d_prefix, prefix.data(), sizeof(int64_t) * (njobs + 1),
                              cudaMemcpyHostToDevice, c->stream));
+    if (kind == MB200_K_STEP3 && p->all_plain && g_plain_lean && njobs <= kMaxJobLaunches) {
+      std::vector<int> rest;
+      p->h_rest_prefix.assign(1, 0);
+      for (int j = 0; j < njobs; ++j) {
+        step3_rest_tiles(((const mb200_step3_job_t *)jobs)[j], rest);
+        p->h_rest_prefix.push_back((int64_t)rest.size());
+      }
+      CUDA_TRY(cudaMalloc((void **)&p->d_rest, sizeof(int) * (rest.size() + 1)));
+      CUDA_TRY(cudaMemcpy(p->d_rest, rest.data(), sizeof(int) * rest.size(), cudaMemcpyHostToDevice));
+    }
     if (any_group) {
       CUDA_TRY(cudaMalloc((void **)&p->d_group, sizeof(int) * njobs));
       CUDA_TRY(cudaMemcpyAsync(p->d_group, group.data(), sizeof(int) * njobs, cudaMemcpyHostToDevice, c->stream));
@@ -483,6 +490,7 @@ void mb200_plan_destroy(mb200_ctx *c, mb200_plan *p) {
   if (p->d_jobs) cudaFree(p->d_jobs);
   if (p->d_prefix) cudaFree(p->d_prefix);
   if (p->d_group) cudaFree(p->d_group);
+  if (p->d_rest) cudaFree(p->d_rest);
   delete p;
 }
 

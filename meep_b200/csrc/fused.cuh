@@ -13,6 +13,8 @@
 #ifndef MEEP_B200_FUSED_CUH
 #define MEEP_B200_FUSED_CUH
 
+#include <vector>
+
 #include "kernels.cuh"
 
 namespace mb200 {
@@ -101,13 +103,6 @@ inline double step3_bytes(const mb200_step3_job_t &J, double R) {
 // chunk of a PML-padded cell: ~89 % of the cells of BASELINE config 2), fused E/H update
 // without f_w.  All loads of a grid point (3 f + 12 g + 3 chi1inv) are issued before the first
 // store, so each warp keeps ~4.6 KB in flight instead of ~1.3 KB.
-// MEEP_B200_PAIR_PLANES=0 (read once by capi.cu into this device flag) switches the two-planes-in-flight
-// form of the B half-step off
-#ifdef __CUDACC__
-__device__ int g_pair_planes = 1;
-__device__ int g_plain_fast = 0; // MEEP_B200_PLAIN_FAST=1: interior threads take the lean march (measured slower)
-__device__ __forceinline__ bool step3_pair_planes() { return g_pair_planes != 0; }
-#endif
 MB200_HD bool step3_is_plain(const mb200_step3_job_t &J) {
   for (int c = 0; c < 3; ++c) {
     const mb200_step3_comp_t &C = J.c[c];
@@ -135,12 +130,14 @@ MB200_HD void keep_above(float v) {
 #endif
 }
 
-// The march of an interior thread of the fast path (see step3_plain_thread): all three components
+// The march of an interior thread of the fast path (see step3_thread_full): all three components
 // updated on every plane, cyclic curl operands G0..G2 with each centre value loaded once, one
 // 32-bit cursor for every array (all arrays of a chunk share an index space of < 2^32 elements) so
 // that an access is one IMAD.WIDE.U32 against a base held in the constant bank.  EPI: the diagonal
-// E = chi1inv D (or H = B / mu) epilogue is fused; HASU: chi1inv is not identically 1.
-template <typename T, bool EPI, bool HASU>
+// E = chi1inv D (or H = B / mu) epilogue is fused; HASU: chi1inv is not identically 1.  NP x-planes
+// are loaded before the first store (the kernel responds to loads in flight per thread).  Same
+// arithmetic, in the same order, as step3_plain_general.
+template <typename T, bool EPI, bool HASU, int NP>
 MB200_HD void step3_plain_fast(const mb200_step3_job_t &J, int64_t i, int64_t sx, int ix0, int ix_end,
                                const bool (&metal_yz)[3]) {
   const T *G0 = (const T *)J.c[1].g1, *G1 = (const T *)J.c[2].g1, *G2 = (const T *)J.c[0].g1;
@@ -151,84 +148,62 @@ MB200_HD void step3_plain_fast(const mb200_step3_job_t &J, int64_t i, int64_t sx
   T *e0 = (T *)J.c[0].e, *e1 = (T *)J.c[1].e, *e2 = (T *)J.c[2].e;
   const T k0 = (T)J.c[0].dtdx, k1 = (T)J.c[1].dtdx, k2 = (T)J.c[2].dtdx;
   const unsigned sxu = (unsigned)sx;
-  unsigned q = (unsigned)i;
-  int ix = ix0;
-#ifdef __CUDA_ARCH__
-  // Without the epilogue (the B half-step of a chunk whose H aliases B) a point has only 12
-  // operands; the kernel is bound by bytes in flight per SM, so two planes are loaded before the
-  // first store (MEEP_B200_PAIR_PLANES=0 switches this off for A/B runs).
-  if (!EPI && step3_pair_planes())
-    for (; ix + 1 < ix_end; ix += 2, q += 2 * sxu) {
-      const unsigned r = q + sxu;
-      const T g0 = ldro(G0 + q), g1 = ldro(G1 + q), g2 = ldro(G2 + q);
-      const T h0 = ldro(G0 + r), h1 = ldro(G1 + r), h2 = ldro(G2 + r);
-      const T a10 = ldro(G2 + (q + s10)), a20 = ldro(G1 + (q + s20));
-      const T a11 = ldro(G0 + (q + s11)), a21 = ldro(G2 + (q + s21));
-      const T a12 = ldro(G1 + (q + s12)), a22 = ldro(G0 + (q + s22));
-      const T b10 = ldro(G2 + (r + s10)), b20 = ldro(G1 + (r + s20));
-      const T b11 = ldro(G0 + (r + s11)), b21 = ldro(G2 + (r + s21));
-      const T b12 = ldro(G1 + (r + s12)), b22 = ldro(G0 + (r + s22));
-      const T v0 = f0[q], v1 = f1[q], v2 = f2[q], x0 = f0[r], x1 = f1[r], x2 = f2[r];
-      keep_above(b12);
-      keep_above(b22);
-      keep_above(x2);
-      T dg = a10 - g2;
-      dg = dg + g1 - a20;
-      f0[q] = v0 - k0 * dg;
-      dg = a11 - g0;
-      dg = dg + g2 - a21;
-      f1[q] = v1 - k1 * dg;
-      dg = a12 - g1;
-      dg = dg + g0 - a22;
-      f2[q] = v2 - k2 * dg;
-      dg = b10 - h2;
-      dg = dg + h1 - b20;
-      f0[r] = x0 - k0 * dg;
-      dg = b11 - h0;
-      dg = dg + h2 - b21;
-      f1[r] = x1 - k1 * dg;
-      dg = b12 - h1;
-      dg = dg + h0 - b22;
-      f2[r] = x2 - k2 * dg;
-    }
-#endif
-  for (; ix < ix_end; ++ix, q += sxu) {
-    // ---- all loads first
-    const T g0 = ldro(G0 + q), g1 = ldro(G1 + q), g2 = ldro(G2 + q);
-    const T a10 = ldro(G2 + (q + s10)), a20 = ldro(G1 + (q + s20)); // component 0: g1 = G2, g2 = G1
-    const T a11 = ldro(G0 + (q + s11)), a21 = ldro(G2 + (q + s21)); // component 1: g1 = G0, g2 = G2
-    const T a12 = ldro(G1 + (q + s12)), a22 = ldro(G0 + (q + s22)); // component 2: g1 = G1, g2 = G0
-    const T v0 = f0[q], v1 = f1[q], v2 = f2[q];
-    T w0 = T(1), w1 = T(1), w2 = T(1);
-    if (HASU) {
-      w0 = ldro(u0 + q);
-      w1 = ldro(u1 + q);
-      w2 = ldro(u2 + q);
-      keep_above(w0);
-      keep_above(w1);
-      keep_above(w2);
-    }
-    keep_above(a12);
-    keep_above(a22);
-    // ---- then arithmetic + stores
-    T dg = a10 - g2;
-    dg = dg + g1 - a20;
-    const T d0 = v0 - k0 * dg;
-    dg = a11 - g0;
-    dg = dg + g2 - a21;
-    const T d1 = v1 - k1 * dg;
-    dg = a12 - g1;
-    dg = dg + g0 - a22;
-    const T d2 = v2 - k2 * dg;
+  struct Plane {
+    T g0, g1, g2, a10, a20, a11, a21, a12, a22, v0, v1, v2, w0, w1, w2;
+  };
+  auto load = [&](unsigned q, Plane &p) {
+    p.g0 = ldro(G0 + q), p.g1 = ldro(G1 + q), p.g2 = ldro(G2 + q);
+    p.a10 = ldro(G2 + (q + s10)), p.a20 = ldro(G1 + (q + s20)); // component 0: g1 = G2, g2 = G1
+    p.a11 = ldro(G0 + (q + s11)), p.a21 = ldro(G2 + (q + s21)); // component 1: g1 = G0, g2 = G2
+    p.a12 = ldro(G1 + (q + s12)), p.a22 = ldro(G0 + (q + s22)); // component 2: g1 = G1, g2 = G0
+    p.v0 = f0[q], p.v1 = f1[q], p.v2 = f2[q];
+    p.w0 = p.w1 = p.w2 = T(1);
+    if (HASU) p.w0 = ldro(u0 + q), p.w1 = ldro(u1 + q), p.w2 = ldro(u2 + q);
+  };
+  auto finish = [&](unsigned q, int ix, const Plane &p) {
+    T dg = p.a10 - p.g2;
+    dg = dg + p.g1 - p.a20;
+    const T d0 = p.v0 - k0 * dg;
+    dg = p.a11 - p.g0;
+    dg = dg + p.g2 - p.a21;
+    const T d1 = p.v1 - k1 * dg;
+    dg = p.a12 - p.g1;
+    dg = dg + p.g0 - p.a22;
+    const T d2 = p.v2 - k2 * dg;
     f0[q] = d0;
     f1[q] = d1;
     f2[q] = d2;
     if (EPI && step3_epi_plane(J, ix)) {
       const T dd0 = metal_yz[0] ? T(0) : d0, dd1 = metal_yz[1] ? T(0) : d1, dd2 = metal_yz[2] ? T(0) : d2;
-      e0[q] = HASU ? dd0 * w0 : dd0;
-      e1[q] = HASU ? dd1 * w1 : dd1;
-      e2[q] = HASU ? dd2 * w2 : dd2;
+      e0[q] = HASU ? dd0 * p.w0 : dd0;
+      e1[q] = HASU ? dd1 * p.w1 : dd1;
+      e2[q] = HASU ? dd2 * p.w2 : dd2;
     }
+  };
+  unsigned q = (unsigned)i;
+  int ix = ix0;
+  if (NP > 1)
+    for (; ix + NP <= ix_end; ix += NP, q += NP * sxu) {
+      Plane p[NP];
+#pragma unroll
+      for (int k = 0; k < NP; ++k)
+        load(q + k * sxu, p[k]);
+      // every load stays above the first store (they were sunk below it otherwise: two memory
+      // latencies per iteration instead of one)
+      keep_above(p[NP - 1].a22);
+      keep_above(p[NP - 1].v2);
+      if (HASU) keep_above(p[NP - 1].w2);
+#pragma unroll
+      for (int k = 0; k < NP; ++k)
+        finish(q + k * sxu, ix + k, p[k]);
+    }
+  for (; ix < ix_end; ++ix, q += sxu) {
+    Plane p;
+    load(q, p);
+    keep_above(p.a22);
+    keep_above(p.v2);
+    if (HASU) keep_above(p.w2);
+    finish(q, ix, p);
   }
 }
 
@@ -273,9 +248,40 @@ MB200_HD void step3_plain_general(const mb200_step3_job_t &J, int64_t i, int64_t
   }
 }
 
-// FAST: interior threads take step3_plain_fast (opt-in per-job kernel only; measured slower than the
-// masked march, see capi.cu) — a template parameter so that the default kernel carries none of it
-template <typename T, bool FAST = false>
+// A "full" thread of the fast path: every component is updated on every plane it marches, no metal
+// x-plane is crossed, and the curl operands are the three arrays of the other field type in cyclic
+// order (g1 of component c = G[(c+2)%3], g2 = G[(c+1)%3]: src/fields.cpp:428-456), so the centre
+// value of each is loaded once for the two components that use it: 15 loads and 6 stores per point
+// instead of 18 and 6, no per-plane predicates, cursors instead of index arithmetic.  Full threads
+// are marched by step3_lean_kernel, all others by the masked march (step3_plain_general).
+MB200_HD bool step3_job_leanable(const mb200_step3_job_t &J) {
+  bool ok = J.c[0].g1 == J.c[1].g2 && J.c[1].g1 == J.c[2].g2 && J.c[2].g1 == J.c[0].g2 &&
+            (int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32);
+  for (int c = 0; c < 3; ++c)
+    ok = ok && (J.c[c].e != nullptr) == (J.c[0].e != nullptr) && (J.c[c].u != nullptr) == (J.c[0].u != nullptr);
+  return ok;
+}
+// (x part: uniform over the CTA; y-z part: per thread)
+MB200_HD bool step3_full_x(const mb200_step3_job_t &J, int ix0, int ix_end) {
+  bool full = true;
+  for (int c = 0; c < 3; ++c) {
+    const mb200_step3_comp_t &C = J.c[c];
+    full = full && ix0 >= C.lo[0] && ix_end - 1 <= C.hi[0] && !(C.metal_lo[0] >= ix0 && C.metal_lo[0] < ix_end) &&
+           !(C.metal_hi[0] >= ix0 && C.metal_hi[0] < ix_end);
+  }
+  return full;
+}
+MB200_HD bool step3_full_yz(const mb200_step3_job_t &J, int iy, int iz) {
+  bool full = true;
+  for (int c = 0; c < 3; ++c) {
+    const mb200_step3_comp_t &C = J.c[c];
+    full = full && iy >= C.lo[1] && iy <= C.hi[1] && iz >= C.lo[2] && iz <= C.hi[2];
+  }
+  return full;
+}
+
+// SKIP_FULL: the full threads of this job are marched by step3_lean_kernel
+template <typename T, bool SKIP_FULL = false>
 MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
   const mb200_box_t box = step3_box(J);
   int ix0, ix_end, iy, iz;
@@ -284,6 +290,7 @@ MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int t
   const int64_t sx = box.s[0];
   ix0 += box.reserved;
   ix_end += box.reserved;
+  if (SKIP_FULL && step3_job_leanable(J) && step3_full_x(J, ix0, ix_end) && step3_full_yz(J, iy, iz)) return;
   bool myz[3], metal_yz[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -292,34 +299,32 @@ MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int t
     metal_yz[c] = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
                   iz == C.metal_hi[2];
   }
-  // Interior CTAs (nearly all of them): every component is updated on every marched plane, no
-  // metal x-plane is crossed, and the curl operands are the three arrays of the other field type in
-  // cyclic order (g1 of component c = G[(c+2)%3], g2 = G[(c+1)%3]: src/fields.cpp:428-456), so the
-  // centre value of each is loaded once for the two components that use it.  Same arithmetic, in
-  // the same order, as the general loop below: 15 loads and 6 stores per point instead of 18 and
-  // 6, no per-plane predicates, cursors instead of index arithmetic.
-  bool full = J.c[0].g1 == J.c[1].g2 && J.c[1].g1 == J.c[2].g2 && J.c[2].g1 == J.c[0].g2 &&
-              (int64_t)(J.n[0] + 1) * (J.n[1] + 1) * (J.n[2] + 1) < ((int64_t)1 << 32);
+  step3_plain_general<T>(J, i, sx, ix0, ix_end, myz, metal_yz);
+}
+
+// The full threads of one job (descriptor in kernel-parameter space: every field is a constant-bank
+// operand).  Planes in flight: two in double without the epilogue (the B half-step of a chunk whose H
+// aliases B: 12 operands per plane), one with it; single precision holds twice as many.
+template <typename T>
+MB200_HD void step3_lean_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
+  const mb200_box_t box = step3_box(J);
+  int ix0, ix_end, iy, iz;
+  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
+  const int64_t i = box_index(box, ix0, iy, iz);
+  ix0 += box.reserved;
+  ix_end += box.reserved;
+  if (!(step3_full_x(J, ix0, ix_end) && step3_full_yz(J, iy, iz))) return;
+  bool metal_yz[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const mb200_step3_comp_t &C = J.c[c];
-    full = full && myz[c] && ix0 >= C.lo[0] && ix_end - 1 <= C.hi[0] &&
-           !(C.metal_lo[0] >= ix0 && C.metal_lo[0] < ix_end) && !(C.metal_hi[0] >= ix0 && C.metal_hi[0] < ix_end) &&
-           (C.e != nullptr) == (J.c[0].e != nullptr) && (C.u != nullptr) == (J.c[0].u != nullptr);
+    metal_yz[c] = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] || iz == C.metal_hi[2];
   }
-#ifdef __CUDA_ARCH__
-  full = full && FAST && g_plain_fast != 0;
-#else
-  full = full && FAST;
-#endif
-  if (full) {
-    const bool epi = J.c[0].e != nullptr, hasu = epi && J.c[0].u != nullptr;
-    if (hasu) step3_plain_fast<T, true, true>(J, i, sx, ix0, ix_end, metal_yz);
-    else if (epi) step3_plain_fast<T, true, false>(J, i, sx, ix0, ix_end, metal_yz);
-    else step3_plain_fast<T, false, false>(J, i, sx, ix0, ix_end, metal_yz);
-    return;
-  }
-  step3_plain_general<T>(J, i, sx, ix0, ix_end, myz, metal_yz);
+  constexpr int kB = 2, kE = sizeof(T) == 4 ? 2 : 1; // (measured: bench/micro/pml_shapes.cu "lean")
+  const bool epi = J.c[0].e != nullptr, hasu = epi && J.c[0].u != nullptr;
+  if (hasu) step3_plain_fast<T, true, true, kE>(J, i, box.s[0], ix0, ix_end, metal_yz);
+  else if (epi) step3_plain_fast<T, true, false, kE>(J, i, box.s[0], ix0, ix_end, metal_yz);
+  else step3_plain_fast<T, false, false, kB>(J, i, box.s[0], ix0, ix_end, metal_yz);
 }
 
 // ---- general path --------------------------------------------------------------------------------
@@ -826,18 +831,51 @@ __global__ void __launch_bounds__(kThreads)
   step3_plain_thread<T>(J, tile, threadIdx.x);
 }
 
-// ---- one job per launch, descriptor in kernel-parameter (constant) space ---------------------------
-// The fast path normally has ONE job per GPU (the interior chunk; up to three when source planes
-// split it).  Staged in shared memory the descriptor costs ~40 LDS per marched plane — pointers,
-// bounds and strides do not fit in registers next to the 18 values in flight.  Passed by value as
-// a __grid_constant__ parameter every field is a constant-bank operand of the instruction that
-// uses it: no load, no register.
+// ---- the fast path as two launches per job: full threads / the rest -------------------------------
+// step3_lean_kernel marches the full threads of ONE job over all its tiles (everybody else returns at
+// once); step3_rest_kernel runs the masked march over the tiles that hold at least one other thread
+// (rest_tiles: the boundary shell of the chunk, listed by the host) and skips the full ones.  Both
+// write disjoint points and read only arrays that neither writes.  One kernel with both marches was
+// measured slower than the masked march alone (joint register allocation); separately compiled, the
+// lean march is 4 % (double) to 19 % (single, B half) faster than the masked one over the same tiles
+// (bench/micro/pml_shapes.cu "lean") — and the second walk over the boundary tiles (16 % of them at
+// 512^3: the iz = 0 column is in every first z-tile) costs more than that, so this pair is opt-in
+// (MEEP_B200_PLAIN_LEAN=1, see capi.cu) and the masked march stays the default.
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 4)
-    step3_plain_job_kernel(const __grid_constant__ mb200_step3_job_t J) {
-  step3_plain_thread<T, true>(J, (int64_t)blockIdx.x, threadIdx.x);
+    step3_lean_kernel(const __grid_constant__ mb200_step3_job_t J) {
+  step3_lean_thread<T>(J, (int64_t)blockIdx.x, threadIdx.x);
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    step3_rest_kernel(const mb200_step3_job_t *__restrict__ job, const int *__restrict__ rest_tiles) {
+  __shared__ mb200_step3_job_t J;
+  const int *src = reinterpret_cast<const int *>(job);
+  int *dst = reinterpret_cast<int *>(&J);
+  for (int k = threadIdx.x; k < (int)(sizeof(J) / sizeof(int)); k += blockDim.x)
+    dst[k] = __ldg(src + k);
+  __syncthreads();
+  step3_plain_thread<T, true>(J, (int64_t)__ldg(rest_tiles + blockIdx.x), threadIdx.x);
 }
 constexpr int kMaxJobLaunches = 8; // more plain jobs than this: one table-driven launch
+
+// tiles of a plain job that hold a thread which is not full (host side, at plan creation)
+inline void step3_rest_tiles(const mb200_step3_job_t &J, std::vector<int> &out) {
+  const mb200_box_t box = step3_box(J);
+  const int t1 = step3_t1(J);
+  const int64_t tiles = box_tiles(box, t1);
+  const bool leanable = step3_job_leanable(J);
+  for (int64_t t = 0; t < tiles; ++t) {
+    bool rest = !leanable;
+    for (int tid = 0; tid < kThreads && !rest; ++tid) {
+      int ix0, ix_end, iy, iz;
+      if (!box_thread_point(box, t, tid, ix0, ix_end, iy, iz, t1)) continue;
+      if (tid == 0 && !step3_full_x(J, ix0 + box.reserved, ix_end + box.reserved)) rest = true;
+      if (!step3_full_yz(J, iy, iz)) rest = true;
+    }
+    if (rest) out.push_back((int)t);
+  }
+}
 
 // ---- job table in kernel-parameter (constant) space ---------------------------------------------
 // The job descriptor is CTA-uniform.  Staging it in shared memory costs an LDS (and a short-
@@ -889,11 +927,13 @@ static void launch_step3_params(const mb200_step3_job_t *h_jobs, const int64_t *
 template <typename T>
 static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
                          int64_t tiles, bool all_plain, int split, cudaStream_t s,
-                         const mb200_step3_job_t *h_jobs, const int64_t *h_prefix, bool per_job) {
-  if (all_plain && per_job && njobs <= kMaxJobLaunches) {
+                         const mb200_step3_job_t *h_jobs, const int64_t *h_prefix, const int *d_rest,
+                         const int64_t *h_rest_prefix) {
+  if (all_plain && d_rest) { // lean + rest launches per job (plan_create listed the rest tiles)
     for (int j = 0; j < njobs; ++j) {
-      const int64_t t = h_prefix[j + 1] - h_prefix[j];
-      if (t > 0) step3_plain_job_kernel<T><<<dim3((unsigned)t), dim3(kThreads), 0, s>>>(h_jobs[j]);
+      const int64_t t = h_prefix[j + 1] - h_prefix[j], r = h_rest_prefix[j + 1] - h_rest_prefix[j];
+      if (t > 0 && r < t) step3_lean_kernel<T><<<dim3((unsigned)t), dim3(kThreads), 0, s>>>(h_jobs[j]);
+      if (r > 0) step3_rest_kernel<T><<<dim3((unsigned)r), dim3(kThreads), 0, s>>>(jobs + j, d_rest + h_rest_prefix[j]);
     }
   }
   else if (all_plain)

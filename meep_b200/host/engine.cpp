@@ -1,5 +1,6 @@
 // engine.cpp — see engine.hpp.
 #include "engine.hpp"
+#include <execinfo.h>
 #include "meep_internals.hpp"
 #include "comm.hpp"
 #include "hostmem.hpp"
@@ -828,6 +829,15 @@ void Engine::leave(fields *f, bool modified) {
     // before and after this call, so hand them back and assume it will modify them.
     sync_host();
     state = HOST_NEWER;
+    if (getenv("MEEP_B200_TRACE_STANDALONE")) {
+      static int shown = 0;
+      if (shown++ < 24) {
+        void *bt[12];
+        const int n = backtrace(bt, 12);
+        fprintf(stderr, "meep_b200: stand-alone entry point (host copy handed back):\n");
+        backtrace_symbols_fd(bt, n, 2);
+      }
+    }
   }
   if (verbose && meep::wall_time() - t_leave > 0.05)
     fprintf(stderr, "meep_b200: leaving an entry point took %.3f s on the host\n", meep::wall_time() - t_leave);

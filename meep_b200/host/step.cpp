@@ -506,6 +506,13 @@ void fields::step_boundaries(field_type ft) {
               runs.push_back(r);
               k += len;
             }
+            if (E.verbose) {
+              int32_t longest = 0;
+              for (const mb200_halo_run_t &r : runs)
+                longest = std::max(longest, r.n);
+              fprintf(stderr, "meep_b200: halo pair (%d -> %d) ft %d: %zu values in %zu runs, longest %d\n", j, i, (int)ft, n,
+                      runs.size(), (int)longest);
+            }
             if (runs.size() * 8 <= n) { // worth it: at least 8 values per run on average
               hj.runs = (const mb200_halo_run_t *)E.aux_upload(runs.data(), runs.size() * sizeof(runs[0]));
               hj.nrun = (int64_t)runs.size();
