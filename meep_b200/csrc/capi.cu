@@ -99,6 +99,8 @@ static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("
 // B half / D-E half at 512^3 double (profiles/README.md, r2d-r2g): masked march 1597 / 2350 us; ONE
 // kernel holding both marches 1639 / 2790 us; more CTAs per SM (5: 1894 us, 6: 2120 us for the B half);
 // operands staged through shared memory with 8-byte cp.async 2518 / 2896 us.
+// MEEP_B200_EDHB_INTERLEAVE=0: the three component jobs of an off-diagonal E update one after the other
+static const bool g_edhb_interleave = !getenv("MEEP_B200_EDHB_INTERLEAVE") || atoi(getenv("MEEP_B200_EDHB_INTERLEAVE")) != 0;
 static const bool g_plain_lean = getenv("MEEP_B200_PLAIN_LEAN") && atoi(getenv("MEEP_B200_PLAIN_LEAN")) != 0;
 
 template <typename T>
