@@ -102,6 +102,7 @@ Engine::Engine(fields *f) : self(f) {
   zero_skip = env_int("MEEP_B200_ZERO_SKIP", 1) != 0;
   p2p = env_int("MEEP_B200_P2P", 1) != 0;
   halo_runs = env_int("MEEP_B200_HALO_RUNS", 1) != 0;
+  halo_sort = env_int("MEEP_B200_HALO_SORT", 1) != 0;
   plain_t1 = env_int("MEEP_B200_PLAIN_T1", 16);
   if (plain_t1 < 0 || plain_t1 > 64) plain_t1 = 16;
   pml_t1 = env_int("MEEP_B200_PML_T1", 16);

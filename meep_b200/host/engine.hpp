@@ -187,6 +187,7 @@ public:
   // sync_host() when images of the volume could be read (symmetries, periodic boundaries) or the
   // box is most of the cell.  The device copy stays the authoritative one.
   void sync_host_region(const meep::volume &where);
+  bool halo_sort = true; // MEEP_B200_HALO_SORT=0: exchange jobs in chunk-pair order
   bool force_reader_sync = false;
   bool forced_download_done = false; // the arrays were all downloaded since force_reader_sync was raised
   double region_fraction_limit = 0.3; // MEEP_B200_REGION_SYNC (0 disables sub-volume downloads)
