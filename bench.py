@@ -355,8 +355,12 @@ def main():
         drv.mb200_bench_probes.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         drv.mb200_bench_probes(h, pv, nprobe)
         drv.mb200_bench_time_step.argtypes = [C.c_void_p]
-        probe = {"after_steps": int(drv.mb200_bench_time_step(h)), "component": "Ez",
-                 "points": "cell centre + (0.35,0.25,0.15) + s_k*(1,-1,1), s_k = +-0.1 k, k=0..7, via fields::get_field",
+        drv.mb200_bench_probe_component.argtypes = [C.c_void_p]
+        drv.mb200_bench_probe_component.restype = C.c_char_p
+        anchor = {"c2": "cell centre", "c3": "source point", "c4": "source point"}[args.workload]
+        probe = {"after_steps": int(drv.mb200_bench_time_step(h)),
+                 "component": drv.mb200_bench_probe_component(h).decode(),
+                 "points": anchor + " + (0.35,0.25,0.15) + s_k*(1,-1,1), s_k = +-0.1 k, k=0..7, via fields::get_field",
                  "values": [float(x) for x in pv]}
 
         # ---- timed region 3 (context for e2e): a COLD run of K steps — every field array starts on the
