@@ -345,18 +345,27 @@ int main(int argc, char **argv) {
         REP(float, "lean_c5_np1", (lean_kernel<float, 5, true, 1><<<g, kThreads>>>(P.J)))
         REP(float, "lean_c3_np3", (lean_kernel<float, 3, true, 3><<<g, kThreads>>>(P.J)))
       }
-      // the product's pair of launches (full threads + boundary shell)
+      // the product's lean + shell launches (MEEP_B200_PLAIN_LEAN=1): full box, two x-slabs, (y, z) shell columns
       {
-        std::vector<int> rest;
-        step3_rest_tiles(P.J, rest);
-        int *d_rest;
-        CK(cudaMalloc((void **)&d_rest, sizeof(int) * (rest.size() + 1)));
-        CK(cudaMemcpy(d_rest, rest.data(), sizeof(int) * rest.size(), cudaMemcpyHostToDevice));
-        const unsigned gr = (unsigned)rest.size();
-        REP(double, "lean_plus_rest", (step3_lean_kernel<double><<<g, kThreads>>>(P.J), step3_rest_kernel<double><<<gr, kThreads>>>(TP.d_jobs, d_rest)))
-        REP(float, "lean_plus_rest", (step3_lean_kernel<float><<<g, kThreads>>>(P.J), step3_rest_kernel<float><<<gr, kThreads>>>(TP.d_jobs, d_rest)))
-        fprintf(stderr, "rest tiles: %zu of %lld\n", rest.size(), (long long)TP.tiles);
-        cudaFree(d_rest);
+        const Step3Shell S = step3_shell(P.J);
+        int *d_cols;
+        CK(cudaMalloc((void **)&d_cols, sizeof(int) * (S.cols.size() + 1)));
+        CK(cudaMemcpy(d_cols, S.cols.data(), sizeof(int) * S.cols.size(), cudaMemcpyHostToDevice));
+        Table TS = upload(S.slabs);
+        const int ncols = (int)S.cols.size();
+        const dim3 gc((unsigned)((ncols + kThreads - 1) / kThreads), (unsigned)((S.hi[0] - S.lo[0] + t1) / t1));
+#define SHELL(T)                                                                                               \
+  (step3_lean_kernel<T><<<g, kThreads>>>(P.J),                                                                 \
+   step3_plain_kernel<T><<<(unsigned)TS.tiles, kThreads>>>(TS.d_jobs, TS.d_prefix, TS.njobs),                  \
+   step3_cols_kernel<T><<<gc, kThreads>>>(TP.d_jobs, d_cols, ncols, S.lo[0], S.hi[0], t1))
+        REP(double, "lean_plus_shell", SHELL(double))
+        REP(float, "lean_plus_shell", SHELL(float))
+#undef SHELL
+        fprintf(stderr, "full box [%d..%d]x[%d..%d]x[%d..%d], %d shell columns, %lld slab tiles of %lld\n", S.lo[0], S.hi[0],
+                S.lo[1], S.hi[1], S.lo[2], S.hi[2], ncols, (long long)TS.tiles, (long long)TP.tiles);
+        cudaFree(d_cols);
+        cudaFree(TS.d_jobs);
+        cudaFree(TS.d_prefix);
       }
 #undef REP
       cudaFree(TP.d_jobs);

@@ -71,8 +71,8 @@ struct mb200_plan {
   double bytes, points;
   size_t job_size;
   bool all_plain; // STEP3: every job qualifies for the fast-path kernel
-  int *d_rest;    // STEP3, all_plain: tiles that hold threads the lean kernel does not march (per job, see h_rest_prefix)
-  std::vector<int64_t> h_rest_prefix;
+  Step3LeanPlan *lean;            // STEP3, all_plain, MEEP_B200_PLAIN_LEAN: the lean + shell launches of every job
+  std::vector<void *> lean_allocs; // device tables of `lean`
   int *d_group;   // EDHB: first job of the component triple a job belongs to (or the job itself), see plan_create
   std::vector<char> h_jobs;       // STEP3: host copy (jobs are passed by value in param space)
   std::vector<int64_t> h_prefix;
@@ -88,25 +88,27 @@ static const bool g_param_jobs = getenv("MEEP_B200_PARAMJOBS") && atoi(getenv("M
 // 6 -> 1.36 ms per step (16 planes per CTA).
 static const int g_split_general = getenv("MEEP_B200_SPLIT_PML") ? atoi(getenv("MEEP_B200_SPLIT_PML")) : 4;
 
-// Fast-path kernel form.  Default: one table-driven launch with the masked march for every thread (the
-// round-1 form).  MEEP_B200_PLAIN_LEAN=1: two launches per job, the lean march (fused.cuh:
-// step3_lean_kernel) for full threads and the masked march for the boundary shell (step3_rest_kernel).
-// Measured (B200, 512^3; bench/micro/pml_shapes.cu "lean", profiles/r2ab_*): over the SAME tiles the
-// separately compiled lean march beats the masked one by 4 % (double, B half, two planes in flight),
-// 1 % (double, D-E half), 19 % and 10 % (single) — but 16 % of the tiles hold a boundary thread (the
-// iz = 0 column sits in every first z-tile) and re-walking them costs more than the lean march gains:
-// whole fast path 3.85 -> 4.15 ms double, 2.52 -> 2.52 ms single.  Earlier forms, per-launch ncu times
-// B half / D-E half at 512^3 double (profiles/README.md, r2d-r2g): masked march 1597 / 2350 us; ONE
-// kernel holding both marches 1639 / 2790 us; more CTAs per SM (5: 1894 us, 6: 2120 us for the B half);
-// operands staged through shared memory with 8-byte cp.async 2518 / 2896 us.
+// Fast-path kernel form.  Default: per job, the lean march (fused.cuh: step3_lean_kernel) over the full
+// box + the masked march over the shell (two x-slab jobs, a list of (y, z) columns) where that pays —
+// single precision, and the half-step without the E/H epilogue in double — and one table-driven launch
+// of the masked march otherwise.  MEEP_B200_PLAIN_LEAN=0: the masked march for everything (the round-1
+// form).  Measured (B200; bench/micro/pml_shapes.cu "lean", profiles/r2ab_*, r2ad_*): lean + shell against
+// masked over the 492^3 interior: -9.8 % (double, B half), +0.7 % (double, D-E half), -17 % / -6 % (single);
+// 1024^3 step 37.70 -> 36.8 ms with every job lean.  Forms that lost, per-launch ncu times B half / D-E
+// half at 512^3 double (profiles/README.md, r2d-r2g): masked march 1597 / 2350 us; ONE kernel holding both
+// marches 1639 / 2790 us; the boundary TILES re-walked by the masked march 3.85 -> 4.15 ms per step; more
+// CTAs per SM (5: 1894 us, 6: 2120 us for the B half); operands staged through shared memory with 8-byte
+// cp.async 2518 / 2896 us.
 // MEEP_B200_EDHB_INTERLEAVE=0: the three component jobs of an off-diagonal E update one after the other
 static const bool g_edhb_interleave = !getenv("MEEP_B200_EDHB_INTERLEAVE") || atoi(getenv("MEEP_B200_EDHB_INTERLEAVE")) != 0;
-static const bool g_plain_lean = getenv("MEEP_B200_PLAIN_LEAN") && atoi(getenv("MEEP_B200_PLAIN_LEAN")) != 0;
+static const bool g_plain_lean = !getenv("MEEP_B200_PLAIN_LEAN") || atoi(getenv("MEEP_B200_PLAIN_LEAN")) != 0;
 
+// *kernels = number of kernels the plan run launched (what mb200_launch_count reports)
 template <typename T>
-static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
+static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run, int *kernels) {
   const dim3 grid((unsigned)p->tiles), block(kThreads);
   cudaStream_t s = c->stream;
+  *kernels = 1;
   switch (p->kind) {
     case MB200_K_CURL:
       curl_kernel<T><<<grid, block, 0, s>>>((const mb200_curl_job_t *)p->d_jobs, p->d_prefix,
@@ -152,6 +154,7 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
                                                     p->njobs, (double *)d_run, J0.nomega);
       flux_final_kernel<<<dim3((unsigned)ceil_div(J0.nomega, kThreads / 32)), block, 0, s>>>(
           (const double *)d_run, p->tiles, J0.nomega, J0.nomega, J0.out);
+      *kernels = 2;
       break;
     }
     case MB200_K_BETA:
@@ -187,9 +190,9 @@ static cudaError_t launch_plan(mb200_ctx *c, mb200_plan *p, const void *d_run) {
                                p->njobs, p->all_plain, s);
         break;
       }
-      launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
+      *kernels = launch_step3<T>((const mb200_step3_job_t *)p->d_jobs, p->d_prefix, p->njobs, p->tiles,
                       p->all_plain, g_split_general, s, (const mb200_step3_job_t *)p->h_jobs.data(),
-                      p->h_prefix.data(), p->d_rest, p->h_rest_prefix.data());
+                      p->h_prefix.data(), p->lean);
       break;
   }
   return cudaGetLastError();
@@ -375,7 +378,7 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
   p->d_jobs = nullptr;
   p->d_prefix = nullptr;
   p->d_group = nullptr;
-  p->d_rest = nullptr;
+  p->lean = nullptr;
   p->bytes = p->points = 0;
   p->all_plain = kind == MB200_K_STEP3 && njobs > 0;
   if (kind == MB200_K_STEP3)
@@ -466,14 +469,46 @@ int mb200_plan_create(mb200_ctx *c, int kind, int dtype, const void *jobs, int n
     CUDA_TRY(cudaMemcpyAsync(p->d_prefix, prefix.data(), sizeof(int64_t) * (njobs + 1),
                              cudaMemcpyHostToDevice, c->stream));
     if (kind == MB200_K_STEP3 && p->all_plain && g_plain_lean && njobs <= kMaxJobLaunches) {
-      std::vector<int> rest;
-      p->h_rest_prefix.assign(1, 0);
+      p->lean = new Step3LeanPlan();
+      auto upload = [&](const void *host, size_t bytes) -> void * {
+        void *d = nullptr;
+        if (cudaMalloc(&d, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+        p->lean_allocs.push_back(d);
+        if (bytes && cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return d;
+      };
       for (int j = 0; j < njobs; ++j) {
-        step3_rest_tiles(((const mb200_step3_job_t *)jobs)[j], rest);
-        p->h_rest_prefix.push_back((int64_t)rest.size());
+        const Step3Shell S = step3_shell(((const mb200_step3_job_t *)jobs)[j]);
+        Step3LeanPlan::Job L;
+        memset(&L, 0, sizeof(L));
+        L.lean = S.lean;
+        if (S.lean) {
+          L.x_lo = S.lo[0];
+          L.x_hi = S.hi[0];
+          L.ncols = (int)S.cols.size();
+          L.d_cols = (const int *)upload(S.cols.data(), S.cols.size() * sizeof(int));
+          L.nslabs = (int)S.slabs.size();
+          std::vector<int64_t> sp(S.slabs.size() + 1, 0);
+          for (size_t k = 0; k < S.slabs.size(); ++k)
+            sp[k + 1] = sp[k] + step3_tiles(S.slabs[k]);
+          L.slab_tiles = sp.back();
+          L.d_slabs = (const mb200_step3_job_t *)upload(S.slabs.data(), S.slabs.size() * sizeof(mb200_step3_job_t));
+          L.d_slab_prefix = (const int64_t *)upload(sp.data(), sp.size() * sizeof(int64_t));
+          if (!L.d_cols || !L.d_slabs || !L.d_slab_prefix) {
+            mb200_plan_destroy(c, p);
+            return fail("mb200_plan_create: out of device memory (lean plan)");
+          }
+        }
+        { // the masked march for the whole job (when the lean march does not pay): its own two-entry prefix
+          const int64_t own[2] = {0, prefix[j + 1] - prefix[j]};
+          L.d_own_prefix = (const int64_t *)upload(own, sizeof(own));
+          if (!L.d_own_prefix) {
+            mb200_plan_destroy(c, p);
+            return fail("mb200_plan_create: out of device memory (lean plan)");
+          }
+        }
+        p->lean->jobs.push_back(L);
       }
-      CUDA_TRY(cudaMalloc((void **)&p->d_rest, sizeof(int) * (rest.size() + 1)));
-      CUDA_TRY(cudaMemcpy(p->d_rest, rest.data(), sizeof(int) * rest.size(), cudaMemcpyHostToDevice));
     }
     if (any_group) {
       CUDA_TRY(cudaMalloc((void **)&p->d_group, sizeof(int) * njobs));
@@ -492,7 +527,9 @@ void mb200_plan_destroy(mb200_ctx *c, mb200_plan *p) {
   if (p->d_jobs) cudaFree(p->d_jobs);
   if (p->d_prefix) cudaFree(p->d_prefix);
   if (p->d_group) cudaFree(p->d_group);
-  if (p->d_rest) cudaFree(p->d_rest);
+  for (void *d : p->lean_allocs)
+    cudaFree(d);
+  delete p->lean;
   delete p;
 }
 
@@ -551,12 +588,13 @@ int mb200_plan_run(mb200_ctx *c, mb200_plan *p, const void *run_data, size_t run
     CUDA_TRY(cudaEventCreate(&rec.b));
     CUDA_TRY(cudaEventRecord(rec.a, c->stream));
   }
-  cudaError_t e = p->dtype == MB200_F64 ? launch_plan<double>(c, p, c->run_buf)
-                                        : launch_plan<float>(c, p, c->run_buf);
+  int kernels = 1;
+  cudaError_t e = p->dtype == MB200_F64 ? launch_plan<double>(c, p, c->run_buf, &kernels)
+                                        : launch_plan<float>(c, p, c->run_buf, &kernels);
   if (e != cudaSuccess)
     return fail("kernel launch (kind %d, %lld tiles) failed: %s", p->kind, (long long)p->tiles,
                 cudaGetErrorString(e));
-  c->launches += 1;
+  c->launches += kernels;
   if (c->profiling) {
     CUDA_TRY(cudaEventRecord(rec.b, c->stream));
     if (rec.slot >= 0)

@@ -261,36 +261,37 @@ MB200_HD bool step3_job_leanable(const mb200_step3_job_t &J) {
     ok = ok && (J.c[c].e != nullptr) == (J.c[0].e != nullptr) && (J.c[c].u != nullptr) == (J.c[0].u != nullptr);
   return ok;
 }
-// (x part: uniform over the CTA; y-z part: per thread)
-MB200_HD bool step3_full_x(const mb200_step3_job_t &J, int ix0, int ix_end) {
-  bool full = true;
-  for (int c = 0; c < 3; ++c) {
-    const mb200_step3_comp_t &C = J.c[c];
-    full = full && ix0 >= C.lo[0] && ix_end - 1 <= C.hi[0] && !(C.metal_lo[0] >= ix0 && C.metal_lo[0] < ix_end) &&
-           !(C.metal_hi[0] >= ix0 && C.metal_hi[0] < ix_end);
+// The full box of a job: the index box on which every thread is full — every component owned in
+// all three directions, no metal x-plane inside (metal y / z planes are handled by the lean march).
+// Empty (lo > hi in some direction) if there is none.
+MB200_HD void step3_full_box(const mb200_step3_job_t &J, int (&lo)[3], int (&hi)[3]) {
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = 0;
+    hi[d] = J.n[d];
+    for (int c = 0; c < 3; ++c) {
+      if (J.c[c].lo[d] > lo[d]) lo[d] = J.c[c].lo[d];
+      if (J.c[c].hi[d] < hi[d]) hi[d] = J.c[c].hi[d];
+    }
   }
-  return full;
-}
-MB200_HD bool step3_full_yz(const mb200_step3_job_t &J, int iy, int iz) {
-  bool full = true;
-  for (int c = 0; c < 3; ++c) {
-    const mb200_step3_comp_t &C = J.c[c];
-    full = full && iy >= C.lo[1] && iy <= C.hi[1] && iz >= C.lo[2] && iz <= C.hi[2];
-  }
-  return full;
+  if (J.ix_lo > lo[0]) lo[0] = J.ix_lo;
+  if (J.ix_hi < hi[0]) hi[0] = J.ix_hi;
+  // metal x-planes are boundary planes of the owned box: cut them off (one at a time is enough —
+  // after a cut the next plane is tested against the shrunken range)
+  for (int pass = 0; pass < 6; ++pass)
+    for (int c = 0; c < 3; ++c) {
+      const int m[2] = {J.c[c].metal_lo[0], J.c[c].metal_hi[0]};
+      for (int k = 0; k < 2; ++k)
+        if (m[k] >= lo[0] && m[k] <= hi[0]) {
+          if (m[k] - lo[0] <= hi[0] - m[k]) lo[0] = m[k] + 1;
+          else hi[0] = m[k] - 1;
+        }
+    }
 }
 
-// SKIP_FULL: the full threads of this job are marched by step3_lean_kernel
-template <typename T, bool SKIP_FULL = false>
-MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
-  const mb200_box_t box = step3_box(J);
-  int ix0, ix_end, iy, iz;
-  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
-  int64_t i = box_index(box, ix0, iy, iz);
-  const int64_t sx = box.s[0];
-  ix0 += box.reserved;
-  ix_end += box.reserved;
-  if (SKIP_FULL && step3_job_leanable(J) && step3_full_x(J, ix0, ix_end) && step3_full_yz(J, iy, iz)) return;
+// one thread of the masked march at loop point (ix0 .. ix_end, iy, iz) of the job (array indices)
+template <typename T>
+MB200_HD void step3_plain_column(const mb200_step3_job_t &J, int ix0, int ix_end, int iy, int iz) {
+  const int64_t i = (int64_t)ix0 * J.stride[0] + (int64_t)iy * J.stride[1] + (int64_t)iz * J.stride[2];
   bool myz[3], metal_yz[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -299,21 +300,35 @@ MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int t
     metal_yz[c] = iy == C.metal_lo[1] || iy == C.metal_hi[1] || iz == C.metal_lo[2] ||
                   iz == C.metal_hi[2];
   }
-  step3_plain_general<T>(J, i, sx, ix0, ix_end, myz, metal_yz);
+  step3_plain_general<T>(J, i, J.stride[0], ix0, ix_end, myz, metal_yz);
 }
 
-// The full threads of one job (descriptor in kernel-parameter space: every field is a constant-bank
-// operand).  Planes in flight: two in double without the epilogue (the B half-step of a chunk whose H
-// aliases B: 12 operands per plane), one with it; single precision holds twice as many.
+template <typename T>
+MB200_HD void step3_plain_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
+  const mb200_box_t box = step3_box(J);
+  int ix0, ix_end, iy, iz;
+  if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
+  step3_plain_column<T>(J, ix0 + box.reserved, ix_end + box.reserved, iy, iz);
+}
+
+// The points of the full box of one job (descriptor in kernel-parameter space: every field is a
+// constant-bank operand), tiled like the job itself with the march clipped to the full x-range.
+// Planes in flight: two in double without the epilogue (the B half-step of a chunk whose H aliases
+// B: 12 operands per plane), one with it; two in single precision.
 template <typename T>
 MB200_HD void step3_lean_thread(const mb200_step3_job_t &J, int64_t tile, int tid) {
   const mb200_box_t box = step3_box(J);
   int ix0, ix_end, iy, iz;
   if (!box_thread_point(box, tile, tid, ix0, ix_end, iy, iz, step3_t1(J))) return;
-  const int64_t i = box_index(box, ix0, iy, iz);
   ix0 += box.reserved;
   ix_end += box.reserved;
-  if (!(step3_full_x(J, ix0, ix_end) && step3_full_yz(J, iy, iz))) return;
+  int lo[3], hi[3];
+  step3_full_box(J, lo, hi);
+  if (iy < lo[1] || iy > hi[1] || iz < lo[2] || iz > hi[2]) return;
+  if (ix0 < lo[0]) ix0 = lo[0];
+  if (ix_end > hi[0] + 1) ix_end = hi[0] + 1;
+  if (ix0 >= ix_end) return;
+  const int64_t i = (int64_t)ix0 * J.stride[0] + (int64_t)iy * J.stride[1] + (int64_t)iz * J.stride[2];
   bool metal_yz[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -322,9 +337,41 @@ MB200_HD void step3_lean_thread(const mb200_step3_job_t &J, int64_t tile, int ti
   }
   constexpr int kB = 2, kE = sizeof(T) == 4 ? 2 : 1; // (measured: bench/micro/pml_shapes.cu "lean")
   const bool epi = J.c[0].e != nullptr, hasu = epi && J.c[0].u != nullptr;
-  if (hasu) step3_plain_fast<T, true, true, kE>(J, i, box.s[0], ix0, ix_end, metal_yz);
-  else if (epi) step3_plain_fast<T, true, false, kE>(J, i, box.s[0], ix0, ix_end, metal_yz);
-  else step3_plain_fast<T, false, false, kB>(J, i, box.s[0], ix0, ix_end, metal_yz);
+  if (hasu) step3_plain_fast<T, true, true, kE>(J, i, J.stride[0], ix0, ix_end, metal_yz);
+  else if (epi) step3_plain_fast<T, true, false, kE>(J, i, J.stride[0], ix0, ix_end, metal_yz);
+  else step3_plain_fast<T, false, false, kB>(J, i, J.stride[0], ix0, ix_end, metal_yz);
+}
+
+// host side, at plan creation: the shell of a plain job
+struct Step3Shell {
+  bool lean;                           // the job has a non-empty full box and the lean march applies
+  int lo[3], hi[3];                    // the full box
+  std::vector<int> cols;               // (y, z) columns outside it
+  std::vector<mb200_step3_job_t> slabs; // x-planes outside it (copies of the job with ix_lo / ix_hi set)
+};
+inline Step3Shell step3_shell(const mb200_step3_job_t &J) {
+  Step3Shell S;
+  step3_full_box(J, S.lo, S.hi);
+  S.lean = step3_job_leanable(J) && S.lo[0] <= S.hi[0] && S.lo[1] <= S.hi[1] && S.lo[2] <= S.hi[2];
+  if (!S.lean) return S;
+  const int row = J.n[2] + 1;
+  for (int iy = 0; iy <= J.n[1]; ++iy)
+    for (int iz = 0; iz <= J.n[2]; ++iz)
+      if (iy < S.lo[1] || iy > S.hi[1] || iz < S.lo[2] || iz > S.hi[2]) S.cols.push_back(iy * row + iz);
+  const int first = J.ix_lo > 0 ? J.ix_lo : 0, last = J.ix_hi < J.n[0] ? J.ix_hi : J.n[0];
+  if (S.lo[0] > first) {
+    mb200_step3_job_t A = J;
+    A.ix_lo = first;
+    A.ix_hi = S.lo[0] - 1;
+    S.slabs.push_back(A);
+  }
+  if (S.hi[0] < last) {
+    mb200_step3_job_t B = J;
+    B.ix_lo = S.hi[0] + 1;
+    B.ix_hi = last;
+    S.slabs.push_back(B);
+  }
+  return S;
 }
 
 // ---- general path --------------------------------------------------------------------------------
@@ -622,7 +669,7 @@ MB200_HD void step3c_march(const mb200_step3_job_t &J, const mb200_step3_comp_t 
 }
 
 #ifdef __CUDACC__
-__device__ int g_pml_pair = 4; // MEEP_B200_PML_PAIR=n: at most n x-planes in flight per thread (1: one plane per iteration)
+__device__ int g_pml_pair = 4; // MEEP_B200_PML_PAIR=0|1: one x-plane per iteration for every variant (A/B switch)
 // The same march with NP x-planes loaded before the first store.  The PML kernel is latency-bound
 // (ncu, 512^3: issue slots 25 % busy, DRAM 52 %, DRAM bytes = 1.03 x algorithmic): with one component
 // per thread a plane keeps only 6-13 loads in flight per thread against 15-18 in the fast path, so the
@@ -831,51 +878,42 @@ __global__ void __launch_bounds__(kThreads)
   step3_plain_thread<T>(J, tile, threadIdx.x);
 }
 
-// ---- the fast path as two launches per job: full threads / the rest -------------------------------
-// step3_lean_kernel marches the full threads of ONE job over all its tiles (everybody else returns at
-// once); step3_rest_kernel runs the masked march over the tiles that hold at least one other thread
-// (rest_tiles: the boundary shell of the chunk, listed by the host) and skips the full ones.  Both
-// write disjoint points and read only arrays that neither writes.  One kernel with both marches was
-// measured slower than the masked march alone (joint register allocation); separately compiled, the
-// lean march is 4 % (double) to 19 % (single, B half) faster than the masked one over the same tiles
-// (bench/micro/pml_shapes.cu "lean") — and the second walk over the boundary tiles (16 % of them at
-// 512^3: the iz = 0 column is in every first z-tile) costs more than that, so this pair is opt-in
-// (MEEP_B200_PLAIN_LEAN=1, see capi.cu) and the masked march stays the default.
+// ---- the fast path as lean + shell launches per job -------------------------------------------------
+// step3_lean_kernel marches the full box of ONE job (step3_full_box) with the lean march.  What is
+// left is a shell one or two points thick: the x-planes below and above the full box go through the
+// ordinary masked kernel as two slab jobs (ix_lo / ix_hi restricted copies of the job), and the
+// (y, z) columns outside the full box — listed by the host — are marched over the full x-range by
+// step3_cols_kernel, one thread per column.  The three launches write disjoint points and read only
+// arrays that none of them writes.  History: one kernel holding both marches was slower than the masked
+// march alone (joint register allocation); re-walking every TILE that holds a non-full thread with the
+// masked march (16 % of the tiles at 512^3: the iz = 0 column sits in every first z-tile) cost more than
+// the lean march gained (profiles/r2ab_*); with the shell as slabs + columns the 1024^3 step went
+// 37.70 -> 36.8 ms with every job lean (profiles/r2ad_*), and the D-E half in double is left to the
+// masked march (see launch_step3).
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 4)
     step3_lean_kernel(const __grid_constant__ mb200_step3_job_t J) {
   step3_lean_thread<T>(J, (int64_t)blockIdx.x, threadIdx.x);
 }
+// cols[k] = iy * (n[2] + 1) + iz of the k-th shell column; blockIdx.y = chunk of planes of the full x-range
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    step3_rest_kernel(const mb200_step3_job_t *__restrict__ job, const int *__restrict__ rest_tiles) {
+    step3_cols_kernel(const mb200_step3_job_t *__restrict__ job, const int *__restrict__ cols, int ncols,
+                      int x_lo, int x_hi, int planes) {
   __shared__ mb200_step3_job_t J;
   const int *src = reinterpret_cast<const int *>(job);
   int *dst = reinterpret_cast<int *>(&J);
   for (int k = threadIdx.x; k < (int)(sizeof(J) / sizeof(int)); k += blockDim.x)
     dst[k] = __ldg(src + k);
   __syncthreads();
-  step3_plain_thread<T, true>(J, (int64_t)__ldg(rest_tiles + blockIdx.x), threadIdx.x);
+  const int k = (int)blockIdx.x * kThreads + (int)threadIdx.x;
+  if (k >= ncols) return;
+  const int col = __ldg(cols + k), row = J.n[2] + 1;
+  const int ix0 = x_lo + (int)blockIdx.y * planes;
+  const int ix_end = ix0 + planes < x_hi + 1 ? ix0 + planes : x_hi + 1;
+  if (ix0 < ix_end) step3_plain_column<T>(J, ix0, ix_end, col / row, col % row);
 }
 constexpr int kMaxJobLaunches = 8; // more plain jobs than this: one table-driven launch
-
-// tiles of a plain job that hold a thread which is not full (host side, at plan creation)
-inline void step3_rest_tiles(const mb200_step3_job_t &J, std::vector<int> &out) {
-  const mb200_box_t box = step3_box(J);
-  const int t1 = step3_t1(J);
-  const int64_t tiles = box_tiles(box, t1);
-  const bool leanable = step3_job_leanable(J);
-  for (int64_t t = 0; t < tiles; ++t) {
-    bool rest = !leanable;
-    for (int tid = 0; tid < kThreads && !rest; ++tid) {
-      int ix0, ix_end, iy, iz;
-      if (!box_thread_point(box, t, tid, ix0, ix_end, iy, iz, t1)) continue;
-      if (tid == 0 && !step3_full_x(J, ix0 + box.reserved, ix_end + box.reserved)) rest = true;
-      if (!step3_full_yz(J, iy, iz)) rest = true;
-    }
-    if (rest) out.push_back((int)t);
-  }
-}
 
 // ---- job table in kernel-parameter (constant) space ---------------------------------------------
 // The job descriptor is CTA-uniform.  Staging it in shared memory costs an LDS (and a short-
@@ -924,17 +962,55 @@ static void launch_step3_params(const mb200_step3_job_t *h_jobs, const int64_t *
   }
 }
 
+// what plan_create prepares for the lean + shell launches of an all-plain plan
+struct Step3LeanPlan {
+  struct Job {
+    bool lean;
+    int x_lo, x_hi, ncols;
+    const int *d_cols;
+    int nslabs;
+    const mb200_step3_job_t *d_slabs; // [nslabs]
+    const int64_t *d_slab_prefix;     // [nslabs + 1]
+    const int64_t *d_own_prefix;      // {0, tiles of the job}: the masked march over the whole job
+    int64_t slab_tiles;
+  };
+  std::vector<Job> jobs;
+};
+
+// returns the number of kernels launched
 template <typename T>
-static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
-                         int64_t tiles, bool all_plain, int split, cudaStream_t s,
-                         const mb200_step3_job_t *h_jobs, const int64_t *h_prefix, const int *d_rest,
-                         const int64_t *h_rest_prefix) {
-  if (all_plain && d_rest) { // lean + rest launches per job (plan_create listed the rest tiles)
+static int launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, int njobs,
+                        int64_t tiles, bool all_plain, int split, cudaStream_t s,
+                        const mb200_step3_job_t *h_jobs, const int64_t *h_prefix, const Step3LeanPlan *lean) {
+  if (all_plain && lean && (int)lean->jobs.size() == njobs) {
+    int launched = 0;
     for (int j = 0; j < njobs; ++j) {
-      const int64_t t = h_prefix[j + 1] - h_prefix[j], r = h_rest_prefix[j + 1] - h_rest_prefix[j];
-      if (t > 0 && r < t) step3_lean_kernel<T><<<dim3((unsigned)t), dim3(kThreads), 0, s>>>(h_jobs[j]);
-      if (r > 0) step3_rest_kernel<T><<<dim3((unsigned)r), dim3(kThreads), 0, s>>>(jobs + j, d_rest + h_rest_prefix[j]);
+      const Step3LeanPlan::Job &L = lean->jobs[j];
+      const int64_t t = h_prefix[j + 1] - h_prefix[j];
+      if (t <= 0) continue;
+      // Where the lean march pays (B200, bench/micro/pml_shapes.cu "lean", 492^3 interior; lean + shell
+      // against the masked march): double without the epilogue -9.8 %, double with it +0.7 %, single
+      // -17 % and -6 %.  So: every job in single precision, the jobs without the epilogue in double.
+      const bool pays = sizeof(T) == 4 || h_jobs[j].c[0].e == nullptr;
+      if (!L.lean || !pays) { // (or no full box / not the cyclic operand layout): the masked march for the whole job
+        step3_plain_kernel<T><<<dim3((unsigned)t), dim3(kThreads), 0, s>>>(jobs + j, L.d_own_prefix, 1);
+        ++launched;
+        continue;
+      }
+      step3_lean_kernel<T><<<dim3((unsigned)t), dim3(kThreads), 0, s>>>(h_jobs[j]);
+      ++launched;
+      if (L.slab_tiles > 0) {
+        step3_plain_kernel<T><<<dim3((unsigned)L.slab_tiles), dim3(kThreads), 0, s>>>(L.d_slabs, L.d_slab_prefix, L.nslabs);
+        ++launched;
+      }
+      if (L.ncols > 0) {
+        ++launched;
+        const int planes = step3_t1(h_jobs[j]);
+        const dim3 grid((unsigned)((L.ncols + kThreads - 1) / kThreads), (unsigned)((L.x_hi - L.x_lo + planes) / planes));
+        step3_cols_kernel<T><<<grid, dim3(kThreads), 0, s>>>(jobs + j, L.d_cols, L.ncols, L.x_lo, L.x_hi, planes);
+      }
     }
+    return launched;
   }
   else if (all_plain)
     step3_plain_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
@@ -952,6 +1028,7 @@ static void launch_step3(const mb200_step3_job_t *jobs, const int64_t *prefix, i
   }
   else
     step3_kernel<T><<<dim3((unsigned)tiles), dim3(kThreads), 0, s>>>(jobs, prefix, njobs);
+  return 1;
 }
 
 #endif // __CUDACC__

@@ -94,7 +94,13 @@ void comm_init() {
     sa.sin_family = AF_INET;
     sa.sin_addr.s_addr = htonl(INADDR_ANY);
     sa.sin_port = htons((uint16_t)port);
-    if (bind(ls, (sockaddr *)&sa, sizeof(sa)) < 0) die("bind");
+    // (a port that is busy for a moment — a short-lived client socket that happened to get this
+    // number — is retried for a few seconds before giving up; the other ranks keep knocking meanwhile)
+    for (int attempt = 0;; ++attempt) {
+      if (bind(ls, (sockaddr *)&sa, sizeof(sa)) == 0) break;
+      if (errno != EADDRINUSE || attempt >= 50) die("bind");
+      usleep(100 * 1000);
+    }
     if (listen(ls, g_size) < 0) die("listen");
     g_peer.assign(g_size, -1);
     for (int k = 1; k < g_size; ++k) {

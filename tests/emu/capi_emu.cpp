@@ -138,6 +138,27 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
         const mb200_step3_job_t &J = ((const mb200_step3_job_t *)p->jobs.data())[j];
         const bool plain = step3_is_plain(J);
         static const bool split = !(getenv("MEEP_B200_SPLIT_PML") && atoi(getenv("MEEP_B200_SPLIT_PML")) == 0);
+        static const bool lean = getenv("MEEP_B200_PLAIN_LEAN") && atoi(getenv("MEEP_B200_PLAIN_LEAN")) != 0;
+        if (plain && lean) {
+          // the lean + shell launches of the device path (fused.cuh: launch_step3), thread by thread
+          const Step3Shell S = step3_shell(J);
+          if (S.lean) {
+            for (int64_t t = 0; t < ntiles; ++t)
+              for (int tid = 0; tid < kThreads; ++tid)
+                step3_lean_thread<T>(J, t, tid);
+            for (const mb200_step3_job_t &slab : S.slabs) {
+              const int64_t st = step3_tiles(slab);
+              for (int64_t t = 0; t < st; ++t)
+                for (int tid = 0; tid < kThreads; ++tid)
+                  step3_plain_thread<T>(slab, t, tid);
+            }
+            const int row = J.n[2] + 1, planes = step3_t1(J);
+            for (int col : S.cols)
+              for (int x0 = S.lo[0]; x0 <= S.hi[0]; x0 += planes)
+                step3_plain_column<T>(J, x0, x0 + planes < S.hi[0] + 1 ? x0 + planes : S.hi[0] + 1, col / row, col % row);
+            break;
+          }
+        }
         for (int64_t t = 0; t < ntiles; ++t) {
           if (!plain && split) {
             for (int c = 0; c < 3; ++c)

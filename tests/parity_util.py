@@ -59,6 +59,25 @@ def run_case(arm, prec, case, nsteps, num_chunks=0, env=None, name="sim_driver",
             os.unlink(path)
 
 
+def free_ports(n=2):
+    """n distinct TCP ports on 127.0.0.1 that are free right now (all held open together, then
+    released): MASTER_PORT for the launcher's contract and MEEP_B200_PORT for the process runtime —
+    deriving the second from the first (MASTER_PORT + 37, the runtime's default) now and then hit a
+    port somebody else was using"""
+    import socket
+    socks = []
+    try:
+        for _ in range(n):
+            s = socket.socket()
+            s.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            s.bind(("127.0.0.1", 0))
+            socks.append(s)
+        return [s.getsockname()[1] for s in socks]
+    finally:
+        for s in socks:
+            s.close()
+
+
 def run_case_mp(arm, prec, case, nsteps, num_chunks, world=2, env=None, name="sim_driver", timeout=900):
     """the same driver as `world` cooperating processes (one per device), launched the way torchrun
     launches ranks: RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT in the environment.
@@ -69,16 +88,13 @@ def run_case_mp(arm, prec, case, nsteps, num_chunks, world=2, env=None, name="si
     exe = driver(name, arm, prec)
     fd, path = tempfile.mkstemp(suffix=".bin", prefix="mb200_%s_%s_mp_" % (case, arm))
     os.close(fd)
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
+    port, rt_port = free_ports(2)
     procs = []
     for r in range(world):
         e = dict(os.environ)
         e.setdefault("OMP_NUM_THREADS", "2")
         e.update({"RANK": str(r), "WORLD_SIZE": str(world), "LOCAL_RANK": str(r),
-                  "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
+                  "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "MEEP_B200_PORT": str(rt_port)})
         if env:
             e.update(env)
         procs.append(subprocess.Popen([exe, case, str(nsteps), path, str(num_chunks)], env=e,

@@ -2,6 +2,7 @@
 translation, lazy allocation, mirror protocol, plan caching) exercised WITHOUT a GPU: the
 drop-in library is linked against the test-only emulator of the C ABI (tests/emu), and the full
 simulations are compared array by array with the unmodified reference build (oracle/_ref)."""
+import numpy as np
 import os
 import subprocess
 
@@ -83,6 +84,24 @@ def test_fused_and_unfused_paths_agree(case, steps):
     compare(b, ref, TOL["f64"])
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("case,steps,chunks", [("c2_3d_pml", 20, 0), ("3d_metal", 20, 1), ("3d_metal", 20, 6),
+                                               ("3d_bloch", 20, 0), ("c2_3d_pml_integrated", 20, 0),
+                                               ("3d_sync_magnetic", 20, 4)])
+def test_lean_plus_shell_decomposition_of_the_fast_path(case, steps, chunks, prec):
+    """MEEP_B200_PLAIN_LEAN=1: every fast-path job is carried out as the lean march over its full box +
+    two x-slab jobs + the list of (y, z) shell columns (csrc/fused.cuh: step3_shell).  The emulator
+    walks exactly those pieces, thread by thread: a point missed or visited twice, or a lean march
+    whose arithmetic differed from the masked one, shows up against the reference."""
+    ref = run_case("ref", prec, case, steps, chunks)
+    got = run_case("emu", prec, case, steps, chunks, env={"MEEP_B200_PLAIN_LEAN": "1"})
+    compare(got, ref, TOL[prec])
+    # and the decomposition is bit-identical to the masked march of the same build
+    same = run_case("emu", prec, case, steps, chunks)
+    for k in same:
+        assert np.array_equal(np.asarray(got[k]), np.asarray(same[k])), k
+
+
 def test_eager_mirror_mode():
     ref = run_case("ref", "f64", "3d_metal", 10)
     got = run_case("emu", "f64", "3d_metal", 10, env={"MEEP_B200_EAGER": "1"})
@@ -158,14 +177,12 @@ def test_process_runtime_reductions_and_broadcasts(world):
     import socket
     from parity_util import driver
     exe = driver("comm_driver", "emu", "f64")
-    sock = socket.socket()
-    sock.bind(("127.0.0.1", 0))
-    port = sock.getsockname()[1]
-    sock.close()
+    from parity_util import free_ports
+    port, rt_port = free_ports(2)
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port))
+                   MASTER_PORT=str(port), MEEP_B200_PORT=str(rt_port))
         procs.append(subprocess.Popen([exe], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     for r, p in enumerate(procs):
         out, _ = p.communicate(timeout=120)
