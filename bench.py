@@ -425,8 +425,9 @@ def main():
                                                    "do not skip (zero-block flags, measured)" if kernel_sum_smaller else "")},
                         "kernels": prof}
 
-        # DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture of this
-        # very configuration (profiles/traffic_<workload>_<n>_<prec>.json).  The capture names the kernel
+        # DRAM bytes per launch (= per plan run: the fast path of a half-step may be several kernels) of the
+        # dominant kernel from a committed ncu capture (`--set full`, or a pass with just the dram byte
+        # counters) of this very configuration (profiles/traffic_<workload>_<n>_<prec>.json).  The capture names the kernel
         # sources it was taken on: a capture of another build is reported as such, not as this build's.
         if roofline and world == 1:
             tf = os.path.join(ROOT, "profiles", "traffic_%s_%d_%s.json" % (args.workload, n, args.prec))
@@ -435,8 +436,8 @@ def main():
                     t = json.load(fh)
                 if t.get("kernel") == dom[0]:
                     roofline["traffic"] = t["dram_bytes_per_launch"]
-                    roofline["traffic_source"] = "%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, " \
-                                                 "mean over the launches of the kernel)" % os.path.relpath(tf, ROOT)
+                    roofline["traffic_source"] = "%s (%s)" % (os.path.relpath(tf, ROOT), t.get(
+                        "how", "ncu, dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of the kernel"))
                     roofline["traffic_build"] = t.get("csrc_stamp")
                     roofline["traffic_build_is_this_build"] = t.get("csrc_stamp") == csrc_stamp()
             except (OSError, KeyError, ValueError):

@@ -49,7 +49,8 @@ def main():
                          "seconds_under_ncu": val("gpu__time_duration.sum", tscale),
                          "registers": int(r[hdr.index("launch__registers_per_thread")]),
                          "grid": int(r[hdr.index("launch__grid_size")])})
-    how = "ncu --set full --clock-control none; dram__bytes_read.sum + dram__bytes_write.sum per launch"
+    how = ("ncu --clock-control none with --set full, or a metrics-only pass (dram__bytes_read.sum, dram__bytes_write.sum, "
+           "gpu__time_duration.sum, launch__registers_per_thread, launch__grid_size); dram__bytes_read.sum + dram__bytes_write.sum per launch")
     per_launch = sum(l["dram_bytes"] for l in launches) / len(launches)
     lean = [i for i, l in enumerate(launches) if "step3_lean_kernel" in l["kernel"]]
     if lean:
