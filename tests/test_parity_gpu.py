@@ -92,9 +92,9 @@ def test_unfused_path_matches_too():
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
-@pytest.mark.parametrize("env", [{"MEEP_B200_PLAIN_LEAN": "1"}, {"MEEP_B200_SPLIT_PML": "3"},
+@pytest.mark.parametrize("env", [{"MEEP_B200_PLAIN_LEAN": "0"}, {"MEEP_B200_SPLIT_PML": "3"},
                                  {"MEEP_B200_SPLIT_PML": "0"}, {"MEEP_B200_PML_PAIR": "1"}],
-                         ids=["lean_plus_rest", "pml_3_ctas_per_sm", "pml_three_components_per_thread", "pml_one_plane"])
+                         ids=["fast_path_masked_march", "pml_3_ctas_per_sm", "pml_three_components_per_thread", "pml_one_plane"])
 def test_opt_in_kernel_forms_match_too(env, prec):
     """the kernel forms kept behind switches (A/B measurements in DESIGN.md section 4) stay correct"""
     ref = run_case("ref", prec, "c2_3d_pml", 60)
