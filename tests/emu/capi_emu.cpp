@@ -138,7 +138,7 @@ template <typename T> static void run_plan(mb200_plan *p, const void *run) {
         const mb200_step3_job_t &J = ((const mb200_step3_job_t *)p->jobs.data())[j];
         const bool plain = step3_is_plain(J);
         static const bool split = !(getenv("MEEP_B200_SPLIT_PML") && atoi(getenv("MEEP_B200_SPLIT_PML")) == 0);
-        static const bool lean = getenv("MEEP_B200_PLAIN_LEAN") && atoi(getenv("MEEP_B200_PLAIN_LEAN")) != 0;
+        static const bool lean = !getenv("MEEP_B200_PLAIN_LEAN") || atoi(getenv("MEEP_B200_PLAIN_LEAN")) != 0; // (the device default)
         if (plain && lean) {
           // the lean + shell launches of the device path (fused.cuh: launch_step3), thread by thread
           const Step3Shell S = step3_shell(J);

@@ -89,15 +89,15 @@ def test_fused_and_unfused_paths_agree(case, steps):
                                                ("3d_bloch", 20, 0), ("c2_3d_pml_integrated", 20, 0),
                                                ("3d_sync_magnetic", 20, 4)])
 def test_lean_plus_shell_decomposition_of_the_fast_path(case, steps, chunks, prec):
-    """MEEP_B200_PLAIN_LEAN=1: every fast-path job is carried out as the lean march over its full box +
+    """The default form of the fast path: every job is carried out as the lean march over its full box +
     two x-slab jobs + the list of (y, z) shell columns (csrc/fused.cuh: step3_shell).  The emulator
     walks exactly those pieces, thread by thread: a point missed or visited twice, or a lean march
     whose arithmetic differed from the masked one, shows up against the reference."""
     ref = run_case("ref", prec, case, steps, chunks)
     got = run_case("emu", prec, case, steps, chunks, env={"MEEP_B200_PLAIN_LEAN": "1"})
     compare(got, ref, TOL[prec])
-    # and the decomposition is bit-identical to the masked march of the same build
-    same = run_case("emu", prec, case, steps, chunks)
+    # and the decomposition is bit-identical to the masked march (MEEP_B200_PLAIN_LEAN=0) of the same build
+    same = run_case("emu", prec, case, steps, chunks, env={"MEEP_B200_PLAIN_LEAN": "0"})
     for k in same:
         assert np.array_equal(np.asarray(got[k]), np.asarray(same[k])), k
 
